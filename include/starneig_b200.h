@@ -1,0 +1,67 @@
+/* starneig_b200.h -- extension entry points of the B200-native Hessenberg library (C ABI).
+ *
+ * The drop-in boundary is <starneig/starneig.h> (same symbols as the reference). The functions below
+ * are additions that the reference does not have: a device-resident variant (no host round trip, for a
+ * downstream GPU stage and for kernel-only timing), per-call statistics for the roofline report, and
+ * unit-level access to the individual kernels so that tests can check each one against the CPU oracle
+ * through the C ABI. All pointers named d* are DEVICE pointers on the current CUDA device.
+ */
+#ifndef STARNEIG_B200_H
+#define STARNEIG_B200_H
+
+#include <starneig/starneig.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Device-resident reduction: same semantics as starneig_SEP_SM_Hessenberg_expert
+ * (reference src/hessenberg/interface.c:138-167) but dA/dQ already live in HBM. Requirements:
+ * 16-byte aligned pointers and even leading dimensions (returns -6 / -8 otherwise).
+ * panel_width < 0 selects the reference default (interface.c:74-78). Blocking. */
+starneig_error_t starneig_b200_hessenberg_device(
+    int n, int begin, int end, int panel_width, double *dA, int ldA, double *dQ, int ldQ);
+
+/* Statistics of the most recent reduction on this process (times in ms, device times from CUDA events). */
+struct starneig_b200_stats {
+    int n, begin, end, panel_width, panels;
+    double wall_ms;          /* host wall clock of the whole call (host API: includes copies) */
+    double h2d_ms, d2h_ms;   /* host<->device staging (host API only) */
+    double device_ms;        /* first kernel to last kernel */
+    double panel_ms;         /* sum over panels: column loops (panel kernels + GEMV) */
+    double trail_ms;         /* sum over panels: trailing right + left updates (critical path) */
+    double other_ms;         /* sum over panels: top rows, partial columns and Q updates */
+    double gemv_ms;          /* sum of GEMV kernel durations (profile level >= 2, else 0) */
+    long long gemv_launches;
+    double gemv_bytes;       /* algorithmic bytes read by all GEMV launches: 8 * sum rows*cols */
+    long long kernel_launches;
+    double gemm_flops;       /* flops executed by the DMMA kernels */
+    long long h2d_bytes, d2h_bytes;
+};
+void starneig_b200_get_stats(struct starneig_b200_stats *stats);
+
+/* 0: no extra events; 1: per-panel phase events (default); 2: additionally time every GEMV launch */
+void starneig_b200_set_profile_level(int level);
+
+/* ---- unit-level kernel access (tests / bench) ---- */
+
+/* C = alpha*op(A)*op(B) + beta*C with the DMMA kernels; transa/transb in {'N','T'}; supported
+ * combinations: NT, TN, NN. Returns 0 or STARNEIG_INVALID_ARGUMENTS. Synchronous. */
+int starneig_b200_dgemm(char transa, char transb, int m, int n, int k, double alpha,
+    const double *dA, int lda, const double *dB, int ldb, double beta, double *dC, int ldc);
+
+/* y = A(m x k) * v with the panel GEMV kernel (v given explicitly). dA may have any 8-byte alignment;
+ * lda must be even. reps > 1 repeats the launch and returns the mean kernel time in ms (CUDA events). */
+int starneig_b200_gemv(int m, int k, const double *dA, int lda, const double *dv, double *dy,
+    int reps, float *mean_ms);
+
+/* one panel factorisation only (columns i .. i+w-1 of the reduction of rows/cols < end), leaving
+ * V, Y, VT (m x w, leading dimension ldw) in the given device buffers; for tests. */
+int starneig_b200_panel(int n, int i, int end, int w, double *dA, int ldA,
+    double *dV, double *dY, double *dVT, int ldw, double *htau);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif

@@ -1,0 +1,7 @@
+"""starneig_b200 -- B200-native (sm_100a) blocked Hessenberg reduction behind StarNEig's C interface.
+
+The product is ``lib/libstarneig.so`` (C ABI, sources in ``csrc/``); this package is the thin host-side
+mirror of the reference interface used by the tests and the benchmark.
+"""
+from .api import *  # noqa: F401,F403
+from .api import lib, get_stats, set_profile_level, hessenberg_device, default_panel_width  # noqa: F401

@@ -1,0 +1,72 @@
+"""ctypes binding of the C-ABI library ``lib/libstarneig.so`` (built by ``csrc/Makefile``).
+
+There is no Python or CPU fallback: if the CUDA library is missing, importing the binding raises.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libstarneig.so")
+
+c_double_p = ctypes.POINTER(ctypes.c_double)
+
+
+class HessenbergConf(ctypes.Structure):
+    """``struct starneig_hessenberg_conf`` (reference src/include/starneig/expert.h:77-92)."""
+    _fields_ = [("tile_size", ctypes.c_int), ("panel_width", ctypes.c_int)]
+
+
+class Stats(ctypes.Structure):
+    """``struct starneig_b200_stats`` (include/starneig_b200.h)."""
+    _fields_ = [
+        ("n", ctypes.c_int), ("begin", ctypes.c_int), ("end", ctypes.c_int),
+        ("panel_width", ctypes.c_int), ("panels", ctypes.c_int),
+        ("wall_ms", ctypes.c_double), ("h2d_ms", ctypes.c_double), ("d2h_ms", ctypes.c_double),
+        ("device_ms", ctypes.c_double), ("panel_ms", ctypes.c_double), ("trail_ms", ctypes.c_double),
+        ("other_ms", ctypes.c_double), ("gemv_ms", ctypes.c_double),
+        ("gemv_launches", ctypes.c_longlong), ("gemv_bytes", ctypes.c_double),
+        ("kernel_launches", ctypes.c_longlong), ("gemm_flops", ctypes.c_double),
+        ("h2d_bytes", ctypes.c_longlong), ("d2h_bytes", ctypes.c_longlong),
+    ]
+
+    def as_dict(self):
+        return {name: getattr(self, name) for name, _ in self._fields_}
+
+
+def load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `make -C starneig_b200/csrc` "
+            "(or __graft_entry__.build()). There is no CPU fallback for the Hessenberg path.")
+    lib = ctypes.CDLL(LIB_PATH, mode=ctypes.RTLD_LOCAL)
+    i, d, vp = ctypes.c_int, ctypes.c_double, ctypes.c_void_p
+
+    lib.starneig_node_init.argtypes = [i, i, ctypes.c_uint]
+    lib.starneig_node_init.restype = None
+    lib.starneig_node_initialized.restype = i
+    lib.starneig_node_finalize.restype = None
+    lib.starneig_node_get_cores.restype = i
+    lib.starneig_node_get_gpus.restype = i
+    lib.starneig_node_set_cores.argtypes = [i]
+    lib.starneig_node_set_gpus.argtypes = [i]
+    lib.starneig_node_enable_pinning.restype = None
+    lib.starneig_node_disable_pinning.restype = None
+    lib.starneig_hessenberg_init_conf.argtypes = [ctypes.POINTER(HessenbergConf)]
+    lib.starneig_hessenberg_init_conf.restype = None
+    lib.starneig_SEP_SM_Hessenberg.argtypes = [i, vp, i, vp, i]
+    lib.starneig_SEP_SM_Hessenberg.restype = i
+    lib.starneig_SEP_SM_Hessenberg_expert.argtypes = [ctypes.POINTER(HessenbergConf), i, i, i, vp, i, vp, i]
+    lib.starneig_SEP_SM_Hessenberg_expert.restype = i
+    lib.starneig_b200_hessenberg_device.argtypes = [i, i, i, i, vp, i, vp, i]
+    lib.starneig_b200_hessenberg_device.restype = i
+    lib.starneig_b200_get_stats.argtypes = [ctypes.POINTER(Stats)]
+    lib.starneig_b200_get_stats.restype = None
+    lib.starneig_b200_set_profile_level.argtypes = [i]
+    lib.starneig_b200_set_profile_level.restype = None
+    lib.starneig_b200_dgemm.argtypes = [ctypes.c_char, ctypes.c_char, i, i, i, d, vp, i, vp, i, d, vp, i]
+    lib.starneig_b200_dgemm.restype = i
+    lib.starneig_b200_gemv.argtypes = [i, i, vp, i, vp, vp, i, ctypes.POINTER(ctypes.c_float)]
+    lib.starneig_b200_gemv.restype = i
+    lib.starneig_b200_panel.argtypes = [i, i, i, i, vp, i, vp, vp, vp, i, vp]
+    lib.starneig_b200_panel.restype = i
+    return lib
