@@ -1,0 +1,130 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads, exports every symbol the headers declare
+(and nothing else), and reproduces the reference's argument/state error behaviour. No compute calls."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+INCLUDE = os.path.join(ROOT, "include")
+
+
+def declared_symbols():
+    names = set()
+    for path in [os.path.join(INCLUDE, "starneig_b200.h")] + [
+            os.path.join(INCLUDE, "starneig", f) for f in sorted(os.listdir(os.path.join(INCLUDE, "starneig")))]:
+        text = open(path).read()
+        text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+        names.update(re.findall(r"\b(starneig_[A-Za-z0-9_]+)\s*\(", text))
+    return names
+
+
+def exported_symbols():
+    from starneig_b200._lib import LIB_PATH
+    out = subprocess.run(["nm", "-D", "--defined-only", LIB_PATH], check=True, capture_output=True, text=True).stdout
+    return {line.split()[-1] for line in out.splitlines() if " T " in line}
+
+
+def test_exports_match_headers():
+    decl, exp = declared_symbols(), exported_symbols()
+    assert decl, "no declarations found"
+    missing = decl - exp
+    assert not missing, f"declared in include/ but not exported: {sorted(missing)}"
+    # everything else is hidden, as in the reference (src/CMakeLists.txt:154-155)
+    extra = {s for s in exp if not s.startswith("starneig_")}
+    assert not extra, f"unexpected exported symbols: {sorted(extra)}"
+
+
+def test_headers_compile_as_c(tmp_path):
+    src = tmp_path / "t.c"
+    src.write_text('#include <starneig/starneig.h>\n#include <starneig_b200.h>\n'
+                   'int main(void){struct starneig_hessenberg_conf c; (void)c; return STARNEIG_SUCCESS;}\n')
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", INCLUDE, "-c", str(src), "-o", str(tmp_path / "t.o")], check=True)
+
+
+def test_c_program_links_against_library(tmp_path):
+    # the reference's own README sample shape: node_init / Hessenberg / node_finalize (README.md:192-199)
+    from starneig_b200._lib import LIB_PATH
+    src = tmp_path / "t.c"
+    src.write_text('#include <starneig/starneig.h>\n#include <stdio.h>\n'
+                   'int main(void){ double A[4]={1,2,3,4}, Q[4]={1,0,0,1};\n'
+                   ' int r0 = starneig_SEP_SM_Hessenberg(2, A, 2, Q, 2);\n'
+                   ' starneig_node_init(1, 0, STARNEIG_NO_MESSAGES);\n'
+                   ' int r1 = starneig_SEP_SM_Hessenberg(0, A, 2, Q, 2);\n'
+                   ' int r2 = starneig_SEP_SM_Hessenberg_expert(0, 2, 0, 3, A, 2, Q, 2);\n'
+                   ' starneig_node_finalize(); printf("%d %d %d\\n", r0, r1, r2); return 0; }\n')
+    exe = tmp_path / "t"
+    libdir = os.path.dirname(LIB_PATH)
+    subprocess.run(["gcc", "-std=c99", "-I", INCLUDE, str(src), "-o", str(exe), "-L", libdir, "-l:libstarneig.so",
+                    f"-Wl,-rpath,{libdir}"], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
+    assert out == ["2", "-1", "-4"]
+
+
+def test_error_codes_and_state_machine(sn):
+    n = 8
+    A = np.zeros((n, n), order="F"); Q = np.asfortranarray(np.eye(n))
+    # before init: argument errors win over NOT_INITIALIZED (interface.c:175-182)
+    assert not sn.starneig_node_initialized()
+    assert sn.starneig_SEP_SM_Hessenberg(0, A, n, Q, n) == -1
+    assert sn.starneig_SEP_SM_Hessenberg(n, A, n, Q, n) == sn.STARNEIG_NOT_INITIALIZED
+    assert sn.starneig_SEP_SM_Hessenberg_expert(None, n, 0, n, A, n, Q, n) == sn.STARNEIG_NOT_INITIALIZED
+    sn.starneig_node_init(1, 0, sn.STARNEIG_NO_MESSAGES)
+    try:
+        assert sn.starneig_node_initialized()
+        assert sn.starneig_node_get_cores() == 1
+        assert sn.starneig_node_get_gpus() == 0
+        # simple interface, interface.c:175-179
+        assert sn.starneig_SEP_SM_Hessenberg(0, A, n, Q, n) == -1
+        assert sn.starneig_SEP_SM_Hessenberg(n, None, n, Q, n) == -2
+        assert sn.starneig_SEP_SM_Hessenberg(n, A, n - 1, Q, n) == -3
+        assert sn.starneig_SEP_SM_Hessenberg(n, A, n, None, n) == -4
+        assert sn.starneig_SEP_SM_Hessenberg(n, A, n, Q, n - 1) == -5
+        # expert interface, interface.c:144-150
+        conf = sn.starneig_hessenberg_init_conf()
+        assert (conf.tile_size, conf.panel_width) == (-1, -1)
+        E = sn.starneig_SEP_SM_Hessenberg_expert
+        assert E(conf, 0, 0, 0, A, n, Q, n) == -2
+        assert E(conf, n, -1, n, A, n, Q, n) == -3
+        assert E(conf, n, 0, n + 1, A, n, Q, n) == -4
+        assert E(conf, n, 0, n, None, n, Q, n) == -5
+        assert E(conf, n, 0, n, A, n - 1, Q, n) == -6
+        assert E(conf, n, 0, n, A, n, None, n) == -7
+        assert E(conf, n, 0, n, A, n, Q, n - 1) == -8
+        # invalid configuration, interface.c:67-84
+        conf.panel_width = 4
+        assert E(conf, n, 0, n, A, n, Q, n) == sn.STARNEIG_INVALID_CONFIGURATION
+        conf.panel_width = -1; conf.tile_size = 7
+        assert E(conf, n, 0, n, A, n, Q, n) == sn.STARNEIG_INVALID_CONFIGURATION
+        # no GPU selected: the CUDA-only path refuses loudly, it never falls back to a CPU implementation
+        conf.tile_size = -1
+        assert E(conf, n, 0, n, A, n, Q, n) == sn.STARNEIG_GENERIC_ERROR
+        assert np.all(A == 0.0)
+    finally:
+        sn.starneig_node_finalize()
+    assert not sn.starneig_node_initialized()
+
+
+def test_double_init_is_fatal(tmp_path):
+    # reference: "The node is already initialized." -> exit(EXIT_FAILURE) (node.c:442-443, common.c:143-152)
+    code = ("import sys; sys.path.insert(0, %r); import starneig_b200 as s; "
+            "s.starneig_node_init(1,0,0x30); s.starneig_node_init(1,0,0x30)") % ROOT
+    r = subprocess.run(["python", "-c", code], capture_output=True, text=True)
+    assert r.returncode != 0
+    assert "[starneig][fatal error] The node is already initialized." in r.stderr
+
+
+def test_product_never_touches_the_oracle():
+    # a product path that routes through the oracle would void every parity claim
+    pkg = os.path.join(ROOT, "starneig_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in text.lower().replace("no cpu fallback", ""), f"{f} mentions the oracle"
+    from starneig_b200._lib import LIB_PATH
+    needed = subprocess.run(["readelf", "-d", LIB_PATH], capture_output=True, text=True).stdout
+    assert "openblas" not in needed.lower() and "liboracle" not in needed.lower()

@@ -1,0 +1,172 @@
+"""GPU parity tests of the whole path through the reference-facing C ABI
+(starneig_node_init / starneig_SEP_SM_Hessenberg[_expert], host buffers in, host buffers out), against the
+CPU oracle on the same reference-test-driver inputs, against the golden fixtures produced by the
+reference's own sources, and -- at sizes the oracle cannot reach quickly -- through the invariants the
+reference test driver checks (test/common/hooks.c:52-57,434-456; test/common/checks.c:180-208).
+
+Tolerances (FP64, u = 2^-52):
+  * entrywise H, Q vs oracle/reference: 200*n*u*max|H| resp. 200*n*u (summation order differs; the Householder
+    sign convention is DLARFG's in both, so no sign fix-up is applied);
+  * residual ||Q H Q^T - A||_F/||A||_F and orthogonality ||Q Q^T - I||_F/sqrt(n): <= 10*n*u (BASELINE.json) and
+    <= 500 u (reference warn threshold);
+  * eigenvalues: 1e-10 * ||A||_F (BASELINE.json).
+"""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN_DIR, golden_cases
+
+pytestmark = pytest.mark.gpu
+U = 2.0 ** -52
+
+
+def _run(sn, n, A, ld, Q, begin=0, end=None, pw=-1, tile=-1):
+    conf = sn.starneig_hessenberg_init_conf()
+    conf.panel_width = pw
+    conf.tile_size = tile
+    return sn.starneig_SEP_SM_Hessenberg_expert(conf, n, begin, n if end is None else end, A, ld, Q, ld)
+
+
+def _check_invariants(ora, n, A, Q, A0, ld, begin=0, end=None, outside=False):
+    assert np.isfinite(A[:n]).all() and np.isfinite(Q[:n]).all()
+    assert ora.hessenberg_form_violations(n, A, ld, begin, end, check_outside=outside) == 0
+    res = ora.residual_u(n, Q, ld, A, ld, A0, ld)
+    orth = ora.orthogonality_u(n, Q, ld)
+    assert res <= max(10.0 * n, 20.0) and res <= 500, res
+    assert orth <= max(10.0 * n, 20.0) and orth <= 500, orth
+
+
+def _check_entrywise(n, A, Q, Aref, Qref):
+    assert np.abs(A[:n] - Aref[:n]).max() <= 200 * n * U * max(1.0, np.abs(Aref[:n]).max())
+    assert np.abs(Q[:n] - Qref[:n]).max() <= 200 * n * U
+    assert np.array_equal(A[:n] == 0.0, Aref[:n] == 0.0)          # same exact-zero pattern
+
+
+@pytest.mark.parametrize("case", golden_cases())
+def test_against_reference_golden(node, ora, case):
+    g = np.load(os.path.join(GOLDEN_DIR, case + ".npz"))
+    n, begin, end = int(g["n"]), int(g["begin"]), int(g["end"])
+    gen, seed = str(g["generator"]), int(g["seed"])
+    A, Q, ld = (ora.fullpos(n, seed) if gen == "fullpos" else ora.full(n, seed) if gen == "full"
+                else ora.partial(n, begin, end, seed))
+    assert np.array_equal(A[:n], g["A0"])
+    assert _run(node, n, A, ld, Q, begin, end, int(g["panel_width"]), int(g["tile_size"])) == 0
+    _check_entrywise(n, A, Q, g["H"], g["Q"])
+
+
+# sizes of the reference ctest matrix (test/CMakeLists.txt:366-406) and the degenerate ones
+@pytest.mark.parametrize("n,pw", [(1, 8), (2, 8), (3, 8), (9, 8), (17, 8), (47, 16), (88, 35), (100, 100),
+                                  (333, 45), (554, 170), (1000, 314), (1500, 400), (2000, -1)])
+def test_against_oracle(node, ora, n, pw):
+    A0, Q0, ld = ora.fullpos(n, 2019)
+    A, Q = A0.copy(order="F"), Q0.copy(order="F")
+    assert _run(node, n, A, ld, Q, pw=pw) == 0
+    _check_invariants(ora, n, A, Q, A0, ld)
+    A2, Q2 = A0.copy(order="F"), Q0.copy(order="F")
+    assert ora.hessenberg_port(n, A2, ld, Q2, ld, 0, n, pw) == 0
+    _check_entrywise(n, A, Q, A2, Q2)
+
+
+@pytest.mark.parametrize("n", [47, 88, 333, 554])
+def test_partial_reduction(node, ora, n):
+    begin, end = n // 4, 3 * n // 4
+    A0, Q0, ld = ora.partial(n, begin, end, 2019)
+    A, Q = A0.copy(order="F"), Q0.copy(order="F")
+    assert _run(node, n, A, ld, Q, begin, end, pw=16) == 0
+    _check_invariants(ora, n, A, Q, A0, ld, begin, end, outside=True)
+    A2, Q2 = A0.copy(order="F"), Q0.copy(order="F")
+    ora.hessenberg_port(n, A2, ld, Q2, ld, begin, end, 16)
+    _check_entrywise(n, A, Q, A2, Q2)
+
+
+def test_simple_interface_wide_ld_and_general_q(node, ora):
+    # examples/sep_sm_full_chain.c:63-75: A in [-1,1], ld = (n/8+1)*8; Q a general orthogonal matrix
+    n = 301
+    ld = (n // 8 + 1) * 8 + 24
+    A0, _, _ = ora.full(n, 5, ld=ld)
+    Qr, _ = np.linalg.qr(np.random.default_rng(1).standard_normal((n, n)))
+    Q0 = np.zeros((ld, n), order="F"); Q0[:n] = Qr
+    A, Q = A0.copy(order="F"), Q0.copy(order="F")
+    assert node.starneig_SEP_SM_Hessenberg(n, A, ld, Q, ld) == 0
+    assert np.array_equal(A[n:], A0[n:]) and np.array_equal(Q[n:], Q0[n:])      # padding rows untouched
+    A2, Q2 = A0.copy(order="F"), Q0.copy(order="F")
+    ora.hessenberg_port(n, A2, ld, Q2, ld)
+    _check_entrywise(n, A, Q, A2, Q2)
+    assert ora.orthogonality_u(n, Q, ld) < 500
+
+
+def test_bitwise_reproducible(node, ora):
+    n = 700
+    A0, Q0, ld = ora.fullpos(n, 3)
+    outs = []
+    for _ in range(2):
+        A, Q = A0.copy(order="F"), Q0.copy(order="F")
+        assert node.starneig_SEP_SM_Hessenberg(n, A, ld, Q, ld) == 0
+        outs.append((A, Q))
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+
+
+def test_pinned_and_pageable_hosts_agree(node, ora):
+    import torch
+    n = 400
+    A0, Q0, ld = ora.fullpos(n, 4)
+    A, Q = A0.copy(order="F"), Q0.copy(order="F")
+    assert node.starneig_SEP_SM_Hessenberg(n, A, ld, Q, ld) == 0
+    tp = torch.empty((2, n, ld), dtype=torch.float64).pin_memory()
+    Ap = tp[0].numpy().T; Qp = tp[1].numpy().T                 # column-major (ld x n) views of pinned memory
+    Ap[...] = A0; Qp[...] = Q0
+    node.starneig_node_disable_pinning()
+    try:
+        assert node.starneig_SEP_SM_Hessenberg(n, Ap, ld, Qp, ld) == 0
+    finally:
+        node.starneig_node_enable_pinning()
+    assert np.array_equal(Ap, A) and np.array_equal(Qp, Q)
+
+
+def test_device_resident_matches_host_api(node, ora):
+    import torch
+    n = 600
+    A0, Q0, ld = ora.fullpos(n, 6)
+    ld = (n + 15) // 16 * 16
+    A0, Q0, ld = ora.fullpos(n, 6, ld=ld)
+    A, Q = A0.copy(order="F"), Q0.copy(order="F")
+    assert node.starneig_SEP_SM_Hessenberg(n, A, ld, Q, ld) == 0
+    Ad = torch.from_numpy(np.ascontiguousarray(A0.T)).cuda()
+    Qd = torch.from_numpy(np.ascontiguousarray(Q0.T)).cuda()
+    assert node.hessenberg_device(n, Ad, ld, Qd, ld) == 0
+    assert np.array_equal(Ad.cpu().numpy().T[:n], A[:n]) and np.array_equal(Qd.cpu().numpy().T[:n], Q[:n])
+    st = node.get_stats()
+    assert st["kernel_launches"] > 0 and st["gemv_launches"] == n - 1
+    # unaligned / odd-ld device buffers are rejected, not silently mishandled
+    assert node.lib().starneig_b200_hessenberg_device(n, 0, n, -1, Ad.data_ptr() + 8, ld, Qd.data_ptr(), ld) == -6
+    assert node.lib().starneig_b200_hessenberg_device(n, 0, n, -1, Ad.data_ptr(), ld, Qd.data_ptr(), n + 1) in (-8,)
+
+
+def test_downstream_eigenvalues(node, ora):
+    # config 5 of BASELINE.json at test size: GPU Hessenberg -> dhseqr (stand-in for starneig_SEP_SM_Schur)
+    # vs the all-CPU chain (oracle Hessenberg -> dhseqr); tolerance 1e-10 * ||A||
+    n = 800
+    A0, Q0, ld = ora.full(n, 12)
+    A, Q = A0.copy(order="F"), Q0.copy(order="F")
+    assert node.starneig_SEP_SM_Hessenberg(n, A, ld, Q, ld) == 0
+    A2, Q2 = A0.copy(order="F"), Q0.copy(order="F")
+    ora.hessenberg_port(n, A2, ld, Q2, ld)
+    ev_gpu = np.sort_complex(ora.eigenvalues(n, A, ld))
+    ev_cpu = np.sort_complex(ora.eigenvalues(n, A2, ld))
+    norm = np.linalg.norm(A0[:n])
+    # match each GPU eigenvalue with the nearest CPU eigenvalue (sorting can swap near-equal real parts)
+    d = np.abs(ev_gpu[:, None] - ev_cpu[None, :]).min(axis=1)
+    assert d.max() <= 1e-10 * norm
+
+
+@pytest.mark.parametrize("n", [4000])
+def test_invariants_at_larger_size(node, ora, n):
+    # size-independent properties: exact-zero Hessenberg form, residual, orthogonality, trace preservation
+    A0, Q0, ld = ora.fullpos(n, 2019)
+    A, Q = A0.copy(order="F"), Q0.copy(order="F")
+    assert node.starneig_SEP_SM_Hessenberg(n, A, ld, Q, ld) == 0
+    _check_invariants(ora, n, A, Q, A0, ld)
+    assert abs(np.trace(A[:n]) - np.trace(A0[:n])) <= 100 * n * U * abs(np.trace(A0[:n]))
+    assert abs(np.linalg.norm(A[:n]) - np.linalg.norm(A0[:n])) <= 100 * n * U * np.linalg.norm(A0[:n])
