@@ -1,0 +1,318 @@
+#!/usr/bin/env python
+"""bench.py -- FP64 Hessenberg GFLOP/s (10 n^3 / 3) of the B200-native path, n = 20000 on 1 GPU.
+
+A "step" is one full reduction (with Q) of a random dense n x n FP64 matrix.
+  value     device-resident arm: A and Q already in HBM when the timed region starts
+            (starneig_b200_hessenberg_device); time = CUDA events on the launching stream.
+  e2e       the reference-facing call starneig_SEP_SM_Hessenberg(n, A, ldA, Q, ldQ) on pinned HOST
+            buffers: H2D of A and Q, the reduction and D2H of H and Q are all inside the timed region.
+  roofline  the dominant kernel (k_col_gemv, the trailing-matrix GEMV): algorithmic bytes (8 * rows * cols
+            per launch) / mean launch duration from CUDA events recorded around every launch during the
+            timed steps, against the measured HBM copy bandwidth in MEASURED_PEAKS.json.
+  cpu_baseline  the reference's own CPU sources (oracle/_ref, sequential StarPU stand-in + threaded
+            OpenBLAS) -- or the oracle port when _ref is absent -- on a bounded sample.
+`--impl reference` times that CPU implementation instead and prints the same JSON line.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "FP64 Hessenberg GFLOP/s (10n^3/3) at n=20k"
+UNIT = "GFLOP/s"
+CPU_SAMPLE_N = 4000          # bounded CPU sample (~10-20 s on the box's cores)
+FALLBACK_HBM_GBS = 6650.0    # /opt/skills/guides/B200_PROFILING.md fallback
+FP64_DMMA_TFLOPS = 37.0      # measured DMMA issue peak (profiles/r1_probe_peaks.log)
+FP64_CUBLAS_TFLOPS = 35.7    # measured cublasDgemm 8192^3 (profiles/r1_probe_peaks.log)
+# dram__bytes_read.sum + dram__bytes_write.sum per k_col_gemv launch from the ncu --set full capture
+# (profiles/), relative to the algorithmic bytes of that launch; None until captured.
+GEMV_TRAFFIC_RATIO = None
+
+
+def flops(n):
+    return 10.0 / 3.0 * float(n) ** 3
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    return FALLBACK_HBM_GBS, "fallback"
+
+
+class ClockSampler:
+    """samples nvidia-smi clocks / throttle reasons while the timed region runs"""
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, power, reasons = [], None, [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])); smax = float(parts[1]); power.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_reference_run(n, threads):
+    """One reduction with the reference's CPU implementation on a fullpos matrix; returns (seconds, kind)."""
+    from oracle.oracle import Oracle, Reference
+    ora = Oracle()
+    A, Q, ld = ora.fullpos(n, 2019)
+    if Reference.available():
+        ref = Reference()
+        ref.set_threads(threads)
+        ref.set_workers(1)          # one "worker": large tiles, parallelism comes from threaded BLAS
+        t0 = time.perf_counter()
+        ret = ref.hessenberg(n, A, ld, Q, ld)
+        dt = time.perf_counter() - t0
+        kind = "reference"
+    else:
+        ora.set_threads(threads)
+        t0 = time.perf_counter()
+        ret = ora.hessenberg_port(n, A, ld, Q, ld)
+        dt = time.perf_counter() - t0
+        kind = "port"
+    assert ret == 0
+    return dt, kind
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    n = args.cpu_n
+    for _ in range(args.warmup):
+        cpu_reference_run(n, cores)
+    times, kind = [], "port"
+    for _ in range(args.steps):
+        dt, kind = cpu_reference_run(n, cores)
+        times.append(dt)
+    ms = 1e3 * sum(times) / len(times)
+    value = flops(n) / (ms * 1e-3) / 1e9
+    sample = (f"full reduction with Q of a fullpos n={n} matrix per step (the n={args.n} workload would take "
+              f"~{(args.n / n) ** 3 * ms / 6e4:.0f} min per step on these cores); "
+              + ("reference src/hessenberg + src/common built from source against a sequential StarPU stand-in, "
+                 "threaded OpenBLAS" if kind == "reference" else "oracle port, threaded OpenBLAS"))
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"Hessenberg reduction with Q, random dense FP64, n={args.n}", "sample_n": n},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    import starneig_b200 as sn
+    n = args.n
+    ld = (n + 15) // 16 * 16
+    sn.starneig_node_init(sn.STARNEIG_USE_ALL, 1, sn.STARNEIG_NO_MESSAGES)
+    sn.set_profile_level(2)
+
+    gen = torch.Generator(device="cuda").manual_seed(2019 + rank)
+    dA0 = torch.rand((n, ld), dtype=torch.float64, device="cuda", generator=gen)   # column-major (ld x n), entries in [0,1)
+    dA = torch.empty_like(dA0)
+    dQ = torch.empty_like(dA0)
+
+    def reset_device():
+        dA.copy_(dA0)
+        dQ.zero_()
+        dQ.view(-1)[:: ld + 1][:n] = 1.0
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident arm ----------------
+    for _ in range(args.warmup):
+        reset_device()
+        assert sn.hessenberg_device(n, dA, ld, dQ, ld) == 0
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    dev_ms, gemv_ms, gemv_bytes, gemv_launches, launches, phase = [], 0.0, 0.0, 0, 0, [0.0, 0.0, 0.0]
+    t_wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        reset_device()
+        torch.cuda.synchronize()
+        assert sn.hessenberg_device(n, dA, ld, dQ, ld) == 0
+        st = sn.get_stats()
+        dev_ms.append(st["device_ms"])
+        gemv_ms += st["gemv_ms"]; gemv_bytes += st["gemv_bytes"]; gemv_launches += st["gemv_launches"]
+        launches += st["kernel_launches"]
+        phase = [phase[0] + st["panel_ms"], phase[1] + st["trail_ms"], phase[2] + st["other_ms"]]
+    barrier()
+    wall_ms_per_step = 1e3 * (time.perf_counter() - t_wall0) / args.steps
+    clocks = sampler.stop()
+    ms_per_step = sum(dev_ms) / len(dev_ms)
+    if world > 1:
+        t = torch.tensor([ms_per_step], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_per_step = float(t.item())
+    value = world * flops(n) / (ms_per_step * 1e-3) / 1e9
+
+    # sanity of the timed result: exact zeros below the sub-diagonal, finite entries
+    H = dA[: min(n, 2048)].T
+    assert torch.isfinite(H).all()
+    assert float(torch.tril(dA[:256, :256].T, diagonal=-2).abs().max()) == 0.0
+
+    # ---------------- end-to-end arm: host buffers through the reference-facing call ----------------
+    hostA0 = dA0.cpu()
+    pinned = torch.empty((2, n, ld), dtype=torch.float64).pin_memory()
+    hA, hQ = pinned[0].numpy().T, pinned[1].numpy().T         # column-major (ld x n) views
+    eye_diag = np.arange(n)
+
+    def reset_host():
+        pinned[0].copy_(hostA0)
+        pinned[1].zero_()
+        hQ[eye_diag, eye_diag] = 1.0
+
+    sn.set_profile_level(1)
+    e2e_ms, h2d, d2h = [], 0, 0
+    for it in range(1 + args.steps):
+        reset_host()
+        barrier()
+        t0 = time.perf_counter()
+        assert sn.starneig_SEP_SM_Hessenberg(n, hA, ld, hQ, ld) == 0
+        dt = 1e3 * (time.perf_counter() - t0)
+        st = sn.get_stats()
+        if it > 0:
+            e2e_ms.append(dt); h2d = st["h2d_bytes"]; d2h = st["d2h_bytes"]
+    e2e_ms_per_step = sum(e2e_ms) / len(e2e_ms)
+    if world > 1:
+        t = torch.tensor([e2e_ms_per_step], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms_per_step = float(t.item())
+    e2e_value = world * flops(n) / (e2e_ms_per_step * 1e-3) / 1e9
+    assert float(np.abs(np.tril(hA[:256, :256], -2)).max()) == 0.0
+    sn.starneig_node_finalize()
+
+    if rank != 0:
+        return
+
+    # ---------------- roofline of the dominant kernel ----------------
+    peak, peak_kind = measured_peaks()
+    achieved = gemv_bytes / gemv_ms / 1e6 if gemv_ms > 0 else None          # GB/s
+    bytes_per_launch = gemv_bytes / max(1, gemv_launches)
+    roofline = {
+        "bound": "hbm", "kernel": "k_col_gemv", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "frac": achieved / peak if achieved else None,
+        "traffic": GEMV_TRAFFIC_RATIO * bytes_per_launch if GEMV_TRAFFIC_RATIO else None,
+        "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind})",
+        "algorithmic_bytes_per_launch": bytes_per_launch, "launches_per_step": gemv_launches // args.steps,
+        "mean_launch_us": 1e3 * gemv_ms / max(1, gemv_launches),
+        "share_of_step": gemv_ms / (ms_per_step * args.steps),
+        # whole-path roofline: T_roof = B / BW_hbm + (8/3 + 2) n^3 / F64_peak
+        "t_roof_ms": 1e3 * (8.0 * (n - 1) * n * (2 * n - 1) / 6.0 / (peak * 1e9) + (14.0 / 3.0) * n ** 3 / (FP64_CUBLAS_TFLOPS * 1e12)),
+        "fp64_peak_tflops": FP64_CUBLAS_TFLOPS, "fp64_peak_source": "cublasDgemm 8192^3 measured on this pool (profiles/r1_probe_peaks.log)",
+    }
+    roofline["path_frac"] = roofline["t_roof_ms"] / ms_per_step
+
+    # ---------------- CPU baseline (bounded sample) ----------------
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        cores = os.cpu_count() or 1
+        dt, kind = cpu_reference_run(args.cpu_n, cores)
+        cpu = {"value": flops(args.cpu_n) / dt / 1e9, "unit": UNIT, "cores": cores, "kind": kind,
+               "sample": f"one full reduction with Q of a fullpos n={args.cpu_n} matrix ({dt:.1f} s); "
+                         f"n={n} would take ~{(n / args.cpu_n) ** 3 * dt / 60:.0f} min at this rate"}
+
+    print(json.dumps({
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"Hessenberg reduction with Q, random dense FP64 n={n} (BASELINE.json configs[2] at 1 GPU)",
+                   "n": n, "panel_width": sn.default_panel_width(n), "ld": ld,
+                   "l2": "inputs (A, Q: 2 x %.1f GB) are larger than the 126 MB L2; no explicit flush" % (n * ld * 8 / 1e9),
+                   "parallelism": "1 GPU" if world == 1 else f"{world} independent replicas"},
+        "wall_ms_per_step": wall_ms_per_step,
+        "phases_ms_per_step": {"column_loops": phase[0] / args.steps, "trailing_updates": phase[1] / args.steps,
+                               "top_and_q_updates": phase[2] / args.steps},
+        "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms_per_step,
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=20000)
+    ap.add_argument("--cpu-n", type=int, default=CPU_SAMPLE_N)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
