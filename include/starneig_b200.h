@@ -31,16 +31,20 @@ struct starneig_b200_stats {
     double panel_ms;         /* sum over panels: column loops (panel kernels + GEMV) */
     double trail_ms;         /* sum over panels: trailing right + left updates (critical path) */
     double other_ms;         /* sum over panels: top rows, partial columns and Q updates */
-    double gemv_ms;          /* sum of GEMV kernel durations (profile level >= 2, else 0) */
+    double gemv_ms;          /* sum of the durations of the event-timed GEMV launches (profile level >= 2) */
     long long gemv_launches;
     double gemv_bytes;       /* algorithmic bytes read by all GEMV launches: 8 * sum rows*cols */
+    long long gemv_timed_launches;  /* launches bracketed by CUDA events: every 8th column at level 2, all at level 3 */
+    double gemv_timed_bytes; /* algorithmic bytes of the timed launches */
+    double finish_update_ms, reflector_ms;   /* same sampling: the two row-block kernels of the timed columns */
     long long kernel_launches;
     double gemm_flops;       /* flops executed by the DMMA kernels */
     long long h2d_bytes, d2h_bytes;
 };
 void starneig_b200_get_stats(struct starneig_b200_stats *stats);
 
-/* 0: no extra events; 1: per-panel phase events (default); 2: additionally time every GEMV launch */
+/* 0: no extra events; 1: per-panel phase events (default); 2: additionally time every 8th GEMV launch;
+ * 3: time every GEMV launch */
 void starneig_b200_set_profile_level(int level);
 
 /* ---- unit-level kernel access (tests / bench) ---- */

@@ -25,6 +25,8 @@ class Stats(ctypes.Structure):
         ("device_ms", ctypes.c_double), ("panel_ms", ctypes.c_double), ("trail_ms", ctypes.c_double),
         ("other_ms", ctypes.c_double), ("gemv_ms", ctypes.c_double),
         ("gemv_launches", ctypes.c_longlong), ("gemv_bytes", ctypes.c_double),
+        ("gemv_timed_launches", ctypes.c_longlong), ("gemv_timed_bytes", ctypes.c_double),
+        ("finish_update_ms", ctypes.c_double), ("reflector_ms", ctypes.c_double),
         ("kernel_launches", ctypes.c_longlong), ("gemm_flops", ctypes.c_double),
         ("h2d_bytes", ctypes.c_longlong), ("d2h_bytes", ctypes.c_longlong),
     ]

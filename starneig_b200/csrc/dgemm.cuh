@@ -71,10 +71,32 @@ __device__ __forceinline__ void load_tile(double *smem, const double *__restrict
     }
 }
 
+// One k-step (4 values of k) of the warp tile: fragments from shared memory, MB x NB DMMAs.
+template <class TA, class TB, int MB, int NB>
+__device__ __forceinline__ void load_frags(double (&af)[MB], double (&bf)[NB], const double *sa, const double *sb,
+                                           int arow, int brow, int kk)
+{
+#pragma unroll
+    for (int i = 0; i < MB; i++) af[i] = sa[TA::offset(arow + i * 8, kk)];
+#pragma unroll
+    for (int j = 0; j < NB; j++) bf[j] = sb[TB::offset(brow + j * 8, kk)];
+}
+
+template <int MB, int NB>
+__device__ __forceinline__ void mma_tile(double (&acc)[MB][NB][2], const double (&af)[MB], const double (&bf)[NB])
+{
+#pragma unroll
+    for (int i = 0; i < MB; i++)
+#pragma unroll
+        for (int j = 0; j < NB; j++) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+}
+
 // grid: (ceil(M/BM), ceil(N/BN), ksplits). With ksplits > 1 each z-slice handles k in
 // [z*klen, (z+1)*klen) and writes alpha*partial to C + z*split_stride (beta must be 0).
-template <bool AK, bool BKM, int WM, int WN, int MB, int NB, int STAGES>
-__global__ void __launch_bounds__(WM * WN * 32)
+// MINB resident CTAs per SM are requested so that one CTA's prologue/epilogue (global latency) is
+// hidden behind another CTA's DMMA main loop.
+template <bool AK, bool BKM, int WM, int WN, int MB, int NB, int STAGES, int MINB>
+__global__ void __launch_bounds__(WM * WN * 32, MINB)
 dgemm_kernel(int M, int N, int K, double alpha, const double *__restrict__ A, int lda,
              const double *__restrict__ B, int ldb, double beta, double *__restrict__ C, int ldc,
              int klen, size_t split_stride)
@@ -83,6 +105,8 @@ dgemm_kernel(int M, int N, int K, double alpha, const double *__restrict__ A, in
     using TA = OperandTile<AK, BM>;
     using TB = OperandTile<BKM, BN>;
     constexpr int STAGE = TA::SIZE + TB::SIZE;
+    constexpr int CS = BM + 2;          // staging stride of the epilogue (conflict-free for the fragment layout)
+    static_assert((size_t)BN * CS <= (size_t)STAGES * STAGE, "epilogue staging must fit in the pipeline buffers");
     extern __shared__ double smem[];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -93,12 +117,23 @@ dgemm_kernel(int M, int N, int K, double alpha, const double *__restrict__ A, in
     const int kend = min(K, kbeg + klen);
     const int ktiles = max(0, (kend - kbeg + GEMM_BK - 1) / GEMM_BK);
     C += (size_t)blockIdx.z * split_stride;
+    const int arow = wm * MB * 8 + g, brow = wn * NB * 8 + g;
 
     double acc[MB][NB][2];
 #pragma unroll
     for (int i = 0; i < MB; i++)
 #pragma unroll
         for (int j = 0; j < NB; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    // pull the C tile towards L2 while the main loop runs (the epilogue reads it when beta != 0)
+    if (beta != 0.0) {
+        constexpr int LINES_PER_COL = BM / 16;      // 128-byte lines per tile column
+        for (int e = tid; e < BN * LINES_PER_COL; e += NT) {
+            int col = e / LINES_PER_COL, r = (e % LINES_PER_COL) * 16;
+            if (n0 + col < N && m0 + r < M)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(C + (size_t)(n0 + col) * ldc + m0 + r));
+        }
+    }
 
     // prologue
 #pragma unroll
@@ -125,41 +160,56 @@ dgemm_kernel(int M, int N, int K, double alpha, const double *__restrict__ A, in
         }
         const double *sa = smem + (kt % STAGES) * STAGE, *sb = sa + TA::SIZE;
         const int krem = kend - (kbeg + kt * GEMM_BK);
-        const int ksteps = krem >= GEMM_BK ? GEMM_BK / 4 : (krem + 3) / 4;
+        if (krem >= GEMM_BK) {
+            // full tile: branch-free, fragments of step ks+1 are fetched while step ks is multiplied
+            double af[2][MB], bf[2][NB];
+            load_frags<TA, TB, MB, NB>(af[0], bf[0], sa, sb, arow, brow, t);
 #pragma unroll
-        for (int ks = 0; ks < GEMM_BK / 4; ks++) {
-            if (ks < ksteps) {
+            for (int ks = 0; ks < GEMM_BK / 4; ks++) {
+                if (ks + 1 < GEMM_BK / 4)
+                    load_frags<TA, TB, MB, NB>(af[(ks + 1) & 1], bf[(ks + 1) & 1], sa, sb, arow, brow, (ks + 1) * 4 + t);
+                mma_tile<MB, NB>(acc, af[ks & 1], bf[ks & 1]);
+            }
+        } else {
+            const int ksteps = (krem + 3) / 4;      // the tile is zero-filled beyond kend
+            for (int ks = 0; ks < ksteps; ks++) {
                 double af[MB], bf[NB];
-#pragma unroll
-                for (int i = 0; i < MB; i++) af[i] = sa[TA::offset((wm * MB + i) * 8 + g, ks * 4 + t)];
-#pragma unroll
-                for (int j = 0; j < NB; j++) bf[j] = sb[TB::offset((wn * NB + j) * 8 + g, ks * 4 + t)];
-#pragma unroll
-                for (int i = 0; i < MB; i++)
-#pragma unroll
-                    for (int j = 0; j < NB; j++) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+                load_frags<TA, TB, MB, NB>(af, bf, sa, sb, arow, brow, ks * 4 + t);
+                mma_tile<MB, NB>(acc, af, bf);
             }
         }
     }
     cp_async_wait<0>();
+    __syncthreads();        // every warp is done with the operand tiles: reuse them as C staging
 
-    // epilogue: thread holds C[row g][cols 2t, 2t+1] of each 8x8 block
+    // epilogue, stage 1: fragments -> shared memory (thread holds C[row g][cols 2t, 2t+1] of each 8x8 block)
+    double *Cs = smem;
 #pragma unroll
-    for (int i = 0; i < MB; i++) {
-        int row = m0 + (wm * MB + i) * 8 + g;
-        if (row >= M) continue;
+    for (int i = 0; i < MB; i++)
 #pragma unroll
-        for (int j = 0; j < NB; j++) {
+        for (int j = 0; j < NB; j++)
 #pragma unroll
-            for (int e = 0; e < 2; e++) {
-                int col = n0 + (wn * NB + j) * 8 + 2 * t + e;
-                if (col < N) {
-                    double *p = C + (size_t)col * ldc + row;
-                    double v = alpha * acc[i][j][e];
-                    if (beta != 0.0) v += beta * *p;
-                    *p = v;
-                }
-            }
+            for (int e = 0; e < 2; e++)
+                Cs[((wn * NB + j) * 8 + 2 * t + e) * CS + (wm * MB + i) * 8 + g] = acc[i][j][e];
+    __syncthreads();
+
+    // stage 2: coalesced read-modify-write of C, one column per warp at a time, lanes along rows
+    constexpr int NWARPS = WM * WN, RPL = BM / 32;
+    const bool use_beta = beta != 0.0;
+    for (int col = warp; col < BN; col += NWARPS) {
+        const int gc = n0 + col;
+        if (gc >= N) break;
+        double *Cg = C + (size_t)gc * ldc + m0;
+        double old[RPL];
+#pragma unroll
+        for (int q = 0; q < RPL; q++) {
+            int r = lane + 32 * q;
+            old[q] = (use_beta && m0 + r < M) ? Cg[r] : 0.0;
+        }
+#pragma unroll
+        for (int q = 0; q < RPL; q++) {
+            int r = lane + 32 * q;
+            if (m0 + r < M) Cg[r] = fma(alpha, Cs[col * CS + r], beta * old[q]);
         }
     }
 }
@@ -176,20 +226,20 @@ __global__ void splitk_reduce_kernel(int rows, int cols, int splits, const doubl
     W[(size_t)c * ldw + r] = s;
 }
 
-template <bool AK, bool BKM, int WM, int WN, int MB, int NB, int STAGES>
+template <bool AK, bool BKM, int WM, int WN, int MB, int NB, int STAGES, int MINB>
 struct GemmConfig {
     static constexpr int BM = WM * MB * 8, BN = WN * NB * 8, NT = WM * WN * 32;
     static constexpr size_t SMEM = (size_t)STAGES * (OperandTile<AK, BM>::SIZE + OperandTile<BKM, BN>::SIZE) * sizeof(double);
     static void prepare()
     {
-        SB_CUDA(cudaFuncSetAttribute(dgemm_kernel<AK, BKM, WM, WN, MB, NB, STAGES>,
+        SB_CUDA(cudaFuncSetAttribute(dgemm_kernel<AK, BKM, WM, WN, MB, NB, STAGES, MINB>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
     }
     static void launch(cudaStream_t st, int M, int N, int K, double alpha, const double *A, int lda, const double *B,
                        int ldb, double beta, double *C, int ldc, int splits, int klen, size_t split_stride)
     {
         dim3 grid(ceil_div(M, BM), ceil_div(N, BN), splits);
-        dgemm_kernel<AK, BKM, WM, WN, MB, NB, STAGES><<<grid, NT, SMEM, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc,
+        dgemm_kernel<AK, BKM, WM, WN, MB, NB, STAGES, MINB><<<grid, NT, SMEM, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc,
                                                                               klen, split_stride);
     }
 };

@@ -29,12 +29,14 @@ namespace sb200 {
 // ---------------------------------------------------------------------------------------------
 // GEMM dispatch
 // ---------------------------------------------------------------------------------------------
-using GemmNT   = GemmConfig<false, false, 2, 4, 8, 4, 4>;     // 128 x 128, rank-nb updates
-using GemmTN13 = GemmConfig<true,  true,  8, 1, 2, 13, 4>;    // 128 x 104, W = A^T VT
-using GemmTN12 = GemmConfig<true,  true,  8, 1, 2, 12, 4>;    // 128 x  96
-using GemmNN13 = GemmConfig<false, true,  8, 1, 2, 13, 4>;    // 128 x 104, W = A VT
-using GemmNN12 = GemmConfig<false, true,  8, 1, 2, 12, 4>;    // 128 x  96
+// <A K-major, B K-major, warps along M, warps along N, 8-row blocks per warp, 8-col blocks per warp, stages, CTAs/SM>
+using GemmNT   = GemmConfig<false, false, 2, 2, 8, 4, 4, 2>;     // 128 x  64, 128 threads: rank-nb updates
+using GemmTN13 = GemmConfig<true,  true,  4, 1, 2, 13, 4, 2>;    //  64 x 104, W = A^T VT
+using GemmTN12 = GemmConfig<true,  true,  4, 1, 2, 12, 4, 2>;    //  64 x  96
+using GemmNN13 = GemmConfig<false, true,  4, 1, 2, 13, 4, 2>;    //  64 x 104, W = A VT
+using GemmNN12 = GemmConfig<false, true,  4, 1, 2, 12, 4, 2>;    //  64 x  96
 
+static void panel_prepare();
 static bool g_gemm_prepared = false;
 static void gemm_prepare()
 {
@@ -52,7 +54,7 @@ struct Workspace {
     size_t wpart_cap = 0;           // doubles
     double *pcol = nullptr, *ypart = nullptr;
     size_t ypart_cap = 0;           // doubles
-    double *s = nullptr, *w2 = nullptr, *w2part = nullptr, *spart = nullptr, *sqpart = nullptr;
+    double *s = nullptr, *w2 = nullptr, *colpart = nullptr, *sqpart = nullptr;
     ColScal *scal = nullptr;
     unsigned *counter = nullptr;
     std::vector<void *> allocs;
@@ -79,16 +81,14 @@ struct Workspace {
         nbp = round_up(nb, 8);
         size_t panel = (size_t)ldv * nbp;
         V = alloc<double>(panel); Y = alloc<double>(panel); VT = alloc<double>(panel); W = alloc<double>(panel);
-        wpart_cap = 4 * (size_t)std::max(ldv, 4096) * nbp;
+        wpart_cap = 8 * (size_t)std::max(ldv, 4096) * nbp;
         Wpart = alloc<double>(wpart_cap);
         pcol = alloc<double>(ldv);
         ypart_cap = (size_t)2 * 148 * 12 * 256 + 4 * (size_t)ldv;
         ypart = alloc<double>(ypart_cap);
         s = alloc<double>(nbp); w2 = alloc<double>(nbp);
-        int rbmax = ceil_div(n, PR) + 1;
-        w2part = alloc<double>((size_t)rbmax * nbp);
-        spart = alloc<double>((size_t)(ceil_div(n, GEMV_SROWS) + 1) * nbp);
-        sqpart = alloc<double>(rbmax);
+        colpart = alloc<double>((size_t)nbp * PANEL_LDB);
+        sqpart = alloc<double>(PANEL_LDB);
         scal = alloc<ColScal>(nbp);
         counter = alloc<unsigned>(4);
         SB_CUDA(cudaMemset(counter, 0, 4 * sizeof(unsigned)));
@@ -112,6 +112,7 @@ struct Context {
         SB_CUDA(cudaGetDevice(&device));
         SB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
         gemm_prepare();
+        panel_prepare();
         ready = true;
     }
     void close()
@@ -156,11 +157,13 @@ static void gemm(Context &ctx, cudaStream_t st, GemmKind kind, int M, int N, int
     // skinny output (N = panel width): pick the column tile with the least padding, split K if the
     // grid would not fill the GPU twice
     int bn = (ceil_div(N, 96) * 96 <= ceil_div(N, 104) * 104) ? 96 : 104;
-    int tiles = ceil_div(M, 128) * ceil_div(N, bn);
+    // 2 CTAs per SM are resident; split K so that the grid is >= ~8 waves (tail quantisation < ~6 %)
+    int tiles = ceil_div(M, 64) * ceil_div(N, bn);
     int splits = 1;
-    if (beta == 0.0 && alpha == 1.0 && ctx.ws.Wpart != nullptr && tiles < 2 * 148) {
-        splits = std::min(16, ceil_div(2 * 148, tiles));
-        splits = std::min(splits, std::max(1, K / 256));
+    const int want = 8 * 2 * 148;
+    if (beta == 0.0 && alpha == 1.0 && ctx.ws.Wpart != nullptr && tiles < want) {
+        splits = std::min(32, ceil_div(want, tiles));
+        splits = std::min(splits, std::max(1, K / 512));
         while (splits > 1 && (size_t)splits * ldc * N > ctx.ws.wpart_cap) splits--;
     }
     int klen = round_up(ceil_div(K, splits), GEMM_BK);
@@ -191,31 +194,87 @@ static PanelArgs make_panel_args(Workspace &ws, int m, double *V, double *Y, dou
     PanelArgs pa;
     pa.m = m; pa.ld = ld; pa.V = V; pa.Y = Y; pa.VT = VT;
     pa.pcol = ws.pcol; pa.ypart = ws.ypart; pa.ldp = round_up(m + 2, 16);
-    pa.s = ws.s; pa.w2 = ws.w2; pa.w2part = ws.w2part; pa.spart = ws.spart; pa.ldw = ws.nbp;
+    pa.s = ws.s; pa.w2 = ws.w2; pa.colpart = ws.colpart; pa.ldt = ws.nbp;
     pa.sqpart = ws.sqpart; pa.scal = ws.scal; pa.counter = ws.counter;
     return pa;
 }
 
-struct GemvPlan { int skip, RB, S, kc, nsb; const double *A0; };
+struct GemvPlan { int skip, RB, S, kc; const double *A0; };
 
-// decomposition of the GEMV over rows [0,m) x columns [0,ncols) starting at `base`
-static GemvPlan plan_gemv(const double *base, int m, int ncols, int j, size_t ypart_cap, int ldp)
+static int g_gemv_slots = 0;    // resident k_col_gemv blocks on the whole GPU (one wave)
+
+// decomposition of the GEMV over rows [0,m) x columns [0,ncols) starting at `base`: row blocks of 256
+// padded rows times S column chunks, sized so that the grid is (at most) one full wave
+static GemvPlan plan_gemv(const double *base, int m, int ncols, size_t ypart_cap, int ldp)
 {
+    if (g_gemv_slots == 0) {
+        int occ = 0, dev = 0, sms = 0;
+        SB_CUDA(cudaGetDevice(&dev));
+        SB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        SB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_col_gemv, GEMV_THREADS, 2048 * sizeof(double)));
+        g_gemv_slots = std::max(1, occ) * sms;
+    }
     GemvPlan p;
     p.skip = (int)(((uintptr_t)base / sizeof(double)) & 1);
     p.A0 = base - p.skip;
     int mp = m + p.skip;
     p.RB = ceil_div(mp, 256);
-    const int slots = 148 * 12;
-    int S = std::max(1, slots / p.RB);
+    int S = std::max(1, g_gemv_slots / p.RB);
     int kc = ceil_div(ncols, S);
     kc = std::max(kc, 16);
-    kc = std::min(round_up(kc, 8), 2048);
+    kc = std::min(round_up(kc, 4), 2048);
     S = ceil_div(ncols, kc);
     while ((size_t)S * ldp > ypart_cap && kc < 2048) { kc *= 2; S = ceil_div(ncols, kc); }
     p.kc = kc; p.S = S;
-    p.nsb = j > 0 ? ceil_div(ncols, GEMV_SROWS) : 0;
     return p;
+}
+
+struct PanelGrid { int blocks; TileGeom tg; size_t smem_fu, smem_rf; };
+static const size_t PANEL_SMEM_MAX = 200 * 1024;
+
+// row blocks (<= PANEL_MAX_BLOCKS) and warp layout of the two row-block kernels for a panel of m rows
+// at column j (cols = number of columns the warps must cover)
+static PanelGrid panel_grid(int m, int cols, int j)
+{
+    PanelGrid g;
+    TileGeom &tg = g.tg;
+    tg.nsub = std::max(1, ceil_div(m, 32 * PANEL_MAX_BLOCKS));
+    g.blocks = ceil_div(m, 32 * tg.nsub);
+    tg.NW = std::max(1, ceil_div(cols, 32));
+    tg.RS = std::max(1, std::min(tg.nsub, (tg.NW <= 16 ? 16 : 32) / tg.NW));      // <= 512 threads unless the panel is wider than 512
+    // a few warps at least: they share the sum over the GEMV partials and hide latency
+    while (tg.NW * tg.RS < 4 && tg.NW * (tg.RS + 1) <= 32 && tg.RS < 4) tg.RS++;
+    g.smem_fu = (size_t)(2 * j + tg.nsub * 4 * tg.NW * 32 + 2 * tg.nsub * 32 + tg.RS * tg.NW * 32) * sizeof(double);
+    g.smem_rf = (size_t)(j + tg.nsub * tg.NW * 32 + tg.nsub * 32 + tg.RS * tg.NW * 32 + 32) * sizeof(double);
+    if (g.smem_fu > PANEL_SMEM_MAX) fatal("matrix too large for the panel kernels' shared-memory layout", __FILE__, __LINE__);
+    return g;
+}
+
+static void panel_prepare()
+{
+    static bool done = false;
+    if (done) return;
+    SB_CUDA(cudaFuncSetAttribute(k_col_finish_update<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM_MAX));
+    SB_CUDA(cudaFuncSetAttribute(k_col_finish_update<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM_MAX));
+    SB_CUDA(cudaFuncSetAttribute(k_col_reflector<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM_MAX));
+    SB_CUDA(cudaFuncSetAttribute(k_col_reflector<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM_MAX));
+    done = true;
+}
+
+static void launch_finish_update(cudaStream_t st, const PanelArgs &pa, int j, int S, double *acol, int do_update)
+{
+    PanelGrid pg = panel_grid(pa.m, j, j);
+    const int threads = 32 * pg.tg.NW * pg.tg.RS;
+    if (threads <= 512) k_col_finish_update<512><<<pg.blocks, threads, pg.smem_fu, st>>>(pa, j, S, acol, do_update, pg.tg);
+    else                k_col_finish_update<1024><<<pg.blocks, threads, pg.smem_fu, st>>>(pa, j, S, acol, do_update, pg.tg);
+}
+
+static void launch_reflector(cudaStream_t st, const PanelArgs &pa, int j, double *acol)
+{
+    PanelGrid pg = panel_grid(pa.m, j, j);
+    const int threads = 32 * pg.tg.NW * pg.tg.RS;
+    if (threads <= 512) k_col_reflector<512><<<pg.blocks, threads, pg.smem_rf, st>>>(pa, j, acol, pg.tg);
+    else                k_col_reflector<1024><<<pg.blocks, threads, pg.smem_rf, st>>>(pa, j, acol, pg.tg);
 }
 
 static void panel_factor(Context &ctx, cudaStream_t st, int i, int end, int w, double *A, int ldA,
@@ -225,42 +284,40 @@ static void panel_factor(Context &ctx, cudaStream_t st, int i, int end, int w, d
     const int m = end - i - 1;
     PanelArgs pa = make_panel_args(ws, m, V, Y, VT, ld);
     SB_CUDA(cudaMemsetAsync(V, 0, (size_t)ld * w * sizeof(double), st));
-    const int rbp = ceil_div(m, PR);
     int S_prev = 0;
     for (int j = 0; j < w; j++) {
         const int c = i + j;
         double *acol = A + (size_t)c * ldA + i + 1;
+        const bool timed = ctx.profile_level >= 3 || (ctx.profile_level == 2 && (j & 7) == 4);
+        if (timed) SB_CUDA(cudaEventRecord(ctx.gemv_event(ctx.gemv_events_used++), st));
         if (j > 0) {
-            size_t sh = (size_t)(2 * j - 1 + 4 * PG * PR + 2 * PR) * sizeof(double);
-            k_col_finish_update<<<rbp, PT, sh, st>>>(pa, j, S_prev, acol, 1);
+            launch_finish_update(st, pa, j, S_prev, acol, 1);
             ctx.stats.kernel_launches++;
         }
-        {
-            size_t sh = (size_t)(j + PG * PR) * sizeof(double);
-            k_col_reflector<<<rbp, PT, sh, st>>>(pa, j, acol);
-            ctx.stats.kernel_launches++;
-        }
+        if (timed) SB_CUDA(cudaEventRecord(ctx.gemv_event(ctx.gemv_events_used++), st));
+        launch_reflector(st, pa, j, acol);
+        ctx.stats.kernel_launches++;
+        if (timed) SB_CUDA(cudaEventRecord(ctx.gemv_event(ctx.gemv_events_used++), st));
         {
             const int ncols = m - j;
             const double *base = A + (size_t)(c + 1) * ldA + i + 1;
-            GemvPlan gp = plan_gemv(base, m, ncols, j, ws.ypart_cap, pa.ldp);
-            size_t sh = (size_t)std::max(gp.kc, GEMV_SROWS) * sizeof(double);
-            const bool timed = ctx.profile_level >= 2;
-            if (timed) SB_CUDA(cudaEventRecord(ctx.gemv_event(ctx.gemv_events_used++), st));
-            k_col_gemv<<<gp.nsb + gp.RB * gp.S, GEMV_THREADS, sh, st>>>(pa, j, ncols, gp.A0, ldA, gp.skip, gp.kc, gp.RB,
-                                                                          gp.S, gp.nsb, acol);
-            if (timed) SB_CUDA(cudaEventRecord(ctx.gemv_event(ctx.gemv_events_used++), st));
+            GemvPlan gp = plan_gemv(base, m, ncols, ws.ypart_cap, pa.ldp);
+            size_t sh = (size_t)gp.kc * sizeof(double);
+            k_col_gemv<<<gp.RB * gp.S, GEMV_THREADS, sh, st>>>(pa, j, ncols, gp.A0, ldA, gp.skip, gp.kc, gp.RB, acol);
+            if (timed) {
+                SB_CUDA(cudaEventRecord(ctx.gemv_event(ctx.gemv_events_used++), st));
+                ctx.stats.gemv_timed_launches++;
+                ctx.stats.gemv_timed_bytes += 8.0 * (double)m * ncols;
+            }
             ctx.stats.kernel_launches++;
             ctx.stats.gemv_launches++;
             ctx.stats.gemv_bytes += 8.0 * (double)m * ncols;
             S_prev = gp.S;
         }
     }
-    {   // finish the last column (Y, VT) without starting a new one
-        size_t sh = (size_t)(2 * w - 1 + 4 * PG * PR + 2 * PR) * sizeof(double);
-        k_col_finish_update<<<rbp, PT, sh, st>>>(pa, w, S_prev, nullptr, 0);
-        ctx.stats.kernel_launches++;
-    }
+    // finish the last column (Y, VT) without starting a new one
+    launch_finish_update(st, pa, w, S_prev, nullptr, 0);
+    ctx.stats.kernel_launches++;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -270,6 +327,7 @@ static void reduce_device(Context &ctx, int n, int begin, int end, int nb, doubl
 {
     Workspace &ws = ctx.ws;
     cudaStream_t st = ctx.stream;
+    nb = std::min(nb, PANEL_MAX_NB);      // wider panels are split; the result only differs in rounding
     ws.ensure(n, nb);
     const int ld = ws.ldv;
     Stats &stt = ctx.stats;
@@ -329,9 +387,10 @@ static void reduce_device(Context &ctx, int n, int begin, int end, int nb, doubl
         }
     }
     if (lvl >= 2) {
-        for (size_t k = 0; k + 1 < ctx.gemv_events_used; k += 2) {
-            SB_CUDA(cudaEventElapsedTime(&ms, ctx.gemv_events[k], ctx.gemv_events[k + 1]));
-            stt.gemv_ms += ms;
+        for (size_t k = 0; k + 3 < ctx.gemv_events_used; k += 4) {
+            SB_CUDA(cudaEventElapsedTime(&ms, ctx.gemv_events[k], ctx.gemv_events[k + 1])); stt.finish_update_ms += ms;
+            SB_CUDA(cudaEventElapsedTime(&ms, ctx.gemv_events[k + 1], ctx.gemv_events[k + 2])); stt.reflector_ms += ms;
+            SB_CUDA(cudaEventElapsedTime(&ms, ctx.gemv_events[k + 2], ctx.gemv_events[k + 3])); stt.gemv_ms += ms;
         }
     }
 }
@@ -595,14 +654,14 @@ int starneig_b200_gemv(int m, int k, const double *dA, int lda, const double *dv
     SB_CUDA(cudaMalloc(&scratch_col, (size_t)(big + 16) * sizeof(double)));
     PanelArgs pa = make_panel_args(ws, m, ws.V, ws.Y, ws.VT, ws.ldv);
     k_set_gemv_inputs<<<ceil_div(k, 256), 256, 0, st>>>(ws.scal, ws.pcol, dv, k);
-    GemvPlan gp = plan_gemv(dA, m, k, 0, ws.ypart_cap, pa.ldp);
-    size_t sh = (size_t)std::max(gp.kc, GEMV_SROWS) * sizeof(double);
+    GemvPlan gp = plan_gemv(dA, m, k, ws.ypart_cap, pa.ldp);
+    size_t sh = (size_t)gp.kc * sizeof(double);
     cudaEvent_t e0, e1;
     SB_CUDA(cudaEventCreate(&e0)); SB_CUDA(cudaEventCreate(&e1));
     if (reps < 1) reps = 1;
     for (int it = 0; it < reps + 1; it++) {
         if (it == 1) SB_CUDA(cudaEventRecord(e0, st));
-        k_col_gemv<<<gp.RB * gp.S, GEMV_THREADS, sh, st>>>(pa, 0, k, gp.A0, lda, gp.skip, gp.kc, gp.RB, gp.S, 0, scratch_col);
+        k_col_gemv<<<gp.RB * gp.S, GEMV_THREADS, sh, st>>>(pa, 0, k, gp.A0, lda, gp.skip, gp.kc, gp.RB, scratch_col);
     }
     SB_CUDA(cudaEventRecord(e1, st));
     k_sum_partials<<<ceil_div(m, 256), 256, 0, st>>>(m, gp.S, ws.ypart, pa.ldp, dy);

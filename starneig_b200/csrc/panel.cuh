@@ -16,13 +16,19 @@
 // identical to the reference; only rounding differs.
 //
 // Per column j of a panel three kernels run back to back on one stream:
-//   k_col_finish_update  (j >= 1) row-parallel: finishes column j-1 (Y, VT) and applies the right
-//                        update p' = p - Y V(j-1,:)^T; reduces  w2 = VT^T p'   (last block sums)
-//   k_col_reflector      row-parallel: p'' = p' - V w2; reduces ||p''(j+1:)||^2; the last block does
-//                        the DLARFG scalar work (beta, tau, 1/(alpha-beta))
+//   k_col_finish_update  (j >= 1) finishes column j-1 (Y, VT), applies the right update
+//                        p' = p - Y V(j-1,:)^T and reduces  w2 = VT^T p'
+//   k_col_reflector      p'' = p' - V w2; reduces ||p''(j+1:)||^2 and z = V(j+1:,:)^T p''(j+1:); the last
+//                        block does the DLARFG scalar work and s = scale*z + V(j,:)^T  ( == V^T v )
 //   k_col_gemv           the HBM-bound GEMV over the trailing matrix with v formed on the fly from
-//                        p'' and the scale; also writes V(:,j), the exact zeros and beta into A, and
-//                        reduces s = V^T v on a few extra blocks
+//                        p'' and the scale; also writes V(:,j), the exact zeros and beta into A
+//
+// Tile scheme of the first two kernels: a block owns 32*nsub rows, split into sub-tiles of 32 rows (one
+// row per lane); warp (g, h) owns the 32 columns [32g, 32g+32) of the sub-tiles h, h+RS, ... Phase A
+// streams the tiles once for the row-wise dot products (reduced across column groups through shared
+// memory), a per-row epilogue forms the new column entries, phase B streams the tile a second time (L2)
+// for the column-wise dot products, reduced across lanes by a shuffle transpose-butterfly. Loads are
+// issued in independent batches of 8 columns with no barrier inside a phase.
 // Cross-block reductions write per-block partials; the block that finishes last adds them in a fixed
 // order, so results are bitwise reproducible run to run.
 #pragma once
@@ -30,11 +36,10 @@
 
 namespace sb200 {
 
-constexpr int PR = 64;              // rows per block in the row-parallel panel kernels
-constexpr int PG = 8;               // column groups (threads per row)
-constexpr int PT = PR * PG;         // 512 threads
+constexpr int PANEL_MAX_BLOCKS = 148;   // row blocks of the panel kernels (<= one per SM)
+constexpr int PANEL_LDB = 160;          // leading dimension of the per-block partial arrays
+constexpr int PANEL_MAX_NB = 1024;      // widest panel the warp-per-32-columns scheme supports
 constexpr int GEMV_THREADS = 128;
-constexpr int GEMV_SROWS = 256;     // rows per s-block in k_col_gemv
 
 struct ColScal {        // DLARFG results for one column
     double tau, beta, scale, alpha;
@@ -49,298 +54,466 @@ struct PanelArgs {
     int ldp;
     double *s;          // nb  s = V^T v
     double *w2;         // nb
-    double *w2part;     // blocks x ldw
-    double *spart;      // blocks x ldw
-    int ldw;
-    double *sqpart;     // blocks
+    double *colpart;    // PANEL_LDB x ldt  per-block partials of the column-wise dot products (column index contiguous)
+    int ldt;
+    double *sqpart;     // PANEL_LDB
     ColScal *scal;      // nb
     unsigned *counter;  // zero-initialised
 };
 
+// Sum over the 32 lanes of a warp of 32 per-lane values each: on return lane l holds
+// sum_over_lanes(v[l]). 16+8+4+2+1 = 31 shuffles instead of 32 five-step butterflies.
+__device__ __forceinline__ double transpose_reduce32(double (&v)[32], int lane)
+{
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        const bool upper = (lane & off) != 0;
+#pragma unroll
+        for (int k = 0; k < off; k++) {
+            double send = upper ? v[k] : v[k + off];
+            double keep = upper ? v[k + off] : v[k];
+            v[k] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+    }
+    return v[0];
+}
+
+// out[t] = sum_{b < nblocks} part[b*ldt + t] for t < ncols, by the calling block; fixed summation order.
+// Warp g owns columns [32g, 32g+32) (+ multiples of 32*nwarps); lane = block index within a chunk of 32
+// blocks: 32 independent loads per lane, then the transpose-butterfly. `apply(t, sum)` is called by the
+// lane that ends up owning column t.
+template <typename F>
+__device__ __forceinline__ void reduce_block_partials(const double *part, int ldt, int ncols, int nblocks, F apply)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    for (int t0 = warp * 32; t0 < ncols; t0 += nwarps * 32) {
+        double acc = 0.0;
+        for (int b0 = 0; b0 < nblocks; b0 += 32) {
+            const int b = b0 + lane;
+            const double2 *p = (const double2 *)(part + (size_t)b * ldt + t0);
+            double v[32];
+#pragma unroll
+            for (int q = 0; q < 16; q++) {
+                double2 x = (b < nblocks && t0 + 2 * q < ncols) ? __ldcg(p + q) : make_double2(0.0, 0.0);
+                v[2 * q] = x.x;
+                v[2 * q + 1] = (t0 + 2 * q + 1 < ncols) ? x.y : 0.0;
+            }
+            acc += transpose_reduce32(v, lane);
+        }
+        if (t0 + lane < ncols) apply(t0 + lane, acc);
+    }
+}
+
+// Sum over the 32 lanes of a warp of 8 per-lane values: on return every lane holds the total of
+// column (lane >> 2) & 7.   4+2+1+2 = 9 shuffles.
+__device__ __forceinline__ double transpose_reduce8(double (&v)[8], int lane)
+{
+    // fully unrolled by hand so that v[] stays in registers
+    {
+        const bool up = (lane & 16) != 0;
+        double s0 = up ? v[0] : v[4], s1 = up ? v[1] : v[5], s2 = up ? v[2] : v[6], s3 = up ? v[3] : v[7];
+        double k0 = up ? v[4] : v[0], k1 = up ? v[5] : v[1], k2 = up ? v[6] : v[2], k3 = up ? v[7] : v[3];
+        v[0] = k0 + __shfl_xor_sync(0xffffffffu, s0, 16);
+        v[1] = k1 + __shfl_xor_sync(0xffffffffu, s1, 16);
+        v[2] = k2 + __shfl_xor_sync(0xffffffffu, s2, 16);
+        v[3] = k3 + __shfl_xor_sync(0xffffffffu, s3, 16);
+    }
+    {
+        const bool up = (lane & 8) != 0;
+        double s0 = up ? v[0] : v[2], s1 = up ? v[1] : v[3];
+        double k0 = up ? v[2] : v[0], k1 = up ? v[3] : v[1];
+        v[0] = k0 + __shfl_xor_sync(0xffffffffu, s0, 8);
+        v[1] = k1 + __shfl_xor_sync(0xffffffffu, s1, 8);
+    }
+    double x;
+    {
+        const bool up = (lane & 4) != 0;
+        double s0 = up ? v[0] : v[1];
+        double k0 = up ? v[1] : v[0];
+        x = k0 + __shfl_xor_sync(0xffffffffu, s0, 4);
+    }
+    x += __shfl_xor_sync(0xffffffffu, x, 2);
+    x += __shfl_xor_sync(0xffffffffu, x, 1);
+    return x;
+}
+
+// Geometry shared by the two row-block kernels: a block owns 32*nsub consecutive rows (sub-tiles of 32
+// rows, one row per lane). Its NW*RS warps are indexed (g, h): g = column group (32 columns), h = row
+// slice; slice h works on sub-tiles h, h+RS, ...  All global loads are issued in independent batches of
+// 8 columns, there is no barrier inside a phase, so many sub-tiles are in flight per SM.
+struct TileGeom {
+    int NW, RS, nsub;
+};
+
 // ------------------------------------------------------------------------------------------------
-// k_col_finish_update: finish column j-1, start column j.   grid = ceil(m / PR), block = PT
+// k_col_finish_update: finish column j-1, start column j.
+//   grid = row blocks (<= PANEL_MAX_BLOCKS), block = 32*NW*RS threads
 //   acol = &A[i+1, i+j] (unused when do_update == 0), S = number of GEMV partials of column j-1
+//   phase A  row-wise dots: Y(r,:)s, Y(r,:)vrow, VT(r,:)s, sum of the GEMV partials
+//   epilogue Y(r,j-1), VT(r,j-1), p'(r)                       (one warp per sub-tile)
+//   phase B  column-wise dots w2part = VT(rows,:)^T p'(rows)  (second read of VT, from L2)
+//   dynamic smem (doubles): 2j + nsub*4*NW*32 + 2*nsub*32 + RS*NW*32
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(PT) k_col_finish_update(PanelArgs a, int j, int S, double *__restrict__ acol, int do_update)
+template <int MAXT>
+__global__ void __launch_bounds__(MAXT) k_col_finish_update(PanelArgs a, int j, int S, double *__restrict__ acol,
+                                                            int do_update, TileGeom tg)
 {
     extern __shared__ double sh[];
     const int jm1 = j - 1;
-    double *s_sh = sh;                         // jm1
-    double *vrow_sh = s_sh + jm1;              // j
-    double *red = vrow_sh + j;                 // 4 * PG * PR
-    double *pv = red + 4 * PG * PR;            // PR
-    double *vtn = pv + PR;                     // PR
+    const int NW = tg.NW, RS = tg.RS, nsub = tg.nsub;
+    const int nwarps = NW * RS;
+    double *s_sh = sh;                             // j   (jm1 used)
+    double *vrow_sh = s_sh + j;                    // j
+    double *red = vrow_sh + j;                     // nsub * 4 * NW * 32
+    double *pv = red + (size_t)nsub * 4 * NW * 32; // nsub * 32
+    double *vtn = pv + nsub * 32;                  // nsub * 32
+    double *colred = vtn + nsub * 32;              // RS * NW * 32
 
-    const int tid = threadIdx.x, lr = tid % PR, g = tid / PR;
-    const int r0 = blockIdx.x * PR, r = r0 + lr;
-    const bool valid = r < a.m;
-    const int ld = a.ld;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int g = w % NW, h = w / NW;
+    const int t0 = g * 32;
+    const int ld = a.ld, m = a.m;
+    const int row0 = blockIdx.x * nsub * 32;
 
-    for (int t = tid; t < jm1; t += PT) s_sh[t] = a.s[t];
+    for (int t = tid; t < jm1; t += blockDim.x) s_sh[t] = a.s[t];
     if (do_update)
-        for (int t = tid; t < j; t += PT) vrow_sh[t] = a.V[(size_t)t * ld + jm1];
+        for (int t = tid; t < j; t += blockDim.x) vrow_sh[t] = a.V[(size_t)t * ld + jm1];
     __syncthreads();
 
-    const double tau = a.scal[jm1].tau;
-    double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
-    if (valid) {
-        const double *Yr = a.Y + r, *VTr = a.VT + r;
-        if (do_update) {
-#pragma unroll 4
-            for (int t = g; t < jm1; t += PG) {
-                double yv = Yr[(size_t)t * ld], vt = VTr[(size_t)t * ld], sv = s_sh[t];
-                d0 = fma(yv, sv, d0);
-                d1 = fma(yv, vrow_sh[t], d1);
-                d2 = fma(vt, sv, d2);
-            }
-        } else {
-#pragma unroll 4
-            for (int t = g; t < jm1; t += PG) {
-                double yv = Yr[(size_t)t * ld], vt = VTr[(size_t)t * ld], sv = s_sh[t];
-                d0 = fma(yv, sv, d0);
-                d2 = fma(vt, sv, d2);
+    // ---- phase A
+    for (int sub = h; sub < nsub; sub += RS) {
+        const int r = row0 + sub * 32 + lane;
+        const bool valid = r < m;
+        double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
+        const double *VTr = a.VT + (size_t)t0 * ld + r;
+        const double *Yr = a.Y + (size_t)t0 * ld + r;
+#pragma unroll
+        for (int bt = 0; bt < 4; bt++) {
+            const int tb = t0 + 8 * bt;
+            if (tb < jm1) {
+                double y8[8], v8[8];
+#pragma unroll
+                for (int q = 0; q < 8; q++) {
+                    const bool ok = valid && tb + q < jm1;
+                    y8[q] = ok ? Yr[(size_t)(8 * bt + q) * ld] : 0.0;
+                    v8[q] = ok ? VTr[(size_t)(8 * bt + q) * ld] : 0.0;
+                }
+#pragma unroll
+                for (int q = 0; q < 8; q++) {
+                    const int t = min(tb + q, jm1 - 1);        // values beyond jm1 are zero
+                    const double sv = s_sh[t];
+                    d0 = fma(y8[q], sv, d0);
+                    d2 = fma(v8[q], sv, d2);
+                    if (do_update) d1 = fma(y8[q], vrow_sh[t], d1);
+                }
             }
         }
-        for (int z = g; z < S; z += PG) d3 += a.ypart[(size_t)z * a.ldp + r];
+        if (valid) {
+            // GEMV partials: independent loads, four accumulators
+            const double *yp = a.ypart + r;
+            const size_t zs = (size_t)a.ldp * NW;
+            double e0 = 0.0, e1 = 0.0, e2 = 0.0, e3 = 0.0;
+            int z = g;
+            for (; z + 3 * NW < S; z += 4 * NW) {
+                const double *q0 = yp + (size_t)z * a.ldp;
+                e0 += q0[0]; e1 += q0[zs]; e2 += q0[2 * zs]; e3 += q0[3 * zs];
+            }
+            for (; z < S; z += NW) e0 += yp[(size_t)z * a.ldp];
+            d3 = (e0 + e1) + (e2 + e3);
+        }
+        double *rd = red + ((size_t)sub * 4 * NW + g) * 32 + lane;
+        rd[0] = d0; rd[NW * 32] = d1; rd[2 * NW * 32] = d2; rd[3 * NW * 32] = d3;
     }
-    red[(0 * PG + g) * PR + lr] = d0;
-    red[(1 * PG + g) * PR + lr] = d1;
-    red[(2 * PG + g) * PR + lr] = d2;
-    red[(3 * PG + g) * PR + lr] = d3;
     __syncthreads();
-    if (g == 0) {
+
+    // ---- per-row epilogue, one warp per sub-tile
+    const double tau = a.scal[jm1].tau;
+    for (int sub = w; sub < nsub; sub += nwarps) {
+        const int r = row0 + sub * 32 + lane;
+        const bool valid = r < m;
+        double vr = 0.0, ac = 0.0;
+        if (valid) {
+            vr = a.V[(size_t)jm1 * ld + r];
+            if (do_update) ac = acol[r];
+        }
+        const double *rd = red + (size_t)sub * 4 * NW * 32 + lane;
         double D0 = 0.0, D1 = 0.0, D2 = 0.0, D3 = 0.0;
-#pragma unroll
-        for (int q = 0; q < PG; q++) {
-            D0 += red[(0 * PG + q) * PR + lr];
-            D1 += red[(1 * PG + q) * PR + lr];
-            D2 += red[(2 * PG + q) * PR + lr];
-            D3 += red[(3 * PG + q) * PR + lr];
+        for (int q = 0; q < NW; q++) {
+            D0 += rd[q * 32]; D1 += rd[(NW + q) * 32]; D2 += rd[(2 * NW + q) * 32]; D3 += rd[(3 * NW + q) * 32];
         }
         double pp = 0.0, vtnew = 0.0;
         if (valid) {
             double ynew = tau * (D3 - D0);                       // finish_column: Y(:,j-1)
             a.Y[(size_t)jm1 * ld + r] = ynew;
-            double vr = a.V[(size_t)jm1 * ld + r];
             vtnew = tau * (vr - D2);                             // VT(:,j-1) = V * T(:,j-1)
             a.VT[(size_t)jm1 * ld + r] = vtnew;
             if (do_update) {
-                pp = acol[r] - (D1 + ynew * vrow_sh[jm1]);       // prepare_column: p - Y V(j-1,:)^T
+                pp = ac - (D1 + ynew * vrow_sh[jm1]);            // prepare_column: p - Y V(j-1,:)^T
                 a.pcol[r] = pp;
             }
         }
-        pv[lr] = pp;
-        vtn[lr] = vtnew;
+        pv[sub * 32 + lane] = pp;
+        vtn[sub * 32 + lane] = vtnew;
     }
     if (!do_update) return;
     __syncthreads();
 
-    // w2part[t] = sum over this block's rows of VT(r,t) * p'(r), one warp per column t
-    const int warp = tid >> 5, lane = tid & 31;
-    double *out = a.w2part + (size_t)blockIdx.x * a.ldw;
-    for (int t = warp; t < j; t += PT / 32) {
-        double acc = 0.0;
+    // ---- phase B: w2part[t] = sum over the block's rows of VT(r,t) * p'(r)
 #pragma unroll
-        for (int k = 0; k < PR / 32; k++) {
-            int l2 = lane + 32 * k, rr = r0 + l2;
-            if (rr < a.m) {
-                double vt = (t == jm1) ? vtn[l2] : a.VT[(size_t)t * ld + rr];
-                acc = fma(vt, pv[l2], acc);
+    for (int bt = 0; bt < 4; bt++) {
+        const int tb = t0 + 8 * bt;
+        double acc[8];
+#pragma unroll
+        for (int q = 0; q < 8; q++) acc[q] = 0.0;
+        if (tb < j) {
+            for (int sub = h; sub < nsub; sub += RS) {
+                const int r = row0 + sub * 32 + lane;
+                const bool valid = r < m;
+                const double p = pv[sub * 32 + lane], vn = vtn[sub * 32 + lane];
+                const double *VTr = a.VT + (size_t)tb * ld + r;
+                double v8[8];
+#pragma unroll
+                for (int q = 0; q < 8; q++) v8[q] = (valid && tb + q < jm1) ? VTr[(size_t)q * ld] : 0.0;
+#pragma unroll
+                for (int q = 0; q < 8; q++) acc[q] = fma(tb + q == jm1 ? vn : v8[q], p, acc[q]);
             }
         }
-        acc = warp_sum(acc);
-        if (lane == 0) out[t] = acc;
+        const double x = transpose_reduce8(acc, lane);
+        if ((lane & 3) == 0) colred[(size_t)h * NW * 32 + t0 + 8 * bt + (lane >> 2)] = x;
+    }
+    __syncthreads();
+    if (h == 0 && t0 + lane < j) {
+        double sum = 0.0;
+        for (int q = 0; q < RS; q++) sum += colred[(size_t)q * NW * 32 + t0 + lane];
+        a.colpart[(size_t)blockIdx.x * a.ldt + t0 + lane] = sum;
     }
     if (last_block_done(a.counter, gridDim.x)) {
-        for (int t = tid; t < j; t += PT) {
-            double sum = 0.0;
-            for (unsigned b = 0; b < gridDim.x; b++) sum += __ldcg(a.w2part + (size_t)b * a.ldw + t);
-            a.w2[t] = sum;
-        }
+        double *w2 = a.w2;
+        reduce_block_partials(a.colpart, a.ldt, j, gridDim.x, [w2](int t, double sum) { w2[t] = sum; });
     }
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_col_reflector: p'' = p' - V(:, :j) w2 ; DLARFG scalars.     grid = ceil(m / PR), block = PT
-//   acol = &A[i+1, i+j]; for j == 0 the column is read from acol directly.
+// k_col_reflector: p'' = p' - V(:, :j) w2 ; DLARFG scalars ; s = V^T v.
+//   grid = row blocks, block = 32*NW*RS threads; acol = &A[i+1, i+j]; for j == 0 the column is read from
+//   acol directly.   dynamic smem (doubles): j + nsub*NW*32 + nsub*32 + RS*NW*32 + 32
 // DLARFG (LAPACK, called at src/hessenberg/cpu.c:140): beta = -sign(alpha) * hypot(alpha, ||x||),
 // tau = (beta - alpha) / beta, v = x / (alpha - beta); ||x|| == 0 (or an empty x) gives tau = 0.
+// With v = (1, scale * x):  s = V(j:, :j)^T v = V(j, :j)^T + scale * V(j+1:, :j)^T x.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(PT) k_col_reflector(PanelArgs a, int j, double *__restrict__ acol)
+template <int MAXT>
+__global__ void __launch_bounds__(MAXT) k_col_reflector(PanelArgs a, int j, double *__restrict__ acol, TileGeom tg)
 {
     extern __shared__ double sh[];
-    double *w2_sh = sh;                 // j
-    double *red = w2_sh + j;            // PG * PR
-    __shared__ double wsum[PR / 32];
+    const int NW = tg.NW, RS = tg.RS, nsub = tg.nsub;
+    const int nwarps = NW * RS;
+    double *w2_sh = sh;                             // j
+    double *red = w2_sh + j;                        // nsub * NW * 32
+    double *pv = red + (size_t)nsub * NW * 32;      // nsub * 32
+    double *colred = pv + nsub * 32;                // RS * NW * 32
+    double *sqred = colred + (size_t)RS * NW * 32;  // 32 (one per warp)
+    __shared__ double scale_sh;
 
-    const int tid = threadIdx.x, lr = tid % PR, g = tid / PR;
-    const int r = blockIdx.x * PR + lr;
-    const bool valid = r < a.m;
-    const int ld = a.ld;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int g = w % NW, h = w / NW;
+    const int t0 = g * 32;
+    const int ld = a.ld, m = a.m;
+    const int row0 = blockIdx.x * nsub * 32;
 
-    for (int t = tid; t < j; t += PT) w2_sh[t] = a.w2[t];
+    for (int t = tid; t < j; t += blockDim.x) w2_sh[t] = a.w2[t];
     __syncthreads();
-    double d = 0.0;
-    if (valid) {
-        const double *Vr = a.V + r;
-#pragma unroll 4
-        for (int t = g; t < j; t += PG) d = fma(Vr[(size_t)t * ld], w2_sh[t], d);
-    }
-    red[g * PR + lr] = d;
-    __syncthreads();
-    if (g == 0) {       // threads 0..PR-1 = the first PR/32 warps
-        double D = 0.0;
+
+    // ---- phase A: d(r) = V(r, :j) w2
+    for (int sub = h; sub < nsub; sub += RS) {
+        const int r = row0 + sub * 32 + lane;
+        const bool valid = r < m;
+        double d = 0.0;
+        const double *Vr = a.V + (size_t)t0 * ld + r;
 #pragma unroll
-        for (int q = 0; q < PG; q++) D += red[q * PR + lr];
-        double sq = 0.0;
+        for (int bt = 0; bt < 4; bt++) {
+            const int tb = t0 + 8 * bt;
+            if (tb < j) {
+                double v8[8];
+#pragma unroll
+                for (int q = 0; q < 8; q++) v8[q] = (valid && tb + q < j) ? Vr[(size_t)(8 * bt + q) * ld] : 0.0;
+#pragma unroll
+                for (int q = 0; q < 8; q++) d = fma(v8[q], w2_sh[min(tb + q, j - 1)], d);
+            }
+        }
+        red[((size_t)sub * NW + g) * 32 + lane] = d;
+    }
+    __syncthreads();
+
+    // ---- per-row epilogue
+    double sq = 0.0;
+    for (int sub = w; sub < nsub; sub += nwarps) {
+        const int r = row0 + sub * 32 + lane;
+        const bool valid = r < m;
+        double base = 0.0;
+        if (valid) base = j > 0 ? a.pcol[r] : acol[r];
+        double D = 0.0;
+        for (int q = 0; q < NW; q++) D += red[((size_t)sub * NW + q) * 32 + lane];
+        double x = 0.0;
         if (valid) {
-            double pp = (j > 0 ? a.pcol[r] : acol[r]) - D;
+            double pp = base - D;
             a.pcol[r] = pp;
             if (r < j) acol[r] = pp;            // final entries of H above the sub-diagonal
             if (r == j) a.scal[j].alpha = pp;
-            if (r > j) sq = pp * pp;
+            if (r > j) x = pp;
         }
-        sq = warp_sum(sq);
-        if ((tid & 31) == 0) wsum[tid >> 5] = sq;
+        sq = fma(x, x, sq);
+        pv[sub * 32 + lane] = x;
     }
+    sq = warp_sum(sq);
+    if (lane == 0) sqred[w] = sq;
     __syncthreads();
+
+    // ---- phase B: zpart[t] = sum over the block's rows > j of V(r,t) * p''(r)
+    if (j > 0) {
+#pragma unroll
+        for (int bt = 0; bt < 4; bt++) {
+            const int tb = t0 + 8 * bt;
+            double acc[8];
+#pragma unroll
+            for (int q = 0; q < 8; q++) acc[q] = 0.0;
+            if (tb < j) {
+                for (int sub = h; sub < nsub; sub += RS) {
+                    const int r = row0 + sub * 32 + lane;
+                    const bool valid = r < m;
+                    const double p = pv[sub * 32 + lane];
+                    const double *Vr = a.V + (size_t)tb * ld + r;
+                    double v8[8];
+#pragma unroll
+                    for (int q = 0; q < 8; q++) v8[q] = (valid && tb + q < j) ? Vr[(size_t)q * ld] : 0.0;
+#pragma unroll
+                    for (int q = 0; q < 8; q++) acc[q] = fma(v8[q], p, acc[q]);
+                }
+            }
+            const double x = transpose_reduce8(acc, lane);
+            if ((lane & 3) == 0) colred[(size_t)h * NW * 32 + t0 + 8 * bt + (lane >> 2)] = x;
+        }
+        __syncthreads();
+        if (h == 0 && t0 + lane < j) {
+            double sum = 0.0;
+            for (int q = 0; q < RS; q++) sum += colred[(size_t)q * NW * 32 + t0 + lane];
+            a.colpart[(size_t)blockIdx.x * a.ldt + t0 + lane] = sum;
+        }
+    }
     if (tid == 0) {
         double sum = 0.0;
-#pragma unroll
-        for (int q = 0; q < PR / 32; q++) sum += wsum[q];
+        for (int q = 0; q < nwarps; q++) sum += sqred[q];
         a.sqpart[blockIdx.x] = sum;
     }
     if (last_block_done(a.counter, gridDim.x)) {
-        if (tid == 0) {
-            double ssq = 0.0;
-            for (unsigned b = 0; b < gridDim.x; b++) ssq += __ldcg(a.sqpart + b);
-            double alpha = __ldcg(&a.scal[j].alpha);
-            double xnorm = sqrt(ssq);
-            double tau = 0.0, beta = alpha, scale = 0.0;
-            if (a.m - j > 1 && xnorm != 0.0) {
-                beta = -copysign(hypot(alpha, xnorm), alpha);
-                tau = (beta - alpha) / beta;
-                scale = 1.0 / (alpha - beta);
+        if (w == 0) {
+            double acc = 0.0;
+#pragma unroll
+            for (int q = 0; q < PANEL_LDB / 32; q++) {
+                int b = lane + 32 * q;
+                acc += b < (int)gridDim.x ? __ldcg(a.sqpart + b) : 0.0;
             }
-            a.scal[j].tau = tau;
-            a.scal[j].beta = beta;
-            a.scal[j].scale = scale;
+            const double ssq = warp_sum(acc);
+            if (lane == 0) {
+                const double alpha = __ldcg(&a.scal[j].alpha);
+                const double xnorm = sqrt(ssq);
+                double tau = 0.0, beta = alpha, scale = 0.0;
+                if (m - j > 1 && xnorm != 0.0) {
+                    beta = -copysign(hypot(alpha, xnorm), alpha);
+                    tau = (beta - alpha) / beta;
+                    scale = 1.0 / (alpha - beta);
+                }
+                a.scal[j].tau = tau;
+                a.scal[j].beta = beta;
+                a.scal[j].scale = scale;
+                scale_sh = scale;
+            }
         }
+        __syncthreads();
+        const double scale = scale_sh;
+        double *s = a.s;
+        const double *Vrow = a.V + j;
+        reduce_block_partials(a.colpart, a.ldt, j, gridDim.x,
+                              [s, Vrow, scale, ld](int t, double sum) { s[t] = fma(scale, sum, Vrow[(size_t)t * ld]); });
     }
 }
 
 // ------------------------------------------------------------------------------------------------
 // k_col_gemv: ypart[z][r] = sum_{k in chunk z} A[i+1+r, c+1+k] * v[k],  v[0] = 1, v[k] = p''[j+k]*scale
 //
-//   A0    16-byte aligned pointer to A[i+1-skip, c+1] (skip in {0,1}); padded row rp = r + skip
 //   ncols = number of columns (m - j)
-//   grid  = nsb + RB*S blocks of 128 threads: the first nsb blocks reduce s = V(j:, :j)^T v over
-//           GEMV_SROWS rows each; GEMV block b: row block b % RB (256 padded rows), chunk b / RB
+//   A0    16-byte aligned pointer to A[i+1-skip, c+1] (skip in {0,1}); padded row rp = r + skip
+//   grid  = RB*S blocks of 128 threads: block b: row block b % RB (256 padded rows), column chunk b / RB
 //   The first row block of every chunk also stores V(j+k, j) = v[k], A[i+1+j+k, c] = (k==0 ? beta : 0).
 // Memory-bound: each thread streams one 16-byte load per column with 8 columns in flight.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(GEMV_THREADS) k_col_gemv(PanelArgs a, int j, int ncols, const double *__restrict__ A0,
-                                                            int lda, int skip, int kc, int RB, int S, int nsb,
-                                                            double *__restrict__ acol)
+__global__ void __launch_bounds__(GEMV_THREADS, 10) k_col_gemv(PanelArgs a, int j, int ncols, const double *__restrict__ A0,
+                                                                int lda, int skip, int kc, int RB,
+                                                                double *__restrict__ acol)
 {
-    extern __shared__ double vs[];      // max(kc, GEMV_SROWS)
+    extern __shared__ double vs[];      // kc
     const int tid = threadIdx.x;
     const int m = a.m;                  // ncols == m - j inside a reduction; free in the unit test (j == 0)
     const double scale = a.scal[j].scale;
-    const unsigned total_blocks = gridDim.x;
 
-    if ((int)blockIdx.x < nsb) {
-        // ---- s-block: rows j + b*GEMV_SROWS ...
-        const int k0 = blockIdx.x * GEMV_SROWS;
-        const int nk = min(GEMV_SROWS, ncols - k0);
-        for (int k = tid; k < GEMV_SROWS; k += GEMV_THREADS)
-            vs[k] = k < nk ? ((k0 + k == 0) ? 1.0 : a.pcol[j + k0 + k] * scale) : 0.0;
-        __syncthreads();
-        const int warp = tid >> 5, lane = tid & 31;
-        double *out = a.spart + (size_t)blockIdx.x * a.ldw;
-        for (int t = warp; t < j; t += GEMV_THREADS / 32) {
-            const double *Vt = a.V + (size_t)t * a.ld + j + k0;
-            double acc = 0.0;
-#pragma unroll
-            for (int q = 0; q < GEMV_SROWS / 32; q++) {
-                int k = lane + 32 * q;
-                if (k < nk) acc = fma(Vt[k], vs[k], acc);
-            }
-            acc = warp_sum(acc);
-            if (lane == 0) out[t] = acc;
-        }
-    } else {
-        // ---- GEMV block
-        const int b = blockIdx.x - nsb;
-        const int rb = b % RB, z = b / RB;
-        const int k0 = z * kc;
-        const int nk = min(kc, ncols - k0);
-        for (int k = tid; k < nk; k += GEMV_THREADS) {
-            double v = (k0 + k == 0) ? 1.0 : a.pcol[j + k0 + k] * scale;
-            vs[k] = v;
-            if (rb == 0) {
-                a.V[(size_t)j * a.ld + j + k0 + k] = v;
-                acol[j + k0 + k] = (k0 + k == 0) ? a.scal[j].beta : 0.0;
-            }
-        }
-        __syncthreads();
-
-        const int mp = m + skip;
-        const int rp = rb * 256 + tid * 2;           // padded row of .x ; rows rp, rp+1
-        double2 acc = make_double2(0.0, 0.0);
-        if (rp < mp) {
-            const double *Ap = A0 + (size_t)k0 * lda + rp;
-            // software pipeline: U loads of the next column group are in flight while the current
-            // group is accumulated (2*U 16-byte loads per thread outstanding)
-            constexpr int U = 4;
-            const size_t step = (size_t)lda;
-            double2 cur[U], nxt[U];
-            int k = 0;
-            if (nk >= U) {
-#pragma unroll
-                for (int u = 0; u < U; u++) cur[u] = __ldcs((const double2 *)(Ap + u * step));
-                const double *Pn = Ap + U * step;
-                for (; k + 2 * U <= nk; k += U) {
-#pragma unroll
-                    for (int u = 0; u < U; u++) nxt[u] = __ldcs((const double2 *)(Pn + u * step));
-                    Pn += U * step;
-#pragma unroll
-                    for (int u = 0; u < U; u++) {
-                        double vk = vs[k + u];
-                        acc.x = fma(cur[u].x, vk, acc.x);
-                        acc.y = fma(cur[u].y, vk, acc.y);
-                    }
-#pragma unroll
-                    for (int u = 0; u < U; u++) cur[u] = nxt[u];
-                }
-#pragma unroll
-                for (int u = 0; u < U; u++) {
-                    double vk = vs[k + u];
-                    acc.x = fma(cur[u].x, vk, acc.x);
-                    acc.y = fma(cur[u].y, vk, acc.y);
-                }
-                k += U;
-            }
-            for (; k < nk; k++) {
-                double vk = vs[k];
-                double2 x = __ldcs((const double2 *)(Ap + (size_t)k * step));
-                acc.x = fma(x.x, vk, acc.x);
-                acc.y = fma(x.y, vk, acc.y);
-            }
-            double *yp = a.ypart + (size_t)z * a.ldp;
-            int r = rp - skip;                       // logical row of .x
-            if (r >= 0) yp[r] = acc.x;
-            if (r + 1 < m) yp[r + 1] = acc.y;
+    const int rb = blockIdx.x % RB, z = blockIdx.x / RB;
+    const int k0 = z * kc;
+    const int nk = min(kc, ncols - k0);
+    for (int k = tid; k < nk; k += GEMV_THREADS) {
+        double v = (k0 + k == 0) ? 1.0 : a.pcol[j + k0 + k] * scale;
+        vs[k] = v;
+        if (rb == 0) {
+            a.V[(size_t)j * a.ld + j + k0 + k] = v;
+            acol[j + k0 + k] = (k0 + k == 0) ? a.scal[j].beta : 0.0;
         }
     }
+    __syncthreads();
 
-    if (nsb > 0 && last_block_done(a.counter, total_blocks)) {
-        for (int t = tid; t < j; t += GEMV_THREADS) {
-            double sum = 0.0;
-            for (int b = 0; b < nsb; b++) sum += __ldcg(a.spart + (size_t)b * a.ldw + t);
-            a.s[t] = sum;
+    const int mp = m + skip;
+    const int rp = rb * 256 + tid * 2;           // padded row of .x ; rows rp, rp+1
+    if (rp >= mp) return;
+    double2 acc = make_double2(0.0, 0.0);
+    const double *Ap = A0 + (size_t)k0 * lda + rp;
+    // software pipeline: U loads of the next column group are in flight while the current
+    // group is accumulated (2*U 16-byte loads per thread outstanding)
+    constexpr int U = 4;
+    const size_t step = (size_t)lda;
+    double2 cur[U], nxt[U];
+    int k = 0;
+    if (nk >= U) {
+#pragma unroll
+        for (int u = 0; u < U; u++) cur[u] = __ldcs((const double2 *)(Ap + u * step));
+        const double *Pn = Ap + U * step;
+        for (; k + 2 * U <= nk; k += U) {
+#pragma unroll
+            for (int u = 0; u < U; u++) nxt[u] = __ldcs((const double2 *)(Pn + u * step));
+            Pn += U * step;
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                double vk = vs[k + u];
+                acc.x = fma(cur[u].x, vk, acc.x);
+                acc.y = fma(cur[u].y, vk, acc.y);
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++) cur[u] = nxt[u];
         }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            double vk = vs[k + u];
+            acc.x = fma(cur[u].x, vk, acc.x);
+            acc.y = fma(cur[u].y, vk, acc.y);
+        }
+        k += U;
     }
+    for (; k < nk; k++) {
+        double vk = vs[k];
+        double2 x = __ldcs((const double2 *)(Ap + (size_t)k * step));
+        acc.x = fma(x.x, vk, acc.x);
+        acc.y = fma(x.y, vk, acc.y);
+    }
+    double *yp = a.ypart + (size_t)z * a.ldp;
+    int r = rp - skip;                       // logical row of .x
+    if (r >= 0) yp[r] = acc.x;
+    if (r + 1 < m) yp[r + 1] = acc.y;
 }
 
 } // namespace sb200

@@ -69,6 +69,9 @@ def test_hess(n, pw, begin=0, end=None, gen="fullpos", ld=None, tol=1e-11, compa
     form = ora.hessenberg_form_violations(n, A, ld, begin, end, check_outside=(gen == "partial"))
     res = ora.residual_u(n, Q, ld, A, ld, A0, ld) if n <= 6000 else float("nan")
     orth = ora.orthogonality_u(n, Q, ld) if n <= 6000 else float("nan")
+    if st['gemv_timed_launches'] > 0:
+        k = st['gemv_timed_launches']
+        print(f"      per timed column: finish_update {1e3*st['finish_update_ms']/k:.1f} us, reflector {1e3*st['reflector_ms']/k:.1f} us, gemv {1e3*st['gemv_ms']/k:.1f} us ({st['gemv_timed_bytes']/max(st['gemv_ms'],1e-9)/1e6:.0f} GB/s)")
     msg = f"hess n={n} pw={pw} [{begin},{end}) {gen} ret={r} wall={dt*1e3:.1f} ms dev={st['device_ms']:.1f} ms (panel {st['panel_ms']:.1f} trail {st['trail_ms']:.1f} other {st['other_ms']:.1f}) form={form} res={res:.1f}u orth={orth:.1f}u"
     good = r == 0 and form == 0 and (not np.isfinite(res) or res < 1000) and (not np.isfinite(orth) or orth < 1000) and np.isfinite(A[:n]).all()
     if compare:
@@ -89,6 +92,17 @@ if "gemm" in which:
 if "gemv" in which:
     for (m, k, off) in [(256, 16, 0), (300, 300, 1), (1000, 777, 2), (1, 1, 0), (5, 9, 1), (4097, 4000, 3), (16384, 16384, 1)]:
         test_gemv(m, k, off)
+if "gemm_perf" in which:
+    for (ta, tb, m, n, k) in [("N","T",16000,15700,312), ("T","N",15700,312,16000), ("N","N",16000,312,16000), ("N","T",4000,3700,312), ("T","N",3700,312,4000), ("N","N",16000,312,4000), ("N","T",16000,16000,296)]:
+        Ar, Ac = (m, k) if ta == 'N' else (k, m)
+        Br, Bc = (k, n) if tb == 'N' else (n, k)
+        At = torch.rand((Ac, Ar), dtype=torch.float64, device=dev); Bt = torch.rand((Bc, Br), dtype=torch.float64, device=dev); Ct = torch.rand((n, m), dtype=torch.float64, device=dev)
+        alpha, beta = (-1.0, 1.0) if (ta, tb) == ('N', 'T') else (1.0, 0.0)
+        for it in range(3):
+            torch.cuda.synchronize(); t0 = time.perf_counter()
+            L.starneig_b200_dgemm(ta.encode(), tb.encode(), m, n, k, alpha, At.data_ptr(), Ar, Bt.data_ptr(), Br, beta, Ct.data_ptr(), m)
+            dt = time.perf_counter() - t0
+        print(f"gemm_perf {ta}{tb} m={m} n={n} k={k}: {dt*1e3:.3f} ms {2.0*m*n*k/dt/1e12:.2f} TFLOP/s")
 if "hess_small" in which:
     for (n, pw) in [(1, 8), (2, 8), (3, 8), (9, 8), (10, 8), (17, 8), (40, 8), (47, 16), (88, 35), (100, 100), (333, 45), (554, 170)]:
         test_hess(n, pw)
@@ -96,6 +110,7 @@ if "hess_small" in which:
     test_hess(333, 35, 83, 249, gen="partial")
     test_hess(201, 32, gen="full", ld=230)
 if "hess_mid" in which:
+    sn.set_profile_level(2)
     test_hess(1000, -1)
     test_hess(2000, -1)
     test_hess(2000, -1)
@@ -104,11 +119,11 @@ if "hess_big" in which:
     sn.set_profile_level(2)
     test_hess(10000, -1, compare=False)
     st = sn.get_stats(); print(st)
-    print(f"gemv: {st['gemv_ms']:.1f} ms for {st['gemv_bytes']/1e9:.1f} GB -> {st['gemv_bytes']/st['gemv_ms']/1e6:.0f} GB/s")
+    print(f"gemv (sampled): {st['gemv_ms']:.1f} ms for {st['gemv_timed_bytes']/1e9:.1f} GB -> {st['gemv_timed_bytes']/st['gemv_ms']/1e6:.0f} GB/s")
 if "hess_20k" in which:
     sn.set_profile_level(2)
     test_hess(20000, -1, compare=False)
     st = sn.get_stats(); print(st)
-    print(f"gemv: {st['gemv_ms']:.1f} ms for {st['gemv_bytes']/1e9:.1f} GB -> {st['gemv_bytes']/st['gemv_ms']/1e6:.0f} GB/s")
+    print(f"gemv (sampled): {st['gemv_ms']:.1f} ms for {st['gemv_timed_bytes']/1e9:.1f} GB -> {st['gemv_timed_bytes']/st['gemv_ms']/1e6:.0f} GB/s")
 sn.starneig_node_finalize()
 print("ALL OK" if ok_all else "SOME FAILED")
