@@ -32,7 +32,7 @@ FP64_DMMA_TFLOPS = 37.0      # measured DMMA issue peak (profiles/r1_probe_peaks
 FP64_CUBLAS_TFLOPS = 35.7    # measured cublasDgemm 8192^3 (profiles/r1_probe_peaks.log)
 # dram__bytes_read.sum + dram__bytes_write.sum per k_col_gemv launch from the ncu --set full capture
 # (profiles/), relative to the algorithmic bytes of that launch; None until captured.
-GEMV_TRAFFIC_RATIO = None
+GEMV_TRAFFIC_RATIO = 1.0015   # profiles/r1_ncu_full_baseline.txt: 3.1807 GB DRAM vs 3.1757 GB algorithmic
 
 
 def flops(n):
@@ -192,6 +192,7 @@ def run_ours(args):
     barrier()
     sampler.start()
     dev_ms, gemv_ms, gemv_bytes, gemv_launches, launches, phase = [], 0.0, 0.0, 0, 0, [0.0, 0.0, 0.0]
+    gemv_tbytes, gemv_tlaunches = 0.0, 0
     t_wall0 = time.perf_counter()
     for _ in range(args.steps):
         reset_device()
@@ -200,6 +201,7 @@ def run_ours(args):
         st = sn.get_stats()
         dev_ms.append(st["device_ms"])
         gemv_ms += st["gemv_ms"]; gemv_bytes += st["gemv_bytes"]; gemv_launches += st["gemv_launches"]
+        gemv_tbytes += st["gemv_timed_bytes"]; gemv_tlaunches += st["gemv_timed_launches"]
         launches += st["kernel_launches"]
         phase = [phase[0] + st["panel_ms"], phase[1] + st["trail_ms"], phase[2] + st["other_ms"]]
     barrier()
@@ -253,7 +255,8 @@ def run_ours(args):
 
     # ---------------- roofline of the dominant kernel ----------------
     peak, peak_kind = measured_peaks()
-    achieved = gemv_bytes / gemv_ms / 1e6 if gemv_ms > 0 else None          # GB/s
+    # gemv_ms covers the event-timed launches only (every 8th column): divide THEIR bytes by THEIR time
+    achieved = gemv_tbytes / gemv_ms / 1e6 if gemv_ms > 0 else None          # GB/s
     bytes_per_launch = gemv_bytes / max(1, gemv_launches)
     roofline = {
         "bound": "hbm", "kernel": "k_col_gemv", "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -261,8 +264,9 @@ def run_ours(args):
         "traffic": GEMV_TRAFFIC_RATIO * bytes_per_launch if GEMV_TRAFFIC_RATIO else None,
         "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind})",
         "algorithmic_bytes_per_launch": bytes_per_launch, "launches_per_step": gemv_launches // args.steps,
-        "mean_launch_us": 1e3 * gemv_ms / max(1, gemv_launches),
-        "share_of_step": gemv_ms / (ms_per_step * args.steps),
+        "timed_launches_per_step": gemv_tlaunches // args.steps,
+        "mean_launch_us": 1e3 * gemv_ms / max(1, gemv_tlaunches),
+        "share_of_step": (gemv_ms * gemv_bytes / max(1.0, gemv_tbytes)) / (ms_per_step * args.steps),
         # whole-path roofline: T_roof = B / BW_hbm + (8/3 + 2) n^3 / F64_peak
         "t_roof_ms": 1e3 * (8.0 * (n - 1) * n * (2 * n - 1) / 6.0 / (peak * 1e9) + (14.0 / 3.0) * n ** 3 / (FP64_CUBLAS_TFLOPS * 1e12)),
         "fp64_peak_tflops": FP64_CUBLAS_TFLOPS, "fp64_peak_source": "cublasDgemm 8192^3 measured on this pool (profiles/r1_probe_peaks.log)",
