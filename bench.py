@@ -141,7 +141,7 @@ def run_reference_arm(args):
                  "threaded OpenBLAS" if kind == "reference" else "oracle port, threaded OpenBLAS"))
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"Hessenberg reduction with Q, random dense FP64, n={args.n}", "sample_n": n},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
@@ -163,20 +163,37 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     import starneig_b200 as sn
+    from starneig_b200 import dist as sdist
     n = args.n
     ld = (n + 15) // 16 * 16
     sn.starneig_node_init(sn.STARNEIG_USE_ALL, 1, sn.STARNEIG_NO_MESSAGES)
     sn.set_profile_level(2)
 
-    gen = torch.Generator(device="cuda").manual_seed(2019 + rank)
+    # The same random matrix on every rank (same seed); a rank keeps only its shards in HBM: its block-cyclic
+    # columns of A (full height) and its row slab of Q. world == 1: the whole matrices.
+    gen = torch.Generator(device="cuda").manual_seed(2019)
     dA0 = torch.rand((n, ld), dtype=torch.float64, device="cuda", generator=gen)   # column-major (ld x n), entries in [0,1)
+    if world > 1:
+        L = sdist.init(n)
+        cols = torch.from_numpy(L.global_cols()).cuda()
+        dA0 = dA0[cols].contiguous()                    # (local_cols, ld): this rank's columns
+        q0, qrows = L.q_row0, L.q_rows
+    else:
+        q0, qrows = 0, n
+    ldq = (max(qrows, 1) + 15) // 16 * 16
     dA = torch.empty_like(dA0)
-    dQ = torch.empty_like(dA0)
+    dQ = torch.zeros((n, ldq), dtype=torch.float64, device="cuda")      # rows [q0, q0+qrows) of Q, all n columns
+    qdiag = torch.arange(q0, q0 + qrows, device="cuda")
 
     def reset_device():
         dA.copy_(dA0)
         dQ.zero_()
-        dQ.view(-1)[:: ld + 1][:n] = 1.0
+        dQ[qdiag, qdiag - q0] = 1.0
+
+    def reduce_device():
+        if world > 1:
+            return sdist.hessenberg_device(n, dA, ld, dQ, ldq)
+        return sn.hessenberg_device(n, dA, ld, dQ, ldq)
 
     def barrier():
         torch.cuda.synchronize()
@@ -184,10 +201,25 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
     # ---------------- device-resident arm ----------------
     for _ in range(args.warmup):
         reset_device()
-        assert sn.hessenberg_device(n, dA, ld, dQ, ld) == 0
+        barrier()
+        assert reduce_device() == 0
     sampler = ClockSampler(local_rank)
     barrier()
     sampler.start()
@@ -196,8 +228,8 @@ def run_ours(args):
     t_wall0 = time.perf_counter()
     for _ in range(args.steps):
         reset_device()
-        torch.cuda.synchronize()
-        assert sn.hessenberg_device(n, dA, ld, dQ, ld) == 0
+        barrier()
+        assert reduce_device() == 0
         st = sn.get_stats()
         dev_ms.append(st["device_ms"])
         gemv_ms += st["gemv_ms"]; gemv_bytes += st["gemv_bytes"]; gemv_launches += st["gemv_launches"]
@@ -207,20 +239,25 @@ def run_ours(args):
     barrier()
     wall_ms_per_step = 1e3 * (time.perf_counter() - t_wall0) / args.steps
     clocks = sampler.stop()
-    ms_per_step = sum(dev_ms) / len(dev_ms)
-    if world > 1:
-        t = torch.tensor([ms_per_step], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_per_step = float(t.item())
-    value = world * flops(n) / (ms_per_step * 1e-3) / 1e9
+    # CUDA events on the launching stream of every rank (first to last kernel of the call), max over ranks
+    ms_per_step = max_over_ranks(sum(dev_ms) / len(dev_ms))
+    value = flops(n) / (ms_per_step * 1e-3) / 1e9
+    launches = int(sum_over_ranks(launches))
 
-    # sanity of the timed result: exact zeros below the sub-diagonal, finite entries
-    H = dA[: min(n, 2048)].T
-    assert torch.isfinite(H).all()
-    assert float(torch.tril(dA[:256, :256].T, diagonal=-2).abs().max()) == 0.0
+    # sanity of the timed result: finite entries; exact zeros below the sub-diagonal (first local columns)
+    assert torch.isfinite(dA[: min(dA.shape[0], 2048)]).all()
+    if world == 1:
+        assert float(torch.tril(dA[:256, :256].T, diagonal=-2).abs().max()) == 0.0
+    else:
+        gc0 = int(cols[0])
+        assert float(dA[0, gc0 + 2: n].abs().max()) == 0.0
 
     # ---------------- end-to-end arm: host buffers through the reference-facing call ----------------
-    hostA0 = dA0.cpu()
+    # world == 1: starneig_SEP_SM_Hessenberg on pinned host arrays. world > 1: every rank process holds the host
+    # matrices (same content) in pinned memory and moves ONLY its shards to its GPU and back inside the timed
+    # region (starneig_b200_dist_hessenberg_host), so the bytes over PCIe add up to A + Q once in each direction.
+    gen = torch.Generator(device="cuda").manual_seed(2019)
+    hostA0 = torch.rand((n, ld), dtype=torch.float64, device="cuda", generator=gen).cpu()
     pinned = torch.empty((2, n, ld), dtype=torch.float64).pin_memory()
     hA, hQ = pinned[0].numpy().T, pinned[1].numpy().T         # column-major (ld x n) views
     eye_diag = np.arange(n)
@@ -236,19 +273,26 @@ def run_ours(args):
         reset_host()
         barrier()
         t0 = time.perf_counter()
-        assert sn.starneig_SEP_SM_Hessenberg(n, hA, ld, hQ, ld) == 0
+        if world > 1:
+            assert sdist.hessenberg_host(n, hA, ld, hQ, ld) == 0
+        else:
+            assert sn.starneig_SEP_SM_Hessenberg(n, hA, ld, hQ, ld) == 0
         dt = 1e3 * (time.perf_counter() - t0)
         st = sn.get_stats()
         if it > 0:
             e2e_ms.append(dt); h2d = st["h2d_bytes"]; d2h = st["d2h_bytes"]
-    e2e_ms_per_step = sum(e2e_ms) / len(e2e_ms)
-    if world > 1:
-        t = torch.tensor([e2e_ms_per_step], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms_per_step = float(t.item())
-    e2e_value = world * flops(n) / (e2e_ms_per_step * 1e-3) / 1e9
-    assert float(np.abs(np.tril(hA[:256, :256], -2)).max()) == 0.0
+    e2e_ms_per_step = max_over_ranks(sum(e2e_ms) / len(e2e_ms))
+    h2d, d2h = int(sum_over_ranks(h2d)), int(sum_over_ranks(d2h))
+    e2e_value = flops(n) / (e2e_ms_per_step * 1e-3) / 1e9
+    if world == 1:
+        assert float(np.abs(np.tril(hA[:256, :256], -2)).max()) == 0.0
+    else:
+        assert float(np.abs(hA[gc0 + 2: n, gc0]).max()) == 0.0
+        sdist.finalize()
     sn.starneig_node_finalize()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
 
     if rank != 0:
         return
@@ -268,7 +312,8 @@ def run_ours(args):
         "mean_launch_us": 1e3 * gemv_ms / max(1, gemv_tlaunches),
         "share_of_step": (gemv_ms * gemv_bytes / max(1.0, gemv_tbytes)) / (ms_per_step * args.steps),
         # whole-path roofline: T_roof = B / BW_hbm + (8/3 + 2) n^3 / F64_peak
-        "t_roof_ms": 1e3 * (8.0 * (n - 1) * n * (2 * n - 1) / 6.0 / (peak * 1e9) + (14.0 / 3.0) * n ** 3 / (FP64_CUBLAS_TFLOPS * 1e12)),
+        # divided by the number of GPUs (T_roof(n, P))
+        "t_roof_ms": 1e3 * (8.0 * (n - 1) * n * (2 * n - 1) / 6.0 / (peak * 1e9) + (14.0 / 3.0) * n ** 3 / (FP64_CUBLAS_TFLOPS * 1e12)) / world,
         "fp64_peak_tflops": FP64_CUBLAS_TFLOPS, "fp64_peak_source": "cublasDgemm 8192^3 measured on this pool (profiles/r1_probe_peaks.log)",
     }
     roofline["path_frac"] = roofline["t_roof_ms"] / ms_per_step
@@ -284,12 +329,14 @@ def run_ours(args):
 
     print(json.dumps({
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"Hessenberg reduction with Q, random dense FP64 n={n} (BASELINE.json configs[2] at 1 GPU)",
                    "n": n, "panel_width": sn.default_panel_width(n), "ld": ld,
                    "l2": "inputs (A, Q: 2 x %.1f GB) are larger than the 126 MB L2; no explicit flush" % (n * ld * 8 / 1e9),
-                   "parallelism": "1 GPU" if world == 1 else f"{world} independent replicas"},
+                   "parallelism": "1 GPU" if world == 1 else
+                   f"{world} GPUs, one process each: A 1-D block-cyclic by columns (block 64), Q by row slabs; per-column GEMV "
+                   "sums and per-panel products exchanged by the kernels over NVLink peer memory (no NCCL on the data path)"},
         "wall_ms_per_step": wall_ms_per_step,
         "phases_ms_per_step": {"column_loops": phase[0] / args.steps, "trailing_updates": phase[1] / args.steps,
                                "top_and_q_updates": phase[2] / args.steps},

@@ -40,12 +40,41 @@ struct starneig_b200_stats {
     long long kernel_launches;
     double gemm_flops;       /* flops executed by the DMMA kernels */
     long long h2d_bytes, d2h_bytes;
+    int ranks;               /* GPUs that took part; device/gemv figures are rank 0's, launches and flops are summed */
 };
 void starneig_b200_get_stats(struct starneig_b200_stats *stats);
 
 /* 0: no extra events; 1: per-panel phase events (default); 2: additionally time every 8th GEMV launch;
  * 3: time every GEMV launch */
 void starneig_b200_set_profile_level(int level);
+
+/* ---- one process per GPU (torchrun): 1-D block-cyclic column shards of A, row slabs of Q ----
+ *
+ * Every rank process selects its CUDA device, calls starneig_node_init, then
+ *   starneig_b200_dist_init(world, rank, n_max, panel_width_max, handle)   -> 64-byte cudaIpcMemHandle of the
+ *       rank's exchange arena (panel_width_max < 8: reference default for n_max),
+ *   all-gathers the handles (e.g. torch.distributed.all_gather) and passes them, in rank order, to
+ *   starneig_b200_dist_connect(handles).
+ * After that the ranks call the reduction collectively. All data-path communication (the per-column sum of
+ * the GEMV partials, the panel gather, the per-panel sum of the top-row products) is done by the kernels over
+ * NVLink peer memory; no NCCL call sits on the path.
+ *
+ * Layout (starneig_b200_dist_layout): global column c belongs to rank (c / col_block) % world; a rank stores
+ * its columns contiguously in ascending global order, full height n (local_cols of them); Q is split by rows:
+ * rank r holds rows [q_row0, q_row0 + q_rows) of all n columns. Host-only arithmetic, no GPU needed. */
+int starneig_b200_dist_layout(int world, int rank, int n, int *col_block, int *local_cols, int *q_row0, int *q_rows);
+int starneig_b200_dist_global_col(int world, int rank, int col_block, int local_col);
+int starneig_b200_dist_init(int world, int rank, int n_max, int panel_width_max, void *handle_out);
+int starneig_b200_dist_connect(const void *handles);
+/* shards already in HBM: dA_loc (n x local_cols, ldA >= n), dQ_loc (q_rows x n, ldQ >= q_rows); 16-byte
+ * aligned, even leading dimensions. Same error numbering as starneig_b200_hessenberg_device. Collective. */
+starneig_error_t starneig_b200_dist_hessenberg_device(
+    int n, int begin, int end, int panel_width, double *dA_loc, int ldA, double *dQ_loc, int ldQ);
+/* host arrays holding the WHOLE matrices (e.g. in memory shared by the rank processes): every rank moves
+ * only its own shards to its GPU and back. Collective. */
+starneig_error_t starneig_b200_dist_hessenberg_host(
+    int n, int begin, int end, int panel_width, double *A, int ldA, double *Q, int ldQ);
+void starneig_b200_dist_finalize(void);
 
 /* ---- unit-level kernel access (tests / bench) ---- */
 

@@ -29,6 +29,7 @@ class Stats(ctypes.Structure):
         ("finish_update_ms", ctypes.c_double), ("reflector_ms", ctypes.c_double),
         ("kernel_launches", ctypes.c_longlong), ("gemm_flops", ctypes.c_double),
         ("h2d_bytes", ctypes.c_longlong), ("d2h_bytes", ctypes.c_longlong),
+        ("ranks", ctypes.c_int),
     ]
 
     def as_dict(self):
@@ -71,4 +72,18 @@ def load():
     lib.starneig_b200_gemv.restype = i
     lib.starneig_b200_panel.argtypes = [i, i, i, i, vp, i, vp, vp, vp, i, vp]
     lib.starneig_b200_panel.restype = i
+    ip = ctypes.POINTER(ctypes.c_int)
+    lib.starneig_b200_dist_layout.argtypes = [i, i, i, ip, ip, ip, ip]
+    lib.starneig_b200_dist_layout.restype = i
+    lib.starneig_b200_dist_global_col.argtypes = [i, i, i, i]
+    lib.starneig_b200_dist_global_col.restype = i
+    lib.starneig_b200_dist_init.argtypes = [i, i, i, i, vp]
+    lib.starneig_b200_dist_init.restype = i
+    lib.starneig_b200_dist_connect.argtypes = [vp]
+    lib.starneig_b200_dist_connect.restype = i
+    lib.starneig_b200_dist_hessenberg_device.argtypes = [i, i, i, i, vp, i, vp, i]
+    lib.starneig_b200_dist_hessenberg_device.restype = i
+    lib.starneig_b200_dist_hessenberg_host.argtypes = [i, i, i, i, vp, i, vp, i]
+    lib.starneig_b200_dist_hessenberg_host.restype = i
+    lib.starneig_b200_dist_finalize.restype = None
     return lib

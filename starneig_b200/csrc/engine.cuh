@@ -1,0 +1,577 @@
+// engine.cuh -- per-rank engine of the B200-native blocked Hessenberg reduction.
+//
+// Replaces, for the path behind starneig_SEP_SM_Hessenberg (reference src/hessenberg/interface.c),
+// the StarPU task graph of src/hessenberg/core.c:351-599 and the tile plumbing of src/common
+// (matrix.c, vector.c, tiles.c, scratch.c): the matrix stays dense and column-major in HBM, the
+// "task graph" is a fixed sequence of kernel launches on one CUDA stream per GPU, and all workspace
+// comes from two arenas owned by the rank (a private one and a peer-visible exchange arena).
+//
+// One `Rank` drives one GPU. P ranks (threads of one process, or one process each) run the same code:
+//   * A is 1-D block-cyclic by columns (ColMap, block width cb), every rank holds full-height columns;
+//     Q is split by rows (its update is a right-multiplication, so row slabs need no communication).
+//   * The panel (w columns) is gathered into a replicated buffer Pan on every rank; the level-2 panel
+//     kernels run redundantly (bitwise identical) on all ranks, so V, Y, VT, tau never travel.
+//   * The one per-column exchange is the sum of the GEMV partials: pushed over NVLink peer stores by the
+//     GEMV kernel itself and consumed by the next k_col_finish_update (panel.cuh, struct Xchg).
+//   * Per panel: trailing right/left updates touch local columns only; the rows above the panel need a
+//     sum over ranks of (i+1) x w products, pulled from the peers' exchange arenas (k_sum_peers).
+//
+// Panel i (columns i .. i+w-1, m = end-i-1 rows below the diagonal), cf. SURVEY.md section 8a:
+//   column loop          k_col_finish_update / k_col_reflector / k_col_gemv     (panel.cuh)
+//   A(i+1:e, i+w:e) -= Y V(w-1:,:)^T                       core.c:523-540, cpu.c:315
+//   A(i+1:e, i+w:e) -= V (A^T VT)^T                        core.c:546-547, cpu.c:373-435
+//   A(0:i+1, i+1:e) -= (A VT) V^T                          core.c:320-327, cpu.c:492-554
+//   A(i+1:e, e:n)   -= V (A^T VT)^T   (partial only)       core.c:329-336
+//   Q(:, i+1:e)     -= (Q VT) V^T                          core.c:338-340
+// with VT = V*T (see panel.cuh). The reference defers the last three to the end of the graph at lower
+// priority; they only depend on this panel's V and VT and touch disjoint data, so issuing them right
+// after the panel is the same computation.
+#pragma once
+#include "panel.cuh"
+#include "dgemm.cuh"
+#include <starneig_b200.h>
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+namespace sb200 {
+
+// ---------------------------------------------------------------------------------------------
+// GEMM dispatch
+// ---------------------------------------------------------------------------------------------
+// <A K-major, B K-major, warps along M, warps along N, 8-row blocks per warp, 8-col blocks per warp, stages, CTAs/SM>
+using GemmNT   = GemmConfig<false, false, 2, 2, 8, 4, 4, 2>;     // 128 x  64, 128 threads: rank-nb updates
+using GemmTN13 = GemmConfig<true,  true,  4, 1, 2, 13, 4, 2>;    //  64 x 104, W = A^T VT
+using GemmTN12 = GemmConfig<true,  true,  4, 1, 2, 12, 4, 2>;    //  64 x  96
+using GemmNN13 = GemmConfig<false, true,  4, 1, 2, 13, 4, 2>;    //  64 x 104, W = A VT
+using GemmNN12 = GemmConfig<false, true,  4, 1, 2, 12, 4, 2>;    //  64 x  96
+
+static const size_t PANEL_SMEM_MAX = 200 * 1024;
+
+// per-device function attributes (opt-in shared memory sizes)
+static void prepare_device_functions()
+{
+    GemmNT::prepare(); GemmTN13::prepare(); GemmTN12::prepare(); GemmNN13::prepare(); GemmNN12::prepare();
+    SB_CUDA(cudaFuncSetAttribute(k_col_finish_update<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM_MAX));
+    SB_CUDA(cudaFuncSetAttribute(k_col_finish_update<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM_MAX));
+    SB_CUDA(cudaFuncSetAttribute(k_col_reflector<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM_MAX));
+    SB_CUDA(cudaFuncSetAttribute(k_col_reflector<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM_MAX));
+    // Force-load every kernel of the multi-GPU path now. With lazy module loading the first launch of a kernel
+    // may need a device-wide synchronisation, which would deadlock against a peer rank's kernel that is already
+    // spinning on a flag this rank has not raised yet.
+    cudaFuncAttributes fa;
+    SB_CUDA(cudaFuncGetAttributes(&fa, k_col_gemv<false>));
+    SB_CUDA(cudaFuncGetAttributes(&fa, k_col_gemv<true>));
+    SB_CUDA(cudaFuncGetAttributes(&fa, k_panel_push));
+    SB_CUDA(cudaFuncGetAttributes(&fa, k_panel_pull));
+    SB_CUDA(cudaFuncGetAttributes(&fa, k_gather_rows));
+    SB_CUDA(cudaFuncGetAttributes(&fa, k_sum_peers));
+    SB_CUDA(cudaFuncGetAttributes(&fa, k_barrier));
+    SB_CUDA(cudaFuncGetAttributes(&fa, splitk_reduce_kernel));
+}
+
+struct Stats : starneig_b200_stats {};
+
+// private workspace of a rank
+struct Workspace {
+    int n_cap = 0, nb_cap = 0;
+    int ldv = 0, nbp = 0;
+    double *V = nullptr, *Y = nullptr, *VT = nullptr, *W = nullptr, *Wpart = nullptr;
+    double *Vg = nullptr, *VTg = nullptr;      // rows of V, VT of the local columns (P > 1)
+    size_t wpart_cap = 0;           // doubles
+    double *pcol = nullptr, *ypart = nullptr;
+    size_t ypart_cap = 0;           // doubles
+    double *s = nullptr, *w2 = nullptr, *colpart = nullptr, *sqpart = nullptr;
+    ColScal *scal = nullptr;
+    unsigned *counter = nullptr;
+    std::vector<void *> allocs;
+
+    template <typename T> T *alloc(size_t count)
+    {
+        void *p = nullptr;
+        SB_CUDA(cudaMalloc(&p, count * sizeof(T) + 256));
+        allocs.push_back(p);
+        return (T *)p;
+    }
+    void release()
+    {
+        for (void *p : allocs) cudaFree(p);
+        allocs.clear();
+        n_cap = nb_cap = 0;
+    }
+    void ensure(int n, int nb, bool dist)
+    {
+        if (n <= n_cap && nb <= nb_cap && (!dist || Vg != nullptr)) return;
+        n = std::max(n, n_cap); nb = std::max(nb, nb_cap);
+        release();
+        n_cap = n; nb_cap = nb;
+        ldv = round_up(n, 16);
+        nbp = round_up(nb, 8);
+        size_t panel = (size_t)ldv * nbp;
+        V = alloc<double>(panel); Y = alloc<double>(panel); VT = alloc<double>(panel); W = alloc<double>(panel);
+        if (dist) { Vg = alloc<double>(panel); VTg = alloc<double>(panel); }
+        else Vg = VTg = nullptr;
+        wpart_cap = 8 * (size_t)std::max(ldv, 4096) * nbp;
+        Wpart = alloc<double>(wpart_cap);
+        pcol = alloc<double>(ldv);
+        ypart_cap = (size_t)2 * 148 * 12 * 256 + 4 * (size_t)ldv;
+        ypart = alloc<double>(ypart_cap);
+        s = alloc<double>(nbp); w2 = alloc<double>(nbp);
+        colpart = alloc<double>((size_t)nbp * PANEL_LDB);
+        sqpart = alloc<double>(PANEL_LDB);
+        scal = alloc<ColScal>(nbp);
+        counter = alloc<unsigned>(4);
+        SB_CUDA(cudaMemset(counter, 0, 4 * sizeof(unsigned)));
+    }
+};
+
+// Peer-visible exchange arena of a rank: ONE cudaMalloc, so one pointer (same process) or one
+// cudaIpcMemHandle (one process per GPU) is all that the ranks exchange. The layout is a pure function
+// of (P, n_cap, nb_cap) and therefore identical on every rank.
+struct ArenaLayout {
+    int P = 0, n_cap = 0, nb_cap = 0, ldv = 0, nbp = 0, ldp = 0;
+    size_t off_bar = 0, off_status = 0, off_rbcount = 0, off_yflag = 0, off_inbox = 0, off_pan = 0, off_wx = 0, bytes = 0;
+    static size_t align(size_t x) { return (x + 255) / 256 * 256; }
+    void set(int P_, int n, int nb)
+    {
+        P = P_; n_cap = n; nb_cap = nb;
+        ldv = round_up(n, 16); nbp = round_up(nb, 8); ldp = round_up(n + 2, 16);
+        size_t o = 0;
+        off_bar = o;      o = align(o + MAX_RANKS * sizeof(unsigned));
+        off_status = o;   o = align(o + sizeof(unsigned));
+        off_rbcount = o;  o = align(o + RB_MAX * sizeof(unsigned));
+        off_yflag = o;    o = align(o + (size_t)2 * P * RB_MAX * sizeof(unsigned));
+        off_inbox = o;    o = align(o + (size_t)2 * P * ldp * sizeof(double));
+        off_pan = o;      o = align(o + (size_t)ldv * nbp * sizeof(double));
+        off_wx = o;       o = align(o + (size_t)ldv * nbp * sizeof(double));
+        bytes = o;
+    }
+};
+
+struct GemvPlan { int skip, RB, S, kc; const double *A0; };
+struct PanelGrid { int blocks; TileGeom tg; size_t smem_fu, smem_rf; };
+
+struct Rank {
+    int P = 1, g = 0, device = 0, cb = 64;
+    bool ready = false;
+    cudaStream_t stream = nullptr;
+    Workspace ws;
+    ArenaLayout al;
+    char *arena = nullptr;                  // own arena (device memory on `device`)
+    char *peer[MAX_RANKS] = {};             // arena base of every rank as seen from this rank (peer[g] == arena)
+    bool arena_is_ipc[MAX_RANKS] = {};
+    unsigned bar_epoch = 0, y_epoch = 0;
+    Stats stats{};
+    int profile_level = 1;
+    int gemv_slots = 0;                     // resident k_col_gemv blocks on the whole GPU (one wave)
+    std::vector<cudaEvent_t> events;        // phase events: 4 per panel
+    std::vector<cudaEvent_t> gemv_events;   // 4 per timed column (profile level 2)
+    size_t gemv_events_used = 0;
+
+    void open(int P_, int g_, int device_)
+    {
+        if (ready) return;
+        P = P_; g = g_; device = device_;
+        SB_CUDA(cudaSetDevice(device));
+        SB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        prepare_device_functions();
+        const char *e = getenv("STARNEIG_B200_COL_BLOCK");
+        if (e && atoi(e) >= 8) cb = atoi(e) / 8 * 8;
+        ready = true;
+    }
+    void close()
+    {
+        if (!ready) return;
+        cudaSetDevice(device);
+        cudaDeviceSynchronize();
+        ws.release();
+        for (auto e : events) cudaEventDestroy(e);
+        for (auto e : gemv_events) cudaEventDestroy(e);
+        events.clear(); gemv_events.clear();
+        for (int s = 0; s < P; s++)
+            if (s != g && arena_is_ipc[s] && peer[s]) { cudaIpcCloseMemHandle(peer[s]); peer[s] = nullptr; }
+        if (arena) cudaFree(arena);
+        arena = nullptr;
+        al = ArenaLayout();
+        cudaStreamDestroy(stream);
+        stream = nullptr;
+        ready = false;
+    }
+    // (re)allocates the own arena for (n, nb); returns true if a new allocation was made (peers must re-exchange)
+    bool ensure_arena(int n, int nb)
+    {
+        if (arena && n <= al.n_cap && nb <= al.nb_cap) return false;
+        n = std::max(n, al.n_cap); nb = std::max(nb, al.nb_cap);
+        SB_CUDA(cudaSetDevice(device));
+        if (arena) { SB_CUDA(cudaDeviceSynchronize()); SB_CUDA(cudaFree(arena)); }
+        al.set(P, n, nb);
+        SB_CUDA(cudaMalloc((void **)&arena, al.bytes));
+        SB_CUDA(cudaMemset(arena, 0, al.off_pan));          // flags, counters, inbox
+        SB_CUDA(cudaDeviceSynchronize());
+        for (int s = 0; s < P; s++) peer[s] = nullptr;
+        peer[g] = arena;
+        bar_epoch = 0; y_epoch = 0;
+        return true;
+    }
+    template <typename T> T *at(int s, size_t off) const { return (T *)(peer[s] + off); }
+
+    cudaEvent_t phase_event(size_t idx)
+    {
+        while (events.size() <= idx) { cudaEvent_t e; SB_CUDA(cudaEventCreate(&e)); events.push_back(e); }
+        return events[idx];
+    }
+    cudaEvent_t gemv_event(size_t idx)
+    {
+        while (gemv_events.size() <= idx) { cudaEvent_t e; SB_CUDA(cudaEventCreate(&e)); gemv_events.push_back(e); }
+        return gemv_events[idx];
+    }
+
+    // -----------------------------------------------------------------------------------------
+    enum GemmKind { GEMM_NT, GEMM_TN, GEMM_NN };
+
+    // C = alpha*op(A)*op(B) + beta*C on the rank's stream; split-K through ws.Wpart for skinny outputs
+    void gemm(GemmKind kind, int M, int N, int K, double alpha, const double *A, int lda,
+              const double *B, int ldb, double beta, double *C, int ldc)
+    {
+        if (M < 1 || N < 1) return;
+        cudaStream_t st = stream;
+        stats.gemm_flops += 2.0 * M * N * (double)K;
+        if (kind == GEMM_NT) {
+            GemmNT::launch(st, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, 1, K, 0);
+            stats.kernel_launches++;
+            return;
+        }
+        // skinny output (N = panel width): pick the column tile with the least padding, split K if the
+        // grid would not fill the GPU twice
+        int bn = (ceil_div(N, 96) * 96 <= ceil_div(N, 104) * 104) ? 96 : 104;
+        // 2 CTAs per SM are resident; split K so that the grid is >= ~8 waves (tail quantisation < ~6 %)
+        int tiles = ceil_div(M, 64) * ceil_div(N, bn);
+        int splits = 1;
+        const int want = 8 * 2 * 148;
+        if (beta == 0.0 && alpha == 1.0 && ws.Wpart != nullptr && tiles < want) {
+            splits = std::min(32, ceil_div(want, tiles));
+            splits = std::min(splits, std::max(1, K / 512));
+            while (splits > 1 && (size_t)splits * ldc * N > ws.wpart_cap) splits--;
+        }
+        int klen = round_up(std::max(1, ceil_div(K, splits)), GEMM_BK);
+        splits = std::max(1, ceil_div(K, klen));
+        double *out = splits > 1 ? ws.Wpart : C;
+        size_t stride = splits > 1 ? (size_t)ldc * N : 0;
+        double b = splits > 1 ? 0.0 : beta;
+        if (kind == GEMM_TN) {
+            if (bn == 96) GemmTN12::launch(st, M, N, K, alpha, A, lda, B, ldb, b, out, ldc, splits, klen, stride);
+            else          GemmTN13::launch(st, M, N, K, alpha, A, lda, B, ldb, b, out, ldc, splits, klen, stride);
+        } else {
+            if (bn == 96) GemmNN12::launch(st, M, N, K, alpha, A, lda, B, ldb, b, out, ldc, splits, klen, stride);
+            else          GemmNN13::launch(st, M, N, K, alpha, A, lda, B, ldb, b, out, ldc, splits, klen, stride);
+        }
+        stats.kernel_launches++;
+        if (splits > 1) {
+            dim3 grid(ceil_div(M, 256), N);
+            splitk_reduce_kernel<<<grid, 256, 0, st>>>(M, N, splits, out, ldc, stride, C, ldc);
+            stats.kernel_launches++;
+        }
+    }
+
+    // -----------------------------------------------------------------------------------------
+    // panel factorisation: columns i .. i+w-1
+    // -----------------------------------------------------------------------------------------
+    PanelArgs make_panel_args(int m, double *V, double *Y, double *VT, int ld)
+    {
+        PanelArgs pa;
+        pa.m = m; pa.ld = ld; pa.V = V; pa.Y = Y; pa.VT = VT;
+        pa.pcol = ws.pcol; pa.ypart = ws.ypart; pa.ldp = round_up(m + 2, 16);
+        pa.s = ws.s; pa.w2 = ws.w2; pa.colpart = ws.colpart; pa.ldt = ws.nbp;
+        pa.sqpart = ws.sqpart; pa.scal = ws.scal; pa.counter = ws.counter;
+        return pa;
+    }
+
+    // decomposition of the GEMV over rows [0,m) x local columns [0,ncols) starting at `base`: row blocks of
+    // 256 padded rows times S column chunks, sized so that the grid is (at most) one full wave
+    GemvPlan plan_gemv(const double *base, int m, int ncols, int ldp)
+    {
+        if (gemv_slots == 0) {
+            int occ = 0, sms = 0;
+            SB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+            SB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_col_gemv<false>, GEMV_THREADS, 2048 * sizeof(double)));
+            gemv_slots = std::max(1, occ) * sms;
+        }
+        GemvPlan p;
+        p.skip = (int)(((uintptr_t)base / sizeof(double)) & 1);
+        p.A0 = base - p.skip;
+        int mp = m + p.skip;
+        p.RB = ceil_div(mp, 256);
+        int S = std::max(1, gemv_slots / p.RB);
+        int kc = ceil_div(std::max(ncols, 1), S);
+        kc = std::max(kc, 16);
+        kc = std::min(round_up(kc, 4), 2048);
+        S = std::max(1, ceil_div(ncols, kc));
+        while ((size_t)S * ldp > ws.ypart_cap && kc < 2048) { kc *= 2; S = std::max(1, ceil_div(ncols, kc)); }
+        p.kc = kc; p.S = S;
+        return p;
+    }
+
+    // row blocks (<= PANEL_MAX_BLOCKS) and warp layout of the two row-block kernels for a panel of m rows
+    // at column j (cols = number of columns the warps must cover)
+    static PanelGrid panel_grid(int m, int cols, int j)
+    {
+        PanelGrid g;
+        TileGeom &tg = g.tg;
+        tg.nsub = std::max(1, ceil_div(m, 32 * PANEL_MAX_BLOCKS));
+        g.blocks = ceil_div(m, 32 * tg.nsub);
+        tg.NW = std::max(1, ceil_div(cols, 32));
+        tg.RS = std::max(1, std::min(tg.nsub, (tg.NW <= 16 ? 16 : 32) / tg.NW));      // <= 512 threads unless the panel is wider than 512
+        // a few warps at least: they share the sum over the GEMV partials and hide latency
+        while (tg.NW * tg.RS < 4 && tg.NW * (tg.RS + 1) <= 32 && tg.RS < 4) tg.RS++;
+        g.smem_fu = (size_t)(2 * j + tg.nsub * 4 * tg.NW * 32 + 2 * tg.nsub * 32 + tg.RS * tg.NW * 32) * sizeof(double);
+        g.smem_rf = (size_t)(j + tg.nsub * tg.NW * 32 + tg.nsub * 32 + tg.RS * tg.NW * 32 + 32) * sizeof(double);
+        if (g.smem_fu > PANEL_SMEM_MAX) fatal("matrix too large for the panel kernels' shared-memory layout", __FILE__, __LINE__);
+        return g;
+    }
+
+    void launch_finish_update(const PanelArgs &pa, int j, int S, const double *yin, double *acol, int do_update, const YWait &yw)
+    {
+        PanelGrid pg = panel_grid(pa.m, j, j);
+        const int threads = 32 * pg.tg.NW * pg.tg.RS;
+        if (threads <= 512) k_col_finish_update<512><<<pg.blocks, threads, pg.smem_fu, stream>>>(pa, j, S, yin, acol, do_update, pg.tg, yw);
+        else                k_col_finish_update<1024><<<pg.blocks, threads, pg.smem_fu, stream>>>(pa, j, S, yin, acol, do_update, pg.tg, yw);
+        stats.kernel_launches++;
+    }
+
+    void launch_reflector(const PanelArgs &pa, int j, double *acol)
+    {
+        PanelGrid pg = panel_grid(pa.m, j, j);
+        const int threads = 32 * pg.tg.NW * pg.tg.RS;
+        if (threads <= 512) k_col_reflector<512><<<pg.blocks, threads, pg.smem_rf, stream>>>(pa, j, acol, pg.tg);
+        else                k_col_reflector<1024><<<pg.blocks, threads, pg.smem_rf, stream>>>(pa, j, acol, pg.tg);
+        stats.kernel_launches++;
+    }
+
+    Xchg make_xchg()
+    {
+        Xchg x;
+        memset(&x, 0, sizeof(x));
+        x.P = P; x.g = g;
+        if (P > 1) {
+            for (int s = 0; s < P; s++) { x.inbox[s] = at<double>(s, al.off_inbox); x.yflag[s] = at<unsigned>(s, al.off_yflag); }
+            x.rbcount = at<unsigned>(g, al.off_rbcount);
+            x.status = at<unsigned>(g, al.off_status);
+        }
+        return x;
+    }
+
+    // Columns i .. i+w-1 of the reduction of rows/cols < end. `pan` points at row i+1 of panel column 0 (leading
+    // dimension ldpan): the matrix itself (P == 1) or the replicated panel buffer. A_loc is the rank's column
+    // storage (leading dimension ldA), cm its column map.
+    void panel_factor(const ColMap &cm, int i, int end, int w, const double *A_loc, int ldA, double *pan, int ldpan,
+                      double *V, double *Y, double *VT, int ld)
+    {
+        cudaStream_t st = stream;
+        const int m = end - i - 1;
+        PanelArgs pa = make_panel_args(m, V, Y, VT, ld);
+        SB_CUDA(cudaMemsetAsync(V, 0, (size_t)ld * w * sizeof(double), st));
+        Xchg x = make_xchg();
+        const int lc_end = cm.lower(end);
+        int S_prev = 0;
+        const double *yin = ws.ypart;
+        YWait yw; memset(&yw, 0, sizeof(yw));
+        for (int j = 0; j <= w; j++) {
+            const int c = i + j;
+            double *acol = j < w ? pan + (size_t)j * ldpan : nullptr;
+            const bool timed = j < w && (profile_level >= 3 || (profile_level == 2 && (j & 7) == 4));
+            if (timed) SB_CUDA(cudaEventRecord(gemv_event(gemv_events_used++), st));
+            // finish column j-1 (Y, VT) and start column j; the last pass (j == w) only finishes
+            if (j > 0) launch_finish_update(pa, j, S_prev, yin, acol, j < w ? 1 : 0, yw);
+            if (j == w) break;
+            if (timed) SB_CUDA(cudaEventRecord(gemv_event(gemv_events_used++), st));
+            launch_reflector(pa, j, acol);
+            if (timed) SB_CUDA(cudaEventRecord(gemv_event(gemv_events_used++), st));
+
+            const int ncols = m - j;                         // length of v
+            const int lc0 = cm.lower(c + 1), nloc = lc_end - lc0;
+            const double *base = A_loc + (size_t)lc0 * ldA + i + 1;
+            GemvPlan gp = plan_gemv(base, m, nloc, pa.ldp);
+            size_t sh = (size_t)gp.kc * sizeof(double);
+            if (P == 1) {
+                k_col_gemv<false><<<gp.RB * gp.S, GEMV_THREADS, sh, st>>>(pa, j, ncols, cm, lc0, nloc, c + 1, gp.A0, ldA, gp.skip,
+                                                                           gp.kc, gp.RB, gp.S, acol, x);
+                S_prev = gp.S;
+            } else {
+                x.epoch = ++y_epoch;
+                k_col_gemv<true><<<gp.RB * gp.S, GEMV_THREADS, sh, st>>>(pa, j, ncols, cm, lc0, nloc, c + 1, gp.A0, ldA, gp.skip,
+                                                                          gp.kc, gp.RB, gp.S, acol, x);
+                const int par = x.epoch & 1;
+                S_prev = P;
+                yin = at<double>(g, al.off_inbox) + (size_t)par * P * pa.ldp;
+                yw.flags = at<unsigned>(g, al.off_yflag) + (size_t)par * P * RB_MAX;
+                yw.epoch = x.epoch; yw.P = P; yw.skip = gp.skip; yw.status = x.status;
+            }
+            if (timed) {
+                SB_CUDA(cudaEventRecord(gemv_event(gemv_events_used++), st));
+                stats.gemv_timed_launches++;
+                stats.gemv_timed_bytes += 8.0 * (double)m * nloc;
+            }
+            stats.kernel_launches++;
+            stats.gemv_launches++;
+            stats.gemv_bytes += 8.0 * (double)m * nloc;
+        }
+    }
+
+    void barrier()
+    {
+        if (P == 1) return;
+        BarPtrs b;
+        for (int s = 0; s < MAX_RANKS; s++) b.p[s] = s < P ? at<unsigned>(s, al.off_bar) : nullptr;
+        k_barrier<<<1, MAX_RANKS, 0, stream>>>(P, g, ++bar_epoch, b, at<unsigned>(g, al.off_status));
+        stats.kernel_launches++;
+    }
+
+    // -----------------------------------------------------------------------------------------
+    // the whole reduction on this rank's shards: A_loc = local columns (full height n, leading dimension ldA),
+    // Q_loc = rows [q0, q0+qrows) of Q (all n columns, leading dimension ldQ). P == 1: the matrices themselves.
+    // -----------------------------------------------------------------------------------------
+    void reduce(int n, int begin, int end, int nb, double *A, int ldA, double *Q, int ldQ, int qrows)
+    {
+        SB_CUDA(cudaSetDevice(device));
+        cudaStream_t st = stream;
+        nb = std::min(nb, PANEL_MAX_NB);      // wider panels are split; the result only differs in rounding
+        ws.ensure(n, nb, P > 1);
+        if (P > 1 && (arena == nullptr || n > al.n_cap || nb > al.nb_cap))
+            fatal("internal error: exchange arena not prepared", __FILE__, __LINE__);
+        const int ld = ws.ldv;
+        const int lvl = profile_level;
+        const ColMap cm{P, g, P == 1 ? std::max(n, 1) : cb};
+        gemv_events_used = 0;
+        int panel = 0;
+        cudaEvent_t ev_first = phase_event(0), ev_last = phase_event(1);
+        barrier();
+        SB_CUDA(cudaEventRecord(ev_first, st));
+
+        PeerPtrs panp, wxp;
+        for (int s = 0; s < MAX_RANKS; s++) {
+            panp.p[s] = (P > 1 && s < P) ? at<double>(s, al.off_pan) : nullptr;
+            wxp.p[s] = (P > 1 && s < P) ? at<double>(s, al.off_wx) : nullptr;
+        }
+        const int lc_end = cm.lower(end);
+
+        for (int i = begin; i < end - 1; i += nb, panel++) {
+            const int w = std::min(nb, end - i - 1);
+            const int m = end - i - 1;
+            if (lvl >= 1) SB_CUDA(cudaEventRecord(phase_event(2 + 4 * panel + 0), st));
+            const int pl0 = cm.lower(i), pl1 = cm.lower(i + w);
+            if (P == 1) {
+                panel_factor(cm, i, end, w, A, ldA, A + (size_t)i * ldA + i + 1, ldA, ws.V, ws.Y, ws.VT, ld);
+            } else {
+                // gather the panel on every rank; the first barrier protects Pan and Wx of the previous panel
+                barrier();
+                if (pl1 > pl0) {
+                    k_panel_push<<<dim3(ceil_div(m, 1024), pl1 - pl0), 256, 0, st>>>(cm, i, pl0, m, A, ldA, panp, al.ldv);
+                    stats.kernel_launches++;
+                }
+                barrier();
+                double *pan = panp.p[g];
+                panel_factor(cm, i, end, w, A, ldA, pan, al.ldv, ws.V, ws.Y, ws.VT, ld);
+                if (pl1 > pl0) {
+                    k_panel_pull<<<dim3(std::min(64, ceil_div(m, 256)), pl1 - pl0), 256, 0, st>>>(cm, i, pl0, m, A, ldA, pan, al.ldv);
+                    stats.kernel_launches++;
+                }
+            }
+            if (lvl >= 1) SB_CUDA(cudaEventRecord(phase_event(2 + 4 * panel + 1), st));
+
+            // rows of V, VT that belong to the local columns of the global range [i+1, end)
+            const int cl0 = cm.lower(i + 1), ncl = lc_end - cl0;
+            const double *Vg = ws.V, *VTg = ws.VT;
+            int ldg = ld;
+            if (P > 1) {
+                Vg = ws.Vg; VTg = ws.VTg;
+                if (ncl > 0) {
+                    k_gather_rows<<<dim3(ceil_div(ncl, 128), w), 128, 0, st>>>(cm, cl0, ncl, i + 1, w, ws.V, ws.VT, ld, ws.Vg, ws.VTg, ldg);
+                    stats.kernel_launches++;
+                }
+            }
+
+            const int tl0 = cm.lower(i + w), ntr = lc_end - tl0;
+            if (ntr > 0) {
+                double *Atr = A + (size_t)tl0 * ldA + i + 1;
+                gemm(GEMM_NT, m, ntr, w, -1.0, ws.Y, ld, Vg + (tl0 - cl0), ldg, 1.0, Atr, ldA);
+                gemm(GEMM_TN, ntr, w, m, 1.0, Atr, ldA, ws.VT, ld, 0.0, ws.W, ld);
+                gemm(GEMM_NT, m, ntr, w, -1.0, ws.V, ld, ws.W, ld, 1.0, Atr, ldA);
+            }
+            if (lvl >= 1) SB_CUDA(cudaEventRecord(phase_event(2 + 4 * panel + 2), st));
+
+            {   // rows above the panel
+                double *X = A + (size_t)cl0 * ldA;
+                if (P == 1) {
+                    gemm(GEMM_NN, i + 1, w, m, 1.0, X, ldA, ws.VT, ld, 0.0, ws.W, ld);
+                } else {
+                    gemm(GEMM_NN, i + 1, w, ncl, 1.0, X, ldA, VTg, ldg, 0.0, wxp.p[g], al.ldv);
+                    barrier();
+                    k_sum_peers<<<dim3(ceil_div(i + 1, 256), w), 256, 0, st>>>(P, i + 1, wxp, al.ldv, ws.W, ld);
+                    stats.kernel_launches++;
+                }
+                gemm(GEMM_NT, i + 1, ncl, w, -1.0, ws.W, ld, Vg, ldg, 1.0, X, ldA);
+            }
+            if (end < n) {   // columns right of the reduced block (partial reduction)
+                const int xl0 = cm.lower(end), nx = cm.lower(n) - xl0;
+                double *X = A + (size_t)xl0 * ldA + i + 1;
+                gemm(GEMM_TN, nx, w, m, 1.0, X, ldA, ws.VT, ld, 0.0, ws.W, ld);
+                gemm(GEMM_NT, m, nx, w, -1.0, ws.V, ld, ws.W, ld, 1.0, X, ldA);
+            }
+            if (qrows > 0) {   // Q <- Q (I - V T V^T) on the rank's rows
+                double *X = Q + (size_t)(i + 1) * ldQ;
+                gemm(GEMM_NN, qrows, w, m, 1.0, X, ldQ, ws.VT, ld, 0.0, ws.W, ld);
+                gemm(GEMM_NT, qrows, m, w, -1.0, ws.W, ld, ws.V, ld, 1.0, X, ldQ);
+            }
+            if (lvl >= 1) SB_CUDA(cudaEventRecord(phase_event(2 + 4 * panel + 3), st));
+        }
+        barrier();
+        SB_CUDA(cudaEventRecord(ev_last, st));
+        SB_CUDA(cudaStreamSynchronize(st));
+        SB_CUDA(cudaGetLastError());
+        if (P > 1) {
+            unsigned status = 0;
+            SB_CUDA(cudaMemcpy(&status, at<unsigned>(g, al.off_status), sizeof(status), cudaMemcpyDeviceToHost));
+            if (status != 0)
+                fatal(status == 2 ? "a cross-GPU wait for GEMV partial sums timed out (peer rank missing or stalled)"
+                                  : "a cross-GPU barrier timed out (peer rank missing or stalled)", __FILE__, __LINE__);
+        }
+
+        stats.panels = panel;
+        float ms = 0.f;
+        SB_CUDA(cudaEventElapsedTime(&ms, ev_first, ev_last));
+        stats.device_ms = ms;
+        if (lvl >= 1) {
+            for (int p = 0; p < panel; p++) {
+                cudaEvent_t *e = &events[2 + 4 * p];
+                SB_CUDA(cudaEventElapsedTime(&ms, e[0], e[1])); stats.panel_ms += ms;
+                SB_CUDA(cudaEventElapsedTime(&ms, e[1], e[2])); stats.trail_ms += ms;
+                SB_CUDA(cudaEventElapsedTime(&ms, e[2], e[3])); stats.other_ms += ms;
+            }
+        }
+        if (lvl >= 2) {
+            for (size_t k = 0; k + 3 < gemv_events_used; k += 4) {
+                SB_CUDA(cudaEventElapsedTime(&ms, gemv_events[k], gemv_events[k + 1])); stats.finish_update_ms += ms;
+                SB_CUDA(cudaEventElapsedTime(&ms, gemv_events[k + 1], gemv_events[k + 2])); stats.reflector_ms += ms;
+                SB_CUDA(cudaEventElapsedTime(&ms, gemv_events[k + 2], gemv_events[k + 3])); stats.gemv_ms += ms;
+            }
+        }
+    }
+};
+
+// the rank's row slab of Q: rows [q0, q1)
+static inline void q_row_range(int P, int g, int n, int *q0, int *q1)
+{
+    const int per = round_up(ceil_div(n, P), 8);
+    *q0 = std::min(n, g * per);
+    *q1 = std::min(n, (g + 1) * per);
+}
+
+static inline int default_panel_width(int n)
+{
+    // reference src/hessenberg/interface.c:74-78
+    int w = (int)std::ceil((0.001875596476 * n + 273.5908216) / 8.0) * 8;
+    return std::max(64, w);
+}
+
+} // namespace sb200

@@ -1,412 +1,183 @@
-// hessenberg.cu -- host driver of the B200-native blocked Hessenberg reduction and its C ABI.
+// hessenberg.cu -- C ABI of the B200-native blocked Hessenberg reduction and the host code that drives
+// the per-GPU engines (engine.cuh).
 //
-// Replaces, for the path behind starneig_SEP_SM_Hessenberg (reference src/hessenberg/interface.c),
-// the StarPU task graph of src/hessenberg/core.c:351-599 and the tile plumbing of src/common
-// (matrix.c, vector.c, tiles.c, scratch.c): here the matrix stays dense and column-major in HBM,
-// the "task graph" is a fixed sequence of kernel launches on CUDA streams, and all workspace comes
-// from one arena owned by the node context.
-//
-// Panel i (columns i .. i+w-1, m = end-i-1 rows below the diagonal), cf. SURVEY.md section 8a:
-//   column loop          k_col_finish_update / k_col_reflector / k_col_gemv     (panel.cuh)
-//   A(i+1:e, i+w:e) -= Y V(w-1:,:)^T                       core.c:523-540, cpu.c:315
-//   A(i+1:e, i+w:e) -= V (A^T VT)^T                        core.c:546-547, cpu.c:373-435
-//   A(0:i+1, i+1:e) -= (A VT) V^T                          core.c:320-327, cpu.c:492-554
-//   A(i+1:e, e:n)   -= V (A^T VT)^T   (partial only)       core.c:329-336
-//   Q(:, i+1:e)     -= (Q VT) V^T                          core.c:338-340
-// with VT = V*T (see panel.cuh). The reference defers the last three to the end of the graph at lower
-// priority; they only depend on this panel's V and VT and touch disjoint data, so issuing them right
-// after the panel is the same computation.
-#include "panel.cuh"
-#include "dgemm.cuh"
-#include <starneig_b200.h>
+// Boundary (reference file:line of what each entry point replaces is in include/starneig/*.h):
+//   starneig_SEP_SM_Hessenberg[_expert]      host pointers in, host pointers out; `gpus` of starneig_node_init
+//                                            selects the number of ranks (1, 2, 4, 8 GPUs of one box), each
+//                                            driven by its own host thread of this process
+//   starneig_b200_hessenberg_device          single GPU, matrices already in HBM
+//   starneig_b200_dist_*                     one PROCESS per GPU (torchrun): the ranks exchange one
+//                                            cudaIpcMemHandle each (through torch.distributed) and then run the
+//                                            same engine; all cross-GPU traffic is NVLink peer stores/loads
+//                                            issued by the kernels themselves
+// There is no CPU implementation of this path: without a GPU every compute entry point fails loudly.
+#include "engine.cuh"
 #include <chrono>
-#include <cmath>
-#include <cstring>
-#include <vector>
+#include <thread>
 
 namespace sb200 {
-
-// ---------------------------------------------------------------------------------------------
-// GEMM dispatch
-// ---------------------------------------------------------------------------------------------
-// <A K-major, B K-major, warps along M, warps along N, 8-row blocks per warp, 8-col blocks per warp, stages, CTAs/SM>
-using GemmNT   = GemmConfig<false, false, 2, 2, 8, 4, 4, 2>;     // 128 x  64, 128 threads: rank-nb updates
-using GemmTN13 = GemmConfig<true,  true,  4, 1, 2, 13, 4, 2>;    //  64 x 104, W = A^T VT
-using GemmTN12 = GemmConfig<true,  true,  4, 1, 2, 12, 4, 2>;    //  64 x  96
-using GemmNN13 = GemmConfig<false, true,  4, 1, 2, 13, 4, 2>;    //  64 x 104, W = A VT
-using GemmNN12 = GemmConfig<false, true,  4, 1, 2, 12, 4, 2>;    //  64 x  96
-
-static void panel_prepare();
-static bool g_gemm_prepared = false;
-static void gemm_prepare()
-{
-    if (g_gemm_prepared) return;
-    GemmNT::prepare(); GemmTN13::prepare(); GemmTN12::prepare(); GemmNN13::prepare(); GemmNN12::prepare();
-    g_gemm_prepared = true;
-}
-
-struct Stats : starneig_b200_stats {};
-
-struct Workspace {
-    int n_cap = 0, nb_cap = 0;
-    int ldv = 0, nbp = 0;
-    double *V = nullptr, *Y = nullptr, *VT = nullptr, *W = nullptr, *Wpart = nullptr;
-    size_t wpart_cap = 0;           // doubles
-    double *pcol = nullptr, *ypart = nullptr;
-    size_t ypart_cap = 0;           // doubles
-    double *s = nullptr, *w2 = nullptr, *colpart = nullptr, *sqpart = nullptr;
-    ColScal *scal = nullptr;
-    unsigned *counter = nullptr;
-    std::vector<void *> allocs;
-
-    template <typename T> T *alloc(size_t count)
-    {
-        void *p = nullptr;
-        SB_CUDA(cudaMalloc(&p, count * sizeof(T) + 256));
-        allocs.push_back(p);
-        return (T *)p;
-    }
-    void release()
-    {
-        for (void *p : allocs) cudaFree(p);
-        allocs.clear();
-        n_cap = nb_cap = 0;
-    }
-    void ensure(int n, int nb)
-    {
-        if (n <= n_cap && nb <= nb_cap) return;
-        release();
-        n_cap = n; nb_cap = nb;
-        ldv = round_up(n, 16);
-        nbp = round_up(nb, 8);
-        size_t panel = (size_t)ldv * nbp;
-        V = alloc<double>(panel); Y = alloc<double>(panel); VT = alloc<double>(panel); W = alloc<double>(panel);
-        wpart_cap = 8 * (size_t)std::max(ldv, 4096) * nbp;
-        Wpart = alloc<double>(wpart_cap);
-        pcol = alloc<double>(ldv);
-        ypart_cap = (size_t)2 * 148 * 12 * 256 + 4 * (size_t)ldv;
-        ypart = alloc<double>(ypart_cap);
-        s = alloc<double>(nbp); w2 = alloc<double>(nbp);
-        colpart = alloc<double>((size_t)nbp * PANEL_LDB);
-        sqpart = alloc<double>(PANEL_LDB);
-        scal = alloc<ColScal>(nbp);
-        counter = alloc<unsigned>(4);
-        SB_CUDA(cudaMemset(counter, 0, 4 * sizeof(unsigned)));
-    }
-};
-
-struct Context {
-    bool ready = false;
-    int device = 0;
-    cudaStream_t stream = nullptr;
-    Workspace ws;
-    Stats stats{};
-    int profile_level = 1;
-    std::vector<cudaEvent_t> events;        // phase events: 4 per panel
-    std::vector<cudaEvent_t> gemv_events;   // 2 per column (profile level 2)
-    size_t gemv_events_used = 0;
-
-    void open()
-    {
-        if (ready) return;
-        SB_CUDA(cudaGetDevice(&device));
-        SB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
-        gemm_prepare();
-        panel_prepare();
-        ready = true;
-    }
-    void close()
-    {
-        if (!ready) return;
-        cudaDeviceSynchronize();
-        ws.release();
-        for (auto e : events) cudaEventDestroy(e);
-        for (auto e : gemv_events) cudaEventDestroy(e);
-        events.clear(); gemv_events.clear();
-        cudaStreamDestroy(stream);
-        stream = nullptr;
-        ready = false;
-    }
-    cudaEvent_t phase_event(size_t idx)
-    {
-        while (events.size() <= idx) { cudaEvent_t e; SB_CUDA(cudaEventCreate(&e)); events.push_back(e); }
-        return events[idx];
-    }
-    cudaEvent_t gemv_event(size_t idx)
-    {
-        while (gemv_events.size() <= idx) { cudaEvent_t e; SB_CUDA(cudaEventCreate(&e)); gemv_events.push_back(e); }
-        return gemv_events[idx];
-    }
-};
-
-static Context g_ctx;
-
-enum GemmKind { GEMM_NT, GEMM_TN, GEMM_NN };
-
-// C = alpha*op(A)*op(B) + beta*C on `st`. Wpart/wpart_cap: split-K scratch (may be null => no split).
-static void gemm(Context &ctx, cudaStream_t st, GemmKind kind, int M, int N, int K, double alpha, const double *A, int lda,
-                 const double *B, int ldb, double beta, double *C, int ldc)
-{
-    if (M < 1 || N < 1) return;
-    ctx.stats.gemm_flops += 2.0 * M * N * (double)K;
-    if (kind == GEMM_NT) {
-        GemmNT::launch(st, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, 1, K, 0);
-        ctx.stats.kernel_launches++;
-        return;
-    }
-    // skinny output (N = panel width): pick the column tile with the least padding, split K if the
-    // grid would not fill the GPU twice
-    int bn = (ceil_div(N, 96) * 96 <= ceil_div(N, 104) * 104) ? 96 : 104;
-    // 2 CTAs per SM are resident; split K so that the grid is >= ~8 waves (tail quantisation < ~6 %)
-    int tiles = ceil_div(M, 64) * ceil_div(N, bn);
-    int splits = 1;
-    const int want = 8 * 2 * 148;
-    if (beta == 0.0 && alpha == 1.0 && ctx.ws.Wpart != nullptr && tiles < want) {
-        splits = std::min(32, ceil_div(want, tiles));
-        splits = std::min(splits, std::max(1, K / 512));
-        while (splits > 1 && (size_t)splits * ldc * N > ctx.ws.wpart_cap) splits--;
-    }
-    int klen = round_up(ceil_div(K, splits), GEMM_BK);
-    splits = ceil_div(K, klen);
-    double *out = splits > 1 ? ctx.ws.Wpart : C;
-    size_t stride = splits > 1 ? (size_t)ldc * N : 0;
-    double b = splits > 1 ? 0.0 : beta;
-    if (kind == GEMM_TN) {
-        if (bn == 96) GemmTN12::launch(st, M, N, K, alpha, A, lda, B, ldb, b, out, ldc, splits, klen, stride);
-        else          GemmTN13::launch(st, M, N, K, alpha, A, lda, B, ldb, b, out, ldc, splits, klen, stride);
-    } else {
-        if (bn == 96) GemmNN12::launch(st, M, N, K, alpha, A, lda, B, ldb, b, out, ldc, splits, klen, stride);
-        else          GemmNN13::launch(st, M, N, K, alpha, A, lda, B, ldb, b, out, ldc, splits, klen, stride);
-    }
-    ctx.stats.kernel_launches++;
-    if (splits > 1) {
-        dim3 grid(ceil_div(M, 256), N);
-        splitk_reduce_kernel<<<grid, 256, 0, st>>>(M, N, splits, out, ldc, stride, C, ldc);
-        ctx.stats.kernel_launches++;
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// panel factorisation: columns i .. i+w-1
-// ---------------------------------------------------------------------------------------------
-static PanelArgs make_panel_args(Workspace &ws, int m, double *V, double *Y, double *VT, int ld)
-{
-    PanelArgs pa;
-    pa.m = m; pa.ld = ld; pa.V = V; pa.Y = Y; pa.VT = VT;
-    pa.pcol = ws.pcol; pa.ypart = ws.ypart; pa.ldp = round_up(m + 2, 16);
-    pa.s = ws.s; pa.w2 = ws.w2; pa.colpart = ws.colpart; pa.ldt = ws.nbp;
-    pa.sqpart = ws.sqpart; pa.scal = ws.scal; pa.counter = ws.counter;
-    return pa;
-}
-
-struct GemvPlan { int skip, RB, S, kc; const double *A0; };
-
-static int g_gemv_slots = 0;    // resident k_col_gemv blocks on the whole GPU (one wave)
-
-// decomposition of the GEMV over rows [0,m) x columns [0,ncols) starting at `base`: row blocks of 256
-// padded rows times S column chunks, sized so that the grid is (at most) one full wave
-static GemvPlan plan_gemv(const double *base, int m, int ncols, size_t ypart_cap, int ldp)
-{
-    if (g_gemv_slots == 0) {
-        int occ = 0, dev = 0, sms = 0;
-        SB_CUDA(cudaGetDevice(&dev));
-        SB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        SB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_col_gemv, GEMV_THREADS, 2048 * sizeof(double)));
-        g_gemv_slots = std::max(1, occ) * sms;
-    }
-    GemvPlan p;
-    p.skip = (int)(((uintptr_t)base / sizeof(double)) & 1);
-    p.A0 = base - p.skip;
-    int mp = m + p.skip;
-    p.RB = ceil_div(mp, 256);
-    int S = std::max(1, g_gemv_slots / p.RB);
-    int kc = ceil_div(ncols, S);
-    kc = std::max(kc, 16);
-    kc = std::min(round_up(kc, 4), 2048);
-    S = ceil_div(ncols, kc);
-    while ((size_t)S * ldp > ypart_cap && kc < 2048) { kc *= 2; S = ceil_div(ncols, kc); }
-    p.kc = kc; p.S = S;
-    return p;
-}
-
-struct PanelGrid { int blocks; TileGeom tg; size_t smem_fu, smem_rf; };
-static const size_t PANEL_SMEM_MAX = 200 * 1024;
-
-// row blocks (<= PANEL_MAX_BLOCKS) and warp layout of the two row-block kernels for a panel of m rows
-// at column j (cols = number of columns the warps must cover)
-static PanelGrid panel_grid(int m, int cols, int j)
-{
-    PanelGrid g;
-    TileGeom &tg = g.tg;
-    tg.nsub = std::max(1, ceil_div(m, 32 * PANEL_MAX_BLOCKS));
-    g.blocks = ceil_div(m, 32 * tg.nsub);
-    tg.NW = std::max(1, ceil_div(cols, 32));
-    tg.RS = std::max(1, std::min(tg.nsub, (tg.NW <= 16 ? 16 : 32) / tg.NW));      // <= 512 threads unless the panel is wider than 512
-    // a few warps at least: they share the sum over the GEMV partials and hide latency
-    while (tg.NW * tg.RS < 4 && tg.NW * (tg.RS + 1) <= 32 && tg.RS < 4) tg.RS++;
-    g.smem_fu = (size_t)(2 * j + tg.nsub * 4 * tg.NW * 32 + 2 * tg.nsub * 32 + tg.RS * tg.NW * 32) * sizeof(double);
-    g.smem_rf = (size_t)(j + tg.nsub * tg.NW * 32 + tg.nsub * 32 + tg.RS * tg.NW * 32 + 32) * sizeof(double);
-    if (g.smem_fu > PANEL_SMEM_MAX) fatal("matrix too large for the panel kernels' shared-memory layout", __FILE__, __LINE__);
-    return g;
-}
-
-static void panel_prepare()
-{
-    static bool done = false;
-    if (done) return;
-    SB_CUDA(cudaFuncSetAttribute(k_col_finish_update<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM_MAX));
-    SB_CUDA(cudaFuncSetAttribute(k_col_finish_update<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM_MAX));
-    SB_CUDA(cudaFuncSetAttribute(k_col_reflector<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM_MAX));
-    SB_CUDA(cudaFuncSetAttribute(k_col_reflector<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM_MAX));
-    done = true;
-}
-
-static void launch_finish_update(cudaStream_t st, const PanelArgs &pa, int j, int S, double *acol, int do_update)
-{
-    PanelGrid pg = panel_grid(pa.m, j, j);
-    const int threads = 32 * pg.tg.NW * pg.tg.RS;
-    if (threads <= 512) k_col_finish_update<512><<<pg.blocks, threads, pg.smem_fu, st>>>(pa, j, S, acol, do_update, pg.tg);
-    else                k_col_finish_update<1024><<<pg.blocks, threads, pg.smem_fu, st>>>(pa, j, S, acol, do_update, pg.tg);
-}
-
-static void launch_reflector(cudaStream_t st, const PanelArgs &pa, int j, double *acol)
-{
-    PanelGrid pg = panel_grid(pa.m, j, j);
-    const int threads = 32 * pg.tg.NW * pg.tg.RS;
-    if (threads <= 512) k_col_reflector<512><<<pg.blocks, threads, pg.smem_rf, st>>>(pa, j, acol, pg.tg);
-    else                k_col_reflector<1024><<<pg.blocks, threads, pg.smem_rf, st>>>(pa, j, acol, pg.tg);
-}
-
-static void panel_factor(Context &ctx, cudaStream_t st, int i, int end, int w, double *A, int ldA,
-                         double *V, double *Y, double *VT, int ld)
-{
-    Workspace &ws = ctx.ws;
-    const int m = end - i - 1;
-    PanelArgs pa = make_panel_args(ws, m, V, Y, VT, ld);
-    SB_CUDA(cudaMemsetAsync(V, 0, (size_t)ld * w * sizeof(double), st));
-    int S_prev = 0;
-    for (int j = 0; j < w; j++) {
-        const int c = i + j;
-        double *acol = A + (size_t)c * ldA + i + 1;
-        const bool timed = ctx.profile_level >= 3 || (ctx.profile_level == 2 && (j & 7) == 4);
-        if (timed) SB_CUDA(cudaEventRecord(ctx.gemv_event(ctx.gemv_events_used++), st));
-        if (j > 0) {
-            launch_finish_update(st, pa, j, S_prev, acol, 1);
-            ctx.stats.kernel_launches++;
-        }
-        if (timed) SB_CUDA(cudaEventRecord(ctx.gemv_event(ctx.gemv_events_used++), st));
-        launch_reflector(st, pa, j, acol);
-        ctx.stats.kernel_launches++;
-        if (timed) SB_CUDA(cudaEventRecord(ctx.gemv_event(ctx.gemv_events_used++), st));
-        {
-            const int ncols = m - j;
-            const double *base = A + (size_t)(c + 1) * ldA + i + 1;
-            GemvPlan gp = plan_gemv(base, m, ncols, ws.ypart_cap, pa.ldp);
-            size_t sh = (size_t)gp.kc * sizeof(double);
-            k_col_gemv<<<gp.RB * gp.S, GEMV_THREADS, sh, st>>>(pa, j, ncols, gp.A0, ldA, gp.skip, gp.kc, gp.RB, acol);
-            if (timed) {
-                SB_CUDA(cudaEventRecord(ctx.gemv_event(ctx.gemv_events_used++), st));
-                ctx.stats.gemv_timed_launches++;
-                ctx.stats.gemv_timed_bytes += 8.0 * (double)m * ncols;
-            }
-            ctx.stats.kernel_launches++;
-            ctx.stats.gemv_launches++;
-            ctx.stats.gemv_bytes += 8.0 * (double)m * ncols;
-            S_prev = gp.S;
-        }
-    }
-    // finish the last column (Y, VT) without starting a new one
-    launch_finish_update(st, pa, w, S_prev, nullptr, 0);
-    ctx.stats.kernel_launches++;
-}
-
-// ---------------------------------------------------------------------------------------------
-// the whole reduction on device-resident A, Q
-// ---------------------------------------------------------------------------------------------
-static void reduce_device(Context &ctx, int n, int begin, int end, int nb, double *A, int ldA, double *Q, int ldQ)
-{
-    Workspace &ws = ctx.ws;
-    cudaStream_t st = ctx.stream;
-    nb = std::min(nb, PANEL_MAX_NB);      // wider panels are split; the result only differs in rounding
-    ws.ensure(n, nb);
-    const int ld = ws.ldv;
-    Stats &stt = ctx.stats;
-    const int lvl = ctx.profile_level;
-    ctx.gemv_events_used = 0;
-    int panel = 0;
-    cudaEvent_t ev_first = ctx.phase_event(0), ev_last = ctx.phase_event(1);
-    SB_CUDA(cudaEventRecord(ev_first, st));
-
-    for (int i = begin; i < end - 1; i += nb, panel++) {
-        const int w = std::min(nb, end - i - 1);
-        const int m = end - i - 1;
-        if (lvl >= 1) SB_CUDA(cudaEventRecord(ctx.phase_event(2 + 4 * panel + 0), st));
-        panel_factor(ctx, st, i, end, w, A, ldA, ws.V, ws.Y, ws.VT, ld);
-        if (lvl >= 1) SB_CUDA(cudaEventRecord(ctx.phase_event(2 + 4 * panel + 1), st));
-
-        const int ntr = end - (i + w);
-        if (ntr > 0) {
-            double *Atr = A + (size_t)(i + w) * ldA + i + 1;
-            gemm(ctx, st, GEMM_NT, m, ntr, w, -1.0, ws.Y, ld, ws.V + (w - 1), ld, 1.0, Atr, ldA);
-            gemm(ctx, st, GEMM_TN, ntr, w, m, 1.0, Atr, ldA, ws.VT, ld, 0.0, ws.W, ld);
-            gemm(ctx, st, GEMM_NT, m, ntr, w, -1.0, ws.V, ld, ws.W, ld, 1.0, Atr, ldA);
-        }
-        if (lvl >= 1) SB_CUDA(cudaEventRecord(ctx.phase_event(2 + 4 * panel + 2), st));
-
-        {   // rows above the panel
-            double *X = A + (size_t)(i + 1) * ldA;
-            gemm(ctx, st, GEMM_NN, i + 1, w, m, 1.0, X, ldA, ws.VT, ld, 0.0, ws.W, ld);
-            gemm(ctx, st, GEMM_NT, i + 1, m, w, -1.0, ws.W, ld, ws.V, ld, 1.0, X, ldA);
-        }
-        if (end < n) {   // columns right of the reduced block (partial reduction)
-            double *X = A + (size_t)end * ldA + i + 1;
-            gemm(ctx, st, GEMM_TN, n - end, w, m, 1.0, X, ldA, ws.VT, ld, 0.0, ws.W, ld);
-            gemm(ctx, st, GEMM_NT, m, n - end, w, -1.0, ws.V, ld, ws.W, ld, 1.0, X, ldA);
-        }
-        {   // Q <- Q (I - V T V^T)
-            double *X = Q + (size_t)(i + 1) * ldQ;
-            gemm(ctx, st, GEMM_NN, n, w, m, 1.0, X, ldQ, ws.VT, ld, 0.0, ws.W, ld);
-            gemm(ctx, st, GEMM_NT, n, m, w, -1.0, ws.W, ld, ws.V, ld, 1.0, X, ldQ);
-        }
-        if (lvl >= 1) SB_CUDA(cudaEventRecord(ctx.phase_event(2 + 4 * panel + 3), st));
-    }
-    SB_CUDA(cudaEventRecord(ev_last, st));
-    SB_CUDA(cudaStreamSynchronize(st));
-    SB_CUDA(cudaGetLastError());
-
-    stt.panels = panel;
-    float ms = 0.f;
-    SB_CUDA(cudaEventElapsedTime(&ms, ev_first, ev_last));
-    stt.device_ms = ms;
-    if (lvl >= 1) {
-        for (int p = 0; p < panel; p++) {
-            cudaEvent_t *e = &ctx.events[2 + 4 * p];
-            SB_CUDA(cudaEventElapsedTime(&ms, e[0], e[1])); stt.panel_ms += ms;
-            SB_CUDA(cudaEventElapsedTime(&ms, e[1], e[2])); stt.trail_ms += ms;
-            SB_CUDA(cudaEventElapsedTime(&ms, e[2], e[3])); stt.other_ms += ms;
-        }
-    }
-    if (lvl >= 2) {
-        for (size_t k = 0; k + 3 < ctx.gemv_events_used; k += 4) {
-            SB_CUDA(cudaEventElapsedTime(&ms, ctx.gemv_events[k], ctx.gemv_events[k + 1])); stt.finish_update_ms += ms;
-            SB_CUDA(cudaEventElapsedTime(&ms, ctx.gemv_events[k + 1], ctx.gemv_events[k + 2])); stt.reflector_ms += ms;
-            SB_CUDA(cudaEventElapsedTime(&ms, ctx.gemv_events[k + 2], ctx.gemv_events[k + 3])); stt.gemv_ms += ms;
-        }
-    }
-}
-
-static int default_panel_width(int n)
-{
-    // reference src/hessenberg/interface.c:74-78
-    int w = (int)std::ceil((0.001875596476 * n + 273.5908216) / 8.0) * 8;
-    return std::max(64, w);
-}
 
 static double wall_ms()
 {
     using namespace std::chrono;
     return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
 }
+
+// device shards of one rank for the host-pointer API (owned by the library)
+struct Shard {
+    double *A = nullptr, *Q = nullptr;
+    size_t capA = 0, capQ = 0;      // doubles
+    int ldA = 0, ldQ = 0, ncols = 0, q0 = 0, qrows = 0;
+    void ensure(const Rank &r, int n)
+    {
+        const ColMap cm{r.P, r.g, r.P == 1 ? std::max(n, 1) : r.cb};
+        ncols = cm.lower(n);
+        int q1;
+        q_row_range(r.P, r.g, n, &q0, &q1);
+        qrows = q1 - q0;
+        ldA = round_up(n, 16);
+        ldQ = round_up(std::max(qrows, 1), 16);
+        size_t needA = (size_t)ldA * std::max(ncols, 1) + 64, needQ = (size_t)ldQ * n + 64;
+        if (needA > capA) { if (A) cudaFree(A); SB_CUDA(cudaMalloc(&A, needA * sizeof(double))); capA = needA; }
+        if (needQ > capQ) { if (Q) cudaFree(Q); SB_CUDA(cudaMalloc(&Q, needQ * sizeof(double))); capQ = needQ; }
+    }
+    void release()
+    {
+        if (A) cudaFree(A);
+        if (Q) cudaFree(Q);
+        A = Q = nullptr; capA = capQ = 0;
+    }
+};
+
+// host <-> device movement of one rank's shards: its column blocks of A, its row slab of Q
+static void shard_copy(const Rank &r, Shard &sh, int n, double *A, int ldA, double *Q, int ldQ, bool to_device)
+{
+    const cudaMemcpyKind kind = to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
+    const int cb = r.P == 1 ? std::max(n, 1) : r.cb;
+    for (int lb = 0; lb * cb < sh.ncols; lb++) {
+        const int gc = (lb * r.P + r.g) * cb, nc = std::min(cb, n - gc);
+        double *d = sh.A + (size_t)lb * cb * sh.ldA, *h = A + (size_t)gc * ldA;
+        if (to_device) SB_CUDA(cudaMemcpy2DAsync(d, (size_t)sh.ldA * 8, h, (size_t)ldA * 8, (size_t)n * 8, nc, kind, r.stream));
+        else           SB_CUDA(cudaMemcpy2DAsync(h, (size_t)ldA * 8, d, (size_t)sh.ldA * 8, (size_t)n * 8, nc, kind, r.stream));
+    }
+    if (sh.qrows > 0) {
+        double *h = Q + sh.q0;
+        if (to_device) SB_CUDA(cudaMemcpy2DAsync(sh.Q, (size_t)sh.ldQ * 8, h, (size_t)ldQ * 8, (size_t)sh.qrows * 8, n, kind, r.stream));
+        else           SB_CUDA(cudaMemcpy2DAsync(h, (size_t)ldQ * 8, sh.Q, (size_t)sh.ldQ * 8, (size_t)sh.qrows * 8, n, kind, r.stream));
+    }
+}
+
+struct HostTimes { double h2d_ms = 0, d2h_ms = 0; long long h2d_bytes = 0, d2h_bytes = 0; };
+
+// upload, reduce, download on one rank (called on the rank's own host thread)
+static void run_rank_host(Rank &r, Shard &sh, int n, int begin, int end, int nb, double *A, int ldA, double *Q, int ldQ, HostTimes *ht)
+{
+    SB_CUDA(cudaSetDevice(r.device));
+    double t1 = wall_ms();
+    shard_copy(r, sh, n, A, ldA, Q, ldQ, true);
+    SB_CUDA(cudaStreamSynchronize(r.stream));
+    double t2 = wall_ms();
+    r.reduce(n, begin, end, nb, sh.A, sh.ldA, sh.Q, sh.ldQ, sh.qrows);
+    double t3 = wall_ms();
+    shard_copy(r, sh, n, A, ldA, Q, ldQ, false);
+    SB_CUDA(cudaStreamSynchronize(r.stream));
+    double t4 = wall_ms();
+    ht->h2d_ms = t2 - t1; ht->d2h_ms = t4 - t3;
+    ht->h2d_bytes = ht->d2h_bytes = ((long long)sh.ncols * n + (long long)sh.qrows * n) * 8;
+}
+
+// the ranks driven by this process: P host threads, one per GPU (P == 1 runs on the caller's thread)
+struct Team {
+    int P = 0;
+    std::vector<Rank *> ranks;
+    std::vector<Shard> shards;
+    Stats stats{};
+    int profile_level = 1;
+
+    void open(int P_)
+    {
+        if (P == P_) return;
+        close();
+        P = P_;
+        int ndev = 0, cur = 0;
+        SB_CUDA(cudaGetDeviceCount(&ndev));
+        SB_CUDA(cudaGetDevice(&cur));
+        for (int g = 0; g < P; g++) {
+            Rank *r = new Rank();
+            // P == 1: the caller's current device (one process per GPU under torchrun); P > 1: devices 0..P-1
+            // (STARNEIG_B200_VIRTUAL_RANKS: several ranks may share a device -- development aid)
+            r->open(P, g, P == 1 ? cur : g % ndev);
+            ranks.push_back(r);
+        }
+        shards.resize(P);
+        for (int g = 0; g < P; g++)
+            for (int s = 0; s < P; s++)
+                if (ranks[g]->device != ranks[s]->device) {
+                    SB_CUDA(cudaSetDevice(ranks[g]->device));
+                    cudaError_t e = cudaDeviceEnablePeerAccess(ranks[s]->device, 0);
+                    if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+                        fatal("cudaDeviceEnablePeerAccess failed: the GPUs of the node must be NVLink peers", __FILE__, __LINE__);
+                    cudaGetLastError();
+                }
+        SB_CUDA(cudaSetDevice(cur));
+    }
+    void close()
+    {
+        if (P == 0) return;
+        int cur = 0;
+        cudaGetDevice(&cur);
+        for (int g = 0; g < P; g++) {
+            cudaSetDevice(ranks[g]->device);
+            shards[g].release();
+            ranks[g]->close();
+            delete ranks[g];
+        }
+        cudaSetDevice(cur);
+        ranks.clear(); shards.clear();
+        P = 0;
+    }
+    void prepare_arenas(int n, int nb)
+    {
+        if (P == 1) return;
+        bool grow = false;
+        for (Rank *r : ranks) grow = grow || r->arena == nullptr || n > r->al.n_cap || nb > r->al.nb_cap;
+        if (!grow) return;
+        int cur = 0;
+        SB_CUDA(cudaGetDevice(&cur));
+        for (Rank *r : ranks) { r->al.n_cap = 0; r->al.nb_cap = 0; r->ensure_arena(n, nb); }    // all ranks re-allocate together
+        for (Rank *r : ranks)
+            for (int s = 0; s < P; s++) r->peer[s] = ranks[s]->arena;
+        SB_CUDA(cudaSetDevice(cur));
+    }
+    template <typename F> void run(F body)
+    {
+        if (P == 1) { body(0); return; }
+        int cur = 0;
+        SB_CUDA(cudaGetDevice(&cur));
+        std::vector<std::thread> th;
+        for (int g = 0; g < P; g++) th.emplace_back([&body, g] { body(g); });
+        for (auto &t : th) t.join();
+        SB_CUDA(cudaSetDevice(cur));
+    }
+    void collect_stats(int n, int begin, int end, int nb)
+    {
+        stats = ranks[0]->stats;
+        stats.n = n; stats.begin = begin; stats.end = end; stats.panel_width = nb; stats.ranks = P;
+        for (int g = 1; g < P; g++) {
+            stats.kernel_launches += ranks[g]->stats.kernel_launches;
+            stats.gemm_flops += ranks[g]->stats.gemm_flops;
+            stats.device_ms = std::max(stats.device_ms, ranks[g]->stats.device_ms);
+        }
+    }
+    void reset_stats()
+    {
+        for (Rank *r : ranks) { memset(&r->stats, 0, sizeof(r->stats)); r->profile_level = profile_level; }
+    }
+};
+
+static Team g_team;
+static Rank *g_dist = nullptr;          // the rank of this process in one-process-per-GPU mode
+static Shard g_dist_shard;
 
 } // namespace sb200
 
@@ -415,6 +186,8 @@ static double wall_ms()
 // =================================================================================================
 extern "C" int starneig_b200_node_messages_enabled(void);
 extern "C" int starneig_b200_node_pinning_enabled(void);
+
+using namespace sb200;
 
 // The Hessenberg path is CUDA-only: without a selected GPU the call fails loudly instead of falling
 // back to a CPU implementation.
@@ -426,16 +199,18 @@ static bool have_gpu()
     return false;
 }
 
-using namespace sb200;
-
-extern "C" void starneig_b200_context_open(void) { g_ctx.open(); }
-extern "C" void starneig_b200_context_close(void) { g_ctx.close(); }
+extern "C" void starneig_b200_context_close(void)
+{
+    g_team.close();
+    if (g_dist) { g_dist_shard.release(); g_dist->close(); delete g_dist; g_dist = nullptr; }
+}
+extern "C" void starneig_b200_staging_release(void) {}
 
 extern "C" __attribute__((visibility("default")))
-void starneig_b200_get_stats(struct starneig_b200_stats *stats) { *stats = g_ctx.stats; }
+void starneig_b200_get_stats(struct starneig_b200_stats *stats) { *stats = g_team.stats; }
 
 extern "C" __attribute__((visibility("default")))
-void starneig_b200_set_profile_level(int level) { g_ctx.profile_level = level; }
+void starneig_b200_set_profile_level(int level) { g_team.profile_level = level; }
 
 extern "C" __attribute__((visibility("default")))
 void starneig_hessenberg_init_conf(struct starneig_hessenberg_conf *conf)
@@ -466,12 +241,6 @@ static starneig_error_t resolve_conf(struct starneig_hessenberg_conf const *conf
     return STARNEIG_SUCCESS;
 }
 
-static void reset_stats(int n, int begin, int end, int nb)
-{
-    memset(&g_ctx.stats, 0, sizeof(g_ctx.stats));
-    g_ctx.stats.n = n; g_ctx.stats.begin = begin; g_ctx.stats.end = end; g_ctx.stats.panel_width = nb;
-}
-
 extern "C" __attribute__((visibility("default")))
 starneig_error_t starneig_b200_hessenberg_device(int n, int begin, int end, int panel_width,
                                                  double *dA, int ldA, double *dQ, int ldQ)
@@ -487,38 +256,16 @@ starneig_error_t starneig_b200_hessenberg_device(int n, int begin, int end, int 
     if (panel_width < 0) panel_width = default_panel_width(n);
     if (panel_width < 8) return STARNEIG_INVALID_CONFIGURATION;
     if (!have_gpu()) return STARNEIG_GENERIC_ERROR;
-    g_ctx.open();
-    reset_stats(n, begin, end, panel_width);
+    g_team.open(1);
+    g_team.reset_stats();
     double t0 = wall_ms();
-    reduce_device(g_ctx, n, begin, end, panel_width, dA, ldA, dQ, ldQ);
-    g_ctx.stats.wall_ms = wall_ms() - t0;
+    g_team.ranks[0]->reduce(n, begin, end, panel_width, dA, ldA, dQ, ldQ, n);
+    g_team.collect_stats(n, begin, end, panel_width);
+    g_team.stats.wall_ms = wall_ms() - t0;
     return STARNEIG_SUCCESS;
 }
 
-// device staging buffers for the host API
 namespace {
-struct Staging {
-    double *dA = nullptr, *dQ = nullptr;
-    size_t cap = 0;     // doubles per matrix
-    int ldd = 0;
-    void ensure(int n)
-    {
-        ldd = round_up(n, 16);
-        size_t need = (size_t)ldd * n + 64;
-        if (need <= cap) return;
-        release();
-        SB_CUDA(cudaMalloc(&dA, need * sizeof(double)));
-        SB_CUDA(cudaMalloc(&dQ, need * sizeof(double)));
-        cap = need;
-    }
-    void release()
-    {
-        if (dA) cudaFree(dA);
-        if (dQ) cudaFree(dQ);
-        dA = dQ = nullptr; cap = 0;
-    }
-} g_staging;
-
 // page-locks a caller buffer for the duration of a call (no-op if it already is pinned or on failure)
 struct ScopedPin {
     void *p = nullptr;
@@ -528,14 +275,12 @@ struct ScopedPin {
         cudaPointerAttributes attr;
         if (cudaPointerGetAttributes(&attr, ptr) == cudaSuccess && attr.type != cudaMemoryTypeUnregistered) return;
         cudaGetLastError();
-        if (cudaHostRegister(ptr, bytes, cudaHostRegisterDefault) == cudaSuccess) p = ptr;
+        if (cudaHostRegister(ptr, bytes, cudaHostRegisterPortable) == cudaSuccess) p = ptr;
         else cudaGetLastError();
     }
     ~ScopedPin() { if (p) cudaHostUnregister(p); }
 };
 }
-
-extern "C" void starneig_b200_staging_release(void) { g_staging.release(); }
 
 extern "C" __attribute__((visibility("default")))
 starneig_error_t starneig_SEP_SM_Hessenberg_expert(struct starneig_hessenberg_conf *conf, int n, int begin, int end,
@@ -556,33 +301,37 @@ starneig_error_t starneig_SEP_SM_Hessenberg_expert(struct starneig_hessenberg_co
     if (ret != STARNEIG_SUCCESS) return ret;
     if (!have_gpu()) return STARNEIG_GENERIC_ERROR;
 
-    g_ctx.open();
-    reset_stats(n, begin, end, nb);
+    const int P = std::min(starneig_node_get_gpus(), MAX_RANKS);
+    g_team.open(P);
+    g_team.reset_stats();
     double t0 = wall_ms();
-    g_staging.ensure(n);
-    const int ldd = g_staging.ldd;
-    cudaStream_t st = g_ctx.stream;
-    const size_t rowbytes = (size_t)n * sizeof(double);
+    {
+        int cur = 0;
+        SB_CUDA(cudaGetDevice(&cur));
+        for (int g = 0; g < P; g++) {
+            SB_CUDA(cudaSetDevice(g_team.ranks[g]->device));
+            g_team.shards[g].ensure(*g_team.ranks[g], n);
+            g_team.ranks[g]->ws.ensure(n, std::min(nb, PANEL_MAX_NB), P > 1);
+        }
+        SB_CUDA(cudaSetDevice(cur));
+    }
+    g_team.prepare_arenas(n, std::min(nb, PANEL_MAX_NB));
+    std::vector<HostTimes> ht(P);
     {
         ScopedPin pinA(A, ((size_t)ldA * (n - 1) + n) * sizeof(double), starneig_b200_node_pinning_enabled());
         ScopedPin pinQ(Q, ((size_t)ldQ * (n - 1) + n) * sizeof(double), starneig_b200_node_pinning_enabled());
-        double t1 = wall_ms();
-        SB_CUDA(cudaMemcpy2DAsync(g_staging.dA, (size_t)ldd * 8, A, (size_t)ldA * 8, rowbytes, n, cudaMemcpyHostToDevice, st));
-        SB_CUDA(cudaMemcpy2DAsync(g_staging.dQ, (size_t)ldd * 8, Q, (size_t)ldQ * 8, rowbytes, n, cudaMemcpyHostToDevice, st));
-        SB_CUDA(cudaStreamSynchronize(st));
-        double t2 = wall_ms();
-        reduce_device(g_ctx, n, begin, end, nb, g_staging.dA, ldd, g_staging.dQ, ldd);
-        double t3 = wall_ms();
-        SB_CUDA(cudaMemcpy2DAsync(A, (size_t)ldA * 8, g_staging.dA, (size_t)ldd * 8, rowbytes, n, cudaMemcpyDeviceToHost, st));
-        SB_CUDA(cudaMemcpy2DAsync(Q, (size_t)ldQ * 8, g_staging.dQ, (size_t)ldd * 8, rowbytes, n, cudaMemcpyDeviceToHost, st));
-        SB_CUDA(cudaStreamSynchronize(st));
-        double t4 = wall_ms();
-        g_ctx.stats.h2d_ms = t2 - t1;
-        g_ctx.stats.d2h_ms = t4 - t3;
-        g_ctx.stats.h2d_bytes = 2 * (long long)rowbytes * n;
-        g_ctx.stats.d2h_bytes = 2 * (long long)rowbytes * n;
+        g_team.run([&](int g) {
+            run_rank_host(*g_team.ranks[g], g_team.shards[g], n, begin, end, nb, A, ldA, Q, ldQ, &ht[g]);
+        });
     }
-    g_ctx.stats.wall_ms = wall_ms() - t0;
+    g_team.collect_stats(n, begin, end, nb);
+    for (int g = 0; g < P; g++) {
+        g_team.stats.h2d_ms = std::max(g_team.stats.h2d_ms, ht[g].h2d_ms);
+        g_team.stats.d2h_ms = std::max(g_team.stats.d2h_ms, ht[g].d2h_ms);
+        g_team.stats.h2d_bytes += ht[g].h2d_bytes;
+        g_team.stats.d2h_bytes += ht[g].d2h_bytes;
+    }
+    g_team.stats.wall_ms = wall_ms() - t0;
     return STARNEIG_SUCCESS;
 }
 
@@ -600,7 +349,149 @@ starneig_error_t starneig_SEP_SM_Hessenberg(int n, double A[], int ldA, double Q
 }
 
 // ---------------------------------------------------------------------------------------------
-// unit-level entry points
+// one process per GPU
+// ---------------------------------------------------------------------------------------------
+extern "C" __attribute__((visibility("default")))
+int starneig_b200_dist_layout(int world, int rank, int n, int *col_block, int *local_cols, int *q_row0, int *q_rows)
+{
+    if (world < 1 || world > MAX_RANKS || rank < 0 || rank >= world || n < 1) return STARNEIG_INVALID_ARGUMENTS;
+    int cb = 64;
+    const char *e = getenv("STARNEIG_B200_COL_BLOCK");
+    if (e && atoi(e) >= 8) cb = atoi(e) / 8 * 8;
+    if (world == 1) cb = n;
+    const ColMap cm{world, rank, cb};
+    int q0, q1;
+    q_row_range(world, rank, n, &q0, &q1);
+    if (col_block) *col_block = cb;
+    if (local_cols) *local_cols = cm.lower(n);
+    if (q_row0) *q_row0 = q0;
+    if (q_rows) *q_rows = q1 - q0;
+    return 0;
+}
+
+extern "C" __attribute__((visibility("default")))
+int starneig_b200_dist_global_col(int world, int rank, int col_block, int local_col)
+{
+    const ColMap cm{world, rank, col_block};
+    return cm.l2g(local_col);
+}
+
+extern "C" __attribute__((visibility("default")))
+int starneig_b200_dist_init(int world, int rank, int n_max, int panel_width_max, void *handle_out)
+{
+    if (!starneig_node_initialized()) return STARNEIG_NOT_INITIALIZED;
+    if (world < 1 || world > MAX_RANKS || rank < 0 || rank >= world || n_max < 1) return STARNEIG_INVALID_ARGUMENTS;
+    if (!have_gpu()) return STARNEIG_GENERIC_ERROR;
+    if (g_dist) { g_dist_shard.release(); g_dist->close(); delete g_dist; g_dist = nullptr; }
+    int dev = 0;
+    SB_CUDA(cudaGetDevice(&dev));
+    g_dist = new Rank();
+    g_dist->open(world, rank, dev);
+    if (panel_width_max < 8) panel_width_max = default_panel_width(n_max);
+    panel_width_max = std::min(panel_width_max, PANEL_MAX_NB);
+    memset(handle_out, 0, 64);
+    if (world > 1) {
+        g_dist->ensure_arena(n_max, panel_width_max);
+        cudaIpcMemHandle_t h;
+        SB_CUDA(cudaIpcGetMemHandle(&h, g_dist->arena));
+        static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+        memcpy(handle_out, &h, 64);
+    }
+    return 0;
+}
+
+extern "C" __attribute__((visibility("default")))
+int starneig_b200_dist_connect(const void *handles)
+{
+    if (!g_dist) return STARNEIG_NOT_INITIALIZED;
+    Rank &r = *g_dist;
+    for (int s = 0; s < r.P; s++) {
+        if (s == r.g) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const char *)handles + 64 * s, 64);
+        void *p = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            fprintf(stderr, "[starneig][error] cudaIpcOpenMemHandle(rank %d) failed: %s\n", s, cudaGetErrorString(e));
+            cudaGetLastError();
+            return STARNEIG_GENERIC_ERROR;
+        }
+        r.peer[s] = (char *)p;
+        r.arena_is_ipc[s] = true;
+    }
+    return 0;
+}
+
+static void dist_collect(Rank &r, int n, int begin, int end, int nb, double wall)
+{
+    g_team.stats = r.stats;
+    g_team.stats.n = n; g_team.stats.begin = begin; g_team.stats.end = end; g_team.stats.panel_width = nb;
+    g_team.stats.ranks = r.P;
+    g_team.stats.wall_ms = wall;
+}
+
+extern "C" __attribute__((visibility("default")))
+starneig_error_t starneig_b200_dist_hessenberg_device(int n, int begin, int end, int panel_width,
+                                                      double *dA_loc, int ldA, double *dQ_loc, int ldQ)
+{
+    if (!g_dist) return STARNEIG_NOT_INITIALIZED;
+    Rank &r = *g_dist;
+    if (n < 1) return -1;
+    if (begin < 0) return -2;
+    if (n < end) return -3;
+    if (dA_loc == NULL) return -5;
+    if (ldA < n || (ldA & 1) || ((uintptr_t)dA_loc & 15)) return -6;
+    if (dQ_loc == NULL) return -7;
+    int q0, q1;
+    q_row_range(r.P, r.g, n, &q0, &q1);
+    if (ldQ < q1 - q0 || (ldQ & 1) || ((uintptr_t)dQ_loc & 15)) return -8;
+    if (panel_width < 0) panel_width = default_panel_width(n);
+    if (panel_width < 8) return STARNEIG_INVALID_CONFIGURATION;
+    if (r.P > 1 && (n > r.al.n_cap || std::min(panel_width, PANEL_MAX_NB) > r.al.nb_cap)) return STARNEIG_INVALID_ARGUMENTS;
+    memset(&r.stats, 0, sizeof(r.stats));
+    r.profile_level = g_team.profile_level;
+    double t0 = wall_ms();
+    r.reduce(n, begin, end, panel_width, dA_loc, ldA, dQ_loc, ldQ, q1 - q0);
+    dist_collect(r, n, begin, end, panel_width, wall_ms() - t0);
+    return STARNEIG_SUCCESS;
+}
+
+extern "C" __attribute__((visibility("default")))
+starneig_error_t starneig_b200_dist_hessenberg_host(int n, int begin, int end, int panel_width,
+                                                    double *A, int ldA, double *Q, int ldQ)
+{
+    if (!g_dist) return STARNEIG_NOT_INITIALIZED;
+    Rank &r = *g_dist;
+    if (n < 1) return -1;
+    if (begin < 0) return -2;
+    if (n < end) return -3;
+    if (A == NULL) return -5;
+    if (ldA < n) return -6;
+    if (Q == NULL) return -7;
+    if (ldQ < n) return -8;
+    if (panel_width < 0) panel_width = default_panel_width(n);
+    if (panel_width < 8) return STARNEIG_INVALID_CONFIGURATION;
+    if (r.P > 1 && (n > r.al.n_cap || std::min(panel_width, PANEL_MAX_NB) > r.al.nb_cap)) return STARNEIG_INVALID_ARGUMENTS;
+    memset(&r.stats, 0, sizeof(r.stats));
+    r.profile_level = g_team.profile_level;
+    double t0 = wall_ms();
+    g_dist_shard.ensure(r, n);
+    HostTimes ht;
+    run_rank_host(r, g_dist_shard, n, begin, end, panel_width, A, ldA, Q, ldQ, &ht);
+    dist_collect(r, n, begin, end, panel_width, wall_ms() - t0);
+    g_team.stats.h2d_ms = ht.h2d_ms; g_team.stats.d2h_ms = ht.d2h_ms;
+    g_team.stats.h2d_bytes = ht.h2d_bytes; g_team.stats.d2h_bytes = ht.d2h_bytes;
+    return STARNEIG_SUCCESS;
+}
+
+extern "C" __attribute__((visibility("default")))
+void starneig_b200_dist_finalize(void)
+{
+    if (g_dist) { g_dist_shard.release(); g_dist->close(); delete g_dist; g_dist = nullptr; }
+}
+
+// ---------------------------------------------------------------------------------------------
+// unit-level entry points (single GPU)
 // ---------------------------------------------------------------------------------------------
 extern "C" __attribute__((visibility("default")))
 int starneig_b200_dgemm(char transa, char transb, int m, int n, int k, double alpha, const double *dA, int lda,
@@ -608,16 +499,17 @@ int starneig_b200_dgemm(char transa, char transb, int m, int n, int k, double al
 {
     if (!starneig_node_initialized()) return STARNEIG_NOT_INITIALIZED;
     if (!have_gpu()) return STARNEIG_GENERIC_ERROR;
-    g_ctx.open();
-    GemmKind kind;
-    if (transa == 'N' && transb == 'T') kind = GEMM_NT;
-    else if (transa == 'T' && transb == 'N') kind = GEMM_TN;
-    else if (transa == 'N' && transb == 'N') kind = GEMM_NN;
+    g_team.open(1);
+    Rank &r = *g_team.ranks[0];
+    Rank::GemmKind kind;
+    if (transa == 'N' && transb == 'T') kind = Rank::GEMM_NT;
+    else if (transa == 'T' && transb == 'N') kind = Rank::GEMM_TN;
+    else if (transa == 'N' && transb == 'N') kind = Rank::GEMM_NN;
     else return STARNEIG_INVALID_ARGUMENTS;
     if (m < 1 || n < 1 || k < 1) return STARNEIG_INVALID_ARGUMENTS;
-    if (kind != GEMM_NT) g_ctx.ws.ensure(std::max(m, 16), std::max(n, 8));
-    gemm(g_ctx, g_ctx.stream, kind, m, n, k, alpha, dA, lda, dB, ldb, beta, dC, ldc);
-    SB_CUDA(cudaStreamSynchronize(g_ctx.stream));
+    if (kind != Rank::GEMM_NT) r.ws.ensure(std::max(m, 16), std::max(n, 8), false);
+    r.gemm(kind, m, n, k, alpha, dA, lda, dB, ldb, beta, dC, ldc);
+    SB_CUDA(cudaStreamSynchronize(r.stream));
     SB_CUDA(cudaGetLastError());
     return 0;
 }
@@ -645,23 +537,28 @@ int starneig_b200_gemv(int m, int k, const double *dA, int lda, const double *dv
     // forms its vector as (1, scale * pcol[1:]), so v[0] must be 1 for an exact match.
     if (!starneig_node_initialized()) return STARNEIG_NOT_INITIALIZED;
     if (m < 1 || k < 1 || (lda & 1)) return STARNEIG_INVALID_ARGUMENTS;
-    g_ctx.open();
-    Workspace &ws = g_ctx.ws;
+    if (!have_gpu()) return STARNEIG_GENERIC_ERROR;
+    g_team.open(1);
+    Rank &r = *g_team.ranks[0];
+    Workspace &ws = r.ws;
     const int big = std::max(std::max(m, k), 16);
-    ws.ensure(big, 8);
-    cudaStream_t st = g_ctx.stream;
+    ws.ensure(big, 8, false);
+    cudaStream_t st = r.stream;
     double *scratch_col = nullptr;
     SB_CUDA(cudaMalloc(&scratch_col, (size_t)(big + 16) * sizeof(double)));
-    PanelArgs pa = make_panel_args(ws, m, ws.V, ws.Y, ws.VT, ws.ldv);
+    PanelArgs pa = r.make_panel_args(m, ws.V, ws.Y, ws.VT, ws.ldv);
     k_set_gemv_inputs<<<ceil_div(k, 256), 256, 0, st>>>(ws.scal, ws.pcol, dv, k);
-    GemvPlan gp = plan_gemv(dA, m, k, ws.ypart_cap, pa.ldp);
+    GemvPlan gp = r.plan_gemv(dA, m, k, pa.ldp);
+    const ColMap cm{1, 0, std::max(k, 1)};
+    Xchg x = r.make_xchg();
     size_t sh = (size_t)gp.kc * sizeof(double);
     cudaEvent_t e0, e1;
     SB_CUDA(cudaEventCreate(&e0)); SB_CUDA(cudaEventCreate(&e1));
     if (reps < 1) reps = 1;
     for (int it = 0; it < reps + 1; it++) {
         if (it == 1) SB_CUDA(cudaEventRecord(e0, st));
-        k_col_gemv<<<gp.RB * gp.S, GEMV_THREADS, sh, st>>>(pa, 0, k, gp.A0, lda, gp.skip, gp.kc, gp.RB, scratch_col);
+        k_col_gemv<false><<<gp.RB * gp.S, GEMV_THREADS, sh, st>>>(pa, 0, k, cm, 0, k, 0, gp.A0, lda, gp.skip, gp.kc, gp.RB, gp.S,
+                                                                   scratch_col, x);
     }
     SB_CUDA(cudaEventRecord(e1, st));
     k_sum_partials<<<ceil_div(m, 256), 256, 0, st>>>(m, gp.S, ws.ypart, pa.ldp, dy);
@@ -681,14 +578,17 @@ int starneig_b200_panel(int n, int i, int end, int w, double *dA, int ldA, doubl
 {
     if (!starneig_node_initialized()) return STARNEIG_NOT_INITIALIZED;
     if (n < 1 || i < 0 || end > n || w < 1 || w > end - i - 1 || (ldA & 1) || ((uintptr_t)dA & 15)) return STARNEIG_INVALID_ARGUMENTS;
-    g_ctx.open();
-    g_ctx.ws.ensure(n, std::max(w, 8));
-    panel_factor(g_ctx, g_ctx.stream, i, end, w, dA, ldA, dV, dY, dVT, ldw);
-    SB_CUDA(cudaStreamSynchronize(g_ctx.stream));
+    if (!have_gpu()) return STARNEIG_GENERIC_ERROR;
+    g_team.open(1);
+    Rank &r = *g_team.ranks[0];
+    r.ws.ensure(n, std::max(w, 8), false);
+    const ColMap cm{1, 0, n};
+    r.panel_factor(cm, i, end, w, dA, ldA, dA + (size_t)i * ldA + i + 1, ldA, dV, dY, dVT, ldw);
+    SB_CUDA(cudaStreamSynchronize(r.stream));
     SB_CUDA(cudaGetLastError());
     if (htau) {
         std::vector<ColScal> sc(w);
-        SB_CUDA(cudaMemcpy(sc.data(), g_ctx.ws.scal, w * sizeof(ColScal), cudaMemcpyDeviceToHost));
+        SB_CUDA(cudaMemcpy(sc.data(), r.ws.scal, w * sizeof(ColScal), cudaMemcpyDeviceToHost));
         for (int j = 0; j < w; j++) htau[j] = sc[j].tau;
     }
     return 0;

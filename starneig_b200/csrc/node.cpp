@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
 #include <thread>
 
 extern "C" void starneig_b200_context_close(void);
@@ -59,6 +60,9 @@ void starneig_node_init(int cores, int gpus, starneig_flag_t flags)
 
     int count = 0;
     if (cudaGetDeviceCount(&count) != cudaSuccess) { cudaGetLastError(); count = 0; }
+    // development aid: STARNEIG_B200_VIRTUAL_RANKS=k lets up to k ranks share the available device(s), so that
+    // the multi-GPU code path can be exercised on a single-GPU box (never set in production)
+    if (count >= 1 && getenv("STARNEIG_B200_VIRTUAL_RANKS")) count = std::max(count, atoi(getenv("STARNEIG_B200_VIRTUAL_RANKS")));
     state.avail_gpus = count;
     unsigned hw = std::thread::hardware_concurrency();
     state.avail_cores = hw ? (int)hw : 1;

@@ -41,9 +41,62 @@ constexpr int PANEL_LDB = 160;          // leading dimension of the per-block pa
 constexpr int PANEL_MAX_NB = 1024;      // widest panel the warp-per-32-columns scheme supports
 constexpr int GEMV_THREADS = 128;
 
+constexpr int MAX_RANKS = 8;            // GPUs of one NVSwitch box
+constexpr int RB_MAX = 512;             // row blocks (256 rows) of the exchanged GEMV result: n <= 131000
+
 struct ColScal {        // DLARFG results for one column
     double tau, beta, scale, alpha;
 };
+
+// 1-D block-cyclic column map: global column c lives on rank (c / cb) % P. The local columns
+// of a rank are ordered by global index, so any global column range [a, b) is the contiguous local range
+// [lower(a), lower(b)). P == 1 is the identity map.
+struct ColMap {
+    int P, g, cb;
+    __host__ __device__ int l2g(int lc) const { return ((lc / cb) * P + g) * cb + lc % cb; }
+    __host__ __device__ int lower(int x) const      // number of owned columns with global index < x
+    {
+        const int B = x / cb, r = B % P;
+        return (B / P) * cb + (r > g ? cb : (r == g ? x % cb : 0));
+    }
+    __host__ __device__ int owner(int c) const { return (c / cb) % P; }
+};
+
+// Cross-GPU exchange of the GEMV result (P > 1): every rank pushes its partial y (summed over its column
+// chunks) into inbox[parity][g] of every rank over NVLink peer stores, 256 rows at a time, and then raises
+// yflag[parity][g][row block] = epoch on that rank. Consumers (k_col_finish_update) poll their own flags.
+struct Xchg {
+    int P, g;
+    unsigned epoch;             // sequence number of this column, monotonic over the life of the arena
+    double *inbox[MAX_RANKS];   // [2][P][ldp] on every rank
+    unsigned *yflag[MAX_RANKS]; // [2][P][RB_MAX] on every rank
+    unsigned *rbcount;          // local, RB_MAX arrival counters (zero between launches)
+    unsigned *status;           // local: set to non-zero when a wait timed out
+};
+
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned *p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned *p, unsigned v)
+{
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// spin until *p has reached `want` (acquire; sequence numbers, wrap-around safe); gives up after ~4 s and
+// reports through *status. ">=": a peer that already left a barrier may have announced the next one.
+__device__ __forceinline__ bool flag_reached(const unsigned *p, unsigned want) { return (int)(ld_acquire_sys(p) - want) >= 0; }
+__device__ __forceinline__ void wait_flag(const unsigned *p, unsigned want, unsigned *status, unsigned code = 1u)
+{
+    if (flag_reached(p, want)) return;
+    if (*(volatile unsigned *)status != 0u) return;      // an earlier wait already failed: do not stall again
+    const long long t0 = clock64();
+    while (!flag_reached(p, want)) {
+        if (clock64() - t0 > 8000000000ll) { atomicExch(status, code); break; }
+        __nanosleep(20);
+    }
+}
 
 struct PanelArgs {
     int m;              // rows of the panel (= end - i - 1); local row r <-> global row i+1+r
@@ -154,9 +207,19 @@ struct TileGeom {
 //   phase B  column-wise dots w2part = VT(rows,:)^T p'(rows)  (second read of VT, from L2)
 //   dynamic smem (doubles): 2j + nsub*4*NW*32 + 2*nsub*32 + RS*NW*32
 // ------------------------------------------------------------------------------------------------
+// The GEMV result of column j-1 arrives as `S` partial vectors yin[z*ldp + r] that are summed here in fixed
+// order: the column chunks of the local GEMV (P == 1) or the inbox slots of the P ranks (P > 1, `yw` non-null:
+// the block first waits until every rank has raised the flags of the 256-row blocks covering its rows).
+struct YWait {
+    const unsigned *flags;      // local yflag + parity*P*RB_MAX, or nullptr (no wait)
+    unsigned epoch;
+    int P, skip;
+    unsigned *status;
+};
+
 template <int MAXT>
-__global__ void __launch_bounds__(MAXT) k_col_finish_update(PanelArgs a, int j, int S, double *__restrict__ acol,
-                                                            int do_update, TileGeom tg)
+__global__ void __launch_bounds__(MAXT) k_col_finish_update(PanelArgs a, int j, int S, const double *__restrict__ yin,
+                                                            double *__restrict__ acol, int do_update, TileGeom tg, YWait yw)
 {
     extern __shared__ double sh[];
     const int jm1 = j - 1;
@@ -184,7 +247,7 @@ __global__ void __launch_bounds__(MAXT) k_col_finish_update(PanelArgs a, int j, 
     for (int sub = h; sub < nsub; sub += RS) {
         const int r = row0 + sub * 32 + lane;
         const bool valid = r < m;
-        double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
+        double d0 = 0.0, d1 = 0.0, d2 = 0.0;
         const double *VTr = a.VT + (size_t)t0 * ld + r;
         const double *Yr = a.Y + (size_t)t0 * ld + r;
 #pragma unroll
@@ -208,21 +271,37 @@ __global__ void __launch_bounds__(MAXT) k_col_finish_update(PanelArgs a, int j, 
                 }
             }
         }
-        if (valid) {
+        double *rd = red + ((size_t)sub * 4 * NW + g) * 32 + lane;
+        rd[0] = d0; rd[NW * 32] = d1; rd[2 * NW * 32] = d2;
+    }
+    if (yw.flags != nullptr) {
+        // multi-GPU: the partial results of the other ranks arrive over NVLink while the products above run
+        const int rows_here = min(nsub * 32, m - row0);
+        if (rows_here > 0) {
+            const int rb_lo = (row0 + yw.skip) >> 8, rb_hi = (row0 + rows_here - 1 + yw.skip) >> 8;
+            const int nrb = rb_hi - rb_lo + 1;
+            for (int t = tid; t < yw.P * nrb; t += blockDim.x)
+                wait_flag(yw.flags + (size_t)(t / nrb) * RB_MAX + rb_lo + t % nrb, yw.epoch, yw.status, 2u);
+        }
+        __syncthreads();
+    }
+    for (int sub = h; sub < nsub; sub += RS) {
+        const int r = row0 + sub * 32 + lane;
+        double d3 = 0.0;
+        if (r < m) {
             // GEMV partials: independent loads, four accumulators
-            const double *yp = a.ypart + r;
+            const double *yp = yin + r;
             const size_t zs = (size_t)a.ldp * NW;
             double e0 = 0.0, e1 = 0.0, e2 = 0.0, e3 = 0.0;
             int z = g;
             for (; z + 3 * NW < S; z += 4 * NW) {
                 const double *q0 = yp + (size_t)z * a.ldp;
-                e0 += q0[0]; e1 += q0[zs]; e2 += q0[2 * zs]; e3 += q0[3 * zs];
+                e0 += __ldcg(q0); e1 += __ldcg(q0 + zs); e2 += __ldcg(q0 + 2 * zs); e3 += __ldcg(q0 + 3 * zs);
             }
-            for (; z < S; z += NW) e0 += yp[(size_t)z * a.ldp];
+            for (; z < S; z += NW) e0 += __ldcg(yp + (size_t)z * a.ldp);
             d3 = (e0 + e1) + (e2 + e3);
         }
-        double *rd = red + ((size_t)sub * 4 * NW + g) * 32 + lane;
-        rd[0] = d0; rd[NW * 32] = d1; rd[2 * NW * 32] = d2; rd[3 * NW * 32] = d3;
+        red[((size_t)sub * 4 * NW + 3 * NW + g) * 32 + lane] = d3;
     }
     __syncthreads();
 
@@ -438,17 +517,22 @@ __global__ void __launch_bounds__(MAXT) k_col_reflector(PanelArgs a, int j, doub
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_col_gemv: ypart[z][r] = sum_{k in chunk z} A[i+1+r, c+1+k] * v[k],  v[0] = 1, v[k] = p''[j+k]*scale
+// k_col_gemv: ypart[z][r] = sum_{local columns lc in chunk z} A_loc[i+1+r, lc] * v[l2g(lc) - (c+1)],
+//             v[0] = 1, v[k] = p''[j+k]*scale      (c = i+j the column being reduced)
 //
-//   ncols = number of columns (m - j)
-//   A0    16-byte aligned pointer to A[i+1-skip, c+1] (skip in {0,1}); padded row rp = r + skip
+//   ncols = m - j: length of v;  the rank's columns of the global range [c+1, e) are the local range
+//           [lc0, lc0+nloc) (ColMap; the whole range when P == 1)
+//   A0    16-byte aligned pointer to A_loc[i+1-skip, lc0] (skip in {0,1}); padded row rp = r + skip
 //   grid  = RB*S blocks of 128 threads: block b: row block b % RB (256 padded rows), column chunk b / RB
-//   The first row block of every chunk also stores V(j+k, j) = v[k], A[i+1+j+k, c] = (k==0 ? beta : 0).
+//   Every block also writes a slice of V(j+k, j) = v[k] and of the panel column (beta, exact zeros).
+//   DIST: the block that finishes a row block last sums the S partials (fixed order) and pushes the 256 rows
+//   to every rank's inbox over NVLink, then raises that rank's flag (see Xchg).
 // Memory-bound: each thread streams one 16-byte load per column with 8 columns in flight.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(GEMV_THREADS, 10) k_col_gemv(PanelArgs a, int j, int ncols, const double *__restrict__ A0,
-                                                                int lda, int skip, int kc, int RB,
-                                                                double *__restrict__ acol)
+template <bool DIST>
+__global__ void __launch_bounds__(GEMV_THREADS, 10) k_col_gemv(PanelArgs a, int j, int ncols, ColMap cm, int lc0, int nloc,
+                                                                int gc0, const double *__restrict__ A0, int lda, int skip,
+                                                                int kc, int RB, int S, double *__restrict__ acol, Xchg x)
 {
     extern __shared__ double vs[];      // kc
     const int tid = threadIdx.x;
@@ -457,63 +541,175 @@ __global__ void __launch_bounds__(GEMV_THREADS, 10) k_col_gemv(PanelArgs a, int 
 
     const int rb = blockIdx.x % RB, z = blockIdx.x / RB;
     const int k0 = z * kc;
-    const int nk = min(kc, ncols - k0);
+    const int nk = max(0, min(kc, nloc - k0));
+    // v for the chunk's columns: global column gc <-> v index gc - gc0  (gc0 = c+1)
     for (int k = tid; k < nk; k += GEMV_THREADS) {
-        double v = (k0 + k == 0) ? 1.0 : a.pcol[j + k0 + k] * scale;
-        vs[k] = v;
-        if (rb == 0) {
-            a.V[(size_t)j * a.ld + j + k0 + k] = v;
-            acol[j + k0 + k] = (k0 + k == 0) ? a.scal[j].beta : 0.0;
+        const int kk = cm.l2g(lc0 + k0 + k) - gc0;
+        vs[k] = (kk == 0) ? 1.0 : a.pcol[j + kk] * scale;
+    }
+    {   // this block's slice of V(:, j) and of the reduced column
+        const int per = (ncols + gridDim.x - 1) / gridDim.x;
+        const int kb = blockIdx.x * per, ke = min(ncols, kb + per);
+        for (int k = kb + tid; k < ke; k += GEMV_THREADS) {
+            a.V[(size_t)j * a.ld + j + k] = (k == 0) ? 1.0 : a.pcol[j + k] * scale;
+            acol[j + k] = (k == 0) ? a.scal[j].beta : 0.0;
         }
     }
     __syncthreads();
 
     const int mp = m + skip;
     const int rp = rb * 256 + tid * 2;           // padded row of .x ; rows rp, rp+1
-    if (rp >= mp) return;
-    double2 acc = make_double2(0.0, 0.0);
-    const double *Ap = A0 + (size_t)k0 * lda + rp;
-    // software pipeline: U loads of the next column group are in flight while the current
-    // group is accumulated (2*U 16-byte loads per thread outstanding)
-    constexpr int U = 4;
-    const size_t step = (size_t)lda;
-    double2 cur[U], nxt[U];
-    int k = 0;
-    if (nk >= U) {
+    const int r = rp - skip;                     // logical row of .x
+    double *yp = a.ypart + (size_t)z * a.ldp;
+    if (rp < mp) {
+        double2 acc = make_double2(0.0, 0.0);
+        const double *Ap = A0 + (size_t)k0 * lda + rp;
+        // software pipeline: U loads of the next column group are in flight while the current
+        // group is accumulated (2*U 16-byte loads per thread outstanding)
+        constexpr int U = 4;
+        const size_t step = (size_t)lda;
+        double2 cur[U], nxt[U];
+        int k = 0;
+        if (nk >= U) {
 #pragma unroll
-        for (int u = 0; u < U; u++) cur[u] = __ldcs((const double2 *)(Ap + u * step));
-        const double *Pn = Ap + U * step;
-        for (; k + 2 * U <= nk; k += U) {
+            for (int u = 0; u < U; u++) cur[u] = __ldcs((const double2 *)(Ap + u * step));
+            const double *Pn = Ap + U * step;
+            for (; k + 2 * U <= nk; k += U) {
 #pragma unroll
-            for (int u = 0; u < U; u++) nxt[u] = __ldcs((const double2 *)(Pn + u * step));
-            Pn += U * step;
+                for (int u = 0; u < U; u++) nxt[u] = __ldcs((const double2 *)(Pn + u * step));
+                Pn += U * step;
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                    double vk = vs[k + u];
+                    acc.x = fma(cur[u].x, vk, acc.x);
+                    acc.y = fma(cur[u].y, vk, acc.y);
+                }
+#pragma unroll
+                for (int u = 0; u < U; u++) cur[u] = nxt[u];
+            }
 #pragma unroll
             for (int u = 0; u < U; u++) {
                 double vk = vs[k + u];
                 acc.x = fma(cur[u].x, vk, acc.x);
                 acc.y = fma(cur[u].y, vk, acc.y);
             }
-#pragma unroll
-            for (int u = 0; u < U; u++) cur[u] = nxt[u];
+            k += U;
         }
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-            double vk = vs[k + u];
-            acc.x = fma(cur[u].x, vk, acc.x);
-            acc.y = fma(cur[u].y, vk, acc.y);
+        for (; k < nk; k++) {
+            double vk = vs[k];
+            double2 xx = __ldcs((const double2 *)(Ap + (size_t)k * step));
+            acc.x = fma(xx.x, vk, acc.x);
+            acc.y = fma(xx.y, vk, acc.y);
         }
-        k += U;
+        if (r >= 0) yp[r] = acc.x;
+        if (r + 1 < m) yp[r + 1] = acc.y;
     }
-    for (; k < nk; k++) {
-        double vk = vs[k];
-        double2 x = __ldcs((const double2 *)(Ap + (size_t)k * step));
-        acc.x = fma(x.x, vk, acc.x);
-        acc.y = fma(x.y, vk, acc.y);
+    if (!DIST) return;
+
+    // ---- multi-GPU tail: last chunk of this row block reduces and pushes
+    __shared__ bool last_sh;
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned ticket = atomicAdd(x.rbcount + rb, 1u);
+        last_sh = (ticket == (unsigned)S - 1);
+        if (last_sh) x.rbcount[rb] = 0;      // re-arm (stream ordered)
     }
-    double *yp = a.ypart + (size_t)z * a.ldp;
-    int r = rp - skip;                       // logical row of .x
-    if (r >= 0) yp[r] = acc.x;
-    if (r + 1 < m) yp[r + 1] = acc.y;
+    __syncthreads();
+    if (!last_sh) return;
+    __threadfence();
+    const int par = x.epoch & 1;
+    if (rp < mp) {
+        // fixed summation order; loads are issued in independent batches of 8 (clamped addresses, no branches)
+        const bool ok0 = r >= 0, ok1 = r + 1 < m;
+        const double *q0 = a.ypart + (ok0 ? r : r + 1), *q1 = a.ypart + (ok1 ? r + 1 : r);
+        double s0 = 0.0, s1 = 0.0;
+        int zz = 0;
+        for (; zz + 8 <= S; zz += 8) {
+            double x0[8], x1[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) { x0[u] = __ldcg(q0 + (size_t)(zz + u) * a.ldp); x1[u] = __ldcg(q1 + (size_t)(zz + u) * a.ldp); }
+#pragma unroll
+            for (int u = 0; u < 8; u++) { s0 += x0[u]; s1 += x1[u]; }
+        }
+        for (; zz < S; zz++) { s0 += __ldcg(q0 + (size_t)zz * a.ldp); s1 += __ldcg(q1 + (size_t)zz * a.ldp); }
+        const size_t slot = ((size_t)par * x.P + x.g) * a.ldp;
+#pragma unroll 1
+        for (int d = 0; d < x.P; d++) {
+            double *dst = x.inbox[(x.g + d) % x.P] + slot + r;      // start with the own inbox, then the neighbours
+            if (ok0) dst[0] = s0;
+            if (ok1) dst[1] = s1;
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid < x.P) st_release_sys(x.yflag[tid] + ((size_t)par * x.P + x.g) * RB_MAX + rb, x.epoch);
+}
+
+// ------------------------------------------------------------------------------------------------
+// multi-GPU helpers
+// ------------------------------------------------------------------------------------------------
+struct PeerPtrs { double *p[MAX_RANKS]; };
+
+// Panel gather: every rank copies its columns of the global range [i, i+w) (rows i+1 .. i+m) into the panel
+// buffer Pan (m x w, leading dimension ldv) of EVERY rank. grid = (row chunks of 1024, local panel columns)
+__global__ void k_panel_push(ColMap cm, int i, int lc_first, int m, const double *__restrict__ Aloc, int lda, PeerPtrs pan, int ldv)
+{
+    const int lc = lc_first + blockIdx.y;
+    const int col = cm.l2g(lc) - i;
+    const double *src = Aloc + (size_t)lc * lda + i + 1;
+    const int r0 = blockIdx.x * 1024;
+    for (int d = 0; d < cm.P; d++) {
+        double *dst = pan.p[(cm.g + d) % cm.P] + (size_t)col * ldv;
+        for (int r = r0 + threadIdx.x; r < min(m, r0 + 1024); r += blockDim.x) dst[r] = src[r];
+    }
+}
+
+// Panel write-back: the reduced panel columns (H entries, exact zeros) return to their owner's local storage
+__global__ void k_panel_pull(ColMap cm, int i, int lc_first, int m, double *__restrict__ Aloc, int lda,
+                             const double *__restrict__ pan, int ldv)
+{
+    const int lc = lc_first + blockIdx.y;
+    const int col = cm.l2g(lc) - i;
+    double *dst = Aloc + (size_t)lc * lda + i + 1;
+    const double *src = pan + (size_t)col * ldv;
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < m; r += gridDim.x * blockDim.x) dst[r] = src[r];
+}
+
+// Vg(x, t) = V(l2g(lc_first + x) - row0g, t): the rows of V / VT that belong to the rank's local columns
+__global__ void k_gather_rows(ColMap cm, int lc_first, int ncl, int row0g, int w, const double *__restrict__ V,
+                              const double *__restrict__ VT, int ld, double *__restrict__ Vg, double *__restrict__ VTg, int ldg)
+{
+    const int xx = blockIdx.x * blockDim.x + threadIdx.x, t = blockIdx.y;
+    if (xx >= ncl) return;
+    const int row = cm.l2g(lc_first + xx) - row0g;
+    Vg[(size_t)t * ldg + xx] = V[(size_t)t * ld + row];
+    VTg[(size_t)t * ldg + xx] = VT[(size_t)t * ld + row];
+}
+
+// out(r, t) = sum over ranks s (fixed order) of part_s(r, t): the all-reduce of the top-row products,
+// pulled from every rank's exchange buffer over NVLink
+__global__ void k_sum_peers(int P, int rows, PeerPtrs part, int ldp, double *__restrict__ out, int ldo)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x, t = blockIdx.y;
+    if (r >= rows) return;
+    double s = 0.0;
+    for (int q = 0; q < P; q++) s += __ldcg(part.p[q] + (size_t)t * ldp + r);
+    out[(size_t)t * ldo + r] = s;
+}
+
+// All-rank barrier on device flags: rank g writes `epoch` into slot g of every rank's bar[] and waits until
+// all P slots of its own bar[] carry it. One block of MAX_RANKS threads. Writes of earlier kernels of this
+// stream are ordered before the flag by the fence; readers acquire.
+struct BarPtrs { unsigned *p[MAX_RANKS]; };
+__global__ void k_barrier(int P, int g, unsigned epoch, BarPtrs bar, unsigned *status)
+{
+    const int t = threadIdx.x;
+    __threadfence_system();
+    if (t < P) st_release_sys(bar.p[t] + g, epoch);
+    if (t < P) wait_flag(bar.p[g] + t, epoch, status);
+    __syncthreads();
+    __threadfence_system();
 }
 
 } // namespace sb200

@@ -3,6 +3,10 @@ import sys
 
 import pytest
 
+# Virtual ranks (several ranks sharing one device in tests/test_gpu_multi.py) need their streams on distinct hardware
+# queues, or a spinning consumer kernel could sit in front of its producer. Must be set before CUDA initialises.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
