@@ -41,6 +41,11 @@ struct starneig_b200_stats {
     double gemm_flops;       /* flops executed by the DMMA kernels */
     long long h2d_bytes, d2h_bytes;
     int ranks;               /* GPUs that took part; device/gemv figures are rank 0's, launches and flops are summed */
+    int fused_panels;        /* panels factorised by the persistent kernel (panel_fused.cuh); then gemv_ms is the
+                              * device-side %globaltimer time of its GEMV phases and every column counts as timed */
+    double fused_kernel_ms;  /* total run time of the persistent panel kernels (device-side timer) */
+    double fused_phase_ms[4];/* its level-2 phases, each including the grid barrier that ends it: finish+update (A),
+                              * w2 reduction (A'), reflector (R), scalars + s (R') */
 };
 void starneig_b200_get_stats(struct starneig_b200_stats *stats);
 

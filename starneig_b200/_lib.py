@@ -29,11 +29,12 @@ class Stats(ctypes.Structure):
         ("finish_update_ms", ctypes.c_double), ("reflector_ms", ctypes.c_double),
         ("kernel_launches", ctypes.c_longlong), ("gemm_flops", ctypes.c_double),
         ("h2d_bytes", ctypes.c_longlong), ("d2h_bytes", ctypes.c_longlong),
-        ("ranks", ctypes.c_int),
+        ("ranks", ctypes.c_int), ("fused_panels", ctypes.c_int), ("fused_kernel_ms", ctypes.c_double),
+        ("fused_phase_ms", ctypes.c_double * 4),
     ]
 
     def as_dict(self):
-        return {name: getattr(self, name) for name, _ in self._fields_}
+        return {name: (list(getattr(self, name)) if name == "fused_phase_ms" else getattr(self, name)) for name, _ in self._fields_}
 
 
 def load():

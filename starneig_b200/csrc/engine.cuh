@@ -28,6 +28,7 @@
 // after the panel is the same computation.
 #pragma once
 #include "panel.cuh"
+#include "panel_fused.cuh"
 #include "dgemm.cuh"
 #include <starneig_b200.h>
 #include <algorithm>
@@ -69,6 +70,8 @@ static void prepare_device_functions()
     SB_CUDA(cudaFuncGetAttributes(&fa, k_sum_peers));
     SB_CUDA(cudaFuncGetAttributes(&fa, k_barrier));
     SB_CUDA(cudaFuncGetAttributes(&fa, splitk_reduce_kernel));
+    SB_CUDA(cudaFuncSetAttribute(k_panel_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM_MAX));
+    SB_CUDA(cudaFuncSetAttribute(k_panel_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM_MAX));
 }
 
 struct Stats : starneig_b200_stats {};
@@ -85,6 +88,8 @@ struct Workspace {
     double *s = nullptr, *w2 = nullptr, *colpart = nullptr, *sqpart = nullptr;
     ColScal *scal = nullptr;
     unsigned *counter = nullptr;
+    unsigned *gbar = nullptr;                   // grid barrier counter of the fused panel kernel
+    unsigned long long *timers = nullptr;       // device-side phase timers of the fused panel kernel (ns)
     std::vector<void *> allocs;
 
     template <typename T> T *alloc(size_t count)
@@ -123,6 +128,9 @@ struct Workspace {
         scal = alloc<ColScal>(nbp);
         counter = alloc<unsigned>(4);
         SB_CUDA(cudaMemset(counter, 0, 4 * sizeof(unsigned)));
+        gbar = alloc<unsigned>(1024);
+        timers = alloc<unsigned long long>(8);
+        SB_CUDA(cudaMemset(timers, 0, 8 * sizeof(unsigned long long)));
     }
 };
 
@@ -165,6 +173,8 @@ struct Rank {
     Stats stats{};
     int profile_level = 1;
     int gemv_slots = 0;                     // resident k_col_gemv blocks on the whole GPU (one wave)
+    int fused = 1;                          // 1: one persistent kernel per panel (panel_fused.cuh); 0: three kernels per column
+    int fused_ctas = 0;                     // grid of the fused kernel (number of SMs; fewer when ranks share a device)
     std::vector<cudaEvent_t> events;        // phase events: 4 per panel
     std::vector<cudaEvent_t> gemv_events;   // 4 per timed column (profile level 2)
     size_t gemv_events_used = 0;
@@ -178,6 +188,14 @@ struct Rank {
         prepare_device_functions();
         const char *e = getenv("STARNEIG_B200_COL_BLOCK");
         if (e && atoi(e) >= 8) cb = atoi(e) / 8 * 8;
+        e = getenv("STARNEIG_B200_FUSED_PANEL");
+        if (e) fused = atoi(e);
+        SB_CUDA(cudaDeviceGetAttribute(&fused_ctas, cudaDevAttrMultiProcessorCount, device));
+        e = getenv("STARNEIG_B200_FUSED_CTAS");
+        if (e && atoi(e) >= 1) fused_ctas = std::min(fused_ctas, atoi(e));
+        int coop = 0;
+        SB_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
+        if (!coop) fused = 0;
         ready = true;
     }
     void close()
@@ -370,9 +388,34 @@ struct Rank {
         cudaStream_t st = stream;
         const int m = end - i - 1;
         PanelArgs pa = make_panel_args(m, V, Y, VT, ld);
-        SB_CUDA(cudaMemsetAsync(V, 0, (size_t)ld * w * sizeof(double), st));
         Xchg x = make_xchg();
         const int lc_end = cm.lower(end);
+        if (fused && w <= FUSED_MAX_NB) {
+            FusedArgs f;
+            memset(&f, 0, sizeof(f));
+            f.a = pa; f.w = w; f.i = i; f.pan = pan; f.ldpan = ldpan; f.Aloc = A_loc; f.lda = ldA; f.cm = cm; f.lc_end = lc_end;
+            f.nsub = std::max(1, ceil_div(m, 32 * fused_ctas));
+            f.gbar = ws.gbar; f.timers = ws.timers;
+            f.x = x;
+            f.x.epoch = y_epoch + 1;
+            const size_t smem = fused_smem_bytes(w, f.nsub);
+            if (smem <= PANEL_SMEM_MAX) {
+                if (P > 1) y_epoch += w;
+                SB_CUDA(cudaMemsetAsync(ws.gbar, 0, 1024 * sizeof(unsigned), st));
+                void *args[] = {&f};
+                const void *fn = P > 1 ? (const void *)k_panel_fused<true> : (const void *)k_panel_fused<false>;
+                SB_CUDA(cudaLaunchCooperativeKernel(fn, dim3(fused_ctas), dim3(FUSED_THREADS), args, smem, st));
+                stats.kernel_launches++;
+                stats.fused_panels++;
+                for (int j = 0; j < w; j++) {
+                    const double bytes = 8.0 * (double)m * (lc_end - cm.lower(i + j + 1));
+                    stats.gemv_bytes += bytes; stats.gemv_timed_bytes += bytes;
+                }
+                stats.gemv_launches += w; stats.gemv_timed_launches += w;
+                return;
+            }
+        }
+        SB_CUDA(cudaMemsetAsync(V, 0, (size_t)ld * w * sizeof(double), st));
         int S_prev = 0;
         const double *yin = ws.ypart;
         YWait yw; memset(&yw, 0, sizeof(yw));
@@ -443,6 +486,7 @@ struct Rank {
         const int lvl = profile_level;
         const ColMap cm{P, g, P == 1 ? std::max(n, 1) : cb};
         gemv_events_used = 0;
+        SB_CUDA(cudaMemsetAsync(ws.timers, 0, 8 * sizeof(unsigned long long), st));
         int panel = 0;
         cudaEvent_t ev_first = phase_event(0), ev_last = phase_event(1);
         barrier();
@@ -549,7 +593,13 @@ struct Rank {
                 SB_CUDA(cudaEventElapsedTime(&ms, e[2], e[3])); stats.other_ms += ms;
             }
         }
-        if (lvl >= 2) {
+        if (stats.fused_panels > 0) {
+            unsigned long long t[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            SB_CUDA(cudaMemcpy(t, ws.timers, sizeof(t), cudaMemcpyDeviceToHost));
+            stats.gemv_ms = 1e-6 * (double)t[0];            // %globaltimer around the GEMV phases (incl. their barrier)
+            stats.fused_kernel_ms = 1e-6 * (double)t[1];
+            for (int k = 0; k < 4; k++) stats.fused_phase_ms[k] = 1e-6 * (double)t[2 + k];
+        } else if (lvl >= 2) {
             for (size_t k = 0; k + 3 < gemv_events_used; k += 4) {
                 SB_CUDA(cudaEventElapsedTime(&ms, gemv_events[k], gemv_events[k + 1])); stats.finish_update_ms += ms;
                 SB_CUDA(cudaEventElapsedTime(&ms, gemv_events[k + 1], gemv_events[k + 2])); stats.reflector_ms += ms;

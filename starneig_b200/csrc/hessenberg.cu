@@ -110,6 +110,13 @@ struct Team {
             ranks.push_back(r);
         }
         shards.resize(P);
+        // ranks that share a device (development aid) must share its SMs: the persistent panel kernels of all of
+        // them have to be co-resident
+        for (int g = 0; g < P; g++) {
+            int sharing = 0;
+            for (int s = 0; s < P; s++) sharing += ranks[s]->device == ranks[g]->device;
+            ranks[g]->fused_ctas = std::max(1, ranks[g]->fused_ctas / sharing);
+        }
         for (int g = 0; g < P; g++)
             for (int s = 0; s < P; s++)
                 if (ranks[g]->device != ranks[s]->device) {

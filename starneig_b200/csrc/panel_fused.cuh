@@ -1,0 +1,526 @@
+// panel_fused.cuh -- the whole panel factorisation (w columns) as ONE persistent cooperative kernel.
+//
+// Same arithmetic as the three per-column kernels of panel.cuh (which stay as the reference path and for
+// panels wider than FUSED_MAX_NB), same reference codelets replaced (src/hessenberg/cpu.c:50-285, the
+// prepare_column / compute_column / finish_column chain of src/hessenberg/core.c:461-517), but the 3*w
+// dependent launches of a panel become one launch: one CTA per SM stays resident, the column loop runs on
+// the device and the grid-wide dependencies are device-side barriers (~1 us) instead of kernel boundaries
+// plus "last block" reductions. This matters twice: the level-2 side work of a column (re-reading Y, V, VT
+// from L2) is latency-bound, and on P GPUs it is replicated on every rank, so it bounds the scaling.
+//
+// Per column j (c = i + j), all CTAs:
+//   [DIST: push own rows of the local GEMV sum to every rank, NVLink peer stores + flags]
+//   A   finish column j-1 (V, Y, VT columns, H entries of the panel column), right-update column j,
+//       partial w2 = VT^T p'                                            -> grid barrier
+//   A'  w2 = sum of the partials (one warp per entry, fixed order)       -> grid barrier
+//   R   p'' = p' - V w2, partial ||x||^2 and z = V^T x                   -> grid barrier
+//   R'  DLARFG scalars (every CTA, identical), s = scale*z + V(j,:)  (one warp per entry)
+//   G   trailing GEMV partials, perfectly balanced 1-D split of (row block, column) items over all
+//       128-thread groups of the grid                                    -> grid barrier
+// Row ownership: CTA b owns rows [b*32*nsub, (b+1)*32*nsub) of the panel in every phase except G, so V, Y,
+// VT columns are written and re-read by the same SM; everything that crosses CTAs inside the launch (pcol, s,
+// w2, partials, scalars, row j of V) is read with ld.global.cg.
+#pragma once
+#include "panel.cuh"
+
+namespace sb200 {
+
+constexpr int FUSED_THREADS = 512;
+constexpr int FUSED_WARPS = FUSED_THREADS / 32;
+constexpr int FUSED_MAX_NB = 32 * FUSED_WARPS;      // 512: one warp per 32 panel columns
+constexpr int FUSED_VB = FUSED_THREADS / 128;        // 128-thread GEMV groups per CTA
+constexpr int FUSED_KC = 512;                        // columns of v staged per group at a time
+constexpr int FUSED_MINSEG = 16;                     // fewest (row block, column) items per group
+
+struct FusedArgs {
+    PanelArgs a;
+    int w;                      // columns of the panel
+    int i;                      // first column (global index)
+    double *pan;                // row i+1 of panel column 0 (in A itself or in the replicated panel buffer)
+    int ldpan;
+    const double *Aloc;         // the rank's column storage
+    int lda;
+    ColMap cm;
+    int lc_end;                 // local index one past the last local column of the reduced block
+    int nsub;                   // 32-row sub-tiles per CTA
+    unsigned *gbar;             // grid barrier counter, zero at launch
+    unsigned long long *timers; // ns on CTA 0: [0] GEMV phases, [1] whole kernel, [2..5] phases A, A', R, R' (each incl. its barrier)
+    Xchg x;                     // DIST only; x.epoch = sequence number of the panel's first column
+};
+
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned *p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+// All CTAs of the (cooperative, co-resident) grid: one arrival counter (red.release) that thread 0 of every CTA
+// polls. Measured on B200 (tools/bar_bench.cu, 148 CTAs): 1.4 us per barrier, faster than slot arrays with a
+// gathering master CTA (2.1 us) or two-level schemes (2.2-2.9 us). `gen` counts the arrivals expected so far.
+__device__ __forceinline__ void grid_barrier(unsigned *bar, unsigned &gen)
+{
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        gen += gridDim.x;
+        asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(bar), "r"(1u) : "memory");
+        while ((int)(ld_acquire_gpu(bar) - gen) < 0) { }
+    }
+    __syncthreads();
+}
+
+// sum over the CTAs that own rows (nblk <= 32*5) of part[bb*ldt], fixed order, by one warp: the (up to) five loads
+// of a lane are independent
+__device__ __forceinline__ double sum_over_ctas(const double *part, size_t ldt, int nblk, int lane)
+{
+    double acc = 0.0;
+    for (int b0 = 0; b0 < nblk; b0 += 160) {
+        double x[5];
+#pragma unroll
+        for (int u = 0; u < 5; u++) {
+            const int bb = b0 + lane + 32 * u;
+            x[u] = bb < nblk ? __ldcg(part + (size_t)bb * ldt) : 0.0;
+        }
+        acc += ((x[0] + x[1]) + (x[2] + x[3])) + x[4];
+    }
+    return warp_sum(acc);
+}
+
+__device__ __forceinline__ void group_barrier(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
+// split of the GEMV over 128-thread groups: items = (row block, local column) pairs in row-block-major order
+struct GemvSplit {
+    int skip, RB, nloc, per;
+    __device__ __forceinline__ int first_group(int rb) const { return (int)(((long long)rb * nloc) / per); }
+    __device__ __forceinline__ int last_group(int rb) const { return (int)((((long long)(rb + 1)) * nloc - 1) / per); }
+};
+
+// sum of S partial values p[z*ld], z < S, in a fixed order; the loads of a batch of 4 are independent
+__device__ __forceinline__ double sum_partials(const double *p, int ld, int S)
+{
+    double e = 0.0;
+    int z = 0;
+    for (; z + 4 <= S; z += 4) {
+        const double x0 = __ldcg(p + (size_t)z * ld), x1 = __ldcg(p + (size_t)(z + 1) * ld);
+        const double x2 = __ldcg(p + (size_t)(z + 2) * ld), x3 = __ldcg(p + (size_t)(z + 3) * ld);
+        e += (x0 + x1) + (x2 + x3);
+    }
+    for (; z < S; z++) e += __ldcg(p + (size_t)z * ld);
+    return e;
+}
+
+// Column-wise dots of one CTA: out[t] = sum over the CTA's rows of M(r, t) * p(r) for t in [tb, tb+NC), t < tmax.
+// One warp; NC columns x NS sub-tiles = 32 independent loads are in flight per lane. p(r) comes from shared
+// memory (pv[sub*32 + lane], zero for rows >= m). Result: see transpose_reduce8 / transpose_reduce32.
+template <int NC, int NS>
+__device__ __forceinline__ void coldots(const double *__restrict__ M, int ld, int tb, int tmax, int row0, int m, int nsub,
+                                        const double *pv, int lane, double (&acc)[NC])
+{
+#pragma unroll
+    for (int q = 0; q < NC; q++) acc[q] = 0.0;
+    for (int sub0 = 0; sub0 < nsub; sub0 += NS) {
+        double v[NS][NC];
+#pragma unroll
+        for (int s = 0; s < NS; s++) {
+            const int r = row0 + (sub0 + s) * 32 + lane;
+            const bool okr = sub0 + s < nsub && r < m;
+            const double *Mr = M + (size_t)tb * ld + r;
+#pragma unroll
+            for (int q = 0; q < NC; q++) v[s][q] = (okr && tb + q < tmax) ? Mr[(size_t)q * ld] : 0.0;
+        }
+#pragma unroll
+        for (int s = 0; s < NS; s++) {
+            const double p = sub0 + s < nsub ? pv[(sub0 + s) * 32 + lane] : 0.0;
+#pragma unroll
+            for (int q = 0; q < NC; q++) acc[q] = fma(v[s][q], p, acc[q]);
+        }
+    }
+}
+
+// partial column dots of the CTA -> colpart[b][t], t < tmax; warps [0, T) share the column batches
+__device__ __forceinline__ void coldots_all(const double *__restrict__ M, int ld, int tmax, int row0, int m, int nsub,
+                                            const double *pv, int wp, int T, int lane, double *out)
+{
+    if (nsub >= 3) {
+        for (int tb = 8 * wp; tb < tmax; tb += 8 * T) {
+            double acc[8];
+            coldots<8, 4>(M, ld, tb, tmax, row0, m, nsub, pv, lane, acc);
+            const double xx = transpose_reduce8(acc, lane);
+            const int t = tb + (lane >> 2);
+            if ((lane & 3) == 0 && t < tmax) out[t] = xx;
+        }
+    } else {
+        for (int tb = 32 * wp; tb < tmax; tb += 32 * T) {
+            double acc[32];
+            coldots<32, 1>(M, ld, tb, tmax, row0, m, nsub, pv, lane, acc);
+            const double xx = transpose_reduce32(acc, lane);
+            if (tb + lane < tmax) out[tb + lane] = xx;
+        }
+    }
+}
+
+constexpr int FUSED_TILE_WARPS = 12;     // warps 0..11: tile phases; warps 12..15: GEMV sums and their exchange
+constexpr int FUSED_XCHG_THREADS = FUSED_THREADS - 32 * FUSED_TILE_WARPS;
+
+template <bool DIST>
+__global__ void __launch_bounds__(FUSED_THREADS, 1) k_panel_fused(FusedArgs f)
+{
+    extern __shared__ double sh[];
+    const PanelArgs &a = f.a;
+    const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
+    const int m = a.m, ld = a.ld, nsub = f.nsub;
+    const int G = gridDim.x, b = blockIdx.x;
+    const int row0 = b * nsub * 32;
+    const int rows_here = max(0, min(nsub * 32, m - row0));
+    const int nblk = (m + nsub * 32 - 1) / (nsub * 32);         // CTAs that own rows
+    constexpr int T = FUSED_TILE_WARPS;
+    unsigned gen = 0;
+    unsigned long long t_gemv = 0, t_begin = 0, t_ph[4] = {0, 0, 0, 0}, t_mark = 0;
+    const bool timer = (b == 0 && tid == 0);
+    if (timer) t_begin = t_mark = globaltimer_ns();
+#define SB_PHASE_MARK(k) do { if (timer) { const unsigned long long now_ = globaltimer_ns(); t_ph[k] += now_ - t_mark; t_mark = now_; } } while (0)
+
+    // GEMV geometry that does not depend on the column
+    GemvSplit gs;
+    {
+        const double *base = f.Aloc + (size_t)f.i + 1;      // parity of the row offset decides the alignment
+        gs.skip = (int)(((uintptr_t)base / sizeof(double)) & 1);
+        gs.RB = (m + gs.skip + 255) >> 8;
+    }
+    __shared__ double scal_sh[4];       // tau, beta, scale of the current column
+
+    for (int j = 0; j <= f.w; j++) {
+        const int jm1 = j - 1;
+        double *acol = f.pan + (size_t)j * f.ldpan;
+        const int NW = max(1, (j + 31) >> 5);
+
+        if (j > 0) {
+            // ================= phase A =================
+            double *s_sh = sh;                             // j
+            double *vrow_sh = s_sh + j;                    // j
+            double *red = vrow_sh + j;                     // nsub * 3 * NW * 32
+            double *pv = red + (size_t)nsub * 3 * NW * 32; // nsub * 32
+            double *ysm = pv + nsub * 32;                  // nsub * 32
+            const bool do_update = j < f.w;
+            const double tau = __ldcg(&a.scal[jm1].tau), beta_prev = __ldcg(&a.scal[jm1].beta),
+                         scale_prev = __ldcg(&a.scal[jm1].scale);
+            double *acol_prev = f.pan + (size_t)jm1 * f.ldpan;
+
+            for (int t = tid; t < jm1; t += FUSED_THREADS) s_sh[t] = __ldcg(a.s + t);
+            if (do_update)
+                for (int t = tid; t < j; t += FUSED_THREADS) vrow_sh[t] = (t == jm1) ? 1.0 : __ldcg(a.V + (size_t)t * ld + jm1);
+            __syncthreads();
+
+            if (wp < T) {
+                // row-wise dots of the CTA's rows with s and with row j-1 of V: 32x32 tiles, 2 x 16 columns of Y and VT
+                // (32 independent loads) in flight per lane
+                for (int item = wp; item < nsub * NW; item += T) {
+                    const int sub = item / NW, g = item - sub * NW, t0 = g * 32;
+                    const int r = row0 + sub * 32 + lane;
+                    const bool valid = r < m;
+                    double d0 = 0.0, d1 = 0.0, d2 = 0.0;
+                    const double *VTr = a.VT + (size_t)t0 * ld + r;
+                    const double *Yr = a.Y + (size_t)t0 * ld + r;
+#pragma unroll
+                    for (int bt = 0; bt < 2; bt++) {
+                        const int tb = t0 + 16 * bt;
+                        if (tb < jm1) {
+                            double y16[16], v16[16];
+#pragma unroll
+                            for (int q = 0; q < 16; q++) {
+                                const bool ok = valid && tb + q < jm1;
+                                y16[q] = ok ? Yr[(size_t)(16 * bt + q) * ld] : 0.0;
+                                v16[q] = ok ? VTr[(size_t)(16 * bt + q) * ld] : 0.0;
+                            }
+#pragma unroll
+                            for (int q = 0; q < 16; q++) {
+                                const int t = min(tb + q, jm1 - 1);        // values beyond jm1 are zero
+                                const double sv = s_sh[t];
+                                d0 = fma(y16[q], sv, d0);
+                                d2 = fma(v16[q], sv, d2);
+                                if (do_update) d1 = fma(y16[q], vrow_sh[t], d1);
+                            }
+                        }
+                    }
+                    double *rd = red + ((size_t)sub * 3 * NW + g) * 32 + lane;
+                    rd[0] = d0; rd[NW * 32] = d1; rd[2 * NW * 32] = d2;
+                }
+            } else {
+                // y(r) of the CTA's rows: sum of the local GEMV partials of column j-1 (fixed order); on P GPUs the
+                // sums travel to every rank's inbox while the tile warps work, then the P contributions are added
+                const int xt = tid - 32 * T;
+                const int nloc_prev = f.lc_end - f.cm.lower(f.i + jm1 + 1);
+                GemvSplit gp = gs;
+                gp.nloc = nloc_prev;
+                gp.per = max(FUSED_MINSEG, (int)(((long long)gs.RB * nloc_prev + G * FUSED_VB - 1) / (G * FUSED_VB)));
+                const unsigned epoch = f.x.epoch + jm1;
+                const int par = epoch & 1;
+                for (int rr = xt; rr < rows_here; rr += FUSED_XCHG_THREADS) {
+                    const int r = row0 + rr;
+                    const int rb = (r + gs.skip) >> 8;
+                    double sum = 0.0;
+                    if (nloc_prev > 0) sum = sum_partials(a.ypart + r, a.ldp, gp.last_group(rb) - gp.first_group(rb) + 1);
+                    if (DIST) {
+                        const size_t slot = ((size_t)par * f.x.P + f.x.g) * a.ldp;
+                        for (int d = 0; d < f.x.P; d++) f.x.inbox[(f.x.g + d) % f.x.P][slot + r] = sum;
+                    } else {
+                        ysm[rr] = sum;
+                    }
+                }
+                if (DIST) {
+                    __threadfence_system();
+                    group_barrier(5, FUSED_XCHG_THREADS);
+                    if (xt < f.x.P && rows_here > 0) {
+                        st_release_sys(f.x.yflag[xt] + ((size_t)par * f.x.P + f.x.g) * RB_MAX + b, epoch);
+                        wait_flag(f.x.yflag[f.x.g] + ((size_t)par * f.x.P + xt) * RB_MAX + b, epoch, f.x.status, 2u);
+                    }
+                    group_barrier(5, FUSED_XCHG_THREADS);
+                    const double *in = f.x.inbox[f.x.g] + (size_t)par * f.x.P * a.ldp + row0;
+                    for (int rr = xt; rr < rows_here; rr += FUSED_XCHG_THREADS) {
+                        double sum = 0.0;
+                        for (int q = 0; q < f.x.P; q++) sum += __ldcg(in + (size_t)q * a.ldp + rr);
+                        ysm[rr] = sum;
+                    }
+                }
+            }
+            __syncthreads();
+
+            // ---- per-row epilogue, one warp per sub-tile
+            for (int sub = wp; sub < nsub; sub += FUSED_WARPS) {
+                const int r = row0 + sub * 32 + lane;
+                const bool valid = r < m;
+                double pp = 0.0;
+                if (valid) {
+                    const double D3 = ysm[sub * 32 + lane];
+                    const double *rd = red + (size_t)sub * 3 * NW * 32 + lane;
+                    double D0 = 0.0, D1 = 0.0, D2 = 0.0;
+                    for (int q = 0; q < NW; q++) { D0 += rd[q * 32]; D1 += rd[(NW + q) * 32]; D2 += rd[(2 * NW + q) * 32]; }
+                    // column j-1 of V and of the reduced matrix (the row owner writes: no cross-CTA traffic)
+                    const double vr = (r < jm1) ? 0.0 : (r == jm1 ? 1.0 : a.pcol[r] * scale_prev);
+                    a.V[(size_t)jm1 * ld + r] = vr;
+                    if (r == jm1) acol_prev[r] = beta_prev;
+                    else if (r > jm1) acol_prev[r] = 0.0;
+                    const double ynew = tau * (D3 - D0);                 // finish_column: Y(:,j-1)
+                    a.Y[(size_t)jm1 * ld + r] = ynew;
+                    a.VT[(size_t)jm1 * ld + r] = tau * (vr - D2);        // VT(:,j-1) = V * T(:,j-1)
+                    if (do_update) {
+                        pp = acol[r] - (D1 + ynew * vrow_sh[jm1]);       // prepare_column: p - Y V(j-1,:)^T
+                        a.pcol[r] = pp;
+                    }
+                }
+                pv[sub * 32 + lane] = pp;
+            }
+            if (!do_update) break;          // j == w: the panel is complete
+            __syncthreads();
+
+            // ---- w2part[t] = sum over the CTA's rows of VT(r,t) * p'(r), t < j (column j-1 was stored just above)
+            coldots_all(a.VT, ld, j, row0, m, nsub, pv, wp, FUSED_WARPS, lane, a.colpart + (size_t)b * a.ldt);
+            grid_barrier(f.gbar, gen);
+            SB_PHASE_MARK(0);
+
+            // ================= A': w2[t] = sum over CTAs (one warp per entry) =================
+            for (int t = b * FUSED_WARPS + wp; t < j; t += G * FUSED_WARPS) {
+                const double acc = sum_over_ctas(a.colpart + t, a.ldt, nblk, lane);
+                if (lane == 0) a.w2[t] = acc;
+            }
+            grid_barrier(f.gbar, gen);
+            SB_PHASE_MARK(1);
+        }
+
+        // ================= phase R: p'' = p' - V w2; ||x||^2, z = V^T x =================
+        {
+            double *w2_sh = sh;                             // j
+            double *red = w2_sh + j;                        // nsub * NW * 32
+            double *pv = red + (size_t)nsub * NW * 32;      // nsub * 32
+            double *sqred = pv + nsub * 32;                 // FUSED_WARPS
+            for (int t = tid; t < j; t += FUSED_THREADS) w2_sh[t] = __ldcg(a.w2 + t);
+            __syncthreads();
+            if (j > 0) {
+                // d(r) = V(r, :j) w2: 32x32 tiles, 32 loads in flight per lane
+                for (int item = wp; item < nsub * NW; item += FUSED_WARPS) {
+                    const int sub = item / NW, g = item - sub * NW, t0 = g * 32;
+                    const int r = row0 + sub * 32 + lane;
+                    const bool valid = r < m;
+                    const double *Vr = a.V + (size_t)t0 * ld + r;
+                    double v32[32];
+#pragma unroll
+                    for (int q = 0; q < 32; q++) v32[q] = (valid && t0 + q < j) ? Vr[(size_t)q * ld] : 0.0;
+                    double d = 0.0;
+#pragma unroll
+                    for (int q = 0; q < 32; q++) d = fma(v32[q], w2_sh[min(t0 + q, j - 1)], d);
+                    red[((size_t)sub * NW + g) * 32 + lane] = d;
+                }
+            }
+            __syncthreads();
+            double sq = 0.0;
+            for (int sub = wp; sub < nsub; sub += FUSED_WARPS) {
+                const int r = row0 + sub * 32 + lane;
+                const bool valid = r < m;
+                double xx = 0.0;
+                if (valid) {
+                    double pp = j > 0 ? a.pcol[r] : acol[r];
+                    if (j > 0) {
+                        double D = 0.0;
+                        for (int q = 0; q < NW; q++) D += red[((size_t)sub * NW + q) * 32 + lane];
+                        pp -= D;
+                    }
+                    a.pcol[r] = pp;
+                    if (r < j) acol[r] = pp;            // final entries of H above the sub-diagonal
+                    if (r == j) a.scal[j].alpha = pp;
+                    if (r > j) xx = pp;
+                }
+                sq = fma(xx, xx, sq);
+                pv[sub * 32 + lane] = xx;
+            }
+            sq = warp_sum(sq);
+            if (lane == 0) sqred[wp] = sq;
+            __syncthreads();
+            if (j > 0) coldots_all(a.V, ld, j, row0, m, nsub, pv, wp, FUSED_WARPS, lane, a.colpart + (size_t)b * a.ldt);
+            if (tid == 0) {
+                double sum = 0.0;
+                for (int q = 0; q < FUSED_WARPS; q++) sum += sqred[q];
+                a.sqpart[b] = sum;
+            }
+            grid_barrier(f.gbar, gen);
+            SB_PHASE_MARK(2);
+        }
+
+        // ================= R': DLARFG scalars (every warp, identical), s = scale*z + V(j,:) =================
+        {
+            // every warp derives the scalars itself (no CTA-wide wait); the z entries it owns are loaded alongside
+            const int t_first = b * FUSED_WARPS + wp;
+            double zsum = 0.0, vjt = 0.0;
+            if (t_first < j) { zsum = sum_over_ctas(a.colpart + t_first, a.ldt, nblk, lane); vjt = __ldcg(a.V + (size_t)t_first * ld + j); }
+            const double ssq = sum_over_ctas(a.sqpart, 1, nblk, lane);
+            const double alpha = __ldcg(&a.scal[j].alpha);
+            const double xnorm = sqrt(ssq);
+            double tau = 0.0, beta = alpha, scale = 0.0;
+            if (m - j > 1 && xnorm != 0.0) {
+                beta = -copysign(hypot(alpha, xnorm), alpha);
+                tau = (beta - alpha) / beta;
+                scale = 1.0 / (alpha - beta);
+            }
+            if (tid == 0) {
+                scal_sh[0] = tau; scal_sh[1] = beta; scal_sh[2] = scale;
+                if (b == 0) { a.scal[j].tau = tau; a.scal[j].beta = beta; a.scal[j].scale = scale; }
+            }
+            if (t_first < j && lane == 0) a.s[t_first] = fma(scale, zsum, vjt);
+            for (int t = t_first + G * FUSED_WARPS; t < j; t += G * FUSED_WARPS) {
+                const double acc = sum_over_ctas(a.colpart + t, a.ldt, nblk, lane);
+                if (lane == 0) a.s[t] = fma(scale, acc, __ldcg(a.V + (size_t)t * ld + j));
+            }
+            __syncthreads();
+        }
+
+        // ================= phase G: GEMV partials =================
+        {
+            SB_PHASE_MARK(3);
+            if (b == 0 && tid == 0) t_gemv -= globaltimer_ns();
+            const double scale = scal_sh[2];
+            const int c = f.i + j;
+            const int lc0 = f.cm.lower(c + 1), nloc = f.lc_end - lc0;
+            const int gc0 = c + 1;
+            GemvSplit gq = gs;
+            gq.nloc = nloc;
+            const long long items = (long long)gs.RB * nloc;
+            gq.per = max(FUSED_MINSEG, (int)((items + G * FUSED_VB - 1) / (G * FUSED_VB)));
+            const int vb = tid >> 7, vt = tid & 127;
+            // groups are spread over the CTAs first (group v lives on CTA v % G), so that a GEMV smaller than the
+            // grid still touches every SM
+            const int v = vb * G + b;
+            double *vs = sh + vb * FUSED_KC;
+            long long it = (long long)v * gq.per;
+            const long long it_end = min(items, it + gq.per);
+            const int mp = m + gs.skip;
+            while (it < it_end) {
+                const int rb = (int)(it / nloc);
+                const int cbeg = (int)(it - (long long)rb * nloc);
+                const int cend = (int)min((long long)nloc, cbeg + (it_end - it));
+                const int rp = rb * 256 + vt * 2;
+                const bool rows_ok = rp < mp;
+                double2 acc = make_double2(0.0, 0.0);
+                const double *Ap = f.Aloc + (size_t)lc0 * f.lda + f.i + 1 - gs.skip + rp;
+                for (int k0 = cbeg; k0 < cend; k0 += FUSED_KC) {
+                    const int nk = min(FUSED_KC, cend - k0);
+                    group_barrier(1 + vb, 128);          // previous chunk's vs fully consumed
+                    for (int k = vt; k < nk; k += 128) {
+                        const int kk = f.cm.l2g(lc0 + k0 + k) - gc0;
+                        vs[k] = (kk == 0) ? 1.0 : __ldcg(a.pcol + j + kk) * scale;
+                    }
+                    group_barrier(1 + vb, 128);
+                    if (rows_ok) {
+                        constexpr int U = 8;
+                        const size_t step = (size_t)f.lda;
+                        const double *P0 = Ap + (size_t)k0 * step;
+                        double2 cur[U], nxt[U];
+                        int k = 0;
+                        if (nk >= U) {
+#pragma unroll
+                            for (int u = 0; u < U; u++) cur[u] = __ldcs((const double2 *)(P0 + u * step));
+                            const double *Pn = P0 + U * step;
+                            for (; k + 2 * U <= nk; k += U) {
+#pragma unroll
+                                for (int u = 0; u < U; u++) nxt[u] = __ldcs((const double2 *)(Pn + u * step));
+                                Pn += U * step;
+#pragma unroll
+                                for (int u = 0; u < U; u++) {
+                                    const double vk = vs[k + u];
+                                    acc.x = fma(cur[u].x, vk, acc.x);
+                                    acc.y = fma(cur[u].y, vk, acc.y);
+                                }
+#pragma unroll
+                                for (int u = 0; u < U; u++) cur[u] = nxt[u];
+                            }
+#pragma unroll
+                            for (int u = 0; u < U; u++) {
+                                const double vk = vs[k + u];
+                                acc.x = fma(cur[u].x, vk, acc.x);
+                                acc.y = fma(cur[u].y, vk, acc.y);
+                            }
+                            k += U;
+                        }
+                        for (; k < nk; k++) {
+                            const double vk = vs[k];
+                            const double2 xx = __ldcs((const double2 *)(P0 + (size_t)k * step));
+                            acc.x = fma(xx.x, vk, acc.x);
+                            acc.y = fma(xx.y, vk, acc.y);
+                        }
+                    }
+                }
+                if (rows_ok) {
+                    double *yp = a.ypart + (size_t)(v - gq.first_group(rb)) * a.ldp;
+                    const int r = rp - gs.skip;
+                    if (r >= 0) yp[r] = acc.x;
+                    if (r + 1 < m) yp[r + 1] = acc.y;
+                }
+                it += cend - cbeg;
+            }
+            grid_barrier(f.gbar, gen);
+            if (timer) { t_mark = globaltimer_ns(); t_gemv += t_mark; }
+        }
+    }
+    if (timer) {
+        f.timers[0] += t_gemv;
+        f.timers[1] += globaltimer_ns() - t_begin;
+        for (int k = 0; k < 4; k++) f.timers[2 + k] += t_ph[k];
+    }
+#undef SB_PHASE_MARK
+}
+
+// dynamic shared memory of k_panel_fused for a panel of m rows and w columns on a grid of G CTAs
+static inline size_t fused_smem_bytes(int w, int nsub)
+{
+    const int NW = std::max(1, (w + 31) / 32);
+    size_t fu = (size_t)2 * w + (size_t)nsub * 3 * NW * 32 + 2 * (size_t)nsub * 32;
+    size_t rf = (size_t)w + (size_t)nsub * NW * 32 + (size_t)nsub * 32 + FUSED_WARPS;
+    size_t d = std::max(std::max(fu, rf), (size_t)FUSED_VB * FUSED_KC);
+    return d * sizeof(double);
+}
+
+} // namespace sb200

@@ -20,7 +20,8 @@ for it in range(reps):
     st = sn.get_stats()
     print(f"ret {ret} wall {time.time()-t0:.3f}s device_ms {st['device_ms']:.1f} panel {st['panel_ms']:.1f} trail {st['trail_ms']:.1f} "
           f"other {st['other_ms']:.1f} h2d {st['h2d_ms']:.1f} d2h {st['d2h_ms']:.1f} launches {st['kernel_launches']} ranks {st['ranks']} "
-          f"GFLOP/s(dev) {10/3*n**3/st['device_ms']/1e6:.0f}", flush=True)
+          f"GFLOP/s(dev) {10/3*n**3/st['device_ms']/1e6:.0f} fused_panels {st['fused_panels']} fused_ms {st['fused_kernel_ms']:.1f} gemv_ms {st['gemv_ms']:.1f} "
+          f"gemv GB/s {st['gemv_timed_bytes']/max(st['gemv_ms'],1e-9)/1e6:.0f} phases A/A'/R/R' {[round(x,1) for x in st['fused_phase_ms']]}", flush=True)
 if n <= 3000:
     A2, Q2 = A0.copy(order="F"), Q0.copy(order="F")
     ora.hessenberg_port(n, A2, ld, Q2, ld, 0, n, pw)
