@@ -150,7 +150,7 @@ struct ArenaLayout {
         off_status = o;   o = align(o + sizeof(unsigned));
         off_rbcount = o;  o = align(o + RB_MAX * sizeof(unsigned));
         off_yflag = o;    o = align(o + (size_t)2 * P * RB_MAX * sizeof(unsigned));
-        off_inbox = o;    o = align(o + (size_t)2 * P * ldp * sizeof(double));
+        off_inbox = o;    o = align(o + (size_t)2 * P * ldp * 16);      // 16-byte LL entries (fused kernel) or doubles
         off_pan = o;      o = align(o + (size_t)ldv * nbp * sizeof(double));
         off_wx = o;       o = align(o + (size_t)ldv * nbp * sizeof(double));
         bytes = o;

@@ -168,6 +168,28 @@ __device__ __forceinline__ void coldots_all(const double *__restrict__ M, int ld
 constexpr int FUSED_TILE_WARPS = 12;     // warps 0..11: tile phases; warps 12..15: GEMV sums and their exchange
 constexpr int FUSED_XCHG_THREADS = FUSED_THREADS - 32 * FUSED_TILE_WARPS;
 
+// "LL" exchange entry (the protocol NCCL uses for latency-bound messages): a double travels as two 8-byte words
+// {low 32 bits, tag} {high 32 bits, tag}; 8-byte stores are atomic over NVLink, so a reader that sees the expected
+// tag in both words has the value, without any fence or separate flag on the critical path.
+__device__ __forceinline__ void ll_store(uint4 *dst, double v, unsigned tag)
+{
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
+    const uint4 e = make_uint4((unsigned)bits, tag, (unsigned)(bits >> 32), tag);
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(dst), "r"(e.x), "r"(e.y), "r"(e.z), "r"(e.w) : "memory");
+}
+__device__ __forceinline__ double ll_load(const uint4 *src, unsigned tag, unsigned *status)
+{
+    uint4 e;
+    long long t0 = 0;
+    for (;;) {
+        asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(e.x), "=r"(e.y), "=r"(e.z), "=r"(e.w) : "l"(src) : "memory");
+        if (e.y == tag && e.w == tag) break;
+        if (t0 == 0) { t0 = clock64(); if (*(volatile unsigned *)status != 0u) break; }
+        else if (clock64() - t0 > 8000000000ll) { atomicExch(status, 2u); break; }
+    }
+    return __longlong_as_double((long long)(((unsigned long long)e.z << 32) | e.x));
+}
+
 template <bool DIST>
 __global__ void __launch_bounds__(FUSED_THREADS, 1) k_panel_fused(FusedArgs f)
 {
@@ -266,25 +288,41 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_panel_fused(FusedArgs f)
                     const int rb = (r + gs.skip) >> 8;
                     double sum = 0.0;
                     if (nloc_prev > 0) sum = sum_partials(a.ypart + r, a.ldp, gp.last_group(rb) - gp.first_group(rb) + 1);
+                    ysm[rr] = sum;
                     if (DIST) {
-                        const size_t slot = ((size_t)par * f.x.P + f.x.g) * a.ldp;
-                        for (int d = 0; d < f.x.P; d++) f.x.inbox[(f.x.g + d) % f.x.P][slot + r] = sum;
-                    } else {
-                        ysm[rr] = sum;
+                        // one 16-byte self-validating entry per row and peer: no fence, no separate flag
+                        const size_t slot = ((size_t)par * f.x.P + f.x.g) * a.ldp + r;
+                        for (int d = 1; d < f.x.P; d++) ll_store((uint4 *)f.x.inbox[(f.x.g + d) % f.x.P] + slot, sum, epoch);
                     }
                 }
                 if (DIST) {
-                    __threadfence_system();
-                    group_barrier(5, FUSED_XCHG_THREADS);
-                    if (xt < f.x.P && rows_here > 0) {
-                        st_release_sys(f.x.yflag[xt] + ((size_t)par * f.x.P + f.x.g) * RB_MAX + b, epoch);
-                        wait_flag(f.x.yflag[f.x.g] + ((size_t)par * f.x.P + xt) * RB_MAX + b, epoch, f.x.status, 2u);
-                    }
-                    group_barrier(5, FUSED_XCHG_THREADS);
-                    const double *in = f.x.inbox[f.x.g] + (size_t)par * f.x.P * a.ldp + row0;
+                    // add the P contributions in rank order (identical on every rank)
+                    const uint4 *in = (const uint4 *)f.x.inbox[f.x.g] + (size_t)par * f.x.P * a.ldp + row0;
                     for (int rr = xt; rr < rows_here; rr += FUSED_XCHG_THREADS) {
+                        // first pass: all P entries in flight at once; stragglers are polled individually
+                        double val[MAX_RANKS];
+                        bool ready[MAX_RANKS];
+#pragma unroll
+                        for (int q = 0; q < MAX_RANKS; q++) {
+                            ready[q] = true; val[q] = 0.0;
+                            if (q < f.x.P && q != f.x.g) {
+                                uint4 e;
+                                asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];"
+                                             : "=r"(e.x), "=r"(e.y), "=r"(e.z), "=r"(e.w) : "l"(in + (size_t)q * a.ldp + rr) : "memory");
+                                ready[q] = (e.y == epoch && e.w == epoch);
+                                val[q] = __longlong_as_double((long long)(((unsigned long long)e.z << 32) | e.x));
+                            }
+                        }
+                        const double own = ysm[rr];
                         double sum = 0.0;
-                        for (int q = 0; q < f.x.P; q++) sum += __ldcg(in + (size_t)q * a.ldp + rr);
+#pragma unroll
+                        for (int q = 0; q < MAX_RANKS; q++) {
+                            if (q < f.x.P) {
+                                double x = (q == f.x.g) ? own : val[q];
+                                if (!ready[q]) x = ll_load(in + (size_t)q * a.ldp + rr, epoch, f.x.status);
+                                sum += x;
+                            }
+                        }
                         ysm[rr] = sum;
                     }
                 }

@@ -1,4 +1,3 @@
-timeout 120 tools/bin/bar_bench 2>&1 | grep -E "^[0789]"
-timeout 200 python tools/multi_check.py 1 2000 -1 2 2>&1 | tail -2
-timeout 200 python tools/multi_check.py 1 20000 -1 2 2>&1 | tail -2
-STARNEIG_B200_FUSED_PANEL=0 timeout 200 python tools/multi_check.py 1 20000 -1 2 2>&1 | tail -2
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node=2 --master-addr 127.0.0.1 --master-port 29511 tests/dist_worker.py --size 1500 --panel 100 --devices 2 2>&1 | tail -3
+timeout 300 python tools/multi_check.py 2 2000 -1 2 2>&1 | tail -2
+timeout 300 python tools/multi_check.py 2 20000 -1 2 2>&1 | tail -2
