@@ -25,10 +25,10 @@
 
 namespace sb200 {
 
-constexpr int FUSED_THREADS = 512;
+constexpr int FUSED_THREADS = 640;
 constexpr int FUSED_WARPS = FUSED_THREADS / 32;
-constexpr int FUSED_MAX_NB = 32 * FUSED_WARPS;      // 512: one warp per 32 panel columns
-constexpr int FUSED_VB = FUSED_THREADS / 128;        // 128-thread GEMV groups per CTA
+constexpr int FUSED_MAX_NB = 512;
+constexpr int FUSED_VB = 4;                          // 128-thread GEMV groups per CTA (warps 0..15); warps 16..19 look ahead
 constexpr int FUSED_KC = 512;                        // columns of v staged per group at a time
 constexpr int FUSED_MINSEG = 16;                     // fewest (row block, column) items per group
 
@@ -101,11 +101,17 @@ struct GemvSplit {
     __device__ __forceinline__ int last_group(int rb) const { return (int)((((long long)(rb + 1)) * nloc - 1) / per); }
 };
 
-// sum of S partial values p[z*ld], z < S, in a fixed order; the loads of a batch of 4 are independent
+// sum of S partial values p[z*ld], z < S, in a fixed order; the loads of a batch are independent
 __device__ __forceinline__ double sum_partials(const double *p, int ld, int S)
 {
     double e = 0.0;
     int z = 0;
+    for (; z + 8 <= S; z += 8) {
+        double x[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) x[u] = __ldcg(p + (size_t)(z + u) * ld);
+        e += ((x[0] + x[1]) + (x[2] + x[3])) + ((x[4] + x[5]) + (x[6] + x[7]));
+    }
     for (; z + 4 <= S; z += 4) {
         const double x0 = __ldcg(p + (size_t)z * ld), x1 = __ldcg(p + (size_t)(z + 1) * ld);
         const double x2 = __ldcg(p + (size_t)(z + 2) * ld), x3 = __ldcg(p + (size_t)(z + 3) * ld);
@@ -143,6 +149,22 @@ __device__ __forceinline__ void coldots(const double *__restrict__ M, int ld, in
     }
 }
 
+// Sum over the 32 lanes of a warp of 16 per-lane values: on return lane l holds the total of column l & 15.
+__device__ __forceinline__ double transpose_reduce16(double (&v)[16], int lane)
+{
+#pragma unroll
+    for (int off = 8; off >= 1; off >>= 1) {
+        const bool upper = (lane & off) != 0;
+#pragma unroll
+        for (int k = 0; k < off; k++) {
+            const double send = upper ? v[k] : v[k + off];
+            const double keep = upper ? v[k + off] : v[k];
+            v[k] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+    }
+    return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 16);
+}
+
 // partial column dots of the CTA -> colpart[b][t], t < tmax; warps [0, T) share the column batches
 __device__ __forceinline__ void coldots_all(const double *__restrict__ M, int ld, int tmax, int row0, int m, int nsub,
                                             const double *pv, int wp, int T, int lane, double *out)
@@ -156,17 +178,14 @@ __device__ __forceinline__ void coldots_all(const double *__restrict__ M, int ld
             if ((lane & 3) == 0 && t < tmax) out[t] = xx;
         }
     } else {
-        for (int tb = 32 * wp; tb < tmax; tb += 32 * T) {
-            double acc[32];
-            coldots<32, 1>(M, ld, tb, tmax, row0, m, nsub, pv, lane, acc);
-            const double xx = transpose_reduce32(acc, lane);
-            if (tb + lane < tmax) out[tb + lane] = xx;
+        for (int tb = 16 * wp; tb < tmax; tb += 16 * T) {
+            double acc[16];
+            coldots<16, 2>(M, ld, tb, tmax, row0, m, nsub, pv, lane, acc);
+            const double xx = transpose_reduce16(acc, lane);
+            if (lane < 16 && tb + lane < tmax) out[tb + lane] = xx;
         }
     }
 }
-
-constexpr int FUSED_TILE_WARPS = 12;     // warps 0..11: tile phases; warps 12..15: GEMV sums and their exchange
-constexpr int FUSED_XCHG_THREADS = FUSED_THREADS - 32 * FUSED_TILE_WARPS;
 
 // "LL" exchange entry (the protocol NCCL uses for latency-bound messages): a double travels as two 8-byte words
 // {low 32 bits, tag} {high 32 bits, tag}; 8-byte stores are atomic over NVLink, so a reader that sees the expected
@@ -190,6 +209,29 @@ __device__ __forceinline__ double ll_load(const uint4 *src, unsigned tag, unsign
     return __longlong_as_double((long long)(((unsigned long long)e.z << 32) | e.x));
 }
 
+constexpr int FUSED_GEMV_WARPS = 4 * FUSED_VB;                       // warps 0..15: the GEMV groups of phase G
+constexpr int FUSED_SHADOW_THREADS = FUSED_THREADS - 32 * FUSED_GEMV_WARPS;      // warps 16..19: look-ahead during phase G
+
+// shared-memory layout (doubles), fixed for the whole launch
+struct FusedSmem {
+    int vs, s, vrow, w2, red, pv, ysm, sqred, total;
+    __host__ __device__ FusedSmem(int w, int nsub)
+    {
+        const int NW = (w + 31) / 32 > 1 ? (w + 31) / 32 : 1;
+        const int wp8 = (w + 8) / 8 * 8;
+        int o = 0;
+        vs = o;    o += FUSED_VB * FUSED_KC;
+        s = o;     o += wp8;
+        vrow = o;  o += wp8;
+        w2 = o;    o += wp8;
+        red = o;   o += nsub * 3 * NW * 32;
+        pv = o;    o += nsub * 32;
+        ysm = o;   o += nsub * 32;
+        sqred = o; o += FUSED_WARPS;
+        total = o;
+    }
+};
+
 template <bool DIST>
 __global__ void __launch_bounds__(FUSED_THREADS, 1) k_panel_fused(FusedArgs f)
 {
@@ -201,8 +243,11 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_panel_fused(FusedArgs f)
     const int row0 = b * nsub * 32;
     const int rows_here = max(0, min(nsub * 32, m - row0));
     const int nblk = (m + nsub * 32 - 1) / (nsub * 32);         // CTAs that own rows
-    constexpr int T = FUSED_TILE_WARPS;
-    unsigned gen = 0;
+    const FusedSmem L(f.w, nsub);
+    double *const vs_all = sh + L.vs, *const s_sh = sh + L.s, *const vrow_sh = sh + L.vrow, *const w2_sh = sh + L.w2;
+    double *const red = sh + L.red, *const pv = sh + L.pv, *const ysm = sh + L.ysm, *const sqred = sh + L.sqred;
+    unsigned gen = 0, gen2 = 0;
+    unsigned *const bar2 = f.gbar + 32;         // arrival counter "s of this column is complete" (look-ahead warps only)
     unsigned long long t_gemv = 0, t_begin = 0, t_ph[4] = {0, 0, 0, 0}, t_mark = 0;
     const bool timer = (b == 0 && tid == 0);
     if (timer) t_begin = t_mark = globaltimer_ns();
@@ -217,88 +262,41 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_panel_fused(FusedArgs f)
     }
     __shared__ double scal_sh[4];       // tau, beta, scale of the current column
 
+    // look-ahead results for column 0 -> 1 do not exist yet: phase A(1) must see zeros (no previous columns)
+    for (int t = tid; t < nsub * 3 * 32; t += FUSED_THREADS) red[t] = 0.0;
+
     for (int j = 0; j <= f.w; j++) {
         const int jm1 = j - 1;
         double *acol = f.pan + (size_t)j * f.ldpan;
         const int NW = max(1, (j + 31) >> 5);
 
         if (j > 0) {
-            // ================= phase A =================
-            double *s_sh = sh;                             // j
-            double *vrow_sh = s_sh + j;                    // j
-            double *red = vrow_sh + j;                     // nsub * 3 * NW * 32
-            double *pv = red + (size_t)nsub * 3 * NW * 32; // nsub * 32
-            double *ysm = pv + nsub * 32;                  // nsub * 32
+            // ================= phase A: finish column j-1, start column j =================
+            // The row-wise products with Y(:, :j-1) and VT(:, :j-1) were computed by the look-ahead warps while the
+            // GEMV of column j-1 was streaming (`red`); what is left on the critical path is y itself.
+            const int NWa = max(1, (jm1 + 31) >> 5);
             const bool do_update = j < f.w;
             const double tau = __ldcg(&a.scal[jm1].tau), beta_prev = __ldcg(&a.scal[jm1].beta),
                          scale_prev = __ldcg(&a.scal[jm1].scale);
             double *acol_prev = f.pan + (size_t)jm1 * f.ldpan;
-
-            for (int t = tid; t < jm1; t += FUSED_THREADS) s_sh[t] = __ldcg(a.s + t);
-            if (do_update)
-                for (int t = tid; t < j; t += FUSED_THREADS) vrow_sh[t] = (t == jm1) ? 1.0 : __ldcg(a.V + (size_t)t * ld + jm1);
-            __syncthreads();
-
-            if (wp < T) {
-                // row-wise dots of the CTA's rows with s and with row j-1 of V: 32x32 tiles, 2 x 16 columns of Y and VT
-                // (32 independent loads) in flight per lane
-                for (int item = wp; item < nsub * NW; item += T) {
-                    const int sub = item / NW, g = item - sub * NW, t0 = g * 32;
-                    const int r = row0 + sub * 32 + lane;
-                    const bool valid = r < m;
-                    double d0 = 0.0, d1 = 0.0, d2 = 0.0;
-                    const double *VTr = a.VT + (size_t)t0 * ld + r;
-                    const double *Yr = a.Y + (size_t)t0 * ld + r;
-#pragma unroll
-                    for (int bt = 0; bt < 2; bt++) {
-                        const int tb = t0 + 16 * bt;
-                        if (tb < jm1) {
-                            double y16[16], v16[16];
-#pragma unroll
-                            for (int q = 0; q < 16; q++) {
-                                const bool ok = valid && tb + q < jm1;
-                                y16[q] = ok ? Yr[(size_t)(16 * bt + q) * ld] : 0.0;
-                                v16[q] = ok ? VTr[(size_t)(16 * bt + q) * ld] : 0.0;
-                            }
-#pragma unroll
-                            for (int q = 0; q < 16; q++) {
-                                const int t = min(tb + q, jm1 - 1);        // values beyond jm1 are zero
-                                const double sv = s_sh[t];
-                                d0 = fma(y16[q], sv, d0);
-                                d2 = fma(v16[q], sv, d2);
-                                if (do_update) d1 = fma(y16[q], vrow_sh[t], d1);
-                            }
-                        }
-                    }
-                    double *rd = red + ((size_t)sub * 3 * NW + g) * 32 + lane;
-                    rd[0] = d0; rd[NW * 32] = d1; rd[2 * NW * 32] = d2;
-                }
-            } else {
+            {
                 // y(r) of the CTA's rows: sum of the local GEMV partials of column j-1 (fixed order); on P GPUs the
-                // sums travel to every rank's inbox while the tile warps work, then the P contributions are added
-                const int xt = tid - 32 * T;
+                // sums travel to every rank as self-validating 16-byte entries and the P contributions are added
                 const int nloc_prev = f.lc_end - f.cm.lower(f.i + jm1 + 1);
                 GemvSplit gp = gs;
                 gp.nloc = nloc_prev;
                 gp.per = max(FUSED_MINSEG, (int)(((long long)gs.RB * nloc_prev + G * FUSED_VB - 1) / (G * FUSED_VB)));
                 const unsigned epoch = f.x.epoch + jm1;
                 const int par = epoch & 1;
-                for (int rr = xt; rr < rows_here; rr += FUSED_XCHG_THREADS) {
+                for (int rr = tid; rr < rows_here; rr += FUSED_THREADS) {
                     const int r = row0 + rr;
                     const int rb = (r + gs.skip) >> 8;
                     double sum = 0.0;
                     if (nloc_prev > 0) sum = sum_partials(a.ypart + r, a.ldp, gp.last_group(rb) - gp.first_group(rb) + 1);
-                    ysm[rr] = sum;
                     if (DIST) {
-                        // one 16-byte self-validating entry per row and peer: no fence, no separate flag
                         const size_t slot = ((size_t)par * f.x.P + f.x.g) * a.ldp + r;
                         for (int d = 1; d < f.x.P; d++) ll_store((uint4 *)f.x.inbox[(f.x.g + d) % f.x.P] + slot, sum, epoch);
-                    }
-                }
-                if (DIST) {
-                    // add the P contributions in rank order (identical on every rank)
-                    const uint4 *in = (const uint4 *)f.x.inbox[f.x.g] + (size_t)par * f.x.P * a.ldp + row0;
-                    for (int rr = xt; rr < rows_here; rr += FUSED_XCHG_THREADS) {
+                        const uint4 *in = (const uint4 *)f.x.inbox[f.x.g] + (size_t)par * f.x.P * a.ldp + r;
                         // first pass: all P entries in flight at once; stragglers are polled individually
                         double val[MAX_RANKS];
                         bool ready[MAX_RANKS];
@@ -308,23 +306,23 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_panel_fused(FusedArgs f)
                             if (q < f.x.P && q != f.x.g) {
                                 uint4 e;
                                 asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];"
-                                             : "=r"(e.x), "=r"(e.y), "=r"(e.z), "=r"(e.w) : "l"(in + (size_t)q * a.ldp + rr) : "memory");
+                                             : "=r"(e.x), "=r"(e.y), "=r"(e.z), "=r"(e.w) : "l"(in + (size_t)q * a.ldp) : "memory");
                                 ready[q] = (e.y == epoch && e.w == epoch);
                                 val[q] = __longlong_as_double((long long)(((unsigned long long)e.z << 32) | e.x));
                             }
                         }
-                        const double own = ysm[rr];
-                        double sum = 0.0;
+                        const double own = sum;
+                        sum = 0.0;
 #pragma unroll
                         for (int q = 0; q < MAX_RANKS; q++) {
                             if (q < f.x.P) {
-                                double x = (q == f.x.g) ? own : val[q];
-                                if (!ready[q]) x = ll_load(in + (size_t)q * a.ldp + rr, epoch, f.x.status);
-                                sum += x;
+                                double xq = (q == f.x.g) ? own : val[q];
+                                if (!ready[q]) xq = ll_load(in + (size_t)q * a.ldp, epoch, f.x.status);
+                                sum += xq;
                             }
                         }
-                        ysm[rr] = sum;
                     }
+                    ysm[rr] = sum;
                 }
             }
             __syncthreads();
@@ -335,12 +333,14 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_panel_fused(FusedArgs f)
                 const bool valid = r < m;
                 double pp = 0.0;
                 if (valid) {
+                    const double pprev = a.pcol[r];
+                    const double ac = do_update ? acol[r] : 0.0;
                     const double D3 = ysm[sub * 32 + lane];
-                    const double *rd = red + (size_t)sub * 3 * NW * 32 + lane;
+                    const double *rd = red + (size_t)sub * 3 * NWa * 32 + lane;
                     double D0 = 0.0, D1 = 0.0, D2 = 0.0;
-                    for (int q = 0; q < NW; q++) { D0 += rd[q * 32]; D1 += rd[(NW + q) * 32]; D2 += rd[(2 * NW + q) * 32]; }
+                    for (int q = 0; q < NWa; q++) { D0 += rd[q * 32]; D1 += rd[(NWa + q) * 32]; D2 += rd[(2 * NWa + q) * 32]; }
                     // column j-1 of V and of the reduced matrix (the row owner writes: no cross-CTA traffic)
-                    const double vr = (r < jm1) ? 0.0 : (r == jm1 ? 1.0 : a.pcol[r] * scale_prev);
+                    const double vr = (r < jm1) ? 0.0 : (r == jm1 ? 1.0 : pprev * scale_prev);
                     a.V[(size_t)jm1 * ld + r] = vr;
                     if (r == jm1) acol_prev[r] = beta_prev;
                     else if (r > jm1) acol_prev[r] = 0.0;
@@ -348,7 +348,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_panel_fused(FusedArgs f)
                     a.Y[(size_t)jm1 * ld + r] = ynew;
                     a.VT[(size_t)jm1 * ld + r] = tau * (vr - D2);        // VT(:,j-1) = V * T(:,j-1)
                     if (do_update) {
-                        pp = acol[r] - (D1 + ynew * vrow_sh[jm1]);       // prepare_column: p - Y V(j-1,:)^T
+                        pp = ac - (D1 + ynew);                           // prepare_column: p - Y V(j-1,:)^T, V(j-1,j-1) = 1
                         a.pcol[r] = pp;
                     }
                 }
@@ -373,10 +373,6 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_panel_fused(FusedArgs f)
 
         // ================= phase R: p'' = p' - V w2; ||x||^2, z = V^T x =================
         {
-            double *w2_sh = sh;                             // j
-            double *red = w2_sh + j;                        // nsub * NW * 32
-            double *pv = red + (size_t)nsub * NW * 32;      // nsub * 32
-            double *sqred = pv + nsub * 32;                 // FUSED_WARPS
             for (int t = tid; t < j; t += FUSED_THREADS) w2_sh[t] = __ldcg(a.w2 + t);
             __syncthreads();
             if (j > 0) {
@@ -454,90 +450,138 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_panel_fused(FusedArgs f)
                 if (lane == 0) a.s[t] = fma(scale, acc, __ldcg(a.V + (size_t)t * ld + j));
             }
             __syncthreads();
+            // "my part of s is written": only the look-ahead warps wait for this, the GEMV starts at once
+            if (tid == 0) asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(bar2), "r"(1u) : "memory");
         }
 
-        // ================= phase G: GEMV partials =================
+        // ================= phase G: GEMV partials (warps 0..11) + look-ahead for column j+1 (warps 12..15) ==========
         {
             SB_PHASE_MARK(3);
-            if (b == 0 && tid == 0) t_gemv -= globaltimer_ns();
+            if (timer) t_gemv -= globaltimer_ns();
             const double scale = scal_sh[2];
-            const int c = f.i + j;
-            const int lc0 = f.cm.lower(c + 1), nloc = f.lc_end - lc0;
-            const int gc0 = c + 1;
-            GemvSplit gq = gs;
-            gq.nloc = nloc;
-            const long long items = (long long)gs.RB * nloc;
-            gq.per = max(FUSED_MINSEG, (int)((items + G * FUSED_VB - 1) / (G * FUSED_VB)));
-            const int vb = tid >> 7, vt = tid & 127;
-            // groups are spread over the CTAs first (group v lives on CTA v % G), so that a GEMV smaller than the
-            // grid still touches every SM
-            const int v = vb * G + b;
-            double *vs = sh + vb * FUSED_KC;
-            long long it = (long long)v * gq.per;
-            const long long it_end = min(items, it + gq.per);
-            const int mp = m + gs.skip;
-            while (it < it_end) {
-                const int rb = (int)(it / nloc);
-                const int cbeg = (int)(it - (long long)rb * nloc);
-                const int cend = (int)min((long long)nloc, cbeg + (it_end - it));
-                const int rp = rb * 256 + vt * 2;
-                const bool rows_ok = rp < mp;
-                double2 acc = make_double2(0.0, 0.0);
-                const double *Ap = f.Aloc + (size_t)lc0 * f.lda + f.i + 1 - gs.skip + rp;
-                for (int k0 = cbeg; k0 < cend; k0 += FUSED_KC) {
-                    const int nk = min(FUSED_KC, cend - k0);
-                    group_barrier(1 + vb, 128);          // previous chunk's vs fully consumed
-                    for (int k = vt; k < nk; k += 128) {
-                        const int kk = f.cm.l2g(lc0 + k0 + k) - gc0;
-                        vs[k] = (kk == 0) ? 1.0 : __ldcg(a.pcol + j + kk) * scale;
-                    }
-                    group_barrier(1 + vb, 128);
-                    if (rows_ok) {
-                        constexpr int U = 8;
-                        const size_t step = (size_t)f.lda;
-                        const double *P0 = Ap + (size_t)k0 * step;
-                        double2 cur[U], nxt[U];
-                        int k = 0;
-                        if (nk >= U) {
+            if (wp < FUSED_GEMV_WARPS) {
+                const int c = f.i + j;
+                const int lc0 = f.cm.lower(c + 1), nloc = f.lc_end - lc0;
+                const int gc0 = c + 1;
+                GemvSplit gq = gs;
+                gq.nloc = nloc;
+                const long long items = (long long)gs.RB * nloc;
+                gq.per = max(FUSED_MINSEG, (int)((items + G * FUSED_VB - 1) / (G * FUSED_VB)));
+                const int vb = tid >> 7, vt = tid & 127;
+                // groups are spread over the CTAs first (group v lives on CTA v % G), so that a GEMV smaller than the
+                // grid still touches every SM
+                const int v = vb * G + b;
+                double *vs = vs_all + vb * FUSED_KC;
+                long long it = (long long)v * gq.per;
+                const long long it_end = min(items, it + gq.per);
+                const int mp = m + gs.skip;
+                while (it < it_end) {
+                    const int rb = (int)(it / nloc);
+                    const int cbeg = (int)(it - (long long)rb * nloc);
+                    const int cend = (int)min((long long)nloc, cbeg + (it_end - it));
+                    const int rp = rb * 256 + vt * 2;
+                    const bool rows_ok = rp < mp;
+                    double2 acc = make_double2(0.0, 0.0);
+                    const double *Ap = f.Aloc + (size_t)lc0 * f.lda + f.i + 1 - gs.skip + rp;
+                    for (int k0 = cbeg; k0 < cend; k0 += FUSED_KC) {
+                        const int nk = min(FUSED_KC, cend - k0);
+                        group_barrier(1 + vb, 128);          // previous chunk's vs fully consumed
+                        for (int k = vt; k < nk; k += 128) {
+                            const int kk = f.cm.l2g(lc0 + k0 + k) - gc0;
+                            vs[k] = (kk == 0) ? 1.0 : __ldcg(a.pcol + j + kk) * scale;
+                        }
+                        group_barrier(1 + vb, 128);
+                        if (rows_ok) {
+                            constexpr int U = 8;
+                            const size_t step = (size_t)f.lda;
+                            const double *P0 = Ap + (size_t)k0 * step;
+                            double2 cur[U], nxt[U];
+                            int k = 0;
+                            if (nk >= U) {
 #pragma unroll
-                            for (int u = 0; u < U; u++) cur[u] = __ldcs((const double2 *)(P0 + u * step));
-                            const double *Pn = P0 + U * step;
-                            for (; k + 2 * U <= nk; k += U) {
+                                for (int u = 0; u < U; u++) cur[u] = __ldcs((const double2 *)(P0 + u * step));
+                                const double *Pn = P0 + U * step;
+                                for (; k + 2 * U <= nk; k += U) {
 #pragma unroll
-                                for (int u = 0; u < U; u++) nxt[u] = __ldcs((const double2 *)(Pn + u * step));
-                                Pn += U * step;
+                                    for (int u = 0; u < U; u++) nxt[u] = __ldcs((const double2 *)(Pn + u * step));
+                                    Pn += U * step;
+#pragma unroll
+                                    for (int u = 0; u < U; u++) {
+                                        const double vk = vs[k + u];
+                                        acc.x = fma(cur[u].x, vk, acc.x);
+                                        acc.y = fma(cur[u].y, vk, acc.y);
+                                    }
+#pragma unroll
+                                    for (int u = 0; u < U; u++) cur[u] = nxt[u];
+                                }
 #pragma unroll
                                 for (int u = 0; u < U; u++) {
                                     const double vk = vs[k + u];
                                     acc.x = fma(cur[u].x, vk, acc.x);
                                     acc.y = fma(cur[u].y, vk, acc.y);
                                 }
-#pragma unroll
-                                for (int u = 0; u < U; u++) cur[u] = nxt[u];
+                                k += U;
                             }
-#pragma unroll
-                            for (int u = 0; u < U; u++) {
-                                const double vk = vs[k + u];
-                                acc.x = fma(cur[u].x, vk, acc.x);
-                                acc.y = fma(cur[u].y, vk, acc.y);
+                            for (; k < nk; k++) {
+                                const double vk = vs[k];
+                                const double2 xx = __ldcs((const double2 *)(P0 + (size_t)k * step));
+                                acc.x = fma(xx.x, vk, acc.x);
+                                acc.y = fma(xx.y, vk, acc.y);
                             }
-                            k += U;
-                        }
-                        for (; k < nk; k++) {
-                            const double vk = vs[k];
-                            const double2 xx = __ldcs((const double2 *)(P0 + (size_t)k * step));
-                            acc.x = fma(xx.x, vk, acc.x);
-                            acc.y = fma(xx.y, vk, acc.y);
                         }
                     }
+                    if (rows_ok) {
+                        double *yp = a.ypart + (size_t)(v - gq.first_group(rb)) * a.ldp;
+                        const int r = rp - gs.skip;
+                        if (r >= 0) yp[r] = acc.x;
+                        if (r + 1 < m) yp[r + 1] = acc.y;
+                    }
+                    it += cend - cbeg;
                 }
-                if (rows_ok) {
-                    double *yp = a.ypart + (size_t)(v - gq.first_group(rb)) * a.ldp;
-                    const int r = rp - gs.skip;
-                    if (r >= 0) yp[r] = acc.x;
-                    if (r + 1 < m) yp[r + 1] = acc.y;
+            } else {
+                // ---- look-ahead for phase A of column j+1: D0 = Y(:, :j) s_j, D1 = Y(:, :j) V(j, :j)^T, D2 = VT(:, :j) s_j.
+                // None of them needs the GEMV result, so they run in the shadow of the HBM-bound GEMV.
+                const int xt = tid - 32 * FUSED_GEMV_WARPS, xw = wp - FUSED_GEMV_WARPS;
+                gen2 += G;
+                if (xt == 0) while ((int)(ld_acquire_gpu(bar2) - gen2) < 0) { }
+                group_barrier(5, FUSED_SHADOW_THREADS);
+                for (int t = xt; t < j; t += FUSED_SHADOW_THREADS) {
+                    s_sh[t] = __ldcg(a.s + t);
+                    vrow_sh[t] = __ldcg(a.V + (size_t)t * ld + j);
                 }
-                it += cend - cbeg;
+                group_barrier(5, FUSED_SHADOW_THREADS);
+                const int NWn = max(1, (j + 31) >> 5);
+                for (int item = xw; item < nsub * NWn; item += FUSED_WARPS - FUSED_GEMV_WARPS) {
+                    const int sub = item / NWn, g = item - sub * NWn, t0 = g * 32;
+                    const int r = row0 + sub * 32 + lane;
+                    const bool valid = r < m;
+                    double d0 = 0.0, d1 = 0.0, d2 = 0.0;
+                    const double *VTr = a.VT + (size_t)t0 * ld + r;
+                    const double *Yr = a.Y + (size_t)t0 * ld + r;
+#pragma unroll
+                    for (int bt = 0; bt < 2; bt++) {
+                        const int tb = t0 + 16 * bt;
+                        if (tb < j) {
+                            double y16[16], v16[16];
+#pragma unroll
+                            for (int q = 0; q < 16; q++) {
+                                const bool ok = valid && tb + q < j;
+                                y16[q] = ok ? Yr[(size_t)(16 * bt + q) * ld] : 0.0;
+                                v16[q] = ok ? VTr[(size_t)(16 * bt + q) * ld] : 0.0;
+                            }
+#pragma unroll
+                            for (int q = 0; q < 16; q++) {
+                                const int t = min(tb + q, j - 1);        // values beyond j are zero
+                                const double sv = s_sh[t];
+                                d0 = fma(y16[q], sv, d0);
+                                d2 = fma(v16[q], sv, d2);
+                                d1 = fma(y16[q], vrow_sh[t], d1);
+                            }
+                        }
+                    }
+                    double *rd = red + ((size_t)sub * 3 * NWn + g) * 32 + lane;
+                    rd[0] = d0; rd[NWn * 32] = d1; rd[2 * NWn * 32] = d2;
+                }
             }
             grid_barrier(f.gbar, gen);
             if (timer) { t_mark = globaltimer_ns(); t_gemv += t_mark; }
@@ -551,14 +595,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_panel_fused(FusedArgs f)
 #undef SB_PHASE_MARK
 }
 
-// dynamic shared memory of k_panel_fused for a panel of m rows and w columns on a grid of G CTAs
-static inline size_t fused_smem_bytes(int w, int nsub)
-{
-    const int NW = std::max(1, (w + 31) / 32);
-    size_t fu = (size_t)2 * w + (size_t)nsub * 3 * NW * 32 + 2 * (size_t)nsub * 32;
-    size_t rf = (size_t)w + (size_t)nsub * NW * 32 + (size_t)nsub * 32 + FUSED_WARPS;
-    size_t d = std::max(std::max(fu, rf), (size_t)FUSED_VB * FUSED_KC);
-    return d * sizeof(double);
-}
+// dynamic shared memory of k_panel_fused for a panel of w columns with nsub sub-tiles per CTA
+static inline size_t fused_smem_bytes(int w, int nsub) { return (size_t)FusedSmem(w, nsub).total * sizeof(double); }
 
 } // namespace sb200
