@@ -225,6 +225,8 @@ def run_ours(args):
     sampler.start()
     dev_ms, gemv_ms, gemv_bytes, gemv_launches, launches, phase = [], 0.0, 0.0, 0, 0, [0.0, 0.0, 0.0]
     gemv_tbytes, gemv_tlaunches = 0.0, 0
+    fused_panels, panels = 0, 0
+    fused_ph = [0.0] * 5
     t_wall0 = time.perf_counter()
     for _ in range(args.steps):
         reset_device()
@@ -235,6 +237,8 @@ def run_ours(args):
         gemv_ms += st["gemv_ms"]; gemv_bytes += st["gemv_bytes"]; gemv_launches += st["gemv_launches"]
         gemv_tbytes += st["gemv_timed_bytes"]; gemv_tlaunches += st["gemv_timed_launches"]
         launches += st["kernel_launches"]
+        fused_panels += st["fused_panels"]; panels += st["panels"]
+        fused_ph = [a + b for a, b in zip(fused_ph, list(st["fused_phase_ms"]) + [st["fused_kernel_ms"]])]
         phase = [phase[0] + st["panel_ms"], phase[1] + st["trail_ms"], phase[2] + st["other_ms"]]
     barrier()
     wall_ms_per_step = 1e3 * (time.perf_counter() - t_wall0) / args.steps
@@ -299,23 +303,49 @@ def run_ours(args):
 
     # ---------------- roofline of the dominant kernel ----------------
     peak, peak_kind = measured_peaks()
-    # gemv_ms covers the event-timed launches only (every 8th column): divide THEIR bytes by THEIR time
-    achieved = gemv_tbytes / gemv_ms / 1e6 if gemv_ms > 0 else None          # GB/s
-    bytes_per_launch = gemv_bytes / max(1, gemv_launches)
-    roofline = {
-        "bound": "hbm", "kernel": "k_col_gemv", "achieved": achieved, "peak": peak, "unit": "GB/s",
-        "frac": achieved / peak if achieved else None,
-        "traffic": GEMV_TRAFFIC_RATIO * bytes_per_launch if GEMV_TRAFFIC_RATIO else None,
-        "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind})",
-        "algorithmic_bytes_per_launch": bytes_per_launch, "launches_per_step": gemv_launches // args.steps,
-        "timed_launches_per_step": gemv_tlaunches // args.steps,
-        "mean_launch_us": 1e3 * gemv_ms / max(1, gemv_tlaunches),
-        "share_of_step": (gemv_ms * gemv_bytes / max(1.0, gemv_tbytes)) / (ms_per_step * args.steps),
-        # whole-path roofline: T_roof = B / BW_hbm + (8/3 + 2) n^3 / F64_peak
-        # divided by the number of GPUs (T_roof(n, P))
-        "t_roof_ms": 1e3 * (8.0 * (n - 1) * n * (2 * n - 1) / 6.0 / (peak * 1e9) + (14.0 / 3.0) * n ** 3 / (FP64_CUBLAS_TFLOPS * 1e12)) / world,
-        "fp64_peak_tflops": FP64_CUBLAS_TFLOPS, "fp64_peak_source": "cublasDgemm 8192^3 measured on this pool (profiles/r1_probe_peaks.log)",
-    }
+    t_roof_ms = 1e3 * (8.0 * (n - 1) * n * (2 * n - 1) / 6.0 / (peak * 1e9) + (14.0 / 3.0) * n ** 3 / (FP64_CUBLAS_TFLOPS * 1e12)) / world
+    if fused_panels == panels and panels > 0:
+        # One persistent kernel per panel (k_panel_fused): a launch streams the trailing matrix once per panel
+        # column. Algorithmic bytes per launch = sum over its columns of 8 * rows * cols; launch duration = CUDA
+        # events around every launch on the launching stream (stats panel_ms), so the level-2 side work and the
+        # grid barriers inside the kernel count against the achieved figure.
+        achieved = gemv_bytes / phase[0] / 1e6
+        bytes_per_launch = gemv_bytes / panels
+        gemv_phase_gbs = gemv_tbytes / gemv_ms / 1e6 if gemv_ms > 0 else None
+        roofline = {
+            "bound": "hbm", "kernel": "k_panel_fused", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "frac": achieved / peak,
+            "traffic": GEMV_TRAFFIC_RATIO * bytes_per_launch if GEMV_TRAFFIC_RATIO else None,
+            "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind})",
+            "algorithmic_bytes_per_launch": bytes_per_launch, "launches_per_step": panels // args.steps,
+            "mean_launch_us": 1e3 * phase[0] / panels,
+            "share_of_step": phase[0] / (ms_per_step * args.steps),
+            # device-side timers of the level-2 phases inside the kernel (each incl. its grid barrier)
+            "phases_ms_per_step": dict(zip(["finish_update", "w2_reduce", "reflector", "scalars_s", "kernel_total"],
+                                           [x / args.steps for x in fused_ph])),
+            # the GEMV phases alone (device-side %globaltimer around them, incl. the grid barrier that ends each)
+            "gemv_phase": {"achieved": gemv_phase_gbs, "frac": gemv_phase_gbs / peak if gemv_phase_gbs else None,
+                           "ms_per_step": gemv_ms / args.steps, "columns_per_step": gemv_launches // args.steps},
+        }
+    else:
+        # three kernels per column: gemv_ms covers the event-timed k_col_gemv launches only (every 8th column):
+        # divide THEIR bytes by THEIR time
+        achieved = gemv_tbytes / gemv_ms / 1e6 if gemv_ms > 0 else None          # GB/s
+        bytes_per_launch = gemv_bytes / max(1, gemv_launches)
+        roofline = {
+            "bound": "hbm", "kernel": "k_col_gemv", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "frac": achieved / peak if achieved else None,
+            "traffic": GEMV_TRAFFIC_RATIO * bytes_per_launch if GEMV_TRAFFIC_RATIO else None,
+            "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind})",
+            "algorithmic_bytes_per_launch": bytes_per_launch, "launches_per_step": gemv_launches // args.steps,
+            "timed_launches_per_step": gemv_tlaunches // args.steps,
+            "mean_launch_us": 1e3 * gemv_ms / max(1, gemv_tlaunches),
+            "share_of_step": (gemv_ms * gemv_bytes / max(1.0, gemv_tbytes)) / (ms_per_step * args.steps),
+        }
+    # whole-path roofline: T_roof(n, P) = (B / BW_hbm + (8/3 + 2) n^3 / F64_peak) / P
+    roofline["t_roof_ms"] = t_roof_ms
+    roofline["fp64_peak_tflops"] = FP64_CUBLAS_TFLOPS
+    roofline["fp64_peak_source"] = "cublasDgemm 8192^3 measured on this pool (profiles/r1_probe_peaks.log)"
     roofline["path_frac"] = roofline["t_roof_ms"] / ms_per_step
 
     # ---------------- CPU baseline (bounded sample) ----------------
