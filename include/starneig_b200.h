@@ -30,7 +30,8 @@ struct starneig_b200_stats {
     double device_ms;        /* first kernel to last kernel */
     double panel_ms;         /* sum over panels: column loops (panel kernels + GEMV) */
     double trail_ms;         /* sum over panels: trailing right + left updates (critical path) */
-    double other_ms;         /* sum over panels: top rows, partial columns and Q updates */
+    double other_ms;         /* sum over panels: top rows, partial columns and Q updates (busy time of the stream they
+                              * ran on: with `overlap` they run concurrently with the next column loops) */
     double gemv_ms;          /* sum of the durations of the event-timed GEMV launches (profile level >= 2) */
     long long gemv_launches;
     double gemv_bytes;       /* algorithmic bytes read by all GEMV launches: 8 * sum rows*cols */
@@ -46,6 +47,8 @@ struct starneig_b200_stats {
     double fused_kernel_ms;  /* total run time of the persistent panel kernels (device-side timer) */
     double fused_phase_ms[4];/* its level-2 phases, each including the grid barrier that ends it: finish+update (A),
                               * w2 reduction (A'), reflector (R), scalars + s (R') */
+    int overlap;             /* 1: the Q / top-row updates ran on the side stream, overlapped with the column loops */
+    double side_tail_ms;     /* end of the last trailing update -> end of the call (what the deferred updates still add) */
 };
 void starneig_b200_get_stats(struct starneig_b200_stats *stats);
 

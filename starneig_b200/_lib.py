@@ -31,6 +31,7 @@ class Stats(ctypes.Structure):
         ("h2d_bytes", ctypes.c_longlong), ("d2h_bytes", ctypes.c_longlong),
         ("ranks", ctypes.c_int), ("fused_panels", ctypes.c_int), ("fused_kernel_ms", ctypes.c_double),
         ("fused_phase_ms", ctypes.c_double * 4),
+        ("overlap", ctypes.c_int), ("side_tail_ms", ctypes.c_double),
     ]
 
     def as_dict(self):

@@ -49,6 +49,7 @@ using GemmNN13 = GemmConfig<false, true,  4, 1, 2, 13, 4, 2>;    //  64 x 104, W
 using GemmNN12 = GemmConfig<false, true,  4, 1, 2, 12, 4, 2>;    //  64 x  96
 
 static const size_t PANEL_SMEM_MAX = 200 * 1024;
+constexpr int PANEL_RING = 3;           // V / VT buffer sets: the deferred updates may lag two panels behind
 
 // per-device function attributes (opt-in shared memory sizes)
 static void prepare_device_functions()
@@ -81,6 +82,10 @@ struct Workspace {
     int n_cap = 0, nb_cap = 0;
     int ldv = 0, nbp = 0;
     double *V = nullptr, *Y = nullptr, *VT = nullptr, *W = nullptr, *Wpart = nullptr;
+    // Ring of V / VT buffers (Vb[0] == V, VTb[0] == VT): panel k factorises into set k % PANEL_RING, so that the
+    // deferred updates of panel k (side stream) can still read its reflectors while the next panels are factorised.
+    double *Vb[PANEL_RING] = {}, *VTb[PANEL_RING] = {};
+    double *Wside = nullptr, *Wpart_side = nullptr;     // W and split-K partials of the side stream
     double *Vg = nullptr, *VTg = nullptr;      // rows of V, VT of the local columns (P > 1)
     size_t wpart_cap = 0;           // doubles
     double *pcol = nullptr, *ypart = nullptr;
@@ -115,10 +120,14 @@ struct Workspace {
         nbp = round_up(nb, 8);
         size_t panel = (size_t)ldv * nbp;
         V = alloc<double>(panel); Y = alloc<double>(panel); VT = alloc<double>(panel); W = alloc<double>(panel);
+        Vb[0] = V; VTb[0] = VT;
+        for (int k = 1; k < PANEL_RING; k++) { Vb[k] = alloc<double>(panel); VTb[k] = alloc<double>(panel); }
+        Wside = alloc<double>(panel);
         if (dist) { Vg = alloc<double>(panel); VTg = alloc<double>(panel); }
         else Vg = VTg = nullptr;
         wpart_cap = 8 * (size_t)std::max(ldv, 4096) * nbp;
         Wpart = alloc<double>(wpart_cap);
+        Wpart_side = alloc<double>(wpart_cap);
         pcol = alloc<double>(ldv);
         ypart_cap = (size_t)2 * 148 * 12 * 256 + 4 * (size_t)ldv;
         ypart = alloc<double>(ypart_cap);
@@ -163,7 +172,12 @@ struct PanelGrid { int blocks; TileGeom tg; size_t smem_fu, smem_rf; };
 struct Rank {
     int P = 1, g = 0, device = 0, cb = 64;
     bool ready = false;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;          // critical path: column loops and trailing updates (highest priority)
+    cudaStream_t side = nullptr;            // deferred updates (Q, rows above the panel), lowest priority
+    cudaEvent_t ev_panel[PANEL_RING] = {}, ev_side[PANEL_RING] = {};
+    int overlap = 1;                        // 1: deferred updates run on `side`, concurrently with the next column loops
+    int overlap_ctas = 0;                   // grid of the fused panel kernel while deferred updates are pending (0: automatic)
+    int side_chunk = 0;                     // rows per launch of the deferred GEMMs (0: one launch)
     Workspace ws;
     ArenaLayout al;
     char *arena = nullptr;                  // own arena (device memory on `device`)
@@ -184,7 +198,14 @@ struct Rank {
         if (ready) return;
         P = P_; g = g_; device = device_;
         SB_CUDA(cudaSetDevice(device));
-        SB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        int prio_lo = 0, prio_hi = 0;
+        SB_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        SB_CUDA(cudaStreamCreateWithPriority(&stream, cudaStreamNonBlocking, prio_hi));
+        SB_CUDA(cudaStreamCreateWithPriority(&side, cudaStreamNonBlocking, prio_lo));
+        for (int k = 0; k < PANEL_RING; k++) {
+            SB_CUDA(cudaEventCreateWithFlags(&ev_panel[k], cudaEventDisableTiming));
+            SB_CUDA(cudaEventCreateWithFlags(&ev_side[k], cudaEventDisableTiming));
+        }
         prepare_device_functions();
         const char *e = getenv("STARNEIG_B200_COL_BLOCK");
         if (e && atoi(e) >= 8) cb = atoi(e) / 8 * 8;
@@ -193,6 +214,12 @@ struct Rank {
         SB_CUDA(cudaDeviceGetAttribute(&fused_ctas, cudaDevAttrMultiProcessorCount, device));
         e = getenv("STARNEIG_B200_FUSED_CTAS");
         if (e && atoi(e) >= 1) fused_ctas = std::min(fused_ctas, atoi(e));
+        e = getenv("STARNEIG_B200_OVERLAP");
+        if (e) overlap = atoi(e);
+        e = getenv("STARNEIG_B200_OVERLAP_CTAS");
+        if (e && atoi(e) >= 1) overlap_ctas = atoi(e);
+        e = getenv("STARNEIG_B200_SIDE_CHUNK");
+        if (e && atoi(e) >= 0) side_chunk = atoi(e);
         int coop = 0;
         SB_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
         if (!coop) fused = 0;
@@ -212,8 +239,10 @@ struct Rank {
         if (arena) cudaFree(arena);
         arena = nullptr;
         al = ArenaLayout();
+        for (int k = 0; k < PANEL_RING; k++) { cudaEventDestroy(ev_panel[k]); cudaEventDestroy(ev_side[k]); }
         cudaStreamDestroy(stream);
-        stream = nullptr;
+        cudaStreamDestroy(side);
+        stream = side = nullptr;
         ready = false;
     }
     // (re)allocates the own arena for (n, nb); returns true if a new allocation was made (peers must re-exchange)
@@ -249,11 +278,13 @@ struct Rank {
     enum GemmKind { GEMM_NT, GEMM_TN, GEMM_NN };
 
     // C = alpha*op(A)*op(B) + beta*C on the rank's stream; split-K through ws.Wpart for skinny outputs
+    // (ws.Wpart_side when issued on the side stream)
     void gemm(GemmKind kind, int M, int N, int K, double alpha, const double *A, int lda,
-              const double *B, int ldb, double beta, double *C, int ldc)
+              const double *B, int ldb, double beta, double *C, int ldc, bool on_side = false)
     {
         if (M < 1 || N < 1) return;
-        cudaStream_t st = stream;
+        cudaStream_t st = on_side ? side : stream;
+        double *wpart = on_side ? ws.Wpart_side : ws.Wpart;
         stats.gemm_flops += 2.0 * M * N * (double)K;
         if (kind == GEMM_NT) {
             GemmNT::launch(st, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, 1, K, 0);
@@ -267,14 +298,14 @@ struct Rank {
         int tiles = ceil_div(M, 64) * ceil_div(N, bn);
         int splits = 1;
         const int want = 8 * 2 * 148;
-        if (beta == 0.0 && alpha == 1.0 && ws.Wpart != nullptr && tiles < want) {
+        if (beta == 0.0 && alpha == 1.0 && wpart != nullptr && tiles < want) {
             splits = std::min(32, ceil_div(want, tiles));
             splits = std::min(splits, std::max(1, K / 512));
             while (splits > 1 && (size_t)splits * ldc * N > ws.wpart_cap) splits--;
         }
         int klen = round_up(std::max(1, ceil_div(K, splits)), GEMM_BK);
         splits = std::max(1, ceil_div(K, klen));
-        double *out = splits > 1 ? ws.Wpart : C;
+        double *out = splits > 1 ? wpart : C;
         size_t stride = splits > 1 ? (size_t)ldc * N : 0;
         double b = splits > 1 ? 0.0 : beta;
         if (kind == GEMM_TN) {
@@ -383,8 +414,9 @@ struct Rank {
     // dimension ldpan): the matrix itself (P == 1) or the replicated panel buffer. A_loc is the rank's column
     // storage (leading dimension ldA), cm its column map.
     void panel_factor(const ColMap &cm, int i, int end, int w, const double *A_loc, int ldA, double *pan, int ldpan,
-                      double *V, double *Y, double *VT, int ld)
+                      double *V, double *Y, double *VT, int ld, int ctas = 0)
     {
+        if (ctas < 1 || ctas > fused_ctas) ctas = fused_ctas;
         cudaStream_t st = stream;
         const int m = end - i - 1;
         PanelArgs pa = make_panel_args(m, V, Y, VT, ld);
@@ -394,7 +426,7 @@ struct Rank {
             FusedArgs f;
             memset(&f, 0, sizeof(f));
             f.a = pa; f.w = w; f.i = i; f.pan = pan; f.ldpan = ldpan; f.Aloc = A_loc; f.lda = ldA; f.cm = cm; f.lc_end = lc_end;
-            f.nsub = std::max(1, ceil_div(m, 32 * fused_ctas));
+            f.nsub = std::max(1, ceil_div(m, 32 * ctas));
             f.gbar = ws.gbar; f.timers = ws.timers;
             f.x = x;
             f.x.epoch = y_epoch + 1;
@@ -404,7 +436,7 @@ struct Rank {
                 SB_CUDA(cudaMemsetAsync(ws.gbar, 0, 1024 * sizeof(unsigned), st));
                 void *args[] = {&f};
                 const void *fn = P > 1 ? (const void *)k_panel_fused<true> : (const void *)k_panel_fused<false>;
-                SB_CUDA(cudaLaunchCooperativeKernel(fn, dim3(fused_ctas), dim3(FUSED_THREADS), args, smem, st));
+                SB_CUDA(cudaLaunchCooperativeKernel(fn, dim3(ctas), dim3(FUSED_THREADS), args, smem, st));
                 stats.kernel_launches++;
                 stats.fused_panels++;
                 for (int j = 0; j < w; j++) {
@@ -470,6 +502,34 @@ struct Rank {
         stats.kernel_launches++;
     }
 
+    // X(rows x m) <- X (I - V T V^T) = X - (X VT) V^T  (reference update_right_a/b, src/hessenberg/cpu.c:443-560),
+    // optionally in row chunks so that no single launch of the side stream holds the SMs for long
+    void deferred_right_update(int rows, int m, int w, double *X, int ldx, const double *V, const double *VT, int ld,
+                               double *W, bool on_side)
+    {
+        const int chunk = (on_side && side_chunk > 0) ? side_chunk : rows;
+        for (int r0 = 0; r0 < rows; r0 += chunk) {
+            const int nr = std::min(chunk, rows - r0);
+            gemm(GEMM_NN, nr, w, m, 1.0, X + r0, ldx, VT, ld, 0.0, W + r0, ld, on_side);
+            gemm(GEMM_NT, nr, m, w, -1.0, W + r0, ld, V, ld, 1.0, X + r0, ldx, on_side);
+        }
+    }
+
+    // Grid of the persistent panel kernel while deferred updates are in flight on the side stream: the SMs it
+    // leaves free are the ones the deferred GEMMs run on. Balance: the column loop is HBM-bound (needs ~3/4 of the
+    // SMs to saturate the memory system), the deferred GEMMs of one panel need
+    // flops / (per-SM DMMA rate * free SMs) seconds and should finish within the column loop of the next panel.
+    int panel_ctas(int m, int w, int n, int qrows, int i) const
+    {
+        if (overlap_ctas > 0) return std::min(overlap_ctas, fused_ctas);
+        const double t_col = 8.0 * (double)m * m * w / 6.3e12 + w * 24e-6;                 // s, all SMs
+        const double side_flops = 4.0 * (double)w * m * ((double)qrows + (P == 1 ? i + 1 : 0));
+        const double per_sm = 26e12 / 148.0;
+        int free_sms = (int)std::ceil(side_flops / (per_sm * t_col));
+        free_sms = std::max(8, std::min(free_sms, fused_ctas / 4));
+        return std::max(1, fused_ctas - free_sms);
+    }
+
     // -----------------------------------------------------------------------------------------
     // the whole reduction on this rank's shards: A_loc = local columns (full height n, leading dimension ldA),
     // Q_loc = rows [q0, q0+qrows) of Q (all n columns, leading dimension ldQ). P == 1: the matrices themselves.
@@ -499,13 +559,26 @@ struct Rank {
         }
         const int lc_end = cm.lower(end);
 
+        // Schedule. Critical path (main stream): column loop of panel k, then its trailing right/left updates. The
+        // updates of Q and of the rows above the panel only need V and VT of panel k and touch data that no later
+        // column loop or trailing update reads, so (overlap) they go to the low-priority side stream and run
+        // concurrently with the column loops of the next panels: those are HBM-bound and leave the FP64 tensor
+        // pipes idle, the deferred GEMMs are tensor-bound and need little bandwidth. The persistent panel kernel
+        // then runs on fewer SMs (panel_ctas) and the deferred GEMMs fill the others.
+        const bool ovl = overlap != 0;
+        int side_pending = 0;           // panels whose deferred updates have been issued
         for (int i = begin; i < end - 1; i += nb, panel++) {
             const int w = std::min(nb, end - i - 1);
             const int m = end - i - 1;
-            if (lvl >= 1) SB_CUDA(cudaEventRecord(phase_event(2 + 4 * panel + 0), st));
+            const int slot = panel % PANEL_RING;
+            double *V = ws.Vb[slot], *VT = ws.VTb[slot];
+            // the buffers of this slot were last read by the deferred updates of panel - PANEL_RING
+            if (ovl && panel >= PANEL_RING) SB_CUDA(cudaStreamWaitEvent(st, ev_side[slot], 0));
+            if (lvl >= 1) SB_CUDA(cudaEventRecord(phase_event(2 + 6 * panel + 0), st));
             const int pl0 = cm.lower(i), pl1 = cm.lower(i + w);
+            const int ctas = (ovl && side_pending > 0) ? panel_ctas(m, w, n, qrows, i) : fused_ctas;
             if (P == 1) {
-                panel_factor(cm, i, end, w, A, ldA, A + (size_t)i * ldA + i + 1, ldA, ws.V, ws.Y, ws.VT, ld);
+                panel_factor(cm, i, end, w, A, ldA, A + (size_t)i * ldA + i + 1, ldA, V, ws.Y, VT, ld, ctas);
             } else {
                 // gather the panel on every rank; the first barrier protects Pan and Wx of the previous panel
                 barrier();
@@ -515,22 +588,23 @@ struct Rank {
                 }
                 barrier();
                 double *pan = panp.p[g];
-                panel_factor(cm, i, end, w, A, ldA, pan, al.ldv, ws.V, ws.Y, ws.VT, ld);
+                panel_factor(cm, i, end, w, A, ldA, pan, al.ldv, V, ws.Y, VT, ld, ctas);
                 if (pl1 > pl0) {
                     k_panel_pull<<<dim3(std::min(64, ceil_div(m, 256)), pl1 - pl0), 256, 0, st>>>(cm, i, pl0, m, A, ldA, pan, al.ldv);
                     stats.kernel_launches++;
                 }
             }
-            if (lvl >= 1) SB_CUDA(cudaEventRecord(phase_event(2 + 4 * panel + 1), st));
+            if (ovl) SB_CUDA(cudaEventRecord(ev_panel[slot], st));
+            if (lvl >= 1) SB_CUDA(cudaEventRecord(phase_event(2 + 6 * panel + 1), st));
 
             // rows of V, VT that belong to the local columns of the global range [i+1, end)
             const int cl0 = cm.lower(i + 1), ncl = lc_end - cl0;
-            const double *Vg = ws.V, *VTg = ws.VT;
+            const double *Vg = V, *VTg = VT;
             int ldg = ld;
             if (P > 1) {
                 Vg = ws.Vg; VTg = ws.VTg;
                 if (ncl > 0) {
-                    k_gather_rows<<<dim3(ceil_div(ncl, 128), w), 128, 0, st>>>(cm, cl0, ncl, i + 1, w, ws.V, ws.VT, ld, ws.Vg, ws.VTg, ldg);
+                    k_gather_rows<<<dim3(ceil_div(ncl, 128), w), 128, 0, st>>>(cm, cl0, ncl, i + 1, w, V, VT, ld, ws.Vg, ws.VTg, ldg);
                     stats.kernel_launches++;
                 }
             }
@@ -539,39 +613,46 @@ struct Rank {
             if (ntr > 0) {
                 double *Atr = A + (size_t)tl0 * ldA + i + 1;
                 gemm(GEMM_NT, m, ntr, w, -1.0, ws.Y, ld, Vg + (tl0 - cl0), ldg, 1.0, Atr, ldA);
-                gemm(GEMM_TN, ntr, w, m, 1.0, Atr, ldA, ws.VT, ld, 0.0, ws.W, ld);
-                gemm(GEMM_NT, m, ntr, w, -1.0, ws.V, ld, ws.W, ld, 1.0, Atr, ldA);
+                gemm(GEMM_TN, ntr, w, m, 1.0, Atr, ldA, VT, ld, 0.0, ws.W, ld);
+                gemm(GEMM_NT, m, ntr, w, -1.0, V, ld, ws.W, ld, 1.0, Atr, ldA);
             }
-            if (lvl >= 1) SB_CUDA(cudaEventRecord(phase_event(2 + 4 * panel + 2), st));
+            if (lvl >= 1) SB_CUDA(cudaEventRecord(phase_event(2 + 6 * panel + 2), st));
 
+            // ---- deferred updates
+            const bool top_on_side = ovl && P == 1;     // P > 1: the sum over ranks uses the main-stream barriers
+            cudaStream_t sq = ovl ? side : st;
+            if (ovl) SB_CUDA(cudaStreamWaitEvent(side, ev_panel[slot], 0));
+            if (lvl >= 1) SB_CUDA(cudaEventRecord(phase_event(2 + 6 * panel + 3), ovl ? side : st));
             {   // rows above the panel
                 double *X = A + (size_t)cl0 * ldA;
                 if (P == 1) {
-                    gemm(GEMM_NN, i + 1, w, m, 1.0, X, ldA, ws.VT, ld, 0.0, ws.W, ld);
+                    double *Wt = top_on_side ? ws.Wside : ws.W;
+                    deferred_right_update(i + 1, m, w, X, ldA, V, VT, ld, Wt, top_on_side);
                 } else {
                     gemm(GEMM_NN, i + 1, w, ncl, 1.0, X, ldA, VTg, ldg, 0.0, wxp.p[g], al.ldv);
                     barrier();
                     k_sum_peers<<<dim3(ceil_div(i + 1, 256), w), 256, 0, st>>>(P, i + 1, wxp, al.ldv, ws.W, ld);
                     stats.kernel_launches++;
+                    gemm(GEMM_NT, i + 1, ncl, w, -1.0, ws.W, ld, Vg, ldg, 1.0, X, ldA);
                 }
-                gemm(GEMM_NT, i + 1, ncl, w, -1.0, ws.W, ld, Vg, ldg, 1.0, X, ldA);
             }
             if (end < n) {   // columns right of the reduced block (partial reduction)
                 const int xl0 = cm.lower(end), nx = cm.lower(n) - xl0;
                 double *X = A + (size_t)xl0 * ldA + i + 1;
-                gemm(GEMM_TN, nx, w, m, 1.0, X, ldA, ws.VT, ld, 0.0, ws.W, ld);
-                gemm(GEMM_NT, m, nx, w, -1.0, ws.V, ld, ws.W, ld, 1.0, X, ldA);
+                gemm(GEMM_TN, nx, w, m, 1.0, X, ldA, VT, ld, 0.0, ws.W, ld);
+                gemm(GEMM_NT, m, nx, w, -1.0, V, ld, ws.W, ld, 1.0, X, ldA);
             }
-            if (qrows > 0) {   // Q <- Q (I - V T V^T) on the rank's rows
-                double *X = Q + (size_t)(i + 1) * ldQ;
-                gemm(GEMM_NN, qrows, w, m, 1.0, X, ldQ, ws.VT, ld, 0.0, ws.W, ld);
-                gemm(GEMM_NT, qrows, m, w, -1.0, ws.W, ld, ws.V, ld, 1.0, X, ldQ);
-            }
-            if (lvl >= 1) SB_CUDA(cudaEventRecord(phase_event(2 + 4 * panel + 3), st));
+            if (qrows > 0)     // Q <- Q (I - V T V^T) on the rank's rows
+                deferred_right_update(qrows, m, w, Q + (size_t)(i + 1) * ldQ, ldQ, V, VT, ld, ovl ? ws.Wside : ws.W, ovl);
+            if (lvl >= 1) SB_CUDA(cudaEventRecord(phase_event(2 + 6 * panel + 4), sq));
+            if (ovl) { SB_CUDA(cudaEventRecord(ev_side[slot], side)); side_pending++; }
         }
         barrier();
+        if (lvl >= 1) SB_CUDA(cudaEventRecord(phase_event(2 + 6 * panel), st));       // end of the critical path
+        if (ovl && side_pending > 0) SB_CUDA(cudaStreamWaitEvent(st, ev_side[(panel - 1) % PANEL_RING], 0));
         SB_CUDA(cudaEventRecord(ev_last, st));
         SB_CUDA(cudaStreamSynchronize(st));
+        SB_CUDA(cudaStreamSynchronize(side));
         SB_CUDA(cudaGetLastError());
         if (P > 1) {
             unsigned status = 0;
@@ -585,13 +666,17 @@ struct Rank {
         float ms = 0.f;
         SB_CUDA(cudaEventElapsedTime(&ms, ev_first, ev_last));
         stats.device_ms = ms;
+        stats.overlap = ovl ? 1 : 0;
         if (lvl >= 1) {
             for (int p = 0; p < panel; p++) {
-                cudaEvent_t *e = &events[2 + 4 * p];
+                cudaEvent_t *e = &events[2 + 6 * p];
                 SB_CUDA(cudaEventElapsedTime(&ms, e[0], e[1])); stats.panel_ms += ms;
                 SB_CUDA(cudaEventElapsedTime(&ms, e[1], e[2])); stats.trail_ms += ms;
-                SB_CUDA(cudaEventElapsedTime(&ms, e[2], e[3])); stats.other_ms += ms;
+                // deferred updates: busy time of the stream they ran on (overlaps the column loops when ovl)
+                SB_CUDA(cudaEventElapsedTime(&ms, e[3], e[4])); stats.other_ms += ms;
             }
+            // what the deferred updates add to the critical path: end of the last trailing update -> end of the call
+            SB_CUDA(cudaEventElapsedTime(&ms, events[2 + 6 * panel], ev_last)); stats.side_tail_ms = ms;
         }
         if (stats.fused_panels > 0) {
             unsigned long long t[8] = {0, 0, 0, 0, 0, 0, 0, 0};
