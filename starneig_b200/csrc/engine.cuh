@@ -47,6 +47,13 @@ using GemmTN13 = GemmConfig<true,  true,  4, 1, 2, 13, 4, 2>;    //  64 x 104, W
 using GemmTN12 = GemmConfig<true,  true,  4, 1, 2, 12, 4, 2>;    //  64 x  96
 using GemmNN13 = GemmConfig<false, true,  4, 1, 2, 13, 4, 2>;    //  64 x 104, W = A VT
 using GemmNN12 = GemmConfig<false, true,  4, 1, 2, 12, 4, 2>;    //  64 x  96
+// "Fat" variants for the side stream: 256 threads x ~200 registers fill the register file of an SM, so a CTA owns
+// its SM exclusively. When it retires the SM is completely free and the (higher-priority, equally SM-exclusive)
+// persistent panel kernel can claim it at once; with the 2-CTAs-per-SM variants an SM never drains while the
+// deferred GEMM still has CTAs queued, and the panel kernel would wait for the whole GEMM to finish.
+using GemmNTfat   = GemmConfig<false, false, 2, 4, 8, 4, 4, 1>;     // 128 x 128
+using GemmNN13fat = GemmConfig<false, true,  8, 1, 2, 13, 4, 1>;    // 128 x 104
+using GemmNN12fat = GemmConfig<false, true,  8, 1, 2, 12, 4, 1>;    // 128 x  96
 
 static const size_t PANEL_SMEM_MAX = 200 * 1024;
 constexpr int PANEL_RING = 3;           // V / VT buffer sets: the deferred updates may lag two panels behind
@@ -55,6 +62,7 @@ constexpr int PANEL_RING = 3;           // V / VT buffer sets: the deferred upda
 static void prepare_device_functions()
 {
     GemmNT::prepare(); GemmTN13::prepare(); GemmTN12::prepare(); GemmNN13::prepare(); GemmNN12::prepare();
+    GemmNTfat::prepare(); GemmNN13fat::prepare(); GemmNN12fat::prepare();
     SB_CUDA(cudaFuncSetAttribute(k_col_finish_update<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM_MAX));
     SB_CUDA(cudaFuncSetAttribute(k_col_finish_update<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM_MAX));
     SB_CUDA(cudaFuncSetAttribute(k_col_reflector<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM_MAX));
@@ -178,6 +186,9 @@ struct Rank {
     int overlap = 1;                        // 1: deferred updates run on `side`, concurrently with the next column loops
     int overlap_ctas = 0;                   // grid of the fused panel kernel while deferred updates are pending (0: automatic)
     int side_chunk = 0;                     // rows per launch of the deferred GEMMs (0: one launch)
+    int side_fat = 1;                       // deferred GEMMs use the SM-exclusive tile configurations
+    double side_rate = 22e12;               // flop/s of the deferred GEMMs if they had the whole GPU (SM-split model)
+    int side_max_sms = 48;
     Workspace ws;
     ArenaLayout al;
     char *arena = nullptr;                  // own arena (device memory on `device`)
@@ -220,6 +231,12 @@ struct Rank {
         if (e && atoi(e) >= 1) overlap_ctas = atoi(e);
         e = getenv("STARNEIG_B200_SIDE_CHUNK");
         if (e && atoi(e) >= 0) side_chunk = atoi(e);
+        e = getenv("STARNEIG_B200_SIDE_FAT");
+        if (e) side_fat = atoi(e);
+        e = getenv("STARNEIG_B200_SIDE_RATE");
+        if (e && atof(e) > 0) side_rate = atof(e) * 1e12;
+        e = getenv("STARNEIG_B200_SIDE_MAX_SMS");
+        if (e && atoi(e) >= 1) side_max_sms = atoi(e);
         int coop = 0;
         SB_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
         if (!coop) fused = 0;
@@ -286,8 +303,10 @@ struct Rank {
         cudaStream_t st = on_side ? side : stream;
         double *wpart = on_side ? ws.Wpart_side : ws.Wpart;
         stats.gemm_flops += 2.0 * M * N * (double)K;
+        const bool fat = on_side && side_fat;
         if (kind == GEMM_NT) {
-            GemmNT::launch(st, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, 1, K, 0);
+            if (fat) GemmNTfat::launch(st, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, 1, K, 0);
+            else     GemmNT::launch(st, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, 1, K, 0);
             stats.kernel_launches++;
             return;
         }
@@ -295,9 +314,9 @@ struct Rank {
         // grid would not fill the GPU twice
         int bn = (ceil_div(N, 96) * 96 <= ceil_div(N, 104) * 104) ? 96 : 104;
         // 2 CTAs per SM are resident; split K so that the grid is >= ~8 waves (tail quantisation < ~6 %)
-        int tiles = ceil_div(M, 64) * ceil_div(N, bn);
+        int tiles = ceil_div(M, fat ? 128 : 64) * ceil_div(N, bn);
         int splits = 1;
-        const int want = 8 * 2 * 148;
+        const int want = fat ? 6 * 148 : 8 * 2 * 148;
         if (beta == 0.0 && alpha == 1.0 && wpart != nullptr && tiles < want) {
             splits = std::min(32, ceil_div(want, tiles));
             splits = std::min(splits, std::max(1, K / 512));
@@ -311,6 +330,9 @@ struct Rank {
         if (kind == GEMM_TN) {
             if (bn == 96) GemmTN12::launch(st, M, N, K, alpha, A, lda, B, ldb, b, out, ldc, splits, klen, stride);
             else          GemmTN13::launch(st, M, N, K, alpha, A, lda, B, ldb, b, out, ldc, splits, klen, stride);
+        } else if (fat) {
+            if (bn == 96) GemmNN12fat::launch(st, M, N, K, alpha, A, lda, B, ldb, b, out, ldc, splits, klen, stride);
+            else          GemmNN13fat::launch(st, M, N, K, alpha, A, lda, B, ldb, b, out, ldc, splits, klen, stride);
         } else {
             if (bn == 96) GemmNN12::launch(st, M, N, K, alpha, A, lda, B, ldb, b, out, ldc, splits, klen, stride);
             else          GemmNN13::launch(st, M, N, K, alpha, A, lda, B, ldb, b, out, ldc, splits, klen, stride);
@@ -524,9 +546,9 @@ struct Rank {
         if (overlap_ctas > 0) return std::min(overlap_ctas, fused_ctas);
         const double t_col = 8.0 * (double)m * m * w / 6.3e12 + w * 24e-6;                 // s, all SMs
         const double side_flops = 4.0 * (double)w * m * ((double)qrows + (P == 1 ? i + 1 : 0));
-        const double per_sm = 26e12 / 148.0;
+        const double per_sm = side_rate / 148.0;
         int free_sms = (int)std::ceil(side_flops / (per_sm * t_col));
-        free_sms = std::max(8, std::min(free_sms, fused_ctas / 4));
+        free_sms = std::max(8, std::min(free_sms, std::min(side_max_sms, fused_ctas / 2)));
         return std::max(1, fused_ctas - free_sms);
     }
 

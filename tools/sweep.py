@@ -15,7 +15,7 @@ A = torch.empty_like(A0)
 Q = torch.zeros((n, ld), dtype=torch.float64, device="cuda")
 ref = None
 KNOBS = ["STARNEIG_B200_OVERLAP", "STARNEIG_B200_OVERLAP_CTAS", "STARNEIG_B200_FUSED_CTAS", "STARNEIG_B200_SIDE_CHUNK",
-         "STARNEIG_B200_FUSED_PANEL"]
+         "STARNEIG_B200_FUSED_PANEL", "STARNEIG_B200_SIDE_FAT", "STARNEIG_B200_SIDE_RATE", "STARNEIG_B200_SIDE_MAX_SMS"]
 for cfg in configs:
     for k in KNOBS:
         os.environ.pop(k, None)
