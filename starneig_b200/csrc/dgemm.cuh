@@ -71,6 +71,55 @@ __device__ __forceinline__ void load_tile(double *smem, const double *__restrict
     }
 }
 
+// Per-thread state of the tile loads of one operand, set up once per CTA: in every full k-tile a thread issues
+// ITERS cp.async whose source addresses differ by a constant stride and whose validity (x inside the operand) does
+// not depend on the k-tile, so the main loop spends ~3 integer instructions per cp.async instead of re-deriving
+// (x, k), the bounds checks and the clamped address each time. Partial k-tiles (the last one) use load_tile.
+// Out-of-range elements are zero-filled (src-size 0: the address is not dereferenced).
+template <bool KMAJOR, int BX, int NTHREADS> struct TileLoader {
+    static constexpr int ELEMS = BX * GEMM_BK;
+    static constexpr int ITERS = (ELEMS + NTHREADS - 1) / NTHREADS;
+    static_assert(KMAJOR ? (NTHREADS % GEMM_BK == 0) : (NTHREADS % BX == 0), "thread count must tile the operand");
+    // MN-major: x fixed, k = k_t + it * (NTHREADS / BX);  K-major: k fixed, x = x_t + it * (NTHREADS / GEMM_BK)
+    static constexpr int STEP = KMAJOR ? NTHREADS / GEMM_BK : NTHREADS / BX;
+    using OT = OperandTile<KMAJOR, BX>;
+    const double *src;      // element of iteration 0 in the current k-tile
+    size_t it_stride;       // doubles between consecutive iterations
+    size_t tile_stride;     // doubles between consecutive k-tiles
+    unsigned mask;          // bit it: the element of iteration `it` has a valid x
+    int soff;               // shared-memory offset (doubles) of iteration 0
+
+    __device__ __forceinline__ void init(const double *g, int ld, int x0, int k0, int X, int tid)
+    {
+        int x, k;
+        if (KMAJOR) { x = tid / GEMM_BK; k = tid % GEMM_BK; }
+        else        { k = tid / BX;      x = tid % BX; }
+        src = KMAJOR ? g + (size_t)(x0 + x) * ld + (k0 + k) : g + (size_t)(k0 + k) * ld + (x0 + x);
+        it_stride = KMAJOR ? (size_t)STEP * ld : (size_t)STEP * ld;
+        tile_stride = KMAJOR ? (size_t)GEMM_BK : (size_t)GEMM_BK * ld;
+        soff = OT::offset(x, k);
+        mask = 0u;
+#pragma unroll
+        for (int it = 0; it < ITERS; it++) {
+            const int xi = KMAJOR ? x + it * STEP : x;
+            if (xi < BX && x0 + xi < X) mask |= 1u << it;
+        }
+    }
+    // full k-tile (all GEMM_BK values of k valid); advances to the next k-tile
+    __device__ __forceinline__ void load_full(double *smem)
+    {
+        const double *p = src;
+#pragma unroll
+        for (int it = 0; it < ITERS; it++) {
+            constexpr int SSTEP = KMAJOR ? STEP * OT::STRIDE : STEP * OT::STRIDE;
+            cp_async8(smem + soff + it * SSTEP, p, (mask >> it) & 1u);
+            p += it_stride;
+        }
+        src += tile_stride;
+    }
+    __device__ __forceinline__ void skip() { src += tile_stride; }
+};
+
 // One k-step (4 values of k) of the warp tile: fragments from shared memory, MB x NB DMMAs.
 template <class TA, class TB, int MB, int NB>
 __device__ __forceinline__ void load_frags(double (&af)[MB], double (&bf)[NB], const double *sa, const double *sb,
@@ -105,8 +154,6 @@ dgemm_kernel(int M, int N, int K, double alpha, const double *__restrict__ A, in
     using TA = OperandTile<AK, BM>;
     using TB = OperandTile<BKM, BN>;
     constexpr int STAGE = TA::SIZE + TB::SIZE;
-    constexpr int CS = BM + 2;          // staging stride of the epilogue (conflict-free for the fragment layout)
-    static_assert((size_t)BN * CS <= (size_t)STAGES * STAGE, "epilogue staging must fit in the pipeline buffers");
     extern __shared__ double smem[];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -135,29 +182,34 @@ dgemm_kernel(int M, int N, int K, double alpha, const double *__restrict__ A, in
         }
     }
 
-    // prologue
-#pragma unroll
-    for (int s = 0; s < STAGES - 1; s++) {
-        if (s < ktiles) {
-            double *sa = smem + s * STAGE, *sb = sa + TA::SIZE;
-            load_tile<AK, BM, NT>(sa, A, lda, m0, kbeg + s * GEMM_BK, M, kend, tid);
-            load_tile<BKM, BN, NT>(sb, B, ldb, n0, kbeg + s * GEMM_BK, N, kend, tid);
+    TileLoader<AK, BM, NT> la;
+    TileLoader<BKM, BN, NT> lb;
+    la.init(A, lda, m0, kbeg, M, tid);
+    lb.init(B, ldb, n0, kbeg, N, tid);
+    // stage tile t (if it exists) into ring slot t % STAGES; one commit group per call
+    auto issue_tile = [&](int t) {
+        if (t < ktiles) {
+            double *sa = smem + (t % STAGES) * STAGE, *sb = sa + TA::SIZE;
+            const int k0 = kbeg + t * GEMM_BK;
+            if (k0 + GEMM_BK <= kend) {
+                la.load_full(sa);
+                lb.load_full(sb);
+            } else {
+                load_tile<AK, BM, NT>(sa, A, lda, m0, k0, M, kend, tid);
+                load_tile<BKM, BN, NT>(sb, B, ldb, n0, k0, N, kend, tid);
+            }
         }
         cp_async_commit();
-    }
+    };
+
+    // prologue
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; s++) issue_tile(s);
 
     for (int kt = 0; kt < ktiles; kt++) {
         cp_async_wait<STAGES - 2>();
         __syncthreads();
-        {   // prefetch tile kt+STAGES-1 into the slot freed by tile kt-1
-            int nk = kt + STAGES - 1;
-            if (nk < ktiles) {
-                double *sa = smem + (nk % STAGES) * STAGE, *sb = sa + TA::SIZE;
-                load_tile<AK, BM, NT>(sa, A, lda, m0, kbeg + nk * GEMM_BK, M, kend, tid);
-                load_tile<BKM, BN, NT>(sb, B, ldb, n0, kbeg + nk * GEMM_BK, N, kend, tid);
-            }
-            cp_async_commit();
-        }
+        issue_tile(kt + STAGES - 1);        // into the slot freed by tile kt-1
         const double *sa = smem + (kt % STAGES) * STAGE, *sb = sa + TA::SIZE;
         const int krem = kend - (kbeg + kt * GEMM_BK);
         if (krem >= GEMM_BK) {
@@ -180,37 +232,28 @@ dgemm_kernel(int M, int N, int K, double alpha, const double *__restrict__ A, in
         }
     }
     cp_async_wait<0>();
-    __syncthreads();        // every warp is done with the operand tiles: reuse them as C staging
 
-    // epilogue, stage 1: fragments -> shared memory (thread holds C[row g][cols 2t, 2t+1] of each 8x8 block)
-    double *Cs = smem;
+    // Epilogue straight from the accumulator fragments: a thread holds C[row g][cols 2t, 2t+1] of each 8x8 block,
+    // so the eight lanes that share t cover eight consecutive rows of one column (64 contiguous bytes): sector-
+    // efficient without a trip through shared memory, no CTA-wide barrier, and all loads of a batch (one column
+    // block: 2*MB values) are in flight together.
+    const bool use_beta = beta != 0.0;
 #pragma unroll
-    for (int i = 0; i < MB; i++)
+    for (int j = 0; j < NB; j++) {
+        const int col = n0 + (wn * NB + j) * 8 + 2 * t;
+        double *Cc = C + (size_t)col * ldc + m0 + wm * MB * 8 + g;
+        const int rbase = m0 + wm * MB * 8 + g;
+        double old[MB][2];
 #pragma unroll
-        for (int j = 0; j < NB; j++)
+        for (int i = 0; i < MB; i++)
 #pragma unroll
             for (int e = 0; e < 2; e++)
-                Cs[((wn * NB + j) * 8 + 2 * t + e) * CS + (wm * MB + i) * 8 + g] = acc[i][j][e];
-    __syncthreads();
-
-    // stage 2: coalesced read-modify-write of C, one column per warp at a time, lanes along rows
-    constexpr int NWARPS = WM * WN, RPL = BM / 32;
-    const bool use_beta = beta != 0.0;
-    for (int col = warp; col < BN; col += NWARPS) {
-        const int gc = n0 + col;
-        if (gc >= N) break;
-        double *Cg = C + (size_t)gc * ldc + m0;
-        double old[RPL];
+                old[i][e] = (use_beta && col + e < N && rbase + i * 8 < M) ? Cc[(size_t)e * ldc + i * 8] : 0.0;
 #pragma unroll
-        for (int q = 0; q < RPL; q++) {
-            int r = lane + 32 * q;
-            old[q] = (use_beta && m0 + r < M) ? Cg[r] : 0.0;
-        }
+        for (int i = 0; i < MB; i++)
 #pragma unroll
-        for (int q = 0; q < RPL; q++) {
-            int r = lane + 32 * q;
-            if (m0 + r < M) Cg[r] = fma(alpha, Cs[col * CS + r], beta * old[q]);
-        }
+            for (int e = 0; e < 2; e++)
+                if (col + e < N && rbase + i * 8 < M) Cc[(size_t)e * ldc + i * 8] = fma(alpha, acc[i][j][e], beta * old[i][e]);
     }
 }
 

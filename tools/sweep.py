@@ -5,6 +5,7 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import starneig_b200 as sn
+from bench import ClockSampler
 
 n = int(sys.argv[1])
 configs = sys.argv[2:] or [""]
@@ -29,16 +30,18 @@ for cfg in configs:
     sn.starneig_node_init(-1, 1, sn.STARNEIG_NO_MESSAGES)
     sn.set_profile_level(1)
     for it in range(reps):
+        sampler = ClockSampler(0); sampler.start()
         A.copy_(A0)
         Q.zero_(); Q[:, :n].fill_diagonal_(1.0)
         torch.cuda.synchronize()
         r = sn.hessenberg_device(n, A, ld, Q, ld)
         torch.cuda.synchronize()
         st = sn.get_stats()
+        ck = sampler.stop()
         gbs = st["gemv_timed_bytes"] / max(st["gemv_ms"], 1e-9) / 1e6
         print(f"[{cfg or 'default':40s}] ret {r} device_ms {st['device_ms']:8.1f} GFLOP/s {10 / 3 * n ** 3 / st['device_ms'] / 1e6:7.0f} "
               f"col {st['panel_ms']:7.1f} trail {st['trail_ms']:6.1f} deferred {st['other_ms']:7.1f} tail {st['side_tail_ms']:6.1f} "
-              f"gemv_ms {st['gemv_ms']:7.1f} ({gbs:5.0f} GB/s) ph {[round(x) for x in st['fused_phase_ms']]} ovl {st['overlap']}", flush=True)
+              f"gemv_ms {st['gemv_ms']:7.1f} ({gbs:5.0f} GB/s) ph {[round(x) for x in st['fused_phase_ms']]} ovl {st['overlap']} sm_mhz {ck['sm_mhz']} pwr_max {ck['power_w_max']} {ck['reasons']}", flush=True)
     sn.starneig_node_finalize()
     if ref is None:
         ref = (A.clone(), Q.clone())
