@@ -88,6 +88,8 @@ template <bool KMAJOR, int BX, int NTHREADS> struct TileLoader {
     size_t tile_stride;     // doubles between consecutive k-tiles
     unsigned mask;          // bit it: the element of iteration `it` has a valid x
     int soff;               // shared-memory offset (doubles) of iteration 0
+    bool last_in_tile;      // ELEMS % NTHREADS != 0: the element of the last iteration exists (x < BX)
+    static_assert(KMAJOR || ELEMS % NTHREADS == 0, "MN-major operands: the thread count must divide the tile");
 
     __device__ __forceinline__ void init(const double *g, int ld, int x0, int k0, int X, int tid)
     {
@@ -99,6 +101,7 @@ template <bool KMAJOR, int BX, int NTHREADS> struct TileLoader {
         tile_stride = KMAJOR ? (size_t)GEMM_BK : (size_t)GEMM_BK * ld;
         soff = OT::offset(x, k);
         mask = 0u;
+        last_in_tile = !KMAJOR || x + (ITERS - 1) * STEP < BX;
 #pragma unroll
         for (int it = 0; it < ITERS; it++) {
             const int xi = KMAJOR ? x + it * STEP : x;
@@ -112,7 +115,9 @@ template <bool KMAJOR, int BX, int NTHREADS> struct TileLoader {
 #pragma unroll
         for (int it = 0; it < ITERS; it++) {
             constexpr int SSTEP = KMAJOR ? STEP * OT::STRIDE : STEP * OT::STRIDE;
-            cp_async8(smem + soff + it * SSTEP, p, (mask >> it) & 1u);
+            // a zero-fill of an element beyond the tile would land in the next stage (or past the allocation)
+            if (ELEMS % NTHREADS == 0 || it + 1 < ITERS || last_in_tile)
+                cp_async8(smem + soff + it * SSTEP, p, (mask >> it) & 1u);
             p += it_stride;
         }
         src += tile_stride;

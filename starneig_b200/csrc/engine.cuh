@@ -183,7 +183,10 @@ struct Rank {
     cudaStream_t stream = nullptr;          // critical path: column loops and trailing updates (highest priority)
     cudaStream_t side = nullptr;            // deferred updates (Q, rows above the panel), lowest priority
     cudaEvent_t ev_panel[PANEL_RING] = {}, ev_side[PANEL_RING] = {};
-    int overlap = 1;                        // 1: deferred updates run on `side`, concurrently with the next column loops
+    // 1: deferred updates run on `side`, concurrently with the next column loops. Off by default: measured on B200 at
+    // n = 20000 (profiles/r1_s5_overlap_sweep.txt) the concurrent DMMA GEMMs cost the HBM-bound column loops far more
+    // (GEMV phases 6335 -> 3850-4540 GB/s) than the 770 ms of deferred work they hide: 5334 ms without, 6216-6854 ms with.
+    int overlap = 0;
     int overlap_ctas = 0;                   // grid of the fused panel kernel while deferred updates are pending (0: automatic)
     int side_chunk = 0;                     // rows per launch of the deferred GEMMs (0: one launch)
     int side_fat = 1;                       // deferred GEMMs use the SM-exclusive tile configurations
