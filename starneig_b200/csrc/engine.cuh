@@ -175,6 +175,17 @@ struct ArenaLayout {
 };
 
 struct GemvPlan { int skip, RB, S, kc; const double *A0; };
+
+// Host staging hooks of a reduction (host-pointer API, hessenberg.cu): the upload of Q hides behind the first
+// column loop and finished columns travel back while the next panels are factorised.
+struct StageHook {
+    // the stream is about to touch Q for the first time
+    virtual void before_q(cudaStream_t s) = 0;
+    // Everything enqueued on `s` so far completes panel [.., final_cols): global columns [0, final_cols) of A and
+    // [0, final_cols] of Q will not change any more.
+    virtual void panel_done(cudaStream_t s, int final_cols) = 0;
+    virtual ~StageHook() {}
+};
 struct PanelGrid { int blocks; TileGeom tg; size_t smem_fu, smem_rf; };
 
 struct Rank {
@@ -183,6 +194,8 @@ struct Rank {
     cudaStream_t stream = nullptr;          // critical path: column loops and trailing updates (highest priority)
     cudaStream_t side = nullptr;            // deferred updates (Q, rows above the panel), lowest priority
     cudaEvent_t ev_panel[PANEL_RING] = {}, ev_side[PANEL_RING] = {};
+    cudaStream_t copy = nullptr;            // host staging that overlaps the reduction (Q upload, write-back of finished columns)
+    cudaEvent_t ev_q_up = nullptr, ev_cols_final = nullptr;
     // 1: deferred updates run on `side`, concurrently with the next column loops. Off by default: measured on B200 at
     // n = 20000 (profiles/r1_s5_overlap_sweep.txt) the concurrent DMMA GEMMs cost the HBM-bound column loops far more
     // (GEMV phases 6335 -> 3850-4540 GB/s) than the 770 ms of deferred work they hide: 5334 ms without, 6216-6854 ms with.
@@ -220,6 +233,9 @@ struct Rank {
             SB_CUDA(cudaEventCreateWithFlags(&ev_panel[k], cudaEventDisableTiming));
             SB_CUDA(cudaEventCreateWithFlags(&ev_side[k], cudaEventDisableTiming));
         }
+        SB_CUDA(cudaStreamCreateWithFlags(&copy, cudaStreamNonBlocking));
+        SB_CUDA(cudaEventCreateWithFlags(&ev_q_up, cudaEventDisableTiming));
+        SB_CUDA(cudaEventCreateWithFlags(&ev_cols_final, cudaEventDisableTiming));
         prepare_device_functions();
         const char *e = getenv("STARNEIG_B200_COL_BLOCK");
         if (e && atoi(e) >= 8) cb = atoi(e) / 8 * 8;
@@ -260,9 +276,11 @@ struct Rank {
         arena = nullptr;
         al = ArenaLayout();
         for (int k = 0; k < PANEL_RING; k++) { cudaEventDestroy(ev_panel[k]); cudaEventDestroy(ev_side[k]); }
+        cudaEventDestroy(ev_q_up); cudaEventDestroy(ev_cols_final);
         cudaStreamDestroy(stream);
         cudaStreamDestroy(side);
-        stream = side = nullptr;
+        cudaStreamDestroy(copy);
+        stream = side = copy = nullptr;
         ready = false;
     }
     // (re)allocates the own arena for (n, nb); returns true if a new allocation was made (peers must re-exchange)
@@ -559,7 +577,7 @@ struct Rank {
     // the whole reduction on this rank's shards: A_loc = local columns (full height n, leading dimension ldA),
     // Q_loc = rows [q0, q0+qrows) of Q (all n columns, leading dimension ldQ). P == 1: the matrices themselves.
     // -----------------------------------------------------------------------------------------
-    void reduce(int n, int begin, int end, int nb, double *A, int ldA, double *Q, int ldQ, int qrows)
+    void reduce(int n, int begin, int end, int nb, double *A, int ldA, double *Q, int ldQ, int qrows, StageHook *hook = nullptr)
     {
         SB_CUDA(cudaSetDevice(device));
         cudaStream_t st = stream;
@@ -667,10 +685,12 @@ struct Rank {
                 gemm(GEMM_TN, nx, w, m, 1.0, X, ldA, VT, ld, 0.0, ws.W, ld);
                 gemm(GEMM_NT, m, nx, w, -1.0, V, ld, ws.W, ld, 1.0, X, ldA);
             }
+            if (hook && panel == 0) hook->before_q(sq);
             if (qrows > 0)     // Q <- Q (I - V T V^T) on the rank's rows
                 deferred_right_update(qrows, m, w, Q + (size_t)(i + 1) * ldQ, ldQ, V, VT, ld, ovl ? ws.Wside : ws.W, ovl);
             if (lvl >= 1) SB_CUDA(cudaEventRecord(phase_event(2 + 6 * panel + 4), sq));
             if (ovl) { SB_CUDA(cudaEventRecord(ev_side[slot], side)); side_pending++; }
+            if (hook) hook->panel_done(sq, i + w);
         }
         barrier();
         if (lvl >= 1) SB_CUDA(cudaEventRecord(phase_event(2 + 6 * panel), st));       // end of the critical path

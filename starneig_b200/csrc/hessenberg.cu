@@ -49,22 +49,92 @@ struct Shard {
     }
 };
 
-// host <-> device movement of one rank's shards: its column blocks of A, its row slab of Q
-static void shard_copy(const Rank &r, Shard &sh, int n, double *A, int ldA, double *Q, int ldQ, bool to_device)
+// Host <-> device movement of one rank's shards (its block-cyclic columns of A, its row slab of Q), overlapped with
+// the reduction where the data dependencies allow it:
+//   * A goes up first on the compute stream (the first GEMV reads all of it); Q goes up on the copy stream and
+//     the first Q update waits for it, so its transfer hides behind the first column loop;
+//   * after panel [i, i+w) global columns [0, i+w) of A and [0, i+w] of Q are final (later panels only touch
+//     columns to their right): they travel back on the copy stream while the next panels are factorised, and
+//     only the columns of the last panel are still on the device when the reduction ends.
+// The copies only overlap when the host buffers are page-locked (caller-pinned or registered for the call by
+// ScopedPin); with pageable memory cudaMemcpy2DAsync blocks the calling thread, so everything stays in
+// order on the compute stream: upload, reduce, download.
+struct HostStage : StageHook {
+    const Rank &r; Shard &sh;
+    const int n; double *const A; const int ldA; double *const Q; const int ldQ;
+    const bool overlap;
+    const int cb;
+    int a_done = 0, q_done = 0;         // local columns of A / columns of Q already on their way back
+
+    HostStage(const Rank &r_, Shard &sh_, int n_, double *A_, int ldA_, double *Q_, int ldQ_, bool overlap_)
+        : r(r_), sh(sh_), n(n_), A(A_), ldA(ldA_), Q(Q_), ldQ(ldQ_), overlap(overlap_), cb(r_.P == 1 ? std::max(n_, 1) : r_.cb) {}
+
+    // local columns [l0, l1) of A: contiguous runs inside one column block
+    void copy_a(int l0, int l1, bool to_device, cudaStream_t st)
+    {
+        const cudaMemcpyKind kind = to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
+        while (l0 < l1) {
+            const int lb = l0 / cb, off = l0 - lb * cb;
+            const int gc = (lb * r.P + r.g) * cb + off;
+            const int nc = std::min(std::min(cb - off, l1 - l0), n - gc);
+            if (nc <= 0) break;
+            double *d = sh.A + (size_t)l0 * sh.ldA, *h = A + (size_t)gc * ldA;
+            if (to_device) SB_CUDA(cudaMemcpy2DAsync(d, (size_t)sh.ldA * 8, h, (size_t)ldA * 8, (size_t)n * 8, nc, kind, st));
+            else           SB_CUDA(cudaMemcpy2DAsync(h, (size_t)ldA * 8, d, (size_t)sh.ldA * 8, (size_t)n * 8, nc, kind, st));
+            l0 += nc;
+        }
+    }
+    // columns [c0, c1) of the rank's row slab of Q
+    void copy_q(int c0, int c1, bool to_device, cudaStream_t st)
+    {
+        if (sh.qrows <= 0 || c1 <= c0) return;
+        const cudaMemcpyKind kind = to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
+        double *d = sh.Q + (size_t)c0 * sh.ldQ, *h = Q + (size_t)c0 * ldQ + sh.q0;
+        if (to_device) SB_CUDA(cudaMemcpy2DAsync(d, (size_t)sh.ldQ * 8, h, (size_t)ldQ * 8, (size_t)sh.qrows * 8, c1 - c0, kind, st));
+        else           SB_CUDA(cudaMemcpy2DAsync(h, (size_t)ldQ * 8, d, (size_t)sh.ldQ * 8, (size_t)sh.qrows * 8, c1 - c0, kind, st));
+    }
+    void upload()
+    {
+        copy_a(0, sh.ncols, true, r.stream);
+        copy_q(0, n, true, overlap ? r.copy : r.stream);
+        if (overlap) SB_CUDA(cudaEventRecord(r.ev_q_up, r.copy));
+        SB_CUDA(cudaStreamSynchronize(r.stream));
+    }
+    void before_q(cudaStream_t s) override
+    {
+        if (overlap) SB_CUDA(cudaStreamWaitEvent(s, r.ev_q_up, 0));
+    }
+    void send_back(int final_cols, cudaStream_t st)
+    {
+        const ColMap cm{r.P, r.g, cb};
+        const int a1 = std::min(sh.ncols, cm.lower(std::min(final_cols, n)));
+        if (a1 > a_done) { copy_a(a_done, a1, false, st); a_done = a1; }
+        const int q1 = std::min(n, final_cols + 1);
+        if (q1 > q_done) { copy_q(q_done, q1, false, st); q_done = q1; }
+    }
+    void panel_done(cudaStream_t s, int final_cols) override
+    {
+        if (!overlap) return;
+        SB_CUDA(cudaEventRecord(r.ev_cols_final, s));
+        SB_CUDA(cudaStreamWaitEvent(r.copy, r.ev_cols_final, 0));
+        send_back(final_cols, r.copy);
+    }
+    // after the reduction (its streams are idle): whatever is still on the device
+    void finish()
+    {
+        cudaStream_t st = overlap ? r.copy : r.stream;
+        a_done = std::min(a_done, sh.ncols);
+        copy_a(a_done, sh.ncols, false, st); a_done = sh.ncols;
+        copy_q(q_done, n, false, st); q_done = n;
+        SB_CUDA(cudaStreamSynchronize(st));
+    }
+};
+
+static bool page_locked(const void *p)
 {
-    const cudaMemcpyKind kind = to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
-    const int cb = r.P == 1 ? std::max(n, 1) : r.cb;
-    for (int lb = 0; lb * cb < sh.ncols; lb++) {
-        const int gc = (lb * r.P + r.g) * cb, nc = std::min(cb, n - gc);
-        double *d = sh.A + (size_t)lb * cb * sh.ldA, *h = A + (size_t)gc * ldA;
-        if (to_device) SB_CUDA(cudaMemcpy2DAsync(d, (size_t)sh.ldA * 8, h, (size_t)ldA * 8, (size_t)n * 8, nc, kind, r.stream));
-        else           SB_CUDA(cudaMemcpy2DAsync(h, (size_t)ldA * 8, d, (size_t)sh.ldA * 8, (size_t)n * 8, nc, kind, r.stream));
-    }
-    if (sh.qrows > 0) {
-        double *h = Q + sh.q0;
-        if (to_device) SB_CUDA(cudaMemcpy2DAsync(sh.Q, (size_t)sh.ldQ * 8, h, (size_t)ldQ * 8, (size_t)sh.qrows * 8, n, kind, r.stream));
-        else           SB_CUDA(cudaMemcpy2DAsync(h, (size_t)ldQ * 8, sh.Q, (size_t)sh.ldQ * 8, (size_t)sh.qrows * 8, n, kind, r.stream));
-    }
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return attr.type == cudaMemoryTypeHost;
 }
 
 struct HostTimes { double h2d_ms = 0, d2h_ms = 0; long long h2d_bytes = 0, d2h_bytes = 0; };
@@ -73,15 +143,18 @@ struct HostTimes { double h2d_ms = 0, d2h_ms = 0; long long h2d_bytes = 0, d2h_b
 static void run_rank_host(Rank &r, Shard &sh, int n, int begin, int end, int nb, double *A, int ldA, double *Q, int ldQ, HostTimes *ht)
 {
     SB_CUDA(cudaSetDevice(r.device));
+    const char *e = getenv("STARNEIG_B200_STAGE_OVERLAP");
+    const bool overlap = (e ? atoi(e) != 0 : true) && page_locked(A) && page_locked(Q);
+    HostStage stage(r, sh, n, A, ldA, Q, ldQ, overlap);
     double t1 = wall_ms();
-    shard_copy(r, sh, n, A, ldA, Q, ldQ, true);
-    SB_CUDA(cudaStreamSynchronize(r.stream));
+    stage.upload();
     double t2 = wall_ms();
-    r.reduce(n, begin, end, nb, sh.A, sh.ldA, sh.Q, sh.ldQ, sh.qrows);
+    r.reduce(n, begin, end, nb, sh.A, sh.ldA, sh.Q, sh.ldQ, sh.qrows, &stage);
     double t3 = wall_ms();
-    shard_copy(r, sh, n, A, ldA, Q, ldQ, false);
-    SB_CUDA(cudaStreamSynchronize(r.stream));
+    stage.finish();
     double t4 = wall_ms();
+    // with overlap: h2d_ms is the upload of A alone (Q hides behind the first column loop) and d2h_ms is what is
+    // left of the write-back once the reduction has ended
     ht->h2d_ms = t2 - t1; ht->d2h_ms = t4 - t3;
     ht->h2d_bytes = ht->d2h_bytes = ((long long)sh.ncols * n + (long long)sh.qrows * n) * 8;
 }
