@@ -98,6 +98,55 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+class SharedHostMatrices:
+    """A and Q (n x ld, C order: row c = column c of the matrix) in one POSIX shared-memory file mapped and
+    page-locked by every rank process; falls back to private pinned arrays when /dev/shm is too small."""
+
+    def __init__(self, n, ld, rank, dist):
+        import numpy as np
+        import torch
+        self.rank, self.dist, self.path, self.registered = rank, dist, None, []
+        nbytes = 2 * n * ld * 8
+        ok = 0
+        if rank == 0:
+            try:
+                st = os.statvfs("/dev/shm")
+                ok = int(st.f_bavail * st.f_frsize > nbytes + (1 << 30))
+            except OSError:
+                ok = 0
+        flag = torch.tensor([ok], device="cuda")
+        dist.broadcast(flag, 0)
+        if int(flag.item()) == 0:
+            self.private = torch.empty((2, n, ld), dtype=torch.float64).pin_memory()
+            self.A, self.Q = self.private[0].numpy(), self.private[1].numpy()
+            return
+        self.path = "/dev/shm/starneig_b200_bench_%s_%d" % (os.environ.get("MASTER_PORT", "0"), os.getuid())
+        if rank == 0:
+            if os.path.exists(self.path):
+                os.unlink(self.path)
+            with open(self.path, "wb") as f:
+                f.truncate(nbytes)
+        dist.barrier()
+        self.map = np.memmap(self.path, dtype=np.float64, mode="r+", shape=(2, n, ld))
+        self.A, self.Q = self.map[0], self.map[1]
+        rt = torch.cuda.cudart()
+        for arr in (self.A, self.Q):
+            err = rt.cudaHostRegister(arr.ctypes.data, arr.nbytes, 0)
+            if int(err) != 0:
+                raise RuntimeError(f"cudaHostRegister of the shared host matrices failed: {err}")
+            self.registered.append(arr.ctypes.data)
+
+    def close(self):
+        import torch
+        rt = torch.cuda.cudart()
+        for ptr in self.registered:
+            rt.cudaHostUnregister(ptr)
+        self.registered = []
+        self.dist.barrier()
+        if self.path and self.rank == 0 and os.path.exists(self.path):
+            os.unlink(self.path)
+
+
 def cpu_reference_run(n, threads):
     """One reduction with the reference's CPU implementation on a fullpos matrix; returns (seconds, kind)."""
     from oracle.oracle import Oracle, Reference
@@ -262,16 +311,31 @@ def run_ours(args):
     # world == 1: starneig_SEP_SM_Hessenberg on pinned host arrays. world > 1: every rank process holds the host
     # matrices (same content) in pinned memory and moves ONLY its shards to its GPU and back inside the timed
     # region (starneig_b200_dist_hessenberg_host), so the bytes over PCIe add up to A + Q once in each direction.
-    gen = torch.Generator(device="cuda").manual_seed(2019)
-    hostA0 = torch.rand((n, ld), dtype=torch.float64, device="cuda", generator=gen).cpu()
-    pinned = torch.empty((2, n, ld), dtype=torch.float64).pin_memory()
-    hA, hQ = pinned[0].numpy().T, pinned[1].numpy().T         # column-major (ld x n) views
-    eye_diag = np.arange(n)
+    shm = None
+    if world == 1:
+        gen = torch.Generator(device="cuda").manual_seed(2019)
+        hostA0 = torch.rand((n, ld), dtype=torch.float64, device="cuda", generator=gen).cpu()
+        pinned = torch.empty((2, n, ld), dtype=torch.float64).pin_memory()
+        hA, hQ = pinned[0].numpy().T, pinned[1].numpy().T         # column-major (ld x n) views
+        eye_diag = np.arange(n)
 
-    def reset_host():
-        pinned[0].copy_(hostA0)
-        pinned[1].zero_()
-        hQ[eye_diag, eye_diag] = 1.0
+        def reset_host():
+            pinned[0].copy_(hostA0)
+            pinned[1].zero_()
+            hQ[eye_diag, eye_diag] = 1.0
+    else:
+        # ONE host copy of A and Q for all rank processes (POSIX shared memory, page-locked by every rank), as the
+        # C ABI words it: "host arrays holding the whole matrices in memory shared by the ranks". Each rank resets,
+        # uploads and writes back only its own shards.
+        shm = SharedHostMatrices(n, ld, rank, dist)
+        hA, hQ = shm.A.T, shm.Q.T
+        hA_t, hQ_t = torch.from_numpy(shm.A), torch.from_numpy(shm.Q)       # (n, ld): row c = column c of the matrix
+        cols_cpu = cols.cpu()
+
+        def reset_host():
+            hA_t[cols_cpu] = dA0.cpu()
+            hQ_t[:, q0:q0 + qrows] = 0.0
+            hQ_t.diagonal()[q0:q0 + qrows] = 1.0
 
     sn.set_profile_level(1)
     e2e_ms, h2d, d2h = [], 0, 0
@@ -295,6 +359,7 @@ def run_ours(args):
     else:
         assert float(np.abs(hA[gc0 + 2: n, gc0]).max()) == 0.0
         sdist.finalize()
+        shm.close()
     sn.starneig_node_finalize()
     if world > 1:
         dist.barrier()
@@ -363,7 +428,7 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"Hessenberg reduction with Q, random dense FP64 n={n} (BASELINE.json configs[2] at 1 GPU)",
+        "config": {"workload": f"Hessenberg reduction with Q, random dense FP64 n={n} (BASELINE.json configs[2] at {world} GPU{'s' if world > 1 else ''})",
                    "n": n, "panel_width": sn.default_panel_width(n), "ld": ld,
                    "l2": "inputs (A, Q: 2 x %.1f GB) are larger than the 126 MB L2; no explicit flush" % (n * ld * 8 / 1e9),
                    "parallelism": "1 GPU" if world == 1 else
