@@ -456,7 +456,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=20000)
+    ap.add_argument("--n", type=int, default=int(os.environ.get("STARNEIG_BENCH_N", "20000")))
     ap.add_argument("--cpu-n", type=int, default=CPU_SAMPLE_N)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
