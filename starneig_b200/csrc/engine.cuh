@@ -141,7 +141,7 @@ struct Workspace {
         ypart = alloc<double>(ypart_cap);
         s = alloc<double>(nbp); w2 = alloc<double>(nbp);
         colpart = alloc<double>((size_t)nbp * PANEL_LDB);
-        sqpart = alloc<double>(PANEL_LDB);
+        sqpart = alloc<double>(3 * PANEL_LDB);
         scal = alloc<ColScal>(nbp);
         counter = alloc<unsigned>(4);
         SB_CUDA(cudaMemset(counter, 0, 4 * sizeof(unsigned)));
@@ -417,7 +417,7 @@ struct Rank {
         // a few warps at least: they share the sum over the GEMV partials and hide latency
         while (tg.NW * tg.RS < 4 && tg.NW * (tg.RS + 1) <= 32 && tg.RS < 4) tg.RS++;
         g.smem_fu = (size_t)(2 * j + tg.nsub * 4 * tg.NW * 32 + 2 * tg.nsub * 32 + tg.RS * tg.NW * 32) * sizeof(double);
-        g.smem_rf = (size_t)(j + tg.nsub * tg.NW * 32 + tg.nsub * 32 + tg.RS * tg.NW * 32 + 32) * sizeof(double);
+        g.smem_rf = (size_t)(j + tg.nsub * tg.NW * 32 + tg.nsub * 32 + tg.RS * tg.NW * 32 + 96) * sizeof(double);
         if (g.smem_fu > PANEL_SMEM_MAX) fatal("matrix too large for the panel kernels' shared-memory layout", __FILE__, __LINE__);
         return g;
     }

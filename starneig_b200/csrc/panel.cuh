@@ -51,6 +51,42 @@ struct ColScal {        // DLARFG results for one column
 // 1-D block-cyclic column map: global column c lives on rank (c / cb) % P. The local columns
 // of a rank are ordered by global index, so any global column range [a, b) is the contiguous local range
 // [lower(a), lower(b)). P == 1 is the identity map.
+// ||x|| without overflow / underflow of the squares: Blue's three-accumulator scheme, the one LAPACK's dnrm2 uses
+// (the reference reaches dnrm2 through dlarfg_, src/hessenberg/cpu.c:140). Entries in the "medium" range
+// [2^-511, 2^486] -- all that occurs for sanely scaled matrices -- accumulate exactly like a plain sum of squares;
+// huge / tiny entries are scaled before they are squared and summed separately.
+constexpr double SUMSQ_TSML = 1.4916681462400413e-154, SUMSQ_TBIG = 1.9979190722022350e+146;
+constexpr double SUMSQ_SSML = 4.4989137945431964e+161, SUMSQ_SBIG = 1.1113793747425387e-162;
+struct SumSq {
+    double med, big, sml;
+    __device__ __forceinline__ void clear() { med = big = sml = 0.0; }
+    __device__ __forceinline__ void add(double x)
+    {
+        const double ax = fabs(x);
+        if (ax > SUMSQ_TBIG) { const double t = x * SUMSQ_SBIG; big = fma(t, t, big); }
+        else if (ax < SUMSQ_TSML) { const double t = x * SUMSQ_SSML; sml = fma(t, t, sml); }
+        else med = fma(x, x, med);          // NaN lands here as well
+    }
+};
+// the norm from the three totals (LAPACK 3.10 dnrm2)
+__device__ __forceinline__ double sumsq_norm(double med, double big, double sml)
+{
+    if (big > 0.0) {
+        if (med > 0.0 || med != med) big += (med * SUMSQ_SBIG) * SUMSQ_SBIG;
+        return sqrt(big) / SUMSQ_SBIG;
+    }
+    if (sml > 0.0) {
+        if (med > 0.0 || med != med) {
+            const double a = sqrt(med), b = sqrt(sml) / SUMSQ_SSML;
+            const double ymin = fmin(a, b), ymax = fmax(a, b);
+            const double q = ymin / ymax;
+            return ymax * sqrt(1.0 + q * q);
+        }
+        return sqrt(sml) / SUMSQ_SSML;
+    }
+    return sqrt(med);
+}
+
 struct ColMap {
     int P, g, cb;
     __host__ __device__ int l2g(int lc) const { return ((lc / cb) * P + g) * cb + lc % cb; }
@@ -109,7 +145,7 @@ struct PanelArgs {
     double *w2;         // nb
     double *colpart;    // PANEL_LDB x ldt  per-block partials of the column-wise dot products (column index contiguous)
     int ldt;
-    double *sqpart;     // PANEL_LDB
+    double *sqpart;     // 3 x PANEL_LDB: per-block sums of squares (medium, big, small range; see SumSq)
     ColScal *scal;      // nb
     unsigned *counter;  // zero-initialised
 };
@@ -390,7 +426,7 @@ __global__ void __launch_bounds__(MAXT) k_col_reflector(PanelArgs a, int j, doub
     double *red = w2_sh + j;                        // nsub * NW * 32
     double *pv = red + (size_t)nsub * NW * 32;      // nsub * 32
     double *colred = pv + nsub * 32;                // RS * NW * 32
-    double *sqred = colred + (size_t)RS * NW * 32;  // 32 (one per warp)
+    double *sqred = colred + (size_t)RS * NW * 32;  // 3 x 32 (one triple per warp)
     __shared__ double scale_sh;
 
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
@@ -424,7 +460,8 @@ __global__ void __launch_bounds__(MAXT) k_col_reflector(PanelArgs a, int j, doub
     __syncthreads();
 
     // ---- per-row epilogue
-    double sq = 0.0;
+    SumSq sq;
+    sq.clear();
     for (int sub = w; sub < nsub; sub += nwarps) {
         const int r = row0 + sub * 32 + lane;
         const bool valid = r < m;
@@ -440,11 +477,12 @@ __global__ void __launch_bounds__(MAXT) k_col_reflector(PanelArgs a, int j, doub
             if (r == j) a.scal[j].alpha = pp;
             if (r > j) x = pp;
         }
-        sq = fma(x, x, sq);
+        sq.add(x);
         pv[sub * 32 + lane] = x;
     }
-    sq = warp_sum(sq);
-    if (lane == 0) sqred[w] = sq;
+    sq.med = warp_sum(sq.med);
+    if (__any_sync(0xffffffffu, sq.big != 0.0 || sq.sml != 0.0)) { sq.big = warp_sum(sq.big); sq.sml = warp_sum(sq.sml); }
+    if (lane == 0) { sqred[w] = sq.med; sqred[32 + w] = sq.big; sqred[64 + w] = sq.sml; }
     __syncthreads();
 
     // ---- phase B: zpart[t] = sum over the block's rows > j of V(r,t) * p''(r)
@@ -478,23 +516,26 @@ __global__ void __launch_bounds__(MAXT) k_col_reflector(PanelArgs a, int j, doub
             a.colpart[(size_t)blockIdx.x * a.ldt + t0 + lane] = sum;
         }
     }
-    if (tid == 0) {
+    if (tid < 3) {
         double sum = 0.0;
-        for (int q = 0; q < nwarps; q++) sum += sqred[q];
-        a.sqpart[blockIdx.x] = sum;
+        for (int q = 0; q < nwarps; q++) sum += sqred[32 * tid + q];
+        a.sqpart[tid * PANEL_LDB + blockIdx.x] = sum;
     }
     if (last_block_done(a.counter, gridDim.x)) {
         if (w == 0) {
-            double acc = 0.0;
+            double acc[3] = {0.0, 0.0, 0.0};
 #pragma unroll
-            for (int q = 0; q < PANEL_LDB / 32; q++) {
-                int b = lane + 32 * q;
-                acc += b < (int)gridDim.x ? __ldcg(a.sqpart + b) : 0.0;
-            }
-            const double ssq = warp_sum(acc);
+            for (int k = 0; k < 3; k++)
+#pragma unroll
+                for (int q = 0; q < PANEL_LDB / 32; q++) {
+                    int b = lane + 32 * q;
+                    acc[k] += b < (int)gridDim.x ? __ldcg(a.sqpart + k * PANEL_LDB + b) : 0.0;
+                }
+#pragma unroll
+            for (int k = 0; k < 3; k++) acc[k] = warp_sum(acc[k]);
             if (lane == 0) {
                 const double alpha = __ldcg(&a.scal[j].alpha);
-                const double xnorm = sqrt(ssq);
+                const double xnorm = sumsq_norm(acc[0], acc[1], acc[2]);
                 double tau = 0.0, beta = alpha, scale = 0.0;
                 if (m - j > 1 && xnorm != 0.0) {
                     beta = -copysign(hypot(alpha, xnorm), alpha);

@@ -92,6 +92,26 @@ __device__ __forceinline__ double sum_over_ctas(const double *part, size_t ldt, 
     return warp_sum(acc);
 }
 
+// the same for three arrays part + k*stride (unit stride inside each), all loads in flight together
+__device__ __forceinline__ void sum3_over_ctas(const double *part, int stride, int nblk, int lane, double (&out)[3])
+{
+    double acc[3] = {0.0, 0.0, 0.0};
+    for (int b0 = 0; b0 < nblk; b0 += 160) {
+        double x[3][5];
+#pragma unroll
+        for (int k = 0; k < 3; k++)
+#pragma unroll
+            for (int u = 0; u < 5; u++) {
+                const int bb = b0 + lane + 32 * u;
+                x[k][u] = bb < nblk ? __ldcg(part + k * stride + bb) : 0.0;
+            }
+#pragma unroll
+        for (int k = 0; k < 3; k++) acc[k] += ((x[k][0] + x[k][1]) + (x[k][2] + x[k][3])) + x[k][4];
+    }
+#pragma unroll
+    for (int k = 0; k < 3; k++) out[k] = warp_sum(acc[k]);
+}
+
 __device__ __forceinline__ void group_barrier(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
 // split of the GEMV over 128-thread groups: items = (row block, local column) pairs in row-block-major order
@@ -227,7 +247,7 @@ struct FusedSmem {
         red = o;   o += nsub * 3 * NW * 32;
         pv = o;    o += nsub * 32;
         ysm = o;   o += nsub * 32;
-        sqred = o; o += FUSED_WARPS;
+        sqred = o; o += 3 * FUSED_WARPS;
         total = o;
     }
 };
@@ -392,7 +412,8 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_panel_fused(FusedArgs f)
                 }
             }
             __syncthreads();
-            double sq = 0.0;
+            SumSq sq;
+            sq.clear();
             for (int sub = wp; sub < nsub; sub += FUSED_WARPS) {
                 const int r = row0 + sub * 32 + lane;
                 const bool valid = r < m;
@@ -409,17 +430,19 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_panel_fused(FusedArgs f)
                     if (r == j) a.scal[j].alpha = pp;
                     if (r > j) xx = pp;
                 }
-                sq = fma(xx, xx, sq);
+                sq.add(xx);
                 pv[sub * 32 + lane] = xx;
             }
-            sq = warp_sum(sq);
-            if (lane == 0) sqred[wp] = sq;
+            // huge / tiny entries (SumSq) are rare: their sums only cost a vote when there are none
+            sq.med = warp_sum(sq.med);
+            if (__any_sync(0xffffffffu, sq.big != 0.0 || sq.sml != 0.0)) { sq.big = warp_sum(sq.big); sq.sml = warp_sum(sq.sml); }
+            if (lane == 0) { sqred[wp] = sq.med; sqred[FUSED_WARPS + wp] = sq.big; sqred[2 * FUSED_WARPS + wp] = sq.sml; }
             __syncthreads();
             if (j > 0) coldots_all(a.V, ld, j, row0, m, nsub, pv, wp, FUSED_WARPS, lane, a.colpart + (size_t)b * a.ldt);
-            if (tid == 0) {
+            if (tid < 3) {
                 double sum = 0.0;
-                for (int q = 0; q < FUSED_WARPS; q++) sum += sqred[q];
-                a.sqpart[b] = sum;
+                for (int q = 0; q < FUSED_WARPS; q++) sum += sqred[tid * FUSED_WARPS + q];
+                a.sqpart[tid * PANEL_LDB + b] = sum;
             }
             grid_barrier(f.gbar, gen);
             SB_PHASE_MARK(2);
@@ -431,9 +454,10 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_panel_fused(FusedArgs f)
             const int t_first = b * FUSED_WARPS + wp;
             double zsum = 0.0, vjt = 0.0;
             if (t_first < j) { zsum = sum_over_ctas(a.colpart + t_first, a.ldt, nblk, lane); vjt = __ldcg(a.V + (size_t)t_first * ld + j); }
-            const double ssq = sum_over_ctas(a.sqpart, 1, nblk, lane);
+            double ssq[3];
+            sum3_over_ctas(a.sqpart, PANEL_LDB, nblk, lane, ssq);
             const double alpha = __ldcg(&a.scal[j].alpha);
-            const double xnorm = sqrt(ssq);
+            const double xnorm = sumsq_norm(ssq[0], ssq[1], ssq[2]);
             double tau = 0.0, beta = alpha, scale = 0.0;
             if (m - j > 1 && xnorm != 0.0) {
                 beta = -copysign(hypot(alpha, xnorm), alpha);

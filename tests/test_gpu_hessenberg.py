@@ -144,6 +144,26 @@ def test_device_resident_matches_host_api(node, ora):
     assert node.lib().starneig_b200_hessenberg_device(n, 0, n, -1, Ad.data_ptr(), ld, Qd.data_ptr(), n + 1) in (-8,)
 
 
+@pytest.mark.parametrize("fused", [1, 0])
+@pytest.mark.parametrize("e", [600, -600])
+def test_extreme_scaling(node, ora, monkeypatch, e, fused):
+    # The reference forms its reflectors with LAPACK dlarfg_ (src/hessenberg/cpu.c:140), whose dnrm2 / dlapy2 neither
+    # overflow nor underflow: a matrix scaled by 2^+-600 (squares of its entries are inf / 0 in FP64) reduces to the
+    # scaled H and the same Q. Both panel paths: the persistent kernel and the three-kernels-per-column one.
+    monkeypatch.setenv("STARNEIG_B200_FUSED_PANEL", str(fused))
+    n, pw = 333, 45
+    A0, Q0, ld = ora.full(n, 7)
+    s = 2.0 ** e
+    A, Q = (A0 * s).copy(order="F"), Q0.copy(order="F")
+    assert _run(node, n, A, ld, Q, pw=pw) == 0
+    A2, Q2 = (A0 * s).copy(order="F"), Q0.copy(order="F")
+    assert ora.hessenberg_port(n, A2, ld, Q2, ld, 0, n, pw) == 0
+    A /= s
+    A2 /= s          # exact: s is a power of two
+    _check_entrywise(n, A, Q, A2, Q2)
+    _check_invariants(ora, n, A, Q, A0, ld)
+
+
 def test_downstream_eigenvalues(node, ora):
     # config 5 of BASELINE.json at test size: GPU Hessenberg -> dhseqr (stand-in for starneig_SEP_SM_Schur)
     # vs the all-CPU chain (oracle Hessenberg -> dhseqr); tolerance 1e-10 * ||A||

@@ -115,6 +115,20 @@ def test_port_nonidentity_q(ora):
     assert ora.orthogonality_u(n, Q, ld) < 500
 
 
+@pytest.mark.parametrize("e", [600, -600])
+def test_port_is_scale_invariant(ora, e):
+    # dlarfg_ (dnrm2 + dlapy2) never squares an entry unscaled: scaling A by a power of two scales H exactly
+    n, pw = 200, 35
+    A0, Q0, ld = ora.full(n, 7)
+    A1, Q1 = A0.copy(order="F"), Q0.copy(order="F")
+    assert ora.hessenberg_port(n, A1, ld, Q1, ld, 0, n, pw) == 0
+    s = 2.0 ** e
+    A2, Q2 = (A0 * s).copy(order="F"), Q0.copy(order="F")
+    assert ora.hessenberg_port(n, A2, ld, Q2, ld, 0, n, pw) == 0
+    assert np.isfinite(A2).all()
+    assert np.array_equal(A2 / s, A1) and np.array_equal(Q2, Q1)
+
+
 def test_eigenvalues_preserved(ora):
     n = 150
     A0, Q0, ld = ora.full(n, 8)
