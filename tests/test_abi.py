@@ -128,3 +128,8 @@ def test_product_never_touches_the_oracle():
     from starneig_b200._lib import LIB_PATH
     needed = subprocess.run(["readelf", "-d", LIB_PATH], capture_output=True, text=True).stdout
     assert "openblas" not in needed.lower() and "liboracle" not in needed.lower()
+    # the C test driver is a client of the library and of a CPU BLAS (for its residual checks), never of the oracle
+    driver = os.path.join(ROOT, "driver", "bin", "starneig-test")
+    if os.path.exists(driver):
+        needed = subprocess.run(["readelf", "-d", driver], capture_output=True, text=True).stdout
+        assert "liboracle" not in needed.lower() and "libstarneig_ref" not in needed.lower()
