@@ -6,9 +6,11 @@ A "step" is one full reduction (with Q) of a random dense n x n FP64 matrix.
             (starneig_b200_hessenberg_device); time = CUDA events on the launching stream.
   e2e       the reference-facing call starneig_SEP_SM_Hessenberg(n, A, ldA, Q, ldQ) on pinned HOST
             buffers: H2D of A and Q, the reduction and D2H of H and Q are all inside the timed region.
-  roofline  the dominant kernel (k_col_gemv, the trailing-matrix GEMV): algorithmic bytes (8 * rows * cols
-            per launch) / mean launch duration from CUDA events recorded around every launch during the
-            timed steps, against the measured HBM copy bandwidth in MEASURED_PEAKS.json.
+  roofline  the dominant kernel (k_panel_fused: one persistent launch per panel that streams the trailing matrix
+            once per panel column): algorithmic GEMV bytes of a launch (sum over its columns of 8 * rows * cols)
+            / mean launch duration from CUDA events recorded around every launch during the timed steps, against
+            the measured HBM copy bandwidth in MEASURED_PEAKS.json. (With STARNEIG_B200_FUSED_PANEL=0 the
+            per-column k_col_gemv launches are the dominant kernel and are reported instead.)
   cpu_baseline  the reference's own CPU sources (oracle/_ref, sequential StarPU stand-in + threaded
             OpenBLAS) -- or the oracle port when _ref is absent -- on a bounded sample.
 `--impl reference` times that CPU implementation instead and prints the same JSON line.
@@ -30,9 +32,13 @@ CPU_SAMPLE_N = 4000          # bounded CPU sample (~10-20 s on the box's cores)
 FALLBACK_HBM_GBS = 6650.0    # /opt/skills/guides/B200_PROFILING.md fallback
 FP64_DMMA_TFLOPS = 37.0      # measured DMMA issue peak (profiles/r1_probe_peaks.log)
 FP64_CUBLAS_TFLOPS = 35.7    # measured cublasDgemm 8192^3 (profiles/r1_probe_peaks.log)
-# dram__bytes_read.sum + dram__bytes_write.sum per k_col_gemv launch from the ncu --set full capture
-# (profiles/), relative to the algorithmic bytes of that launch; None until captured.
-GEMV_TRAFFIC_RATIO = 1.0015   # profiles/r1_ncu_full_baseline.txt: 3.1807 GB DRAM vs 3.1757 GB algorithmic
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full captures (profiles/), relative to
+# the algorithmic GEMV bytes of that launch.
+# k_panel_fused (profiles/r1_s4_ncu_full_fused_and_dgemm.txt, panel i=624): 944.8 GB DRAM vs 929.5 GB algorithmic; the
+# extra 1.6 % is the level-2 side traffic of the panel (Y, V, VT re-read per column once they no longer fit in L2)
+FUSED_TRAFFIC_RATIO = 1.016
+# k_col_gemv alone (profiles/r1_ncu_full_baseline.txt): 3.1807 GB DRAM vs 3.1757 GB algorithmic
+GEMV_TRAFFIC_RATIO = 1.0015
 
 
 def flops(n):
@@ -382,7 +388,7 @@ def run_ours(args):
         roofline = {
             "bound": "hbm", "kernel": "k_panel_fused", "achieved": achieved, "peak": peak, "unit": "GB/s",
             "frac": achieved / peak,
-            "traffic": GEMV_TRAFFIC_RATIO * bytes_per_launch if GEMV_TRAFFIC_RATIO else None,
+            "traffic": FUSED_TRAFFIC_RATIO * bytes_per_launch if FUSED_TRAFFIC_RATIO else None,
             "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind})",
             "algorithmic_bytes_per_launch": bytes_per_launch, "launches_per_step": panels // args.steps,
             "mean_launch_us": 1e3 * phase[0] / panels,
