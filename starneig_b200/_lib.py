@@ -38,12 +38,16 @@ class Stats(ctypes.Structure):
         return {name: (list(getattr(self, name)) if name == "fused_phase_ms" else getattr(self, name)) for name, _ in self._fields_}
 
 
-def load():
-    if not os.path.exists(LIB_PATH):
-        raise ImportError(
-            f"{LIB_PATH} is missing: build it with `make -C starneig_b200/csrc` "
-            "(or __graft_entry__.build()). There is no CPU fallback for the Hessenberg path.")
-    lib = ctypes.CDLL(LIB_PATH, mode=ctypes.RTLD_LOCAL)
+def load(path=None):
+    """Binds the C ABI. `path` is only given by tests/test_cusim.py, which binds the same entry points of the
+    kernel-logic emulator build of the library (tests/cusim); the product always loads LIB_PATH."""
+    if path is None:
+        path = LIB_PATH
+        if not os.path.exists(path):
+            raise ImportError(
+                f"{LIB_PATH} is missing: build it with `make -C starneig_b200/csrc` "
+                "(or __graft_entry__.build()). There is no CPU fallback for the Hessenberg path.")
+    lib = ctypes.CDLL(path, mode=ctypes.RTLD_LOCAL)
     i, d, vp = ctypes.c_int, ctypes.c_double, ctypes.c_void_p
 
     lib.starneig_node_init.argtypes = [i, i, ctypes.c_uint]

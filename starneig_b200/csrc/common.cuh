@@ -4,6 +4,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstdint>
+#ifdef SB_CUSIM
+#include "cusim_device.h"       // tests/cusim/include: the emulator's versions of the hardware primitives below
+#endif
 
 namespace sb200 {
 
@@ -22,6 +25,80 @@ namespace sb200 {
         if (err__ != cudaSuccess)                                            \
             ::sb200::fatal(cudaGetErrorString(err__), __FILE__, __LINE__);   \
     } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// Hardware primitives. Everything that is inline PTX or launch syntax lives here, in one place. With
+// -DSB_CUSIM (tests/cusim: the kernel-logic emulator of the test suite, never part of the product) the same
+// names are provided by cusim_device.h on top of host threads/fibers, so that the kernels and the engine can
+// be compiled unchanged by g++ and stepped through on a machine without a GPU.
+// ---------------------------------------------------------------------------------------------
+#ifndef SB_CUSIM
+#define SB_DYNAMIC_SMEM(type, name) extern __shared__ type name[]
+#define SB_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+// cooperative launch (all CTAs co-resident) of a kernel that takes one argument
+#define SB_LAUNCH_COOP(kernel, grid, block, smem, stream, arg)                                           \
+    do {                                                                                                 \
+        void *args__[] = {(void *)&(arg)};                                                               \
+        SB_CUDA(cudaLaunchCooperativeKernel((const void *)kernel, dim3(grid), dim3(block), args__, (smem), (stream))); \
+    } while (0)
+
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned *p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void red_release_gpu_add(unsigned *p, unsigned v)
+{
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned *p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned *p, unsigned v)
+{
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// 16-byte volatile accesses (one transaction each): the carriers of the "LL" exchange entries
+__device__ __forceinline__ uint4 ld_volatile_v4(const uint4 *p)
+{
+    uint4 e;
+    asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(e.x), "=r"(e.y), "=r"(e.z), "=r"(e.w) : "l"(p) : "memory");
+    return e;
+}
+__device__ __forceinline__ void st_volatile_v4(uint4 *p, uint4 e)
+{
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(e.x), "r"(e.y), "r"(e.z), "r"(e.w) : "memory");
+}
+// named barrier `id` (1..15) over `nthreads` threads of the CTA
+__device__ __forceinline__ void group_barrier(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+__device__ __forceinline__ unsigned long long globaltimer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// 8-byte asynchronous global -> shared copy; !valid: the 8 destination bytes are zero-filled (src-size 0)
+__device__ __forceinline__ void cp_async8(void *smem_dst, const void *gmem_src, bool valid)
+{
+    unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+    int src_size = valid ? 8 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(dst), "l"(gmem_src), "r"(src_size));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+// FP64 tensor-core instruction (SASS DMMA.8x8x4): C(8x8) += A(8x4) B(4x8); lane l holds A[l/4][l%4], B[l%4][l/4],
+// C[l/4][2*(l%4) + {0,1}]
+__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+#endif
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline int round_up(int a, int b) { return ceil_div(a, b) * b; }

@@ -25,21 +25,6 @@ namespace sb200 {
 
 constexpr int GEMM_BK = 16;
 
-__device__ __forceinline__ void cp_async8(void *smem_dst, const void *gmem_src, bool valid)
-{
-    unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
-    int src_size = valid ? 8 : 0;      // src_size 0 => the 8 destination bytes are zero-filled
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(dst), "l"(gmem_src), "r"(src_size));
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
-
-__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b)
-{
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
-}
-
 template <bool KMAJOR, int BX> struct OperandTile {
     // shared-memory footprint of one stage, in doubles; strides are == 4 (mod 16) doubles so that the
     // 16 lanes of a half-warp (4 k-values x 4 rows) hit 16 distinct 8-byte banks
@@ -159,7 +144,7 @@ dgemm_kernel(int M, int N, int K, double alpha, const double *__restrict__ A, in
     using TA = OperandTile<AK, BM>;
     using TB = OperandTile<BKM, BN>;
     constexpr int STAGE = TA::SIZE + TB::SIZE;
-    extern __shared__ double smem[];
+    SB_DYNAMIC_SMEM(double, smem);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = warp % WM, wn = warp / WM;
@@ -183,7 +168,7 @@ dgemm_kernel(int M, int N, int K, double alpha, const double *__restrict__ A, in
         for (int e = tid; e < BN * LINES_PER_COL; e += NT) {
             int col = e / LINES_PER_COL, r = (e % LINES_PER_COL) * 16;
             if (n0 + col < N && m0 + r < M)
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(C + (size_t)(n0 + col) * ldc + m0 + r));
+                prefetch_l2(C + (size_t)(n0 + col) * ldc + m0 + r);
         }
     }
 
@@ -287,8 +272,8 @@ struct GemmConfig {
                        int ldb, double beta, double *C, int ldc, int splits, int klen, size_t split_stride)
     {
         dim3 grid(ceil_div(M, BM), ceil_div(N, BN), splits);
-        dgemm_kernel<AK, BKM, WM, WN, MB, NB, STAGES, MINB><<<grid, NT, SMEM, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc,
-                                                                              klen, split_stride);
+        SB_LAUNCH((dgemm_kernel<AK, BKM, WM, WN, MB, NB, STAGES, MINB>), grid, NT, SMEM, st, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc,
+                  klen, split_stride);
     }
 };
 

@@ -361,7 +361,7 @@ struct Rank {
         stats.kernel_launches++;
         if (splits > 1) {
             dim3 grid(ceil_div(M, 256), N);
-            splitk_reduce_kernel<<<grid, 256, 0, st>>>(M, N, splits, out, ldc, stride, C, ldc);
+            SB_LAUNCH(splitk_reduce_kernel, grid, 256, 0, st, M, N, splits, out, ldc, stride, C, ldc);
             stats.kernel_launches++;
         }
     }
@@ -426,8 +426,8 @@ struct Rank {
     {
         PanelGrid pg = panel_grid(pa.m, j, j);
         const int threads = 32 * pg.tg.NW * pg.tg.RS;
-        if (threads <= 512) k_col_finish_update<512><<<pg.blocks, threads, pg.smem_fu, stream>>>(pa, j, S, yin, acol, do_update, pg.tg, yw);
-        else                k_col_finish_update<1024><<<pg.blocks, threads, pg.smem_fu, stream>>>(pa, j, S, yin, acol, do_update, pg.tg, yw);
+        if (threads <= 512) SB_LAUNCH((k_col_finish_update<512>), pg.blocks, threads, pg.smem_fu, stream, pa, j, S, yin, acol, do_update, pg.tg, yw);
+        else                SB_LAUNCH((k_col_finish_update<1024>), pg.blocks, threads, pg.smem_fu, stream, pa, j, S, yin, acol, do_update, pg.tg, yw);
         stats.kernel_launches++;
     }
 
@@ -435,8 +435,8 @@ struct Rank {
     {
         PanelGrid pg = panel_grid(pa.m, j, j);
         const int threads = 32 * pg.tg.NW * pg.tg.RS;
-        if (threads <= 512) k_col_reflector<512><<<pg.blocks, threads, pg.smem_rf, stream>>>(pa, j, acol, pg.tg);
-        else                k_col_reflector<1024><<<pg.blocks, threads, pg.smem_rf, stream>>>(pa, j, acol, pg.tg);
+        if (threads <= 512) SB_LAUNCH((k_col_reflector<512>), pg.blocks, threads, pg.smem_rf, stream, pa, j, acol, pg.tg);
+        else                SB_LAUNCH((k_col_reflector<1024>), pg.blocks, threads, pg.smem_rf, stream, pa, j, acol, pg.tg);
         stats.kernel_launches++;
     }
 
@@ -477,9 +477,8 @@ struct Rank {
             if (smem <= PANEL_SMEM_MAX) {
                 if (P > 1) y_epoch += w;
                 SB_CUDA(cudaMemsetAsync(ws.gbar, 0, 1024 * sizeof(unsigned), st));
-                void *args[] = {&f};
-                const void *fn = P > 1 ? (const void *)k_panel_fused<true> : (const void *)k_panel_fused<false>;
-                SB_CUDA(cudaLaunchCooperativeKernel(fn, dim3(ctas), dim3(FUSED_THREADS), args, smem, st));
+                if (P > 1) SB_LAUNCH_COOP(k_panel_fused<true>, ctas, FUSED_THREADS, smem, st, f);
+                else       SB_LAUNCH_COOP(k_panel_fused<false>, ctas, FUSED_THREADS, smem, st, f);
                 stats.kernel_launches++;
                 stats.fused_panels++;
                 for (int j = 0; j < w; j++) {
@@ -512,12 +511,12 @@ struct Rank {
             GemvPlan gp = plan_gemv(base, m, nloc, pa.ldp);
             size_t sh = (size_t)gp.kc * sizeof(double);
             if (P == 1) {
-                k_col_gemv<false><<<gp.RB * gp.S, GEMV_THREADS, sh, st>>>(pa, j, ncols, cm, lc0, nloc, c + 1, gp.A0, ldA, gp.skip,
+                SB_LAUNCH((k_col_gemv<false>), gp.RB * gp.S, GEMV_THREADS, sh, st, pa, j, ncols, cm, lc0, nloc, c + 1, gp.A0, ldA, gp.skip,
                                                                            gp.kc, gp.RB, gp.S, acol, x);
                 S_prev = gp.S;
             } else {
                 x.epoch = ++y_epoch;
-                k_col_gemv<true><<<gp.RB * gp.S, GEMV_THREADS, sh, st>>>(pa, j, ncols, cm, lc0, nloc, c + 1, gp.A0, ldA, gp.skip,
+                SB_LAUNCH((k_col_gemv<true>), gp.RB * gp.S, GEMV_THREADS, sh, st, pa, j, ncols, cm, lc0, nloc, c + 1, gp.A0, ldA, gp.skip,
                                                                           gp.kc, gp.RB, gp.S, acol, x);
                 const int par = x.epoch & 1;
                 S_prev = P;
@@ -541,7 +540,7 @@ struct Rank {
         if (P == 1) return;
         BarPtrs b;
         for (int s = 0; s < MAX_RANKS; s++) b.p[s] = s < P ? at<unsigned>(s, al.off_bar) : nullptr;
-        k_barrier<<<1, MAX_RANKS, 0, stream>>>(P, g, ++bar_epoch, b, at<unsigned>(g, al.off_status));
+        SB_LAUNCH(k_barrier, 1, MAX_RANKS, 0, stream, P, g, ++bar_epoch, b, at<unsigned>(g, al.off_status));
         stats.kernel_launches++;
     }
 
@@ -626,14 +625,14 @@ struct Rank {
                 // gather the panel on every rank; the first barrier protects Pan and Wx of the previous panel
                 barrier();
                 if (pl1 > pl0) {
-                    k_panel_push<<<dim3(ceil_div(m, 1024), pl1 - pl0), 256, 0, st>>>(cm, i, pl0, m, A, ldA, panp, al.ldv);
+                    SB_LAUNCH(k_panel_push, dim3(ceil_div(m, 1024), pl1 - pl0), 256, 0, st, cm, i, pl0, m, A, ldA, panp, al.ldv);
                     stats.kernel_launches++;
                 }
                 barrier();
                 double *pan = panp.p[g];
                 panel_factor(cm, i, end, w, A, ldA, pan, al.ldv, V, ws.Y, VT, ld, ctas);
                 if (pl1 > pl0) {
-                    k_panel_pull<<<dim3(std::min(64, ceil_div(m, 256)), pl1 - pl0), 256, 0, st>>>(cm, i, pl0, m, A, ldA, pan, al.ldv);
+                    SB_LAUNCH(k_panel_pull, dim3(std::min(64, ceil_div(m, 256)), pl1 - pl0), 256, 0, st, cm, i, pl0, m, A, ldA, pan, al.ldv);
                     stats.kernel_launches++;
                 }
             }
@@ -647,7 +646,7 @@ struct Rank {
             if (P > 1) {
                 Vg = ws.Vg; VTg = ws.VTg;
                 if (ncl > 0) {
-                    k_gather_rows<<<dim3(ceil_div(ncl, 128), w), 128, 0, st>>>(cm, cl0, ncl, i + 1, w, V, VT, ld, ws.Vg, ws.VTg, ldg);
+                    SB_LAUNCH(k_gather_rows, dim3(ceil_div(ncl, 128), w), 128, 0, st, cm, cl0, ncl, i + 1, w, V, VT, ld, ws.Vg, ws.VTg, ldg);
                     stats.kernel_launches++;
                 }
             }
@@ -674,7 +673,7 @@ struct Rank {
                 } else {
                     gemm(GEMM_NN, i + 1, w, ncl, 1.0, X, ldA, VTg, ldg, 0.0, wxp.p[g], al.ldv);
                     barrier();
-                    k_sum_peers<<<dim3(ceil_div(i + 1, 256), w), 256, 0, st>>>(P, i + 1, wxp, al.ldv, ws.W, ld);
+                    SB_LAUNCH(k_sum_peers, dim3(ceil_div(i + 1, 256), w), 256, 0, st, P, i + 1, wxp, al.ldv, ws.W, ld);
                     stats.kernel_launches++;
                     gemm(GEMM_NT, i + 1, ncl, w, -1.0, ws.W, ld, Vg, ldg, 1.0, X, ldA);
                 }

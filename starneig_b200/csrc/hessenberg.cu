@@ -627,7 +627,7 @@ int starneig_b200_gemv(int m, int k, const double *dA, int lda, const double *dv
     double *scratch_col = nullptr;
     SB_CUDA(cudaMalloc(&scratch_col, (size_t)(big + 16) * sizeof(double)));
     PanelArgs pa = r.make_panel_args(m, ws.V, ws.Y, ws.VT, ws.ldv);
-    k_set_gemv_inputs<<<ceil_div(k, 256), 256, 0, st>>>(ws.scal, ws.pcol, dv, k);
+    SB_LAUNCH(k_set_gemv_inputs, ceil_div(k, 256), 256, 0, st, ws.scal, ws.pcol, dv, k);
     GemvPlan gp = r.plan_gemv(dA, m, k, pa.ldp);
     const ColMap cm{1, 0, std::max(k, 1)};
     Xchg x = r.make_xchg();
@@ -637,11 +637,11 @@ int starneig_b200_gemv(int m, int k, const double *dA, int lda, const double *dv
     if (reps < 1) reps = 1;
     for (int it = 0; it < reps + 1; it++) {
         if (it == 1) SB_CUDA(cudaEventRecord(e0, st));
-        k_col_gemv<false><<<gp.RB * gp.S, GEMV_THREADS, sh, st>>>(pa, 0, k, cm, 0, k, 0, gp.A0, lda, gp.skip, gp.kc, gp.RB, gp.S,
+        SB_LAUNCH((k_col_gemv<false>), gp.RB * gp.S, GEMV_THREADS, sh, st, pa, 0, k, cm, 0, k, 0, gp.A0, lda, gp.skip, gp.kc, gp.RB, gp.S,
                                                                    scratch_col, x);
     }
     SB_CUDA(cudaEventRecord(e1, st));
-    k_sum_partials<<<ceil_div(m, 256), 256, 0, st>>>(m, gp.S, ws.ypart, pa.ldp, dy);
+    SB_LAUNCH(k_sum_partials, ceil_div(m, 256), 256, 0, st, m, gp.S, ws.ypart, pa.ldp, dy);
     SB_CUDA(cudaStreamSynchronize(st));
     SB_CUDA(cudaGetLastError());
     float ms = 0.f;

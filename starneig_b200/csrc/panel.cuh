@@ -110,16 +110,6 @@ struct Xchg {
     unsigned *status;           // local: set to non-zero when a wait timed out
 };
 
-__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned *p)
-{
-    unsigned v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_sys(unsigned *p, unsigned v)
-{
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
 // spin until *p has reached `want` (acquire; sequence numbers, wrap-around safe); gives up after ~4 s and
 // reports through *status. ">=": a peer that already left a barrier may have announced the next one.
 __device__ __forceinline__ bool flag_reached(const unsigned *p, unsigned want) { return (int)(ld_acquire_sys(p) - want) >= 0; }
@@ -257,7 +247,7 @@ template <int MAXT>
 __global__ void __launch_bounds__(MAXT) k_col_finish_update(PanelArgs a, int j, int S, const double *__restrict__ yin,
                                                             double *__restrict__ acol, int do_update, TileGeom tg, YWait yw)
 {
-    extern __shared__ double sh[];
+    SB_DYNAMIC_SMEM(double, sh);
     const int jm1 = j - 1;
     const int NW = tg.NW, RS = tg.RS, nsub = tg.nsub;
     const int nwarps = NW * RS;
@@ -419,7 +409,7 @@ __global__ void __launch_bounds__(MAXT) k_col_finish_update(PanelArgs a, int j, 
 template <int MAXT>
 __global__ void __launch_bounds__(MAXT) k_col_reflector(PanelArgs a, int j, double *__restrict__ acol, TileGeom tg)
 {
-    extern __shared__ double sh[];
+    SB_DYNAMIC_SMEM(double, sh);
     const int NW = tg.NW, RS = tg.RS, nsub = tg.nsub;
     const int nwarps = NW * RS;
     double *w2_sh = sh;                             // j
@@ -575,7 +565,7 @@ __global__ void __launch_bounds__(GEMV_THREADS, 10) k_col_gemv(PanelArgs a, int 
                                                                 int gc0, const double *__restrict__ A0, int lda, int skip,
                                                                 int kc, int RB, int S, double *__restrict__ acol, Xchg x)
 {
-    extern __shared__ double vs[];      // kc
+    SB_DYNAMIC_SMEM(double, vs);        // kc
     const int tid = threadIdx.x;
     const int m = a.m;                  // ncols == m - j inside a reduction; free in the unit test (j == 0)
     const double scale = a.scal[j].scale;

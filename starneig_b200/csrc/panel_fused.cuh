@@ -48,19 +48,6 @@ struct FusedArgs {
     Xchg x;                     // DIST only; x.epoch = sequence number of the panel's first column
 };
 
-__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned *p)
-{
-    unsigned v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ unsigned long long globaltimer_ns()
-{
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-    return t;
-}
-
 // All CTAs of the (cooperative, co-resident) grid: one arrival counter (red.release) that thread 0 of every CTA
 // polls. Measured on B200 (tools/bar_bench.cu, 148 CTAs): 1.4 us per barrier, faster than slot arrays with a
 // gathering master CTA (2.1 us) or two-level schemes (2.2-2.9 us). `gen` counts the arrivals expected so far.
@@ -69,7 +56,7 @@ __device__ __forceinline__ void grid_barrier(unsigned *bar, unsigned &gen)
     __syncthreads();
     if (threadIdx.x == 0) {
         gen += gridDim.x;
-        asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(bar), "r"(1u) : "memory");
+        red_release_gpu_add(bar, 1u);
         while ((int)(ld_acquire_gpu(bar) - gen) < 0) { }
     }
     __syncthreads();
@@ -111,8 +98,6 @@ __device__ __forceinline__ void sum3_over_ctas(const double *part, int stride, i
 #pragma unroll
     for (int k = 0; k < 3; k++) out[k] = warp_sum(acc[k]);
 }
-
-__device__ __forceinline__ void group_barrier(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
 // split of the GEMV over 128-thread groups: items = (row block, local column) pairs in row-block-major order
 struct GemvSplit {
@@ -213,15 +198,14 @@ __device__ __forceinline__ void coldots_all(const double *__restrict__ M, int ld
 __device__ __forceinline__ void ll_store(uint4 *dst, double v, unsigned tag)
 {
     const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
-    const uint4 e = make_uint4((unsigned)bits, tag, (unsigned)(bits >> 32), tag);
-    asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(dst), "r"(e.x), "r"(e.y), "r"(e.z), "r"(e.w) : "memory");
+    st_volatile_v4(dst, make_uint4((unsigned)bits, tag, (unsigned)(bits >> 32), tag));
 }
 __device__ __forceinline__ double ll_load(const uint4 *src, unsigned tag, unsigned *status)
 {
     uint4 e;
     long long t0 = 0;
     for (;;) {
-        asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(e.x), "=r"(e.y), "=r"(e.z), "=r"(e.w) : "l"(src) : "memory");
+        e = ld_volatile_v4(src);
         if (e.y == tag && e.w == tag) break;
         if (t0 == 0) { t0 = clock64(); if (*(volatile unsigned *)status != 0u) break; }
         else if (clock64() - t0 > 8000000000ll) { atomicExch(status, 2u); break; }
@@ -234,7 +218,7 @@ constexpr int FUSED_SHADOW_THREADS = FUSED_THREADS - 32 * FUSED_GEMV_WARPS;     
 
 // shared-memory layout (doubles), fixed for the whole launch
 struct FusedSmem {
-    int vs, s, vrow, w2, red, pv, ysm, sqred, total;
+    int vs, s, vrow, w2, red, pv, ysm, sqred, scal, total;
     __host__ __device__ FusedSmem(int w, int nsub)
     {
         const int NW = (w + 31) / 32 > 1 ? (w + 31) / 32 : 1;
@@ -248,6 +232,7 @@ struct FusedSmem {
         pv = o;    o += nsub * 32;
         ysm = o;   o += nsub * 32;
         sqred = o; o += 3 * FUSED_WARPS;
+        scal = o;  o += 4;
         total = o;
     }
 };
@@ -255,7 +240,7 @@ struct FusedSmem {
 template <bool DIST>
 __global__ void __launch_bounds__(FUSED_THREADS, 1) k_panel_fused(FusedArgs f)
 {
-    extern __shared__ double sh[];
+    SB_DYNAMIC_SMEM(double, sh);
     const PanelArgs &a = f.a;
     const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
     const int m = a.m, ld = a.ld, nsub = f.nsub;
@@ -280,7 +265,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_panel_fused(FusedArgs f)
         gs.skip = (int)(((uintptr_t)base / sizeof(double)) & 1);
         gs.RB = (m + gs.skip + 255) >> 8;
     }
-    __shared__ double scal_sh[4];       // tau, beta, scale of the current column
+    double *const scal_sh = sh + L.scal;    // tau, beta, scale of the current column
 
     // look-ahead results for column 0 -> 1 do not exist yet: phase A(1) must see zeros (no previous columns)
     for (int t = tid; t < nsub * 3 * 32; t += FUSED_THREADS) red[t] = 0.0;
@@ -324,9 +309,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_panel_fused(FusedArgs f)
                         for (int q = 0; q < MAX_RANKS; q++) {
                             ready[q] = true; val[q] = 0.0;
                             if (q < f.x.P && q != f.x.g) {
-                                uint4 e;
-                                asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];"
-                                             : "=r"(e.x), "=r"(e.y), "=r"(e.z), "=r"(e.w) : "l"(in + (size_t)q * a.ldp) : "memory");
+                                const uint4 e = ld_volatile_v4(in + (size_t)q * a.ldp);
                                 ready[q] = (e.y == epoch && e.w == epoch);
                                 val[q] = __longlong_as_double((long long)(((unsigned long long)e.z << 32) | e.x));
                             }
@@ -475,7 +458,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_panel_fused(FusedArgs f)
             }
             __syncthreads();
             // "my part of s is written": only the look-ahead warps wait for this, the GEMV starts at once
-            if (tid == 0) asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(bar2), "r"(1u) : "memory");
+            if (tid == 0) red_release_gpu_add(bar2, 1u);
         }
 
         // ================= phase G: GEMV partials (warps 0..11) + look-ahead for column j+1 (warps 12..15) ==========

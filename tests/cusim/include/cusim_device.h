@@ -1,0 +1,156 @@
+// cusim_device.h -- device-side half of the kernel-logic emulator (see cuda_runtime.h in this directory).
+// TEST INFRASTRUCTURE, not part of the product. Included by starneig_b200/csrc/common.cuh when SB_CUSIM is defined;
+// it provides, on top of fibers (one per CUDA thread, cusim.cpp), exactly the names common.cuh otherwise implements
+// with inline PTX, plus the CUDA built-ins the kernels use:
+//   threadIdx / blockIdx / blockDim / gridDim, __syncthreads, named barriers, warp shuffles and votes (every
+//   participating lane must arrive, as on the hardware), the m8n8k4 FP64 MMA with the hardware's fragment layout,
+//   acquire/release and volatile accesses (each polling access yields to the other fibers, other blocks and other
+//   ranks), cp.async as an immediate copy with zero-fill, atomics, clocks.
+// Dynamic shared memory and cudaMalloc memory start out as NaN patterns, so a kernel that relies on zero-initialised
+// memory fails here even though the arithmetic is otherwise identical to the GPU's (same fma/sqrt/hypot in IEEE double).
+#pragma once
+#include <cuda_runtime.h>
+#include <cmath>
+#include <algorithm>
+#include <tuple>
+#include <utility>
+
+#define __global__ static
+#define __device__
+#define __host__
+#define __forceinline__ inline __attribute__((always_inline))
+#define __launch_bounds__(...)
+#define __shared__ static thread_local
+
+namespace cusim {
+void cta_barrier();
+void named_barrier(int id, int nthreads);
+void poll_yield();
+// all-to-all of up to 16 bytes per lane inside the warp; blocks until all live lanes of the warp arrived
+void warp_exchange(const void *mine, size_t bytes, void *all /* 32 x 16 bytes */);
+unsigned long long now_ns();
+
+template <class K, class... Args>
+static inline void launch(K kernel, dim3 grid, dim3 block, size_t smem, cudaStream_t, Args... args)
+{
+    run_grid(grid, block, smem, false, [=]() { kernel(args...); });
+}
+template <class K, class Arg>
+static inline void launch_coop(K kernel, dim3 grid, dim3 block, size_t smem, cudaStream_t, const Arg &arg)
+{
+    const Arg copy = arg;
+    run_grid(grid, block, smem, true, [=]() { kernel(copy); });
+}
+} // namespace cusim
+
+#define threadIdx (::cusim::g_thread->t_idx)
+#define blockIdx (::cusim::g_thread->b_idx)
+#define blockDim (::cusim::g_thread->b_dim)
+#define gridDim (::cusim::g_thread->g_dim)
+
+#define SB_DYNAMIC_SMEM(type, name) type *const name = (type *)::cusim::g_thread->smem
+#define SB_LAUNCH(kernel, grid, block, smem, stream, ...) ::cusim::launch(kernel, dim3(grid), dim3(block), (smem), (stream), __VA_ARGS__)
+#define SB_LAUNCH_COOP(kernel, grid, block, smem, stream, arg) ::cusim::launch_coop(kernel, dim3(grid), dim3(block), (smem), (stream), (arg))
+
+static inline void __syncthreads() { ::cusim::cta_barrier(); }
+static inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+static inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+static inline void __nanosleep(unsigned) { ::cusim::poll_yield(); }
+static inline long long clock64() { return (long long)::cusim::now_ns(); }      // "cycles" = ns: time-outs stay in seconds
+static inline long long __double_as_longlong(double v) { long long r; memcpy(&r, &v, 8); return r; }
+static inline double __longlong_as_double(long long v) { double r; memcpy(&r, &v, 8); return r; }
+
+// cache-hinted loads: a real (re)load from memory, never a value the compiler kept in a register
+template <class T> static inline T __ldcg(const T *p)
+{
+    T v;
+    asm volatile("" ::: "memory");
+    memcpy(&v, (const void *)p, sizeof(T));
+    asm volatile("" ::: "memory");
+    return v;
+}
+template <class T> static inline T __ldcs(const T *p) { return __ldcg(p); }
+
+template <class T> static inline T __shfl_xor_sync(unsigned, T v, int lane_mask)
+{
+    static_assert(sizeof(T) <= 16, "shuffle payload");
+    alignas(16) unsigned char all[32][16];
+    ::cusim::warp_exchange(&v, sizeof(T), all);
+    T r;
+    memcpy(&r, all[(::cusim::g_thread->lane ^ (unsigned)lane_mask) & 31], sizeof(T));
+    return r;
+}
+static inline int __any_sync(unsigned, int pred)
+{
+    alignas(16) unsigned char all[32][16];
+    const int mine = pred ? 1 : 0;
+    ::cusim::warp_exchange(&mine, sizeof(int), all);
+    int any = 0;
+    const unsigned nl = std::min(32u, ::cusim::g_thread->b_dim.x * ::cusim::g_thread->b_dim.y * ::cusim::g_thread->b_dim.z
+                                          - 32u * ::cusim::g_thread->warp);
+    for (unsigned l = 0; l < nl; l++) { int v; memcpy(&v, all[l], sizeof(int)); any |= v; }
+    return any;
+}
+
+static inline unsigned atomicAdd(unsigned *p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+static inline unsigned atomicExch(unsigned *p, unsigned v) { return __atomic_exchange_n(p, v, __ATOMIC_SEQ_CST); }
+
+// CUDA's integer min/max overloads (the kernels mix int and long long)
+static inline int min(int a, int b) { return a < b ? a : b; }
+static inline int max(int a, int b) { return a > b ? a : b; }
+static inline long long min(long long a, long long b) { return a < b ? a : b; }
+static inline long long max(long long a, long long b) { return a > b ? a : b; }
+static inline long long min(long long a, int b) { return a < b ? a : b; }
+static inline long long min(int a, long long b) { return a < b ? a : b; }
+static inline long long max(long long a, int b) { return a > b ? a : b; }
+static inline long long max(int a, long long b) { return a > b ? a : b; }
+static inline unsigned min(unsigned a, unsigned b) { return a < b ? a : b; }
+static inline unsigned max(unsigned a, unsigned b) { return a > b ? a : b; }
+static inline size_t min(size_t a, size_t b) { return a < b ? a : b; }
+static inline size_t max(size_t a, size_t b) { return a > b ? a : b; }
+using std::fma; using std::sqrt; using std::fabs; using std::hypot; using std::copysign; using std::fmin; using std::fmax;
+
+namespace sb200 {
+// ---- the primitives of common.cuh ----------------------------------------------------------------------------
+static inline unsigned ld_acquire_gpu(const unsigned *p) { ::cusim::poll_yield(); return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
+static inline unsigned ld_acquire_sys(const unsigned *p) { ::cusim::poll_yield(); return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
+static inline void red_release_gpu_add(unsigned *p, unsigned v) { __atomic_fetch_add(p, v, __ATOMIC_RELEASE); }
+static inline void st_release_sys(unsigned *p, unsigned v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
+// 16-byte entries: two 8-byte words, each accessed atomically (what the LL protocol assumes of the interconnect)
+static inline uint4 ld_volatile_v4(const uint4 *p)
+{
+    ::cusim::poll_yield();
+    const unsigned long long lo = __atomic_load_n((const unsigned long long *)p, __ATOMIC_RELAXED);
+    const unsigned long long hi = __atomic_load_n((const unsigned long long *)p + 1, __ATOMIC_RELAXED);
+    return make_uint4((unsigned)lo, (unsigned)(lo >> 32), (unsigned)hi, (unsigned)(hi >> 32));
+}
+static inline void st_volatile_v4(uint4 *p, uint4 e)
+{
+    __atomic_store_n((unsigned long long *)p, (unsigned long long)e.x | ((unsigned long long)e.y << 32), __ATOMIC_RELAXED);
+    __atomic_store_n((unsigned long long *)p + 1, (unsigned long long)e.z | ((unsigned long long)e.w << 32), __ATOMIC_RELAXED);
+}
+static inline void group_barrier(int id, int nthreads) { ::cusim::named_barrier(id, nthreads); }
+static inline unsigned long long globaltimer_ns() { return ::cusim::now_ns(); }
+static inline void prefetch_l2(const void *) {}
+static inline void cp_async8(void *smem_dst, const void *gmem_src, bool valid)
+{
+    if (valid) memcpy(smem_dst, gmem_src, 8);
+    else memset(smem_dst, 0, 8);
+}
+static inline void cp_async_commit() {}
+template <int N> static inline void cp_async_wait() {}
+// mma.sync.m8n8k4.f64: lane l holds A[l/4][l%4], B[l%4][l/4] and C[l/4][2*(l%4) + {0,1}]; the products of one
+// output element are accumulated in ascending k with fused multiply-adds
+static inline void dmma884(double &c0, double &c1, double a, double b)
+{
+    alignas(16) double all[32][2];
+    const double mine[2] = {a, b};
+    ::cusim::warp_exchange(mine, 16, all);
+    const unsigned lane = ::cusim::g_thread->lane, g = lane >> 2, t = lane & 3;
+    for (int k = 0; k < 4; k++) {
+        const double av = all[g * 4 + k][0];
+        c0 = fma(av, all[(2 * t) * 4 + k][1], c0);
+        c1 = fma(av, all[(2 * t + 1) * 4 + k][1], c1);
+    }
+}
+} // namespace sb200

@@ -128,6 +128,12 @@ def test_product_never_touches_the_oracle():
     from starneig_b200._lib import LIB_PATH
     needed = subprocess.run(["readelf", "-d", LIB_PATH], capture_output=True, text=True).stdout
     assert "openblas" not in needed.lower() and "liboracle" not in needed.lower()
+    # ... nor the kernel-logic emulator of the test suite (tests/cusim): the shipped library is the nvcc build, it
+    # links the real CUDA runtime and contains none of the emulator's symbols
+    assert "libcudart" in needed.lower() and "starneig_sim" not in needed.lower()
+    syms = subprocess.run(["nm", "-D", "--defined-only", LIB_PATH], capture_output=True, text=True).stdout
+    assert "cusim" not in syms.lower()
+    assert "__cudaRegisterFatBinary" in subprocess.run(["nm", "-D", LIB_PATH], capture_output=True, text=True).stdout
     # the C test driver is a client of the library and of a CPU BLAS (for its residual checks), never of the oracle
     driver = os.path.join(ROOT, "driver", "bin", "starneig-test")
     if os.path.exists(driver):

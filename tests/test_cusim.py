@@ -1,0 +1,191 @@
+"""Kernel-logic tests on a machine WITHOUT a GPU: the product's CUDA sources under the emulator of tests/cusim.
+
+`tests/cusim` compiles the PRODUCT sources (starneig_b200/csrc/hessenberg.cu, engine.cuh, panel*.cuh, dgemm.cuh,
+node.cpp) unchanged with g++ against a stand-in CUDA runtime: every CUDA thread is a fiber, block/named barriers, warp
+shuffles, the m8n8k4 FP64 MMA fragment layout, cooperative grids, acquire/release flags and the 16-byte LL entries of the
+multi-GPU exchange behave as the kernels assume, ranks are host threads that really run concurrently. What these tests
+pin is therefore the LOGIC of the kernels and of the launch sequence (indexing, barrier structure, exchange protocol,
+edge cases) -- through the same C ABI and against the same oracle as the GPU parity tests -- not their speed, and not the
+GPU's memory model. It is test infrastructure: the product library never links or loads it
+(tests/test_abi.py::test_product_never_touches_the_oracle), and the GPU tests (-m gpu) remain the parity gate.
+
+Tolerances as in tests/test_gpu_hessenberg.py: entrywise 200*n*u, residual / orthogonality <= 10*n*u and <= 500 u.
+"""
+import os
+import platform
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SIM_DIR = os.path.join(ROOT, "tests", "cusim")
+SIM_LIB = os.path.join(SIM_DIR, "_build", "libstarneig_sim.so")
+U = 2.0 ** -52
+
+pytestmark = pytest.mark.skipif(platform.machine() != "x86_64", reason="the emulator's context switch is x86-64 only")
+
+
+@pytest.fixture(scope="module")
+def simlib():
+    r = subprocess.run(["make", "-C", SIM_DIR], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    from starneig_b200 import _lib
+    return _lib.load(SIM_LIB)
+
+
+class _Env:
+    def __init__(self, **kv):
+        self.kv = {k: str(v) for k, v in kv.items()}
+
+    def __enter__(self):
+        self.old = {k: os.environ.get(k) for k in self.kv}
+        os.environ.update(self.kv)
+
+    def __exit__(self, *a):
+        for k, v in self.old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+@pytest.fixture()
+def sim(simlib, monkeypatch):
+    """the host-side mirror (starneig_b200.api) bound to the emulator build for the duration of one test"""
+    import starneig_b200
+    from starneig_b200 import api
+    monkeypatch.setattr(api, "_handle", simlib)
+    yield starneig_b200
+    if simlib.starneig_node_initialized():
+        simlib.starneig_node_finalize()
+
+
+def _reduce(sn, ora, n, pw, gpus=1, begin=0, end=None, generator="fullpos", ld_extra=0):
+    end = n if end is None else end
+    if generator == "partial":
+        A0, Q0, ld = ora.partial(n, begin, end, 2019)
+    else:
+        A0, Q0, ld = ora.fullpos(n, 2019)
+    if ld_extra:
+        ld2 = ld + ld_extra
+        A0 = np.asfortranarray(np.vstack([A0, np.full((ld_extra, A0.shape[1]), np.nan)]))
+        Q0 = np.asfortranarray(np.vstack([Q0, np.full((ld_extra, Q0.shape[1]), np.nan)]))
+        ld = ld2
+    A, Q = A0.copy(order="F"), Q0.copy(order="F")
+    sn.starneig_node_init(sn.STARNEIG_USE_ALL, gpus, sn.STARNEIG_NO_MESSAGES)
+    try:
+        conf = sn.starneig_hessenberg_init_conf()
+        conf.panel_width = pw
+        ret = sn.starneig_SEP_SM_Hessenberg_expert(conf, n, begin, end, A, ld, Q, ld)
+        stats = sn.get_stats()
+    finally:
+        sn.starneig_node_finalize()
+    assert ret == 0
+    A2, Q2 = A0.copy(order="F"), Q0.copy(order="F")
+    assert ora.hessenberg_port(n, A2, ld, Q2, ld, begin, end, pw) == 0
+    assert np.isfinite(A[:n]).all() and np.isfinite(Q[:n]).all()
+    assert np.abs(A[:n] - A2[:n]).max() <= 200 * n * U * max(1.0, np.abs(A2[:n]).max())
+    assert np.abs(Q[:n] - Q2[:n]).max() <= 200 * n * U
+    assert np.array_equal(A[:n] == 0.0, A2[:n] == 0.0)
+    assert ora.hessenberg_form_violations(n, A, ld, begin, end, check_outside=(generator == "partial")) == 0
+    res, orth = ora.residual_u(n, Q, ld, A, ld, A0, ld), ora.orthogonality_u(n, Q, ld)
+    assert res <= max(10.0 * n, 20.0) and res <= 500 and orth <= max(10.0 * n, 20.0) and orth <= 500
+    if ld_extra:
+        assert np.isnan(A[ld - ld_extra:]).all() and np.isnan(Q[ld - ld_extra:]).all()      # padding rows stay untouched
+    return A, Q, stats
+
+
+# the persistent panel kernel + DMMA updates, one rank; degenerate sizes, odd sizes, panel wider than the matrix
+@pytest.mark.parametrize("n,pw", [(1, 8), (2, 8), (3, 8), (9, 8), (17, 8), (47, 16), (88, 35), (100, 100), (131, 24)])
+def test_sim_fused_single_rank(sim, ora, n, pw):
+    _, _, st = _reduce(sim, ora, n, pw)
+    assert st["fused_panels"] == st["panels"] and (n < 3 or st["kernel_launches"] > 0)
+
+
+def test_sim_more_ctas_than_rows(sim, ora):
+    with _Env(CUSIM_SMS=8):
+        _reduce(sim, ora, 60, 16)
+
+
+def test_sim_several_subtiles_per_cta(sim, ora):
+    with _Env(CUSIM_SMS=1):
+        _reduce(sim, ora, 90, 16)          # nsub = 3: one CTA owns three 32-row sub-tiles
+
+
+# the three-kernels-per-column path (panels wider than FUSED_MAX_NB, devices without cooperative launch)
+@pytest.mark.parametrize("n,pw", [(47, 16), (100, 40)])
+def test_sim_unfused_single_rank(sim, ora, n, pw):
+    with _Env(STARNEIG_B200_FUSED_PANEL=0):
+        _, _, st = _reduce(sim, ora, n, pw)
+    assert st["fused_panels"] == 0
+
+
+@pytest.mark.parametrize("n", [47, 88])
+def test_sim_partial_reduction(sim, ora, n):
+    _reduce(sim, ora, n, 16, begin=n // 4, end=3 * n // 4, generator="partial")
+
+
+def test_sim_padded_leading_dimension(sim, ora):
+    _reduce(sim, ora, 50, 16, ld_extra=6)
+
+
+# multi-GPU engine: ranks are host threads with their own schedulers, exchanging through "peer" memory
+@pytest.mark.parametrize("gpus,n,pw,cb", [(2, 96, 16, 8), (3, 70, 16, 8), (4, 120, 24, 16)])
+def test_sim_multi_rank_fused(sim, ora, gpus, n, pw, cb):
+    with _Env(STARNEIG_B200_COL_BLOCK=cb, CUSIM_SMS=2):
+        _, _, st = _reduce(sim, ora, n, pw, gpus=gpus)
+    assert st["ranks"] == gpus and st["fused_panels"] == st["panels"]
+
+
+def test_sim_multi_rank_unfused(sim, ora):
+    with _Env(STARNEIG_B200_COL_BLOCK=8, STARNEIG_B200_FUSED_PANEL=0):
+        _, _, st = _reduce(sim, ora, 72, 16, gpus=2)
+    assert st["ranks"] == 2 and st["fused_panels"] == 0
+
+
+def test_sim_multi_rank_partial(sim, ora):
+    with _Env(STARNEIG_B200_COL_BLOCK=8, CUSIM_SMS=2):
+        _reduce(sim, ora, 88, 16, gpus=2, begin=22, end=66, generator="partial")
+
+
+def test_sim_results_do_not_depend_on_the_schedule(sim, ora, simlib):
+    """fixed-order reductions: the result is bitwise the same whatever order the threads are resumed in"""
+    A1, Q1, _ = _reduce(sim, ora, 64, 16)
+    r = subprocess.run(["python", "-c", (
+        "import sys, numpy as np; sys.path.insert(0, %r)\n"
+        "import starneig_b200 as sn\n"
+        "from starneig_b200 import api, _lib\n"
+        "from oracle.oracle import Oracle\n"
+        "api._handle = _lib.load(%r)\n"
+        "A, Q, ld = Oracle().fullpos(64, 2019)\n"
+        "sn.starneig_node_init(-1, 1, sn.STARNEIG_NO_MESSAGES)\n"
+        "conf = sn.starneig_hessenberg_init_conf(); conf.panel_width = 16\n"
+        "assert sn.starneig_SEP_SM_Hessenberg_expert(conf, 64, 0, 64, A, ld, Q, ld) == 0\n"
+        "sn.starneig_node_finalize()\n"
+        "np.save(sys.argv[1], np.stack([A[:64], Q[:64]]))\n") % (ROOT, SIM_LIB), "/tmp/cusim_shuffled.npy"],
+        env=dict(os.environ, CUSIM_SHUFFLE="7"), capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    AQ = np.load("/tmp/cusim_shuffled.npy")
+    assert np.array_equal(AQ[0], A1[:64]) and np.array_equal(AQ[1], Q1[:64])
+
+
+def test_sim_dgemm_kinds(sim, simlib):
+    """the three operand layouts of the DMMA kernel (fragment layout of mma.m8n8k4 emulated lane by lane), edges,
+    odd offsets, split-K"""
+    import ctypes
+    rng = np.random.default_rng(1)
+    sim.starneig_node_init(sim.STARNEIG_USE_ALL, 1, sim.STARNEIG_NO_MESSAGES)
+    try:
+        for (ta, tb, m, n, k) in [("N", "T", 70, 37, 21), ("T", "N", 45, 13, 600), ("N", "N", 83, 29, 1100), ("N", "T", 130, 66, 4)]:
+            a = np.asfortranarray(rng.standard_normal((m, k) if ta == "N" else (k, m)))
+            b = np.asfortranarray(rng.standard_normal((n, k) if tb == "T" else (k, n)))
+            c = np.asfortranarray(rng.standard_normal((m, n)))
+            want = 0.75 * (a if ta == "N" else a.T) @ (b.T if tb == "T" else b) + (1.0 if ta == "N" and tb == "T" else 0.0) * c
+            beta = 1.0 if (ta, tb) == ("N", "T") else 0.0
+            ret = simlib.starneig_b200_dgemm(ta.encode(), tb.encode(), m, n, k, 0.75, a.ctypes.data, a.shape[0], b.ctypes.data,
+                                             b.shape[0], beta, c.ctypes.data, c.shape[0])
+            assert ret == 0
+            assert np.abs(c - want).max() <= 50 * k * U * np.abs(want).max()
+    finally:
+        sim.starneig_node_finalize()
