@@ -93,19 +93,25 @@ template <bool KMAJOR, int BX, int NTHREADS> struct TileLoader {
             if (xi < BX && x0 + xi < X) mask |= 1u << it;
         }
     }
-    // full k-tile (all GEMM_BK values of k valid); advances to the next k-tile
+    // Full k-tile (all GEMM_BK values of k valid), one iteration at a time, so that the main loop can spread the
+    // cp.async of the next stage between the DMMAs of the current one instead of issuing them as one burst in front
+    // of them (inline asm statements keep their source order). Iterations must be issued in order 0 .. ITERS-1; `it`
+    // is a compile-time constant after unrolling. The last iteration advances to the next k-tile.
+    const double *cur;      // source of the next iteration inside the current k-tile
+    __device__ __forceinline__ void load_iter(double *smem, int it)
+    {
+        constexpr int SSTEP = STEP * OT::STRIDE;
+        if (it == 0) cur = src;
+        // a zero-fill of an element beyond the tile would land in the next stage (or past the allocation)
+        if (ELEMS % NTHREADS == 0 || it + 1 < ITERS || last_in_tile)
+            cp_async8(smem + soff + it * SSTEP, cur, (mask >> it) & 1u);
+        cur += it_stride;
+        if (it == ITERS - 1) src += tile_stride;
+    }
     __device__ __forceinline__ void load_full(double *smem)
     {
-        const double *p = src;
 #pragma unroll
-        for (int it = 0; it < ITERS; it++) {
-            constexpr int SSTEP = KMAJOR ? STEP * OT::STRIDE : STEP * OT::STRIDE;
-            // a zero-fill of an element beyond the tile would land in the next stage (or past the allocation)
-            if (ELEMS % NTHREADS == 0 || it + 1 < ITERS || last_in_tile)
-                cp_async8(smem + soff + it * SSTEP, p, (mask >> it) & 1u);
-            p += it_stride;
-        }
-        src += tile_stride;
+        for (int it = 0; it < ITERS; it++) load_iter(smem, it);
     }
     __device__ __forceinline__ void skip() { src += tile_stride; }
 };
@@ -121,20 +127,32 @@ __device__ __forceinline__ void load_frags(double (&af)[MB], double (&bf)[NB], c
     for (int j = 0; j < NB; j++) bf[j] = sb[TB::offset(brow + j * 8, kk)];
 }
 
-template <int MB, int NB>
-__device__ __forceinline__ void mma_tile(double (&acc)[MB][NB][2], const double (&af)[MB], const double (&bf)[NB])
+// `between(d)` is called after the d-th DMMA of the step (d = 0 .. MB*NB-1): the hook through which the main loop
+// slips the next stage's cp.async between the tensor instructions
+template <int MB, int NB, class F>
+__device__ __forceinline__ void mma_tile(double (&acc)[MB][NB][2], const double (&af)[MB], const double (&bf)[NB], F between)
 {
 #pragma unroll
     for (int i = 0; i < MB; i++)
 #pragma unroll
-        for (int j = 0; j < NB; j++) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        for (int j = 0; j < NB; j++) {
+            dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+            between(i * NB + j);
+        }
+}
+template <int MB, int NB>
+__device__ __forceinline__ void mma_tile(double (&acc)[MB][NB][2], const double (&af)[MB], const double (&bf)[NB])
+{
+    mma_tile<MB, NB>(acc, af, bf, [](int) {});
 }
 
 // grid: (ceil(M/BM), ceil(N/BN), ksplits). With ksplits > 1 each z-slice handles k in
 // [z*klen, (z+1)*klen) and writes alpha*partial to C + z*split_stride (beta must be 0).
 // MINB resident CTAs per SM are requested so that one CTA's prologue/epilogue (global latency) is
 // hidden behind another CTA's DMMA main loop.
-template <bool AK, bool BKM, int WM, int WN, int MB, int NB, int STAGES, int MINB>
+// ILV: the cp.async of the next stage are issued between the DMMAs of the current one (see TileLoader::load_iter)
+// instead of as one burst after the barrier.
+template <bool AK, bool BKM, int WM, int WN, int MB, int NB, int STAGES, int MINB, bool ILV = false>
 __global__ void __launch_bounds__(WM * WN * 32, MINB)
 dgemm_kernel(int M, int N, int K, double alpha, const double *__restrict__ A, int lda,
              const double *__restrict__ B, int ldb, double beta, double *__restrict__ C, int ldc,
@@ -196,30 +214,54 @@ dgemm_kernel(int M, int N, int K, double alpha, const double *__restrict__ A, in
 #pragma unroll
     for (int s = 0; s < STAGES - 1; s++) issue_tile(s);
 
+    constexpr int KSTEPS = GEMM_BK / 4;
     for (int kt = 0; kt < ktiles; kt++) {
         cp_async_wait<STAGES - 2>();
         __syncthreads();
-        issue_tile(kt + STAGES - 1);        // into the slot freed by tile kt-1
+        // tile kt + STAGES - 1 goes into the ring slot freed by tile kt - 1 (all warps are past the barrier above)
+        const int tn = kt + STAGES - 1;
+        const bool next_full = ILV && tn < ktiles && kbeg + (tn + 1) * GEMM_BK <= kend;
+        double *san = smem + (tn % STAGES) * STAGE, *sbn = san + TA::SIZE;
+        if (!ILV) issue_tile(tn);
         const double *sa = smem + (kt % STAGES) * STAGE, *sb = sa + TA::SIZE;
         const int krem = kend - (kbeg + kt * GEMM_BK);
         if (krem >= GEMM_BK) {
-            // full tile: branch-free, fragments of step ks+1 are fetched while step ks is multiplied
+            // full tile: branch-free, fragments of step ks+1 are fetched while step ks is multiplied, and a quarter of
+            // the next stage's cp.async follows each step's DMMAs
             double af[2][MB], bf[2][NB];
             load_frags<TA, TB, MB, NB>(af[0], bf[0], sa, sb, arow, brow, t);
 #pragma unroll
-            for (int ks = 0; ks < GEMM_BK / 4; ks++) {
-                if (ks + 1 < GEMM_BK / 4)
+            for (int ks = 0; ks < KSTEPS; ks++) {
+                if (ks + 1 < KSTEPS)
                     load_frags<TA, TB, MB, NB>(af[(ks + 1) & 1], bf[(ks + 1) & 1], sa, sb, arow, brow, (ks + 1) * 4 + t);
-                mma_tile<MB, NB>(acc, af[ks & 1], bf[ks & 1]);
+                // the C = ITERS_A + ITERS_B cp.async of the next stage are spread evenly over the D DMMAs of this tile
+                if (!ILV) mma_tile<MB, NB>(acc, af[ks & 1], bf[ks & 1]);
+                else mma_tile<MB, NB>(acc, af[ks & 1], bf[ks & 1], [&](int dd) {
+                    constexpr int CA = decltype(la)::ITERS, CB = decltype(lb)::ITERS, C = CA + CB, D = KSTEPS * MB * NB;
+                    const int d = ks * MB * NB + dd;
+#pragma unroll
+                    for (int c = d * C / D; c < (d + 1) * C / D; c++) {
+                        if (next_full) {
+                            if (c < CA) la.load_iter(san, c);
+                            else        lb.load_iter(sbn, c - CA);
+                        }
+                    }
+                });
+            }
+            if (ILV && tn < ktiles && !next_full) {
+                const int k0 = kbeg + tn * GEMM_BK;
+                load_tile<AK, BM, NT>(san, A, lda, m0, k0, M, kend, tid);
+                load_tile<BKM, BN, NT>(sbn, B, ldb, n0, k0, N, kend, tid);
             }
         } else {
-            const int ksteps = (krem + 3) / 4;      // the tile is zero-filled beyond kend
+            const int ksteps = (krem + 3) / 4;      // the tile is zero-filled beyond kend; it is the last one
             for (int ks = 0; ks < ksteps; ks++) {
                 double af[MB], bf[NB];
                 load_frags<TA, TB, MB, NB>(af, bf, sa, sb, arow, brow, ks * 4 + t);
                 mma_tile<MB, NB>(acc, af, bf);
             }
         }
+        if (ILV) cp_async_commit();
     }
     cp_async_wait<0>();
 
@@ -259,20 +301,20 @@ __global__ void splitk_reduce_kernel(int rows, int cols, int splits, const doubl
     W[(size_t)c * ldw + r] = s;
 }
 
-template <bool AK, bool BKM, int WM, int WN, int MB, int NB, int STAGES, int MINB>
+template <bool AK, bool BKM, int WM, int WN, int MB, int NB, int STAGES, int MINB, bool ILV = false>
 struct GemmConfig {
     static constexpr int BM = WM * MB * 8, BN = WN * NB * 8, NT = WM * WN * 32;
     static constexpr size_t SMEM = (size_t)STAGES * (OperandTile<AK, BM>::SIZE + OperandTile<BKM, BN>::SIZE) * sizeof(double);
     static void prepare()
     {
-        SB_CUDA(cudaFuncSetAttribute(dgemm_kernel<AK, BKM, WM, WN, MB, NB, STAGES, MINB>,
+        SB_CUDA(cudaFuncSetAttribute(dgemm_kernel<AK, BKM, WM, WN, MB, NB, STAGES, MINB, ILV>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
     }
     static void launch(cudaStream_t st, int M, int N, int K, double alpha, const double *A, int lda, const double *B,
                        int ldb, double beta, double *C, int ldc, int splits, int klen, size_t split_stride)
     {
         dim3 grid(ceil_div(M, BM), ceil_div(N, BN), splits);
-        SB_LAUNCH((dgemm_kernel<AK, BKM, WM, WN, MB, NB, STAGES, MINB>), grid, NT, SMEM, st, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc,
+        SB_LAUNCH((dgemm_kernel<AK, BKM, WM, WN, MB, NB, STAGES, MINB, ILV>), grid, NT, SMEM, st, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc,
                   klen, split_stride);
     }
 };

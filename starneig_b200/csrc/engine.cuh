@@ -47,6 +47,13 @@ using GemmTN13 = GemmConfig<true,  true,  4, 1, 2, 13, 4, 2>;    //  64 x 104, W
 using GemmTN12 = GemmConfig<true,  true,  4, 1, 2, 12, 4, 2>;    //  64 x  96
 using GemmNN13 = GemmConfig<false, true,  4, 1, 2, 13, 4, 2>;    //  64 x 104, W = A VT
 using GemmNN12 = GemmConfig<false, true,  4, 1, 2, 12, 4, 2>;    //  64 x  96
+// The same tiles with the next stage's cp.async spread between the DMMAs (dgemm.cuh, ILV). Opt-in
+// (STARNEIG_B200_GEMM_ILV=1) until it has been timed on a B200 against the burst variants (tools/gemm_sweep.cu).
+using GemmNTi   = GemmConfig<false, false, 2, 2, 8, 4, 4, 2, true>;
+using GemmTN13i = GemmConfig<true,  true,  4, 1, 2, 13, 4, 2, true>;
+using GemmTN12i = GemmConfig<true,  true,  4, 1, 2, 12, 4, 2, true>;
+using GemmNN13i = GemmConfig<false, true,  4, 1, 2, 13, 4, 2, true>;
+using GemmNN12i = GemmConfig<false, true,  4, 1, 2, 12, 4, 2, true>;
 // "Fat" variants for the side stream: 256 threads x ~200 registers fill the register file of an SM, so a CTA owns
 // its SM exclusively. When it retires the SM is completely free and the (higher-priority, equally SM-exclusive)
 // persistent panel kernel can claim it at once; with the 2-CTAs-per-SM variants an SM never drains while the
@@ -63,6 +70,7 @@ static void prepare_device_functions()
 {
     GemmNT::prepare(); GemmTN13::prepare(); GemmTN12::prepare(); GemmNN13::prepare(); GemmNN12::prepare();
     GemmNTfat::prepare(); GemmNN13fat::prepare(); GemmNN12fat::prepare();
+    GemmNTi::prepare(); GemmTN13i::prepare(); GemmTN12i::prepare(); GemmNN13i::prepare(); GemmNN12i::prepare();
     SB_CUDA(cudaFuncSetAttribute(k_col_finish_update<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM_MAX));
     SB_CUDA(cudaFuncSetAttribute(k_col_finish_update<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM_MAX));
     SB_CUDA(cudaFuncSetAttribute(k_col_reflector<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM_MAX));
@@ -216,6 +224,7 @@ struct Rank {
     int gemv_slots = 0;                     // resident k_col_gemv blocks on the whole GPU (one wave)
     int fused = 1;                          // 1: one persistent kernel per panel (panel_fused.cuh); 0: three kernels per column
     int fused_ctas = 0;                     // grid of the fused kernel (number of SMs; fewer when ranks share a device)
+    int gemm_ilv = 0;                       // 1: DMMA kernels with interleaved cp.async (GemmNTi, ...)
     std::vector<cudaEvent_t> events;        // phase events: 4 per panel
     std::vector<cudaEvent_t> gemv_events;   // 4 per timed column (profile level 2)
     size_t gemv_events_used = 0;
@@ -244,6 +253,8 @@ struct Rank {
         SB_CUDA(cudaDeviceGetAttribute(&fused_ctas, cudaDevAttrMultiProcessorCount, device));
         e = getenv("STARNEIG_B200_FUSED_CTAS");
         if (e && atoi(e) >= 1) fused_ctas = std::min(fused_ctas, atoi(e));
+        e = getenv("STARNEIG_B200_GEMM_ILV");
+        if (e) gemm_ilv = atoi(e);
         e = getenv("STARNEIG_B200_OVERLAP");
         if (e) overlap = atoi(e);
         e = getenv("STARNEIG_B200_OVERLAP_CTAS");
@@ -326,8 +337,9 @@ struct Rank {
         stats.gemm_flops += 2.0 * M * N * (double)K;
         const bool fat = on_side && side_fat;
         if (kind == GEMM_NT) {
-            if (fat) GemmNTfat::launch(st, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, 1, K, 0);
-            else     GemmNT::launch(st, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, 1, K, 0);
+            if (fat)           GemmNTfat::launch(st, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, 1, K, 0);
+            else if (gemm_ilv) GemmNTi::launch(st, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, 1, K, 0);
+            else               GemmNT::launch(st, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, 1, K, 0);
             stats.kernel_launches++;
             return;
         }
@@ -348,12 +360,18 @@ struct Rank {
         double *out = splits > 1 ? wpart : C;
         size_t stride = splits > 1 ? (size_t)ldc * N : 0;
         double b = splits > 1 ? 0.0 : beta;
-        if (kind == GEMM_TN) {
+        if (kind == GEMM_TN && gemm_ilv) {
+            if (bn == 96) GemmTN12i::launch(st, M, N, K, alpha, A, lda, B, ldb, b, out, ldc, splits, klen, stride);
+            else          GemmTN13i::launch(st, M, N, K, alpha, A, lda, B, ldb, b, out, ldc, splits, klen, stride);
+        } else if (kind == GEMM_TN) {
             if (bn == 96) GemmTN12::launch(st, M, N, K, alpha, A, lda, B, ldb, b, out, ldc, splits, klen, stride);
             else          GemmTN13::launch(st, M, N, K, alpha, A, lda, B, ldb, b, out, ldc, splits, klen, stride);
         } else if (fat) {
             if (bn == 96) GemmNN12fat::launch(st, M, N, K, alpha, A, lda, B, ldb, b, out, ldc, splits, klen, stride);
             else          GemmNN13fat::launch(st, M, N, K, alpha, A, lda, B, ldb, b, out, ldc, splits, klen, stride);
+        } else if (gemm_ilv) {
+            if (bn == 96) GemmNN12i::launch(st, M, N, K, alpha, A, lda, B, ldb, b, out, ldc, splits, klen, stride);
+            else          GemmNN13i::launch(st, M, N, K, alpha, A, lda, B, ldb, b, out, ldc, splits, klen, stride);
         } else {
             if (bn == 96) GemmNN12::launch(st, M, N, K, alpha, A, lda, B, ldb, b, out, ldc, splits, klen, stride);
             else          GemmNN13::launch(st, M, N, K, alpha, A, lda, B, ldb, b, out, ldc, splits, klen, stride);

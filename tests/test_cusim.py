@@ -121,6 +121,14 @@ def test_sim_unfused_single_rank(sim, ora, n, pw):
     assert st["fused_panels"] == 0
 
 
+def test_sim_interleaved_gemm_variant(sim, ora):
+    """ILV kernels (cp.async of the next stage between the DMMAs): same arithmetic, bitwise the same result"""
+    A, Q, _ = _reduce(sim, ora, 88, 35)
+    with _Env(STARNEIG_B200_GEMM_ILV=1):
+        A1, Q1, _ = _reduce(sim, ora, 88, 35)
+    assert np.array_equal(A, A1) and np.array_equal(Q, Q1)
+
+
 @pytest.mark.parametrize("n", [47, 88])
 def test_sim_partial_reduction(sim, ora, n):
     _reduce(sim, ora, n, 16, begin=n // 4, end=3 * n // 4, generator="partial")
@@ -170,11 +178,13 @@ def test_sim_results_do_not_depend_on_the_schedule(sim, ora, simlib):
     assert np.array_equal(AQ[0], A1[:64]) and np.array_equal(AQ[1], Q1[:64])
 
 
-def test_sim_dgemm_kinds(sim, simlib):
+@pytest.mark.parametrize("ilv", [0, 1])
+def test_sim_dgemm_kinds(sim, simlib, ilv, monkeypatch):
     """the three operand layouts of the DMMA kernel (fragment layout of mma.m8n8k4 emulated lane by lane), edges,
     odd offsets, split-K"""
     import ctypes
     rng = np.random.default_rng(1)
+    monkeypatch.setenv("STARNEIG_B200_GEMM_ILV", str(ilv))
     sim.starneig_node_init(sim.STARNEIG_USE_ALL, 1, sim.STARNEIG_NO_MESSAGES)
     try:
         for (ta, tb, m, n, k) in [("N", "T", 70, 37, 21), ("T", "N", 45, 13, 600), ("N", "N", 83, 29, 1100), ("N", "T", 130, 66, 4)]:

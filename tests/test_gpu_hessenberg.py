@@ -164,6 +164,22 @@ def test_extreme_scaling(node, ora, monkeypatch, e, fused):
     _check_invariants(ora, n, A, Q, A0, ld)
 
 
+def test_interleaved_gemm_variant(node, ora, monkeypatch):
+    # DMMA kernels with the next stage's cp.async issued between the tensor instructions (dgemm.cuh, ILV): opt-in
+    # variant, same arithmetic in the same order as the default kernels => bitwise the same H and Q
+    n, pw = 700, 120
+    A0, Q0, ld = ora.fullpos(n, 2019)
+    A, Q = A0.copy(order="F"), Q0.copy(order="F")
+    assert _run(node, n, A, ld, Q, pw=pw) == 0
+    node.starneig_node_finalize()
+    monkeypatch.setenv("STARNEIG_B200_GEMM_ILV", "1")
+    node.starneig_node_init(node.STARNEIG_USE_ALL, 1, node.STARNEIG_NO_MESSAGES)
+    A1, Q1 = A0.copy(order="F"), Q0.copy(order="F")
+    assert _run(node, n, A1, ld, Q1, pw=pw) == 0
+    assert np.array_equal(A1[:n], A[:n]) and np.array_equal(Q1[:n], Q[:n])
+    _check_invariants(ora, n, A1, Q1, A0, ld)
+
+
 def test_downstream_eigenvalues(node, ora):
     # config 5 of BASELINE.json at test size: GPU Hessenberg -> dhseqr (stand-in for starneig_SEP_SM_Schur)
     # vs the all-CPU chain (oracle Hessenberg -> dhseqr); tolerance 1e-10 * ||A||

@@ -127,6 +127,9 @@ static void run_cublas(cublasHandle_t h, const Shape &s, Buffers &b, int reps, c
 #define RUN(AK, BK_, WM, WN, MB, NB, ST, MINB, SPL)                                                                    \
     run_config<CFG(AK, BK_, WM, WN, MB, NB, ST, MINB)>(#WM "x" #WN " warps, " #MB "x" #NB " blocks, " #ST " st, " #MINB "/SM", s, b, reps, SPL, st)
 
+#define RUNI(AK, BK_, WM, WN, MB, NB, ST, MINB, SPL)                                                                   \
+    run_config<GemmConfig<AK, BK_, WM, WN, MB, NB, ST, MINB, true>>(#WM "x" #WN " warps, " #MB "x" #NB " blocks, " #ST " st, " #MINB "/SM ILV", s, b, reps, SPL, st)
+
 int main(int argc, char **argv)
 {
     const int n = argc > 1 ? atoi(argv[1]) : 20000;
@@ -160,7 +163,10 @@ int main(int argc, char **argv)
         printf("NT  C(%d x %d) -= A(%d x %d) B(%d x %d)^T\n", s.M, s.N, s.M, s.K, s.N, s.K);
         run_cublas(h, s, b, reps, st);
         RUN(false, false, 2, 2, 8, 4, 4, 2, 1);     // product configuration (GemmNT)
+        RUNI(false, false, 2, 2, 8, 4, 4, 2, 1);    // product configuration with interleaved cp.async (GemmNTi)
         RUN(false, false, 2, 4, 8, 4, 4, 1, 1);     // product side-stream configuration (GemmNTfat)
+        RUNI(false, false, 4, 2, 4, 4, 4, 2, 1);    // 128 x 64, 256 threads, 2 CTAs/SM, interleaved
+        RUNI(false, false, 2, 2, 4, 4, 4, 4, 1);    // 64 x 64, 4 CTAs/SM, interleaved
         RUN(false, false, 2, 2, 8, 4, 3, 2, 1);
         RUN(false, false, 2, 2, 8, 4, 5, 2, 1);
         RUN(false, false, 2, 2, 4, 8, 4, 2, 1);
@@ -181,6 +187,7 @@ int main(int argc, char **argv)
         const int t13 = ceil_div(s.M, 64) * ceil_div(s.N, 104);
         const int spl = std::min(32, std::max(1, std::min(ceil_div(8 * 2 * 148, t13), s.K / 512)));
         RUN(true, true, 4, 1, 2, 13, 4, 2, spl);    // product configuration (GemmTN13)
+        RUNI(true, true, 4, 1, 2, 13, 4, 2, spl);   // interleaved cp.async (GemmTN13i)
         RUN(true, true, 4, 1, 2, 13, 4, 2, 1);
         RUN(true, true, 4, 1, 2, 13, 3, 2, spl);
         RUN(true, true, 4, 1, 2, 13, 5, 2, spl);
@@ -199,6 +206,7 @@ int main(int argc, char **argv)
         const int t13 = ceil_div(s.M, 64) * ceil_div(s.N, 104);
         const int spl = std::min(32, std::max(1, std::min(ceil_div(8 * 2 * 148, t13), s.K / 512)));
         RUN(false, true, 4, 1, 2, 13, 4, 2, spl);   // product configuration (GemmNN13)
+        RUNI(false, true, 4, 1, 2, 13, 4, 2, spl);  // interleaved cp.async (GemmNN13i)
         RUN(false, true, 4, 1, 2, 13, 4, 2, 1);
         RUN(false, true, 8, 1, 2, 13, 4, 1, spl);   // product side-stream configuration (GemmNN13fat)
         RUN(false, true, 4, 1, 2, 13, 3, 2, spl);
