@@ -87,6 +87,39 @@ __device__ __forceinline__ double sumsq_norm(double med, double big, double sml)
     return sqrt(med);
 }
 
+// DLARFG scalars (LAPACK dlarfg, called by the reference at src/hessenberg/cpu.c:140) from alpha and the three sums
+// of squares of x: beta = -sign(alpha) ||(alpha, x)||, tau = (beta - alpha) / beta, v = x * scale, scale = 1 / (alpha - beta).
+// LAPACK's rescaling branch (|beta| < safmin = 2^-969: x, alpha are multiplied by 1/safmin = 2^969 and the norm is taken
+// again; in IEEE double one round always suffices) is reproduced without a second pass over x: such an x lives entirely
+// in the small-range accumulator, sml = sum (x 2^537)^2 exactly scaled, so ||2^969 x|| = sqrt(sml) 2^432. Then `xmul`
+// = 2^969 is returned: the caller multiplies x (its copy in pcol, and z = V^T x) by it before v = x * scale is formed,
+// because 2^969 * scale itself may overflow. beta is scaled back (it may be denormal, as in LAPACK).
+struct Reflector { double tau, beta, scale, xmul; };
+constexpr double DLARFG_SAFMIN = 2.0041683600089728e-292;      // dlamch('S') / dlamch('E') = 2^-969
+constexpr double DLARFG_RSAFMN = 4.9896007738368e+291;         // 2^969
+__device__ __forceinline__ Reflector dlarfg_scalars(double alpha, double med, double big, double sml, bool has_x)
+{
+    Reflector f;
+    f.tau = 0.0; f.beta = alpha; f.scale = 0.0; f.xmul = 1.0;
+    const double xnorm = sumsq_norm(med, big, sml);
+    if (!has_x || xnorm == 0.0) return f;
+    double beta = -copysign(hypot(alpha, xnorm), alpha);
+    if (fabs(beta) < DLARFG_SAFMIN) {
+        const double as = alpha * DLARFG_RSAFMN;
+        const double xs = sqrt(sml) * 1.1090678776483259e+130;                 // 2^432 = 2^969 / 2^537
+        beta = -copysign(hypot(as, xs), as);
+        f.tau = (beta - as) / beta;
+        f.scale = 1.0 / (as - beta);
+        f.beta = beta * DLARFG_SAFMIN;
+        f.xmul = DLARFG_RSAFMN;
+        return f;
+    }
+    f.tau = (beta - alpha) / beta;
+    f.scale = 1.0 / (alpha - beta);
+    f.beta = beta;
+    return f;
+}
+
 struct ColMap {
     int P, g, cb;
     __host__ __device__ int l2g(int lc) const { return ((lc / cb) * P + g) * cb + lc % cb; }
@@ -417,7 +450,7 @@ __global__ void __launch_bounds__(MAXT) k_col_reflector(PanelArgs a, int j, doub
     double *pv = red + (size_t)nsub * NW * 32;      // nsub * 32
     double *colred = pv + nsub * 32;                // RS * NW * 32
     double *sqred = colred + (size_t)RS * NW * 32;  // 3 x 32 (one triple per warp)
-    __shared__ double scale_sh;
+    __shared__ double scale_sh, xmul_sh;
 
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int g = w % NW, h = w / NW;
@@ -525,20 +558,30 @@ __global__ void __launch_bounds__(MAXT) k_col_reflector(PanelArgs a, int j, doub
             for (int k = 0; k < 3; k++) acc[k] = warp_sum(acc[k]);
             if (lane == 0) {
                 const double alpha = __ldcg(&a.scal[j].alpha);
-                const double xnorm = sumsq_norm(acc[0], acc[1], acc[2]);
-                double tau = 0.0, beta = alpha, scale = 0.0;
-                if (m - j > 1 && xnorm != 0.0) {
-                    beta = -copysign(hypot(alpha, xnorm), alpha);
-                    tau = (beta - alpha) / beta;
-                    scale = 1.0 / (alpha - beta);
-                }
-                a.scal[j].tau = tau;
-                a.scal[j].beta = beta;
-                a.scal[j].scale = scale;
-                scale_sh = scale;
+                const Reflector f = dlarfg_scalars(alpha, acc[0], acc[1], acc[2], m - j > 1);
+                a.scal[j].tau = f.tau;
+                a.scal[j].beta = f.beta;
+                a.scal[j].scale = f.scale;
+                scale_sh = f.scale;
+                xmul_sh = f.xmul;
             }
         }
         __syncthreads();
+        if (xmul_sh != 1.0) {
+            // LAPACK's rescaling branch (denormal-range column), all of it by this one block: x is multiplied by 2^969
+            // (the GEMV kernel that forms v = x * scale is the next launch on the stream) and s = V^T v is taken
+            // directly from the rescaled x -- the per-block partials of z were summed in denormal arithmetic
+            const double xmul = xmul_sh, scale = scale_sh;
+            for (int r = j + 1 + tid; r < m; r += blockDim.x) a.pcol[r] *= xmul;
+            __syncthreads();
+            for (int t = w; t < j; t += nwarps) {
+                double acc = 0.0;
+                for (int r = j + 1 + lane; r < m; r += 32) acc = fma(a.V[(size_t)t * ld + r], a.pcol[r], acc);
+                acc = warp_sum(acc);
+                if (lane == 0) a.s[t] = fma(scale, acc, a.V[(size_t)t * ld + j]);
+            }
+            return;
+        }
         const double scale = scale_sh;
         double *s = a.s;
         const double *Vrow = a.V + j;

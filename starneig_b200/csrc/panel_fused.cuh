@@ -237,6 +237,30 @@ struct FusedSmem {
     }
 };
 
+// LAPACK's DLARFG rescaling branch inside the persistent kernel (a column in the denormal range; every CTA takes it
+// together): the row owners multiply x by 2^969 before anybody forms v = x * scale, and z = V^T x is taken again from the
+// rescaled x (the first one was summed in denormal arithmetic, too coarse for T). Two more grid barriers in such a
+// column. Kept out of line: it must not cost the common path registers. Returns the z entry of this warp.
+// (All arguments by value: taking the address of the kernel's parameter block or of `gen` would move them to local memory.)
+// The caller advances its barrier generation by two barriers.
+__device__ __noinline__ double fused_rescale_x(double *pcol, const double *V, int ld, double *colpart, int ldt, int m, int nsub,
+                                               unsigned *gbar, unsigned gen, double *pv, int j, double xmul, int t_first)
+{
+    const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
+    const int b = blockIdx.x;
+    const int row0 = b * nsub * 32;
+    const int rows_here = max(0, min(nsub * 32, m - row0));
+    const int nblk = (m + nsub * 32 - 1) / (nsub * 32);
+    grid_barrier(gbar, gen);                // nobody reads the old z partials any more
+    for (int rr = tid; rr < rows_here; rr += FUSED_THREADS)
+        if (row0 + rr > j) pcol[row0 + rr] *= xmul;
+    for (int rr = tid; rr < nsub * 32; rr += FUSED_THREADS) pv[rr] *= xmul;
+    __syncthreads();
+    if (j > 0) coldots_all(V, ld, j, row0, m, nsub, pv, wp, FUSED_WARPS, lane, colpart + (size_t)b * ldt);
+    grid_barrier(gbar, gen);
+    return t_first < j ? sum_over_ctas(colpart + t_first, ldt, nblk, lane) : 0.0;
+}
+
 template <bool DIST>
 __global__ void __launch_bounds__(FUSED_THREADS, 1) k_panel_fused(FusedArgs f)
 {
@@ -440,16 +464,15 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_panel_fused(FusedArgs f)
             double ssq[3];
             sum3_over_ctas(a.sqpart, PANEL_LDB, nblk, lane, ssq);
             const double alpha = __ldcg(&a.scal[j].alpha);
-            const double xnorm = sumsq_norm(ssq[0], ssq[1], ssq[2]);
-            double tau = 0.0, beta = alpha, scale = 0.0;
-            if (m - j > 1 && xnorm != 0.0) {
-                beta = -copysign(hypot(alpha, xnorm), alpha);
-                tau = (beta - alpha) / beta;
-                scale = 1.0 / (alpha - beta);
-            }
+            const Reflector rf = dlarfg_scalars(alpha, ssq[0], ssq[1], ssq[2], m - j > 1);
+            const double tau = rf.tau, beta = rf.beta, scale = rf.scale;
             if (tid == 0) {
                 scal_sh[0] = tau; scal_sh[1] = beta; scal_sh[2] = scale;
                 if (b == 0) { a.scal[j].tau = tau; a.scal[j].beta = beta; a.scal[j].scale = scale; }
+            }
+            if (rf.xmul != 1.0) {       // denormal-range column
+                zsum = fused_rescale_x(a.pcol, a.V, ld, a.colpart, a.ldt, m, nsub, f.gbar, gen, pv, j, rf.xmul, t_first);
+                gen += 2 * G;
             }
             if (t_first < j && lane == 0) a.s[t_first] = fma(scale, zsum, vjt);
             for (int t = t_first + G * FUSED_WARPS; t < j; t += G * FUSED_WARPS) {

@@ -129,6 +129,34 @@ def test_sim_interleaved_gemm_variant(sim, ora):
     assert np.array_equal(A, A1) and np.array_equal(Q, Q1)
 
 
+@pytest.mark.parametrize("fused", [1, 0])
+@pytest.mark.parametrize("e", [600, -600, -1040])
+def test_sim_extreme_scaling(sim, ora, e, fused):
+    """2^+-600: the squares of the entries overflow / underflow (Blue's sums of squares). 2^-1040: the matrix lives in
+    the denormal range, LAPACK's dlarfg takes its rescaling branch (|beta| < safmin) and so must the kernels: Q stays
+    orthogonal to a few u although the data itself carries only ~34 bits there."""
+    n, pw = 60, 16
+    A0, Q0, ld = ora.full(n, 7)
+    s = 2.0 ** e
+    A, Q = (A0 * s).copy(order="F"), Q0.copy(order="F")
+    with _Env(STARNEIG_B200_FUSED_PANEL=fused):
+        sim.starneig_node_init(sim.STARNEIG_USE_ALL, 1, sim.STARNEIG_NO_MESSAGES)
+        try:
+            conf = sim.starneig_hessenberg_init_conf()
+            conf.panel_width = pw
+            assert sim.starneig_SEP_SM_Hessenberg_expert(conf, n, 0, n, A, ld, Q, ld) == 0
+        finally:
+            sim.starneig_node_finalize()
+    A2, Q2 = (A0 * s).copy(order="F"), Q0.copy(order="F")
+    assert ora.hessenberg_port(n, A2, ld, Q2, ld, 0, n, pw) == 0
+    assert np.isfinite(A[:n]).all() and np.isfinite(Q[:n]).all()
+    assert ora.hessenberg_form_violations(n, A, ld) == 0
+    assert ora.orthogonality_u(n, Q, ld) <= 50
+    tol = 200 * n * U if e > -1000 else 1e-6          # denormal data: 2^-1040 leaves 34 significant bits
+    assert np.abs(A[:n] - A2[:n]).max() <= tol * np.abs(A2[:n]).max()
+    assert np.abs(Q[:n] - Q2[:n]).max() <= tol
+
+
 @pytest.mark.parametrize("n", [47, 88])
 def test_sim_partial_reduction(sim, ora, n):
     _reduce(sim, ora, n, 16, begin=n // 4, end=3 * n // 4, generator="partial")

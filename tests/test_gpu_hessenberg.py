@@ -164,6 +164,27 @@ def test_extreme_scaling(node, ora, monkeypatch, e, fused):
     _check_invariants(ora, n, A, Q, A0, ld)
 
 
+@pytest.mark.parametrize("fused", [1, 0])
+def test_denormal_range_takes_dlarfg_rescaling_branch(node, ora, monkeypatch, fused):
+    # A matrix scaled by 2^-1040 lives in the denormal range: LAPACK's dlarfg (reference src/hessenberg/cpu.c:140)
+    # rescales x and alpha by 1/safmin before it forms the reflector, and so do the kernels (dlarfg_scalars, panel.cuh).
+    # The data itself carries only ~34 bits there, so H and Q agree with the reference to that level only -- but Q stays
+    # orthogonal to a few u and nothing overflows (without the branch: 1 / (alpha - beta) = inf => NaN).
+    monkeypatch.setenv("STARNEIG_B200_FUSED_PANEL", str(fused))
+    n, pw = 333, 45
+    A0, Q0, ld = ora.full(n, 7)
+    s = 2.0 ** -1040
+    A, Q = (A0 * s).copy(order="F"), Q0.copy(order="F")
+    assert _run(node, n, A, ld, Q, pw=pw) == 0
+    A2, Q2 = (A0 * s).copy(order="F"), Q0.copy(order="F")
+    assert ora.hessenberg_port(n, A2, ld, Q2, ld, 0, n, pw) == 0
+    assert np.isfinite(A[:n]).all() and np.isfinite(Q[:n]).all()
+    assert ora.hessenberg_form_violations(n, A, ld) == 0
+    assert ora.orthogonality_u(n, Q, ld) <= 500
+    assert np.abs(A[:n] - A2[:n]).max() <= 1e-5 * np.abs(A2[:n]).max()
+    assert np.abs(Q[:n] - Q2[:n]).max() <= 1e-5
+
+
 def test_interleaved_gemm_variant(node, ora, monkeypatch):
     # DMMA kernels with the next stage's cp.async issued between the tensor instructions (dgemm.cuh, ILV): opt-in
     # variant, same arithmetic in the same order as the default kernels => bitwise the same H and Q
