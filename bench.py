@@ -318,6 +318,22 @@ def run_ours(args):
     # matrices (same content) in pinned memory and moves ONLY its shards to its GPU and back inside the timed
     # region (starneig_b200_dist_hessenberg_host), so the bytes over PCIe add up to A + Q once in each direction.
     shm = None
+    if args.no_e2e:
+        if world > 1:
+            sdist.finalize()
+        sn.starneig_node_finalize()
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                              "warmup": args.warmup, "ms_per_step": ms_per_step, "config": {"n": n}, "e2e": None,
+                              "note": "development run (--no-e2e): device-resident arm only, not a bench line",
+                              "phases_ms_per_step": {"column_loops": phase[0] / args.steps, "trailing_updates": phase[1] / args.steps,
+                                                     "deferred_busy": phase[2] / args.steps},
+                              "fused_phases_ms_per_step": [x / args.steps for x in fused_ph],
+                              "gemv_ms_per_step": gemv_ms / args.steps, "gpu_launches": launches, "clocks": clocks}))
+        return
     if world == 1:
         gen = torch.Generator(device="cuda").manual_seed(2019)
         hostA0 = torch.rand((n, ld), dtype=torch.float64, device="cuda", generator=gen).cpu()
@@ -465,6 +481,8 @@ def main():
     ap.add_argument("--n", type=int, default=int(os.environ.get("STARNEIG_BENCH_N", "20000")))
     ap.add_argument("--cpu-n", type=int, default=CPU_SAMPLE_N)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true",
+                    help="skip the host-buffer arm (development runs at sizes whose host copies do not fit comfortably)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

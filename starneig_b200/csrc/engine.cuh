@@ -766,6 +766,9 @@ static inline void q_row_range(int P, int g, int n, int *q0, int *q1)
 
 static inline int default_panel_width(int n)
 {
+    // tuning aid (tools/sweep.py): another "automatic" width without touching the caller's configuration
+    const char *e = getenv("STARNEIG_B200_AUTO_PANEL_WIDTH");
+    if (e && atoi(e) >= 8) return atoi(e);
     // reference src/hessenberg/interface.c:74-78
     int w = (int)std::ceil((0.001875596476 * n + 273.5908216) / 8.0) * 8;
     return std::max(64, w);

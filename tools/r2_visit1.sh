@@ -1,0 +1,22 @@
+#!/bin/bash
+# Round-2 visit 1 (ONE GPU, ~15 min of box time): parity gate, the tuning sweeps that decide the defaults (DMMA tile
+# configurations incl. the interleaved-cp.async variants against cuBLAS on the exact shapes; panel width; ILV), the bench
+# line, the ncu launch list of the bench command and one full capture of the dominant kernels. Everything lands in
+# gpurun_out/.   usage: gpurun --timeout 1100 -- bash tools/r2_visit1.sh
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/smi.txt
+(timeout 420 python -m pytest tests -m gpu -x -q 2>&1 | tail -5) | tee gpurun_out/pytest_gpu.log
+(timeout 150 tools/bin/gemm_sweep 20000 2 3 2>&1) > gpurun_out/gemm_sweep_p2.txt; tail -50 gpurun_out/gemm_sweep_p2.txt
+(timeout 100 tools/bin/gemm_sweep 20000 40 3 2>&1) > gpurun_out/gemm_sweep_p40.txt
+: > gpurun_out/sweep.log
+for cfg in "" "GEMM_ILV=1" "AUTO_PANEL_WIDTH=256" "AUTO_PANEL_WIDTH=192" "AUTO_PANEL_WIDTH=384" "GEMM_ILV=1,AUTO_PANEL_WIDTH=256"; do
+    timeout 90 python tools/sweep.py 20000 "$cfg" 2>&1 | grep -v "zeros below" | tee -a gpurun_out/sweep.log
+done
+timeout 300 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench exit $?"
+cat gpurun_out/bench.json; tail -3 gpurun_out/bench.err
+timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/launches_bench_n20000.csv \
+    python bench.py --steps 1 --warmup 0 --no-cpu --no-e2e > gpurun_out/ncu_list.log 2>&1; echo "ncu list exit $?"
+timeout 200 ncu --set full --clock-control none --import-source on -k regex:dgemm_kernel --launch-skip 8 -c 8 -o gpurun_out/dgemm_full -f \
+    python tools/run_once.py 20000 > gpurun_out/ncu_dgemm.log 2>&1; echo "ncu dgemm exit $?"
+(timeout 90 driver/bin/starneig-test --experiment hessenberg --n 10000 --seed 2019 --gpus 1 --repeat 1 --warmup 1 --hooks hessenberg residual 2>&1; echo "driver exit $?") | tee gpurun_out/driver_n10000.log
+ls -la gpurun_out | tail -20
