@@ -87,8 +87,10 @@ static void prepare_device_functions()
     SB_CUDA(cudaFuncGetAttributes(&fa, k_sum_peers));
     SB_CUDA(cudaFuncGetAttributes(&fa, k_barrier));
     SB_CUDA(cudaFuncGetAttributes(&fa, splitk_reduce_kernel));
-    SB_CUDA(cudaFuncSetAttribute(k_panel_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM_MAX));
-    SB_CUDA(cudaFuncSetAttribute(k_panel_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM_MAX));
+    SB_CUDA(cudaFuncSetAttribute((k_panel_fused<false, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM_MAX));
+    SB_CUDA(cudaFuncSetAttribute((k_panel_fused<true, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM_MAX));
+    SB_CUDA(cudaFuncSetAttribute((k_panel_fused<false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM_MAX));
+    SB_CUDA(cudaFuncSetAttribute((k_panel_fused<true, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM_MAX));
 }
 
 struct Stats : starneig_b200_stats {};
@@ -109,6 +111,7 @@ struct Workspace {
     double *s = nullptr, *w2 = nullptr, *colpart = nullptr, *sqpart = nullptr;
     ColScal *scal = nullptr;
     unsigned *counter = nullptr;
+    uint4 *w2part_ll = nullptr, *w2_ll = nullptr;       // LL entries of the w2 reduction (fused kernel, LLRED)
     unsigned *gbar = nullptr;                   // grid barrier counter of the fused panel kernel
     unsigned long long *timers = nullptr;       // device-side phase timers of the fused panel kernel (ns)
     std::vector<void *> allocs;
@@ -125,6 +128,14 @@ struct Workspace {
         for (void *p : allocs) cudaFree(p);
         allocs.clear();
         n_cap = nb_cap = 0;
+        w2part_ll = w2_ll = nullptr;
+    }
+    // the column sequence numbers restart (new exchange arena): no stale LL entry may carry a tag that will be reused
+    void reset_ll()
+    {
+        if (!w2part_ll) return;
+        SB_CUDA(cudaMemset(w2part_ll, 0, (size_t)nbp * PANEL_LDB * sizeof(uint4)));
+        SB_CUDA(cudaMemset(w2_ll, 0, nbp * sizeof(uint4)));
     }
     void ensure(int n, int nb, bool dist)
     {
@@ -153,6 +164,10 @@ struct Workspace {
         scal = alloc<ColScal>(nbp);
         counter = alloc<unsigned>(4);
         SB_CUDA(cudaMemset(counter, 0, 4 * sizeof(unsigned)));
+        w2part_ll = alloc<uint4>((size_t)nbp * PANEL_LDB);
+        w2_ll = alloc<uint4>(nbp);
+        SB_CUDA(cudaMemset(w2part_ll, 0, (size_t)nbp * PANEL_LDB * sizeof(uint4)));       // tag 0 is never used
+        SB_CUDA(cudaMemset(w2_ll, 0, nbp * sizeof(uint4)));
         gbar = alloc<unsigned>(1024);
         timers = alloc<unsigned long long>(8);
         SB_CUDA(cudaMemset(timers, 0, 8 * sizeof(unsigned long long)));
@@ -225,6 +240,7 @@ struct Rank {
     int fused = 1;                          // 1: one persistent kernel per panel (panel_fused.cuh); 0: three kernels per column
     int fused_ctas = 0;                     // grid of the fused kernel (number of SMs; fewer when ranks share a device)
     int gemm_ilv = 0;                       // 1: DMMA kernels with interleaved cp.async (GemmNTi, ...)
+    int fused_ll = 0;                       // 1: fused panel kernel with the LL-entry w2 reduction (two grid barriers fewer per column)
     std::vector<cudaEvent_t> events;        // phase events: 4 per panel
     std::vector<cudaEvent_t> gemv_events;   // 4 per timed column (profile level 2)
     size_t gemv_events_used = 0;
@@ -255,6 +271,8 @@ struct Rank {
         if (e && atoi(e) >= 1) fused_ctas = std::min(fused_ctas, atoi(e));
         e = getenv("STARNEIG_B200_GEMM_ILV");
         if (e) gemm_ilv = atoi(e);
+        e = getenv("STARNEIG_B200_FUSED_LL");
+        if (e) fused_ll = atoi(e);
         e = getenv("STARNEIG_B200_OVERLAP");
         if (e) overlap = atoi(e);
         e = getenv("STARNEIG_B200_OVERLAP_CTAS");
@@ -308,6 +326,7 @@ struct Rank {
         for (int s = 0; s < P; s++) peer[s] = nullptr;
         peer[g] = arena;
         bar_epoch = 0; y_epoch = 0;
+        ws.reset_ll();
         return true;
     }
     template <typename T> T *at(int s, size_t off) const { return (T *)(peer[s] + off); }
@@ -467,6 +486,8 @@ struct Rank {
             for (int s = 0; s < P; s++) { x.inbox[s] = at<double>(s, al.off_inbox); x.yflag[s] = at<unsigned>(s, al.off_yflag); }
             x.rbcount = at<unsigned>(g, al.off_rbcount);
             x.status = at<unsigned>(g, al.off_status);
+        } else {
+            x.status = ws.counter + 3;      // time-out word of the LL waits inside the fused kernel
         }
         return x;
     }
@@ -491,12 +512,15 @@ struct Rank {
             f.gbar = ws.gbar; f.timers = ws.timers;
             f.x = x;
             f.x.epoch = y_epoch + 1;
+            f.w2part_ll = ws.w2part_ll; f.w2_ll = ws.w2_ll;
             const size_t smem = fused_smem_bytes(w, f.nsub);
             if (smem <= PANEL_SMEM_MAX) {
-                if (P > 1) y_epoch += w;
+                y_epoch += w;
                 SB_CUDA(cudaMemsetAsync(ws.gbar, 0, 1024 * sizeof(unsigned), st));
-                if (P > 1) SB_LAUNCH_COOP(k_panel_fused<true>, ctas, FUSED_THREADS, smem, st, f);
-                else       SB_LAUNCH_COOP(k_panel_fused<false>, ctas, FUSED_THREADS, smem, st, f);
+                if (P > 1 && fused_ll) SB_LAUNCH_COOP((k_panel_fused<true, true>), ctas, FUSED_THREADS, smem, st, f);
+                else if (P > 1)        SB_LAUNCH_COOP((k_panel_fused<true, false>), ctas, FUSED_THREADS, smem, st, f);
+                else if (fused_ll)     SB_LAUNCH_COOP((k_panel_fused<false, true>), ctas, FUSED_THREADS, smem, st, f);
+                else                   SB_LAUNCH_COOP((k_panel_fused<false, false>), ctas, FUSED_THREADS, smem, st, f);
                 stats.kernel_launches++;
                 stats.fused_panels++;
                 for (int j = 0; j < w; j++) {
@@ -716,6 +740,11 @@ struct Rank {
         SB_CUDA(cudaStreamSynchronize(st));
         SB_CUDA(cudaStreamSynchronize(side));
         SB_CUDA(cudaGetLastError());
+        if (P == 1 && fused_ll) {
+            unsigned status = 0;
+            SB_CUDA(cudaMemcpy(&status, ws.counter + 3, sizeof(status), cudaMemcpyDeviceToHost));
+            if (status != 0) fatal("a wait inside the persistent panel kernel timed out", __FILE__, __LINE__);
+        }
         if (P > 1) {
             unsigned status = 0;
             SB_CUDA(cudaMemcpy(&status, at<unsigned>(g, al.off_status), sizeof(status), cudaMemcpyDeviceToHost));

@@ -45,7 +45,9 @@ struct FusedArgs {
     int nsub;                   // 32-row sub-tiles per CTA
     unsigned *gbar;             // grid barrier counter, zero at launch
     unsigned long long *timers; // ns on CTA 0: [0] GEMV phases, [1] whole kernel, [2..5] phases A, A', R, R' (each incl. its barrier)
-    Xchg x;                     // DIST only; x.epoch = sequence number of the panel's first column
+    Xchg x;                     // x.epoch = sequence number of the panel's first column (tags of all LL entries); rest DIST only
+    uint4 *w2part_ll;           // LLRED: PANEL_LDB x ldt self-validating per-CTA partials of w2 = VT^T p'
+    uint4 *w2_ll;               // LLRED: ldt self-validating entries of w2
 };
 
 // All CTAs of the (cooperative, co-resident) grid: one arrival counter (red.release) that thread 0 of every CTA
@@ -62,6 +64,27 @@ __device__ __forceinline__ void grid_barrier(unsigned *bar, unsigned &gen)
     __syncthreads();
 }
 
+// "LL" exchange entry (the protocol NCCL uses for latency-bound messages): a double travels as two 8-byte words
+// {low 32 bits, tag} {high 32 bits, tag}; 8-byte stores are atomic over NVLink, so a reader that sees the expected
+// tag in both words has the value, without any fence or separate flag on the critical path.
+__device__ __forceinline__ void ll_store(uint4 *dst, double v, unsigned tag)
+{
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
+    st_volatile_v4(dst, make_uint4((unsigned)bits, tag, (unsigned)(bits >> 32), tag));
+}
+__device__ __forceinline__ double ll_load(const uint4 *src, unsigned tag, unsigned *status)
+{
+    uint4 e;
+    long long t0 = 0;
+    for (;;) {
+        e = ld_volatile_v4(src);
+        if (e.y == tag && e.w == tag) break;
+        if (t0 == 0) { t0 = clock64(); if (*(volatile unsigned *)status != 0u) break; }
+        else if (clock64() - t0 > 8000000000ll) { atomicExch(status, 2u); break; }
+    }
+    return __longlong_as_double((long long)(((unsigned long long)e.z << 32) | e.x));
+}
+
 // sum over the CTAs that own rows (nblk <= 32*5) of part[bb*ldt], fixed order, by one warp: the (up to) five loads
 // of a lane are independent
 __device__ __forceinline__ double sum_over_ctas(const double *part, size_t ldt, int nblk, int lane)
@@ -74,6 +97,32 @@ __device__ __forceinline__ double sum_over_ctas(const double *part, size_t ldt, 
             const int bb = b0 + lane + 32 * u;
             x[u] = bb < nblk ? __ldcg(part + (size_t)bb * ldt) : 0.0;
         }
+        acc += ((x[0] + x[1]) + (x[2] + x[3])) + x[4];
+    }
+    return warp_sum(acc);
+}
+
+// the same over self-validating LL entries (tag = sequence number of the column): no grid barrier between the CTAs that
+// write the partials and the warp that sums them -- the reader polls until every entry carries the tag
+__device__ __forceinline__ double sum_over_ctas_ll(const uint4 *part, size_t ldt, int nblk, int lane, unsigned tag, unsigned *status)
+{
+    double acc = 0.0;
+    for (int b0 = 0; b0 < nblk; b0 += 160) {
+        double x[5];
+        bool ready[5];
+#pragma unroll
+        for (int u = 0; u < 5; u++) {       // first pass: all loads in flight together
+            const int bb = b0 + lane + 32 * u;
+            x[u] = 0.0; ready[u] = true;
+            if (bb < nblk) {
+                const uint4 e = ld_volatile_v4(part + (size_t)bb * ldt);
+                ready[u] = (e.y == tag && e.w == tag);
+                x[u] = __longlong_as_double((long long)(((unsigned long long)e.z << 32) | e.x));
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 5; u++)
+            if (!ready[u]) x[u] = ll_load(part + (size_t)(b0 + lane + 32 * u) * ldt, tag, status);
         acc += ((x[0] + x[1]) + (x[2] + x[3])) + x[4];
     }
     return warp_sum(acc);
@@ -172,7 +221,8 @@ __device__ __forceinline__ double transpose_reduce16(double (&v)[16], int lane)
 
 // partial column dots of the CTA -> colpart[b][t], t < tmax; warps [0, T) share the column batches
 __device__ __forceinline__ void coldots_all(const double *__restrict__ M, int ld, int tmax, int row0, int m, int nsub,
-                                            const double *pv, int wp, int T, int lane, double *out)
+                                            const double *pv, int wp, int T, int lane, double *out,
+                                            uint4 *out_ll = nullptr, unsigned tag = 0u)
 {
     if (nsub >= 3) {
         for (int tb = 8 * wp; tb < tmax; tb += 8 * T) {
@@ -180,37 +230,16 @@ __device__ __forceinline__ void coldots_all(const double *__restrict__ M, int ld
             coldots<8, 4>(M, ld, tb, tmax, row0, m, nsub, pv, lane, acc);
             const double xx = transpose_reduce8(acc, lane);
             const int t = tb + (lane >> 2);
-            if ((lane & 3) == 0 && t < tmax) out[t] = xx;
+            if ((lane & 3) == 0 && t < tmax) { if (out_ll) ll_store(out_ll + t, xx, tag); else out[t] = xx; }
         }
     } else {
         for (int tb = 16 * wp; tb < tmax; tb += 16 * T) {
             double acc[16];
             coldots<16, 2>(M, ld, tb, tmax, row0, m, nsub, pv, lane, acc);
             const double xx = transpose_reduce16(acc, lane);
-            if (lane < 16 && tb + lane < tmax) out[tb + lane] = xx;
+            if (lane < 16 && tb + lane < tmax) { if (out_ll) ll_store(out_ll + tb + lane, xx, tag); else out[tb + lane] = xx; }
         }
     }
-}
-
-// "LL" exchange entry (the protocol NCCL uses for latency-bound messages): a double travels as two 8-byte words
-// {low 32 bits, tag} {high 32 bits, tag}; 8-byte stores are atomic over NVLink, so a reader that sees the expected
-// tag in both words has the value, without any fence or separate flag on the critical path.
-__device__ __forceinline__ void ll_store(uint4 *dst, double v, unsigned tag)
-{
-    const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
-    st_volatile_v4(dst, make_uint4((unsigned)bits, tag, (unsigned)(bits >> 32), tag));
-}
-__device__ __forceinline__ double ll_load(const uint4 *src, unsigned tag, unsigned *status)
-{
-    uint4 e;
-    long long t0 = 0;
-    for (;;) {
-        e = ld_volatile_v4(src);
-        if (e.y == tag && e.w == tag) break;
-        if (t0 == 0) { t0 = clock64(); if (*(volatile unsigned *)status != 0u) break; }
-        else if (clock64() - t0 > 8000000000ll) { atomicExch(status, 2u); break; }
-    }
-    return __longlong_as_double((long long)(((unsigned long long)e.z << 32) | e.x));
 }
 
 constexpr int FUSED_GEMV_WARPS = 4 * FUSED_VB;                       // warps 0..15: the GEMV groups of phase G
@@ -261,7 +290,9 @@ __device__ __noinline__ double fused_rescale_x(double *pcol, const double *V, in
     return t_first < j ? sum_over_ctas(colpart + t_first, ldt, nblk, lane) : 0.0;
 }
 
-template <bool DIST>
+// LLRED: the reduction w2 = sum over CTAs of VT^T p' travels as self-validating LL entries (partials -> reducing warps ->
+// every CTA), which removes the two grid barriers around phase A'. Opt-in (STARNEIG_B200_FUSED_LL=1) until timed on a B200.
+template <bool DIST, bool LLRED>
 __global__ void __launch_bounds__(FUSED_THREADS, 1) k_panel_fused(FusedArgs f)
 {
     SB_DYNAMIC_SMEM(double, sh);
@@ -385,22 +416,26 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_panel_fused(FusedArgs f)
             __syncthreads();
 
             // ---- w2part[t] = sum over the CTA's rows of VT(r,t) * p'(r), t < j (column j-1 was stored just above)
-            coldots_all(a.VT, ld, j, row0, m, nsub, pv, wp, FUSED_WARPS, lane, a.colpart + (size_t)b * a.ldt);
-            grid_barrier(f.gbar, gen);
+            const unsigned tag = f.x.epoch + j;
+            coldots_all(a.VT, ld, j, row0, m, nsub, pv, wp, FUSED_WARPS, lane, a.colpart + (size_t)b * a.ldt,
+                        LLRED ? f.w2part_ll + (size_t)b * a.ldt : nullptr, tag);
+            if (!LLRED) grid_barrier(f.gbar, gen);
             SB_PHASE_MARK(0);
 
             // ================= A': w2[t] = sum over CTAs (one warp per entry) =================
             for (int t = b * FUSED_WARPS + wp; t < j; t += G * FUSED_WARPS) {
-                const double acc = sum_over_ctas(a.colpart + t, a.ldt, nblk, lane);
-                if (lane == 0) a.w2[t] = acc;
+                const double acc = LLRED ? sum_over_ctas_ll(f.w2part_ll + t, a.ldt, nblk, lane, tag, f.x.status)
+                                         : sum_over_ctas(a.colpart + t, a.ldt, nblk, lane);
+                if (lane == 0) { if (LLRED) ll_store(f.w2_ll + t, acc, tag); else a.w2[t] = acc; }
             }
-            grid_barrier(f.gbar, gen);
+            if (!LLRED) grid_barrier(f.gbar, gen);
             SB_PHASE_MARK(1);
         }
 
         // ================= phase R: p'' = p' - V w2; ||x||^2, z = V^T x =================
         {
-            for (int t = tid; t < j; t += FUSED_THREADS) w2_sh[t] = __ldcg(a.w2 + t);
+            for (int t = tid; t < j; t += FUSED_THREADS)
+                w2_sh[t] = LLRED ? ll_load(f.w2_ll + t, f.x.epoch + j, f.x.status) : __ldcg(a.w2 + t);
             __syncthreads();
             if (j > 0) {
                 // d(r) = V(r, :j) w2: 32x32 tiles, 32 loads in flight per lane

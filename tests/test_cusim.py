@@ -121,6 +121,18 @@ def test_sim_unfused_single_rank(sim, ora, n, pw):
     assert st["fused_panels"] == 0
 
 
+@pytest.mark.parametrize("gpus,n,pw,sms", [(1, 131, 24, 4), (1, 90, 16, 1), (2, 96, 16, 2)])
+def test_sim_ll_reduction_variant(sim, ora, gpus, n, pw, sms):
+    """persistent panel kernel with the w2 reduction carried by self-validating LL entries instead of two grid barriers
+    (STARNEIG_B200_FUSED_LL=1): same partial sums in the same order => bitwise the same H and Q"""
+    with _Env(STARNEIG_B200_COL_BLOCK=8, CUSIM_SMS=sms):
+        A, Q, _ = _reduce(sim, ora, n, pw, gpus=gpus)
+        with _Env(STARNEIG_B200_FUSED_LL=1):
+            A1, Q1, st = _reduce(sim, ora, n, pw, gpus=gpus)
+    assert st["fused_panels"] == st["panels"]
+    assert np.array_equal(A, A1) and np.array_equal(Q, Q1)
+
+
 def test_sim_interleaved_gemm_variant(sim, ora):
     """ILV kernels (cp.async of the next stage between the DMMAs): same arithmetic, bitwise the same result"""
     A, Q, _ = _reduce(sim, ora, 88, 35)

@@ -185,6 +185,23 @@ def test_denormal_range_takes_dlarfg_rescaling_branch(node, ora, monkeypatch, fu
     assert np.abs(Q[:n] - Q2[:n]).max() <= 1e-5
 
 
+def test_ll_reduction_variant(node, ora, monkeypatch):
+    # persistent panel kernel with the w2 reduction carried by self-validating LL entries instead of two grid barriers
+    # (opt-in, STARNEIG_B200_FUSED_LL=1): same partial sums in the same order => bitwise the same H and Q
+    n, pw = 1500, 200
+    A0, Q0, ld = ora.fullpos(n, 2019)
+    A, Q = A0.copy(order="F"), Q0.copy(order="F")
+    assert _run(node, n, A, ld, Q, pw=pw) == 0
+    node.starneig_node_finalize()
+    monkeypatch.setenv("STARNEIG_B200_FUSED_LL", "1")
+    node.starneig_node_init(node.STARNEIG_USE_ALL, 1, node.STARNEIG_NO_MESSAGES)
+    for _ in range(2):          # twice: the tags of the second call continue where the first one stopped
+        A1, Q1 = A0.copy(order="F"), Q0.copy(order="F")
+        assert _run(node, n, A1, ld, Q1, pw=pw) == 0
+        assert np.array_equal(A1[:n], A[:n]) and np.array_equal(Q1[:n], Q[:n])
+    _check_invariants(ora, n, A1, Q1, A0, ld)
+
+
 def test_interleaved_gemm_variant(node, ora, monkeypatch):
     # DMMA kernels with the next stage's cp.async issued between the tensor instructions (dgemm.cuh, ILV): opt-in
     # variant, same arithmetic in the same order as the default kernels => bitwise the same H and Q
