@@ -89,6 +89,12 @@ __device__ __forceinline__ void cp_async8(void *smem_dst, const void *gmem_src, 
     int src_size = valid ? 8 : 0;
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(dst), "l"(gmem_src), "r"(src_size));
 }
+// 16-byte variant (both addresses 16-byte aligned): copies the first src_bytes (0, 8 or 16) bytes, zero-fills the rest
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src, int src_bytes)
+{
+    unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(gmem_src), "r"(src_bytes));
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 // FP64 tensor-core instruction (SASS DMMA.8x8x4): C(8x8) += A(8x4) B(4x8); lane l holds A[l/4][l%4], B[l%4][l/4],

@@ -61,50 +61,65 @@ __device__ __forceinline__ void load_tile(double *smem, const double *__restrict
 // not depend on the k-tile, so the main loop spends ~3 integer instructions per cp.async instead of re-deriving
 // (x, k), the bounds checks and the clamped address each time. Partial k-tiles (the last one) use load_tile.
 // Out-of-range elements are zero-filled (src-size 0: the address is not dereferenced).
-template <bool KMAJOR, int BX, int NTHREADS> struct TileLoader {
-    static constexpr int ELEMS = BX * GEMM_BK;
-    static constexpr int ITERS = (ELEMS + NTHREADS - 1) / NTHREADS;
-    static_assert(KMAJOR ? (NTHREADS % GEMM_BK == 0) : (NTHREADS % BX == 0), "thread count must tile the operand");
-    // MN-major: x fixed, k = k_t + it * (NTHREADS / BX);  K-major: k fixed, x = x_t + it * (NTHREADS / GEMM_BK)
-    static constexpr int STEP = KMAJOR ? NTHREADS / GEMM_BK : NTHREADS / BX;
+// VEC = 2: a thread moves two neighbouring elements per iteration (neighbours along x for MN-major operands, along k
+// for K-major ones) -- with ONE 16-byte cp.async when the operand allows it (16-byte aligned base, even leading
+// dimension: `vec16`, decided at run time per operand), else with two 8-byte ones. Half as many iterations either way.
+template <bool KMAJOR, int BX, int NTHREADS, int VEC = 1> struct TileLoader {
+    static constexpr int UNITS = BX * GEMM_BK / VEC;            // VEC-element units of a tile
+    static constexpr int ITERS = (UNITS + NTHREADS - 1) / NTHREADS;
+    static constexpr int UPL = (KMAJOR ? GEMM_BK : BX) / VEC;   // units per line (line = fixed k for MN-major, fixed x for K-major)
+    static_assert((KMAJOR ? GEMM_BK : BX) % VEC == 0 && NTHREADS % UPL == 0, "thread count must tile the operand");
+    // MN-major: x fixed, k = k_t + it * STEP;  K-major: k fixed, x = x_t + it * STEP
+    static constexpr int STEP = NTHREADS / UPL;
     using OT = OperandTile<KMAJOR, BX>;
-    const double *src;      // element of iteration 0 in the current k-tile
+    const double *src;      // first element of iteration 0 in the current k-tile
     size_t it_stride;       // doubles between consecutive iterations
     size_t tile_stride;     // doubles between consecutive k-tiles
-    unsigned mask;          // bit it: the element of iteration `it` has a valid x
+    unsigned mask;          // K-major: bit it = the x of iteration `it` is inside the operand; MN-major: valid elements of the unit
     int soff;               // shared-memory offset (doubles) of iteration 0
-    bool last_in_tile;      // ELEMS % NTHREADS != 0: the element of the last iteration exists (x < BX)
-    static_assert(KMAJOR || ELEMS % NTHREADS == 0, "MN-major operands: the thread count must divide the tile");
+    bool last_in_tile;      // UNITS % NTHREADS != 0: the unit of the last iteration exists (x < BX)
+    bool vec16;             // VEC == 2: one 16-byte copy per unit
+    static_assert(KMAJOR || UNITS % NTHREADS == 0, "MN-major operands: the thread count must divide the tile");
 
     __device__ __forceinline__ void init(const double *g, int ld, int x0, int k0, int X, int tid)
     {
         int x, k;
-        if (KMAJOR) { x = tid / GEMM_BK; k = tid % GEMM_BK; }
-        else        { k = tid / BX;      x = tid % BX; }
+        if (KMAJOR) { x = tid / UPL; k = (tid % UPL) * VEC; }
+        else        { k = tid / UPL; x = (tid % UPL) * VEC; }
         src = KMAJOR ? g + (size_t)(x0 + x) * ld + (k0 + k) : g + (size_t)(k0 + k) * ld + (x0 + x);
-        it_stride = KMAJOR ? (size_t)STEP * ld : (size_t)STEP * ld;
+        it_stride = (size_t)STEP * ld;
         tile_stride = KMAJOR ? (size_t)GEMM_BK : (size_t)GEMM_BK * ld;
         soff = OT::offset(x, k);
+        vec16 = VEC == 2 && ((uintptr_t)g & 15) == 0 && (ld & 1) == 0;      // x0, k0 are even
         mask = 0u;
         last_in_tile = !KMAJOR || x + (ITERS - 1) * STEP < BX;
+        if (KMAJOR) {
 #pragma unroll
-        for (int it = 0; it < ITERS; it++) {
-            const int xi = KMAJOR ? x + it * STEP : x;
-            if (xi < BX && x0 + xi < X) mask |= 1u << it;
+            for (int it = 0; it < ITERS; it++) {
+                const int xi = x + it * STEP;
+                if (xi < BX && x0 + xi < X) mask |= 1u << it;
+            }
+        } else {
+            mask = (unsigned)max(0, min(VEC, X - (x0 + x)));
         }
     }
     // Full k-tile (all GEMM_BK values of k valid), one iteration at a time, so that the main loop can spread the
     // cp.async of the next stage between the DMMAs of the current one instead of issuing them as one burst in front
-    // of them (inline asm statements keep their source order). Iterations must be issued in order 0 .. ITERS-1; `it`
-    // is a compile-time constant after unrolling. The last iteration advances to the next k-tile.
+    // of them. Iterations must be issued in order 0 .. ITERS-1; `it` is a compile-time constant after unrolling. The
+    // last iteration advances to the next k-tile.
     const double *cur;      // source of the next iteration inside the current k-tile
     __device__ __forceinline__ void load_iter(double *smem, int it)
     {
         constexpr int SSTEP = STEP * OT::STRIDE;
         if (it == 0) cur = src;
-        // a zero-fill of an element beyond the tile would land in the next stage (or past the allocation)
-        if (ELEMS % NTHREADS == 0 || it + 1 < ITERS || last_in_tile)
-            cp_async8(smem + soff + it * SSTEP, cur, (mask >> it) & 1u);
+        // a zero-fill of a unit beyond the tile would land in the next stage (or past the allocation)
+        if (UNITS % NTHREADS == 0 || it + 1 < ITERS || last_in_tile) {
+            const int nvalid = KMAJOR ? (((mask >> it) & 1u) ? VEC : 0) : (int)mask;
+            double *dst = smem + soff + it * SSTEP;
+            if (VEC == 1) cp_async8(dst, cur, nvalid != 0);
+            else if (vec16) cp_async16(dst, cur, 8 * nvalid);
+            else { cp_async8(dst, cur, nvalid >= 1); cp_async8(dst + 1, cur + 1, nvalid >= 2); }
+        }
         cur += it_stride;
         if (it == ITERS - 1) src += tile_stride;
     }
@@ -150,15 +165,19 @@ __device__ __forceinline__ void mma_tile(double (&acc)[MB][NB][2], const double 
 // [z*klen, (z+1)*klen) and writes alpha*partial to C + z*split_stride (beta must be 0).
 // MINB resident CTAs per SM are requested so that one CTA's prologue/epilogue (global latency) is
 // hidden behind another CTA's DMMA main loop.
-// ILV: the cp.async of the next stage are issued between the DMMAs of the current one (see TileLoader::load_iter)
-// instead of as one burst after the barrier.
-template <bool AK, bool BKM, int WM, int WN, int MB, int NB, int STAGES, int MINB, bool ILV = false>
+// OPT bit 0 (ILV): the cp.async of the next stage are issued between the DMMAs of the current one (see
+// TileLoader::load_iter) instead of as one burst after the barrier. OPT bit 1 (V16): two elements per thread and
+// iteration, one 16-byte cp.async each where the operand is 16-byte aligned (TileLoader, VEC = 2).
+constexpr int GEMM_OPT_ILV = 1, GEMM_OPT_V16 = 2;
+template <bool AK, bool BKM, int WM, int WN, int MB, int NB, int STAGES, int MINB, int OPT = 0>
 __global__ void __launch_bounds__(WM * WN * 32, MINB)
 dgemm_kernel(int M, int N, int K, double alpha, const double *__restrict__ A, int lda,
              const double *__restrict__ B, int ldb, double beta, double *__restrict__ C, int ldc,
              int klen, size_t split_stride)
 {
     constexpr int BM = WM * MB * 8, BN = WN * NB * 8, NT = WM * WN * 32;
+    constexpr bool ILV = (OPT & GEMM_OPT_ILV) != 0;
+    constexpr int VEC = (OPT & GEMM_OPT_V16) ? 2 : 1;
     using TA = OperandTile<AK, BM>;
     using TB = OperandTile<BKM, BN>;
     constexpr int STAGE = TA::SIZE + TB::SIZE;
@@ -190,8 +209,8 @@ dgemm_kernel(int M, int N, int K, double alpha, const double *__restrict__ A, in
         }
     }
 
-    TileLoader<AK, BM, NT> la;
-    TileLoader<BKM, BN, NT> lb;
+    TileLoader<AK, BM, NT, VEC> la;
+    TileLoader<BKM, BN, NT, VEC> lb;
     la.init(A, lda, m0, kbeg, M, tid);
     lb.init(B, ldb, n0, kbeg, N, tid);
     // stage tile t (if it exists) into ring slot t % STAGES; one commit group per call
@@ -301,20 +320,20 @@ __global__ void splitk_reduce_kernel(int rows, int cols, int splits, const doubl
     W[(size_t)c * ldw + r] = s;
 }
 
-template <bool AK, bool BKM, int WM, int WN, int MB, int NB, int STAGES, int MINB, bool ILV = false>
+template <bool AK, bool BKM, int WM, int WN, int MB, int NB, int STAGES, int MINB, int OPT = 0>
 struct GemmConfig {
     static constexpr int BM = WM * MB * 8, BN = WN * NB * 8, NT = WM * WN * 32;
     static constexpr size_t SMEM = (size_t)STAGES * (OperandTile<AK, BM>::SIZE + OperandTile<BKM, BN>::SIZE) * sizeof(double);
     static void prepare()
     {
-        SB_CUDA(cudaFuncSetAttribute(dgemm_kernel<AK, BKM, WM, WN, MB, NB, STAGES, MINB, ILV>,
+        SB_CUDA(cudaFuncSetAttribute(dgemm_kernel<AK, BKM, WM, WN, MB, NB, STAGES, MINB, OPT>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
     }
     static void launch(cudaStream_t st, int M, int N, int K, double alpha, const double *A, int lda, const double *B,
                        int ldb, double beta, double *C, int ldc, int splits, int klen, size_t split_stride)
     {
         dim3 grid(ceil_div(M, BM), ceil_div(N, BN), splits);
-        SB_LAUNCH((dgemm_kernel<AK, BKM, WM, WN, MB, NB, STAGES, MINB, ILV>), grid, NT, SMEM, st, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc,
+        SB_LAUNCH((dgemm_kernel<AK, BKM, WM, WN, MB, NB, STAGES, MINB, OPT>), grid, NT, SMEM, st, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc,
                   klen, split_stride);
     }
 };

@@ -47,13 +47,17 @@ using GemmTN13 = GemmConfig<true,  true,  4, 1, 2, 13, 4, 2>;    //  64 x 104, W
 using GemmTN12 = GemmConfig<true,  true,  4, 1, 2, 12, 4, 2>;    //  64 x  96
 using GemmNN13 = GemmConfig<false, true,  4, 1, 2, 13, 4, 2>;    //  64 x 104, W = A VT
 using GemmNN12 = GemmConfig<false, true,  4, 1, 2, 12, 4, 2>;    //  64 x  96
-// The same tiles with the next stage's cp.async spread between the DMMAs (dgemm.cuh, ILV). Opt-in
-// (STARNEIG_B200_GEMM_ILV=1) until it has been timed on a B200 against the burst variants (tools/gemm_sweep.cu).
-using GemmNTi   = GemmConfig<false, false, 2, 2, 8, 4, 4, 2, true>;
-using GemmTN13i = GemmConfig<true,  true,  4, 1, 2, 13, 4, 2, true>;
-using GemmTN12i = GemmConfig<true,  true,  4, 1, 2, 12, 4, 2, true>;
-using GemmNN13i = GemmConfig<false, true,  4, 1, 2, 13, 4, 2, true>;
-using GemmNN12i = GemmConfig<false, true,  4, 1, 2, 12, 4, 2, true>;
+// The same tiles with the loader options of dgemm.cuh (OPT bit 0: the next stage's cp.async spread between the DMMAs;
+// bit 1: 16-byte cp.async where the operand is aligned). Opt-in (STARNEIG_B200_GEMM_OPT=1|2|3) until they have been
+// timed on a B200 against the default kernels (tools/gemm_sweep.cu).
+template <int OPT> struct GemmOpt {
+    using NT   = GemmConfig<false, false, 2, 2, 8, 4, 4, 2, OPT>;
+    using TN13 = GemmConfig<true,  true,  4, 1, 2, 13, 4, 2, OPT>;
+    using TN12 = GemmConfig<true,  true,  4, 1, 2, 12, 4, 2, OPT>;
+    using NN13 = GemmConfig<false, true,  4, 1, 2, 13, 4, 2, OPT>;
+    using NN12 = GemmConfig<false, true,  4, 1, 2, 12, 4, 2, OPT>;
+    static void prepare() { NT::prepare(); TN13::prepare(); TN12::prepare(); NN13::prepare(); NN12::prepare(); }
+};
 // "Fat" variants for the side stream: 256 threads x ~200 registers fill the register file of an SM, so a CTA owns
 // its SM exclusively. When it retires the SM is completely free and the (higher-priority, equally SM-exclusive)
 // persistent panel kernel can claim it at once; with the 2-CTAs-per-SM variants an SM never drains while the
@@ -70,7 +74,7 @@ static void prepare_device_functions()
 {
     GemmNT::prepare(); GemmTN13::prepare(); GemmTN12::prepare(); GemmNN13::prepare(); GemmNN12::prepare();
     GemmNTfat::prepare(); GemmNN13fat::prepare(); GemmNN12fat::prepare();
-    GemmNTi::prepare(); GemmTN13i::prepare(); GemmTN12i::prepare(); GemmNN13i::prepare(); GemmNN12i::prepare();
+    GemmOpt<1>::prepare(); GemmOpt<2>::prepare(); GemmOpt<3>::prepare();
     SB_CUDA(cudaFuncSetAttribute(k_col_finish_update<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM_MAX));
     SB_CUDA(cudaFuncSetAttribute(k_col_finish_update<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM_MAX));
     SB_CUDA(cudaFuncSetAttribute(k_col_reflector<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM_MAX));
@@ -239,7 +243,7 @@ struct Rank {
     int gemv_slots = 0;                     // resident k_col_gemv blocks on the whole GPU (one wave)
     int fused = 1;                          // 1: one persistent kernel per panel (panel_fused.cuh); 0: three kernels per column
     int fused_ctas = 0;                     // grid of the fused kernel (number of SMs; fewer when ranks share a device)
-    int gemm_ilv = 0;                       // 1: DMMA kernels with interleaved cp.async (GemmNTi, ...)
+    int gemm_opt = 0;                       // loader options of the DMMA kernels (GemmOpt<1..3>), 0: the default kernels
     int fused_ll = 0;                       // 1: fused panel kernel with the LL-entry w2 reduction (two grid barriers fewer per column)
     std::vector<cudaEvent_t> events;        // phase events: 4 per panel
     std::vector<cudaEvent_t> gemv_events;   // 4 per timed column (profile level 2)
@@ -269,8 +273,8 @@ struct Rank {
         SB_CUDA(cudaDeviceGetAttribute(&fused_ctas, cudaDevAttrMultiProcessorCount, device));
         e = getenv("STARNEIG_B200_FUSED_CTAS");
         if (e && atoi(e) >= 1) fused_ctas = std::min(fused_ctas, atoi(e));
-        e = getenv("STARNEIG_B200_GEMM_ILV");
-        if (e) gemm_ilv = atoi(e);
+        e = getenv("STARNEIG_B200_GEMM_OPT");
+        if (e) gemm_opt = atoi(e) & 3;
         e = getenv("STARNEIG_B200_FUSED_LL");
         if (e) fused_ll = atoi(e);
         e = getenv("STARNEIG_B200_OVERLAP");
@@ -356,9 +360,13 @@ struct Rank {
         stats.gemm_flops += 2.0 * M * N * (double)K;
         const bool fat = on_side && side_fat;
         if (kind == GEMM_NT) {
-            if (fat)           GemmNTfat::launch(st, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, 1, K, 0);
-            else if (gemm_ilv) GemmNTi::launch(st, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, 1, K, 0);
-            else               GemmNT::launch(st, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, 1, K, 0);
+            if (fat) GemmNTfat::launch(st, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, 1, K, 0);
+            else switch (gemm_opt) {
+                case 1:  GemmOpt<1>::NT::launch(st, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, 1, K, 0); break;
+                case 2:  GemmOpt<2>::NT::launch(st, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, 1, K, 0); break;
+                case 3:  GemmOpt<3>::NT::launch(st, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, 1, K, 0); break;
+                default: GemmNT::launch(st, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, 1, K, 0);
+            }
             stats.kernel_launches++;
             return;
         }
@@ -379,22 +387,25 @@ struct Rank {
         double *out = splits > 1 ? wpart : C;
         size_t stride = splits > 1 ? (size_t)ldc * N : 0;
         double b = splits > 1 ? 0.0 : beta;
-        if (kind == GEMM_TN && gemm_ilv) {
-            if (bn == 96) GemmTN12i::launch(st, M, N, K, alpha, A, lda, B, ldb, b, out, ldc, splits, klen, stride);
-            else          GemmTN13i::launch(st, M, N, K, alpha, A, lda, B, ldb, b, out, ldc, splits, klen, stride);
+#define SB_SKINNY(CFG) CFG::launch(st, M, N, K, alpha, A, lda, B, ldb, b, out, ldc, splits, klen, stride)
+        if (kind == GEMM_NN && fat) {
+            if (bn == 96) SB_SKINNY(GemmNN12fat); else SB_SKINNY(GemmNN13fat);
         } else if (kind == GEMM_TN) {
-            if (bn == 96) GemmTN12::launch(st, M, N, K, alpha, A, lda, B, ldb, b, out, ldc, splits, klen, stride);
-            else          GemmTN13::launch(st, M, N, K, alpha, A, lda, B, ldb, b, out, ldc, splits, klen, stride);
-        } else if (fat) {
-            if (bn == 96) GemmNN12fat::launch(st, M, N, K, alpha, A, lda, B, ldb, b, out, ldc, splits, klen, stride);
-            else          GemmNN13fat::launch(st, M, N, K, alpha, A, lda, B, ldb, b, out, ldc, splits, klen, stride);
-        } else if (gemm_ilv) {
-            if (bn == 96) GemmNN12i::launch(st, M, N, K, alpha, A, lda, B, ldb, b, out, ldc, splits, klen, stride);
-            else          GemmNN13i::launch(st, M, N, K, alpha, A, lda, B, ldb, b, out, ldc, splits, klen, stride);
+            switch (gemm_opt) {
+                case 1:  if (bn == 96) SB_SKINNY(GemmOpt<1>::TN12); else SB_SKINNY(GemmOpt<1>::TN13); break;
+                case 2:  if (bn == 96) SB_SKINNY(GemmOpt<2>::TN12); else SB_SKINNY(GemmOpt<2>::TN13); break;
+                case 3:  if (bn == 96) SB_SKINNY(GemmOpt<3>::TN12); else SB_SKINNY(GemmOpt<3>::TN13); break;
+                default: if (bn == 96) SB_SKINNY(GemmTN12); else SB_SKINNY(GemmTN13);
+            }
         } else {
-            if (bn == 96) GemmNN12::launch(st, M, N, K, alpha, A, lda, B, ldb, b, out, ldc, splits, klen, stride);
-            else          GemmNN13::launch(st, M, N, K, alpha, A, lda, B, ldb, b, out, ldc, splits, klen, stride);
+            switch (gemm_opt) {
+                case 1:  if (bn == 96) SB_SKINNY(GemmOpt<1>::NN12); else SB_SKINNY(GemmOpt<1>::NN13); break;
+                case 2:  if (bn == 96) SB_SKINNY(GemmOpt<2>::NN12); else SB_SKINNY(GemmOpt<2>::NN13); break;
+                case 3:  if (bn == 96) SB_SKINNY(GemmOpt<3>::NN12); else SB_SKINNY(GemmOpt<3>::NN13); break;
+                default: if (bn == 96) SB_SKINNY(GemmNN12); else SB_SKINNY(GemmNN13);
+            }
         }
+#undef SB_SKINNY
         stats.kernel_launches++;
         if (splits > 1) {
             dim3 grid(ceil_div(M, 256), N);

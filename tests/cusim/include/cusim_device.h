@@ -11,6 +11,8 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <algorithm>
 #include <tuple>
 #include <utility>
@@ -137,6 +139,12 @@ static inline void cp_async8(void *smem_dst, const void *gmem_src, bool valid)
 {
     if (valid) memcpy(smem_dst, gmem_src, 8);
     else memset(smem_dst, 0, 8);
+}
+static inline void cp_async16(void *smem_dst, const void *gmem_src, int src_bytes)
+{
+    if ((((uintptr_t)smem_dst) | ((uintptr_t)gmem_src)) & 15) { fprintf(stderr, "cusim: misaligned 16-byte cp.async\n"); abort(); }
+    memset(smem_dst, 0, 16);
+    if (src_bytes > 0) memcpy(smem_dst, gmem_src, (size_t)src_bytes);
 }
 static inline void cp_async_commit() {}
 template <int N> static inline void cp_async_wait() {}

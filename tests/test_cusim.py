@@ -133,10 +133,12 @@ def test_sim_ll_reduction_variant(sim, ora, gpus, n, pw, sms):
     assert np.array_equal(A, A1) and np.array_equal(Q, Q1)
 
 
-def test_sim_interleaved_gemm_variant(sim, ora):
-    """ILV kernels (cp.async of the next stage between the DMMAs): same arithmetic, bitwise the same result"""
+@pytest.mark.parametrize("opt", [1, 2, 3])
+def test_sim_gemm_loader_options(sim, ora, opt):
+    """DMMA kernels with the loader options of dgemm.cuh (1: cp.async of the next stage between the DMMAs, 2: 16-byte
+    cp.async where the operand is aligned, 3: both): same arithmetic, bitwise the same result"""
     A, Q, _ = _reduce(sim, ora, 88, 35)
-    with _Env(STARNEIG_B200_GEMM_ILV=1):
+    with _Env(STARNEIG_B200_GEMM_OPT=opt):
         A1, Q1, _ = _reduce(sim, ora, 88, 35)
     assert np.array_equal(A, A1) and np.array_equal(Q, Q1)
 
@@ -218,24 +220,31 @@ def test_sim_results_do_not_depend_on_the_schedule(sim, ora, simlib):
     assert np.array_equal(AQ[0], A1[:64]) and np.array_equal(AQ[1], Q1[:64])
 
 
-@pytest.mark.parametrize("ilv", [0, 1])
-def test_sim_dgemm_kinds(sim, simlib, ilv, monkeypatch):
-    """the three operand layouts of the DMMA kernel (fragment layout of mma.m8n8k4 emulated lane by lane), edges,
-    odd offsets, split-K"""
-    import ctypes
+@pytest.mark.parametrize("opt", [0, 1, 2, 3])
+def test_sim_dgemm_kinds(sim, simlib, opt, monkeypatch):
+    """the three operand layouts of the DMMA kernel (fragment layout of mma.m8n8k4 emulated lane by lane), edges, odd
+    sizes, split-K; operands at 16-byte aligned and at odd (8-byte aligned) offsets -- the 16-byte cp.async path (opt 2, 3)
+    must only be taken for the former (the emulator aborts on a misaligned 16-byte copy)"""
     rng = np.random.default_rng(1)
-    monkeypatch.setenv("STARNEIG_B200_GEMM_ILV", str(ilv))
+    monkeypatch.setenv("STARNEIG_B200_GEMM_OPT", str(opt))
     sim.starneig_node_init(sim.STARNEIG_USE_ALL, 1, sim.STARNEIG_NO_MESSAGES)
     try:
-        for (ta, tb, m, n, k) in [("N", "T", 70, 37, 21), ("T", "N", 45, 13, 600), ("N", "N", 83, 29, 1100), ("N", "T", 130, 66, 4)]:
-            a = np.asfortranarray(rng.standard_normal((m, k) if ta == "N" else (k, m)))
-            b = np.asfortranarray(rng.standard_normal((n, k) if tb == "T" else (k, n)))
-            c = np.asfortranarray(rng.standard_normal((m, n)))
-            want = 0.75 * (a if ta == "N" else a.T) @ (b.T if tb == "T" else b) + (1.0 if ta == "N" and tb == "T" else 0.0) * c
-            beta = 1.0 if (ta, tb) == ("N", "T") else 0.0
-            ret = simlib.starneig_b200_dgemm(ta.encode(), tb.encode(), m, n, k, 0.75, a.ctypes.data, a.shape[0], b.ctypes.data,
-                                             b.shape[0], beta, c.ctypes.data, c.shape[0])
-            assert ret == 0
-            assert np.abs(c - want).max() <= 50 * k * U * np.abs(want).max()
+        for (ta, tb, m, n, k) in [("N", "T", 70, 37, 21), ("T", "N", 45, 13, 600), ("N", "N", 83, 29, 1100), ("N", "T", 130, 66, 4),
+                                  ("N", "T", 64, 64, 48), ("T", "N", 129, 104, 40)]:
+            for (offa, offb) in [(0, 0), (1, 0), (0, 1), (1, 1)]:
+                # operands as sub-matrices starting at row offa / offb of 16-byte aligned, even-ld arrays
+                ra, ca = ((m, k) if ta == "N" else (k, m))
+                rb, cb = ((n, k) if tb == "T" else (k, n))
+                lda, ldb, ldc = (ra + offa + 3) // 2 * 2, (rb + offb + 3) // 2 * 2, (m + 1) // 2 * 2
+                abuf = np.asfortranarray(rng.standard_normal((lda, ca)))
+                bbuf = np.asfortranarray(rng.standard_normal((ldb, cb)))
+                c = np.asfortranarray(rng.standard_normal((ldc, n)))
+                a, b = abuf[offa:offa + ra], bbuf[offb:offb + rb]
+                beta = 1.0 if (ta, tb) == ("N", "T") else 0.0
+                want = 0.75 * (a if ta == "N" else a.T) @ (b.T if tb == "T" else b) + beta * c[:m]
+                ret = simlib.starneig_b200_dgemm(ta.encode(), tb.encode(), m, n, k, 0.75, abuf.ctypes.data + 8 * offa, lda,
+                                                 bbuf.ctypes.data + 8 * offb, ldb, beta, c.ctypes.data, ldc)
+                assert ret == 0
+                assert np.abs(c[:m] - want).max() <= 50 * k * U * np.abs(want).max(), (ta, tb, m, n, k, offa, offb)
     finally:
         sim.starneig_node_finalize()

@@ -202,15 +202,17 @@ def test_ll_reduction_variant(node, ora, monkeypatch):
     _check_invariants(ora, n, A1, Q1, A0, ld)
 
 
-def test_interleaved_gemm_variant(node, ora, monkeypatch):
-    # DMMA kernels with the next stage's cp.async issued between the tensor instructions (dgemm.cuh, ILV): opt-in
-    # variant, same arithmetic in the same order as the default kernels => bitwise the same H and Q
+@pytest.mark.parametrize("opt", [1, 2, 3])
+def test_gemm_loader_options(node, ora, monkeypatch, opt):
+    # DMMA kernels with the loader options of dgemm.cuh (1: the next stage's cp.async between the tensor instructions,
+    # 2: 16-byte cp.async where the operand is aligned, 3: both): opt-in variants, same arithmetic in the same order as
+    # the default kernels => bitwise the same H and Q
     n, pw = 700, 120
     A0, Q0, ld = ora.fullpos(n, 2019)
     A, Q = A0.copy(order="F"), Q0.copy(order="F")
     assert _run(node, n, A, ld, Q, pw=pw) == 0
     node.starneig_node_finalize()
-    monkeypatch.setenv("STARNEIG_B200_GEMM_ILV", "1")
+    monkeypatch.setenv("STARNEIG_B200_GEMM_OPT", str(opt))
     node.starneig_node_init(node.STARNEIG_USE_ALL, 1, node.STARNEIG_NO_MESSAGES)
     A1, Q1 = A0.copy(order="F"), Q0.copy(order="F")
     assert _run(node, n, A1, ld, Q1, pw=pw) == 0

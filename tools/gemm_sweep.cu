@@ -127,8 +127,10 @@ static void run_cublas(cublasHandle_t h, const Shape &s, Buffers &b, int reps, c
 #define RUN(AK, BK_, WM, WN, MB, NB, ST, MINB, SPL)                                                                    \
     run_config<CFG(AK, BK_, WM, WN, MB, NB, ST, MINB)>(#WM "x" #WN " warps, " #MB "x" #NB " blocks, " #ST " st, " #MINB "/SM", s, b, reps, SPL, st)
 
-#define RUNI(AK, BK_, WM, WN, MB, NB, ST, MINB, SPL)                                                                   \
-    run_config<GemmConfig<AK, BK_, WM, WN, MB, NB, ST, MINB, true>>(#WM "x" #WN " warps, " #MB "x" #NB " blocks, " #ST " st, " #MINB "/SM ILV", s, b, reps, SPL, st)
+// the same with the loader options of dgemm.cuh: OPT 1 = interleaved cp.async, 2 = 16-byte cp.async, 3 = both
+#define RUNO(OPT, AK, BK_, WM, WN, MB, NB, ST, MINB, SPL)                                                              \
+    run_config<GemmConfig<AK, BK_, WM, WN, MB, NB, ST, MINB, OPT>>(#WM "x" #WN " warps, " #MB "x" #NB " blocks, " #ST " st, " #MINB "/SM opt" #OPT, s, b, reps, SPL, st)
+#define RUNI(AK, BK_, WM, WN, MB, NB, ST, MINB, SPL) RUNO(1, AK, BK_, WM, WN, MB, NB, ST, MINB, SPL)
 
 int main(int argc, char **argv)
 {
@@ -163,7 +165,11 @@ int main(int argc, char **argv)
         printf("NT  C(%d x %d) -= A(%d x %d) B(%d x %d)^T\n", s.M, s.N, s.M, s.K, s.N, s.K);
         run_cublas(h, s, b, reps, st);
         RUN(false, false, 2, 2, 8, 4, 4, 2, 1);     // product configuration (GemmNT)
-        RUNI(false, false, 2, 2, 8, 4, 4, 2, 1);    // product configuration with interleaved cp.async (GemmNTi)
+        RUNO(1, false, false, 2, 2, 8, 4, 4, 2, 1);     // product tile, interleaved cp.async (GemmOpt<1>::NT)
+        RUNO(2, false, false, 2, 2, 8, 4, 4, 2, 1);     // product tile, 16-byte cp.async where aligned (GemmOpt<2>::NT)
+        RUNO(3, false, false, 2, 2, 8, 4, 4, 2, 1);     // both
+        RUNO(2, false, false, 2, 4, 8, 4, 4, 1, 1);     // 128 x 128, 256 threads, 16-byte cp.async
+        RUNO(2, false, false, 4, 2, 4, 4, 4, 2, 1);     // 128 x 64, 256 threads, 2 CTAs/SM, 16-byte cp.async
         RUN(false, false, 2, 4, 8, 4, 4, 1, 1);     // product side-stream configuration (GemmNTfat)
         RUNI(false, false, 4, 2, 4, 4, 4, 2, 1);    // 128 x 64, 256 threads, 2 CTAs/SM, interleaved
         RUNI(false, false, 2, 2, 4, 4, 4, 4, 1);    // 64 x 64, 4 CTAs/SM, interleaved
@@ -187,7 +193,9 @@ int main(int argc, char **argv)
         const int t13 = ceil_div(s.M, 64) * ceil_div(s.N, 104);
         const int spl = std::min(32, std::max(1, std::min(ceil_div(8 * 2 * 148, t13), s.K / 512)));
         RUN(true, true, 4, 1, 2, 13, 4, 2, spl);    // product configuration (GemmTN13)
-        RUNI(true, true, 4, 1, 2, 13, 4, 2, spl);   // interleaved cp.async (GemmTN13i)
+        RUNO(1, true, true, 4, 1, 2, 13, 4, 2, spl);    // interleaved cp.async (GemmOpt<1>::TN13)
+        RUNO(2, true, true, 4, 1, 2, 13, 4, 2, spl);    // 16-byte cp.async where aligned
+        RUNO(3, true, true, 4, 1, 2, 13, 4, 2, spl);
         RUN(true, true, 4, 1, 2, 13, 4, 2, 1);
         RUN(true, true, 4, 1, 2, 13, 3, 2, spl);
         RUN(true, true, 4, 1, 2, 13, 5, 2, spl);
@@ -206,7 +214,10 @@ int main(int argc, char **argv)
         const int t13 = ceil_div(s.M, 64) * ceil_div(s.N, 104);
         const int spl = std::min(32, std::max(1, std::min(ceil_div(8 * 2 * 148, t13), s.K / 512)));
         RUN(false, true, 4, 1, 2, 13, 4, 2, spl);   // product configuration (GemmNN13)
-        RUNI(false, true, 4, 1, 2, 13, 4, 2, spl);  // interleaved cp.async (GemmNN13i)
+        RUNO(1, false, true, 4, 1, 2, 13, 4, 2, spl);   // interleaved cp.async (GemmOpt<1>::NN13)
+        RUNO(2, false, true, 4, 1, 2, 13, 4, 2, spl);   // 16-byte cp.async where aligned
+        RUNO(3, false, true, 4, 1, 2, 13, 4, 2, spl);
+        RUNO(2, false, true, 8, 1, 2, 13, 4, 1, spl);   // 128 x 104, 256 threads, 16-byte cp.async
         RUN(false, true, 4, 1, 2, 13, 4, 2, 1);
         RUN(false, true, 8, 1, 2, 13, 4, 1, spl);   // product side-stream configuration (GemmNN13fat)
         RUN(false, true, 4, 1, 2, 13, 3, 2, spl);
