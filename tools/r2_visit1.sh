@@ -19,4 +19,5 @@ timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --
 timeout 200 ncu --set full --clock-control none --import-source on -k regex:dgemm_kernel --launch-skip 8 -c 8 -o gpurun_out/dgemm_full -f \
     python tools/run_once.py 20000 > gpurun_out/ncu_dgemm.log 2>&1; echo "ncu dgemm exit $?"
 (timeout 90 driver/bin/starneig-test --experiment hessenberg --n 10000 --seed 2019 --gpus 1 --repeat 1 --warmup 1 --hooks hessenberg residual 2>&1; echo "driver exit $?") | tee gpurun_out/driver_n10000.log
+(timeout 200 python tools/chain_check.py 4000 2>&1 | tail -5) | tee gpurun_out/chain_n4000.log
 ls -la gpurun_out | tail -20
