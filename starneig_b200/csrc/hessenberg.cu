@@ -96,6 +96,13 @@ struct HostStage : StageHook {
     void upload()
     {
         copy_a(0, sh.ncols, true, r.stream);
+        if (overlap) {
+            // Q follows A over the link (the copy stream waits for A's upload): started together the two uploads
+            // would share the host-to-device bandwidth and delay A, which the first GEMV is waiting for, while Q is
+            // not needed before the first panel's column loop has finished
+            SB_CUDA(cudaEventRecord(r.ev_cols_final, r.stream));
+            SB_CUDA(cudaStreamWaitEvent(r.copy, r.ev_cols_final, 0));
+        }
         copy_q(0, n, true, overlap ? r.copy : r.stream);
         if (overlap) SB_CUDA(cudaEventRecord(r.ev_q_up, r.copy));
         SB_CUDA(cudaStreamSynchronize(r.stream));

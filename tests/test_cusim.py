@@ -188,6 +188,13 @@ def test_sim_multi_rank_fused(sim, ora, gpus, n, pw, cb):
     assert st["ranks"] == gpus and st["fused_panels"] == st["panels"]
 
 
+def test_sim_eight_ranks(sim, ora):
+    """the full width of one NVSwitch box: 8 ranks, one (emulated) SM each, column blocks of 8"""
+    with _Env(STARNEIG_B200_COL_BLOCK=8, CUSIM_SMS=1, CUSIM_DEVICES=8):
+        _, _, st = _reduce(sim, ora, 150, 24, gpus=8)
+    assert st["ranks"] == 8 and st["fused_panels"] == st["panels"]
+
+
 def test_sim_multi_rank_unfused(sim, ora):
     with _Env(STARNEIG_B200_COL_BLOCK=8, STARNEIG_B200_FUSED_PANEL=0):
         _, _, st = _reduce(sim, ora, 72, 16, gpus=2)
