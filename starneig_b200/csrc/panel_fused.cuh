@@ -607,6 +607,13 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_panel_fused(FusedArgs f)
                 // ---- look-ahead for phase A of column j+1: D0 = Y(:, :j) s_j, D1 = Y(:, :j) V(j, :j)^T, D2 = VT(:, :j) s_j.
                 // None of them needs the GEMV result, so they run in the shadow of the HBM-bound GEMV.
                 const int xt = tid - 32 * FUSED_GEMV_WARPS, xw = wp - FUSED_GEMV_WARPS;
+                if (LLRED && j + 1 < f.w) {
+                    // The next panel column was last touched by the previous panel's trailing update and has long been
+                    // evicted by the streaming GEMVs: pull the CTA's rows of it towards L2 now, phase A reads them on
+                    // the critical path (one 128-byte line per thread)
+                    const int r = row0 + 16 * xt;
+                    if (16 * xt < rows_here && r < m) prefetch_l2(f.pan + (size_t)(j + 1) * f.ldpan + r);
+                }
                 gen2 += G;
                 if (xt == 0) while ((int)(ld_acquire_gpu(bar2) - gen2) < 0) { }
                 group_barrier(5, FUSED_SHADOW_THREADS);
