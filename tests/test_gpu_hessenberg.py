@@ -164,62 +164,6 @@ def test_extreme_scaling(node, ora, monkeypatch, e, fused):
     _check_invariants(ora, n, A, Q, A0, ld)
 
 
-@pytest.mark.parametrize("fused", [1, 0])
-def test_denormal_range_takes_dlarfg_rescaling_branch(node, ora, monkeypatch, fused):
-    # A matrix scaled by 2^-1040 lives in the denormal range: LAPACK's dlarfg (reference src/hessenberg/cpu.c:140)
-    # rescales x and alpha by 1/safmin before it forms the reflector, and so do the kernels (dlarfg_scalars, panel.cuh).
-    # The data itself carries only ~34 bits there, so H and Q agree with the reference to that level only -- but Q stays
-    # orthogonal to a few u and nothing overflows (without the branch: 1 / (alpha - beta) = inf => NaN).
-    monkeypatch.setenv("STARNEIG_B200_FUSED_PANEL", str(fused))
-    n, pw = 333, 45
-    A0, Q0, ld = ora.full(n, 7)
-    s = 2.0 ** -1040
-    A, Q = (A0 * s).copy(order="F"), Q0.copy(order="F")
-    assert _run(node, n, A, ld, Q, pw=pw) == 0
-    A2, Q2 = (A0 * s).copy(order="F"), Q0.copy(order="F")
-    assert ora.hessenberg_port(n, A2, ld, Q2, ld, 0, n, pw) == 0
-    assert np.isfinite(A[:n]).all() and np.isfinite(Q[:n]).all()
-    assert ora.hessenberg_form_violations(n, A, ld) == 0
-    assert ora.orthogonality_u(n, Q, ld) <= 500
-    assert np.abs(A[:n] - A2[:n]).max() <= 1e-5 * np.abs(A2[:n]).max()
-    assert np.abs(Q[:n] - Q2[:n]).max() <= 1e-5
-
-
-def test_ll_reduction_variant(node, ora, monkeypatch):
-    # persistent panel kernel with the w2 reduction carried by self-validating LL entries instead of two grid barriers
-    # (opt-in, STARNEIG_B200_FUSED_LL=1): same partial sums in the same order => bitwise the same H and Q
-    n, pw = 1500, 200
-    A0, Q0, ld = ora.fullpos(n, 2019)
-    A, Q = A0.copy(order="F"), Q0.copy(order="F")
-    assert _run(node, n, A, ld, Q, pw=pw) == 0
-    node.starneig_node_finalize()
-    monkeypatch.setenv("STARNEIG_B200_FUSED_LL", "1")
-    node.starneig_node_init(node.STARNEIG_USE_ALL, 1, node.STARNEIG_NO_MESSAGES)
-    for _ in range(2):          # twice: the tags of the second call continue where the first one stopped
-        A1, Q1 = A0.copy(order="F"), Q0.copy(order="F")
-        assert _run(node, n, A1, ld, Q1, pw=pw) == 0
-        assert np.array_equal(A1[:n], A[:n]) and np.array_equal(Q1[:n], Q[:n])
-    _check_invariants(ora, n, A1, Q1, A0, ld)
-
-
-@pytest.mark.parametrize("opt", [1, 2, 3])
-def test_gemm_loader_options(node, ora, monkeypatch, opt):
-    # DMMA kernels with the loader options of dgemm.cuh (1: the next stage's cp.async between the tensor instructions,
-    # 2: 16-byte cp.async where the operand is aligned, 3: both): opt-in variants, same arithmetic in the same order as
-    # the default kernels => bitwise the same H and Q
-    n, pw = 700, 120
-    A0, Q0, ld = ora.fullpos(n, 2019)
-    A, Q = A0.copy(order="F"), Q0.copy(order="F")
-    assert _run(node, n, A, ld, Q, pw=pw) == 0
-    node.starneig_node_finalize()
-    monkeypatch.setenv("STARNEIG_B200_GEMM_OPT", str(opt))
-    node.starneig_node_init(node.STARNEIG_USE_ALL, 1, node.STARNEIG_NO_MESSAGES)
-    A1, Q1 = A0.copy(order="F"), Q0.copy(order="F")
-    assert _run(node, n, A1, ld, Q1, pw=pw) == 0
-    assert np.array_equal(A1[:n], A[:n]) and np.array_equal(Q1[:n], Q[:n])
-    _check_invariants(ora, n, A1, Q1, A0, ld)
-
-
 def test_downstream_eigenvalues(node, ora):
     # config 5 of BASELINE.json at test size: GPU Hessenberg -> dhseqr (stand-in for starneig_SEP_SM_Schur)
     # vs the all-CPU chain (oracle Hessenberg -> dhseqr); tolerance 1e-10 * ||A||

@@ -5,7 +5,7 @@
 # gpurun_out/.   usage: gpurun --timeout 1100 -- bash tools/r2_visit1.sh
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/smi.txt
-(timeout 420 python -m pytest tests -m gpu -x -q 2>&1 | tail -5) | tee gpurun_out/pytest_gpu.log
+(STARNEIG_TEST_OPTIN=1 timeout 480 python -m pytest tests -m gpu -q 2>&1 | tail -12) | tee gpurun_out/pytest_gpu.log
 (timeout 150 tools/bin/gemm_sweep 20000 2 3 2>&1) > gpurun_out/gemm_sweep_p2.txt; tail -50 gpurun_out/gemm_sweep_p2.txt
 (timeout 100 tools/bin/gemm_sweep 20000 40 3 2>&1) > gpurun_out/gemm_sweep_p40.txt
 : > gpurun_out/sweep.log
