@@ -116,6 +116,8 @@ struct Workspace {
     ColScal *scal = nullptr;
     unsigned *counter = nullptr;
     uint4 *w2part_ll = nullptr, *w2_ll = nullptr;       // LL entries of the w2 reduction (fused kernel, LLRED)
+    uint4 *ypart_ll = nullptr;                          // LL entries of the GEMV partials (fused kernel, LLRED)
+    double *pcol2 = nullptr;                            // second column buffer (fused kernel, LLRED)
     unsigned *gbar = nullptr;                   // grid barrier counter of the fused panel kernel
     unsigned long long *timers = nullptr;       // device-side phase timers of the fused panel kernel (ns)
     std::vector<void *> allocs;
@@ -132,7 +134,7 @@ struct Workspace {
         for (void *p : allocs) cudaFree(p);
         allocs.clear();
         n_cap = nb_cap = 0;
-        w2part_ll = w2_ll = nullptr;
+        w2part_ll = w2_ll = ypart_ll = nullptr;
     }
     // the column sequence numbers restart (new exchange arena): no stale LL entry may carry a tag that will be reused
     void reset_ll()
@@ -140,6 +142,7 @@ struct Workspace {
         if (!w2part_ll) return;
         SB_CUDA(cudaMemset(w2part_ll, 0, (size_t)nbp * PANEL_LDB * sizeof(uint4)));
         SB_CUDA(cudaMemset(w2_ll, 0, nbp * sizeof(uint4)));
+        SB_CUDA(cudaMemset(ypart_ll, 0, ypart_cap * sizeof(uint4)));
     }
     void ensure(int n, int nb, bool dist)
     {
@@ -162,6 +165,9 @@ struct Workspace {
         pcol = alloc<double>(ldv);
         ypart_cap = (size_t)2 * 148 * 12 * 256 + 4 * (size_t)ldv;
         ypart = alloc<double>(ypart_cap);
+        ypart_ll = alloc<uint4>(ypart_cap);
+        SB_CUDA(cudaMemset(ypart_ll, 0, ypart_cap * sizeof(uint4)));
+        pcol2 = alloc<double>(ldv);
         s = alloc<double>(nbp); w2 = alloc<double>(nbp);
         colpart = alloc<double>((size_t)nbp * PANEL_LDB);
         sqpart = alloc<double>(3 * PANEL_LDB);
@@ -523,7 +529,7 @@ struct Rank {
             f.gbar = ws.gbar; f.timers = ws.timers;
             f.x = x;
             f.x.epoch = y_epoch + 1;
-            f.w2part_ll = ws.w2part_ll; f.w2_ll = ws.w2_ll;
+            f.w2part_ll = ws.w2part_ll; f.w2_ll = ws.w2_ll; f.ypart_ll = ws.ypart_ll; f.pcol2 = ws.pcol2;
             const size_t smem = fused_smem_bytes(w, f.nsub);
             if (smem <= PANEL_SMEM_MAX) {
                 y_epoch += w;

@@ -48,6 +48,8 @@ struct FusedArgs {
     Xchg x;                     // x.epoch = sequence number of the panel's first column (tags of all LL entries); rest DIST only
     uint4 *w2part_ll;           // LLRED: PANEL_LDB x ldt self-validating per-CTA partials of w2 = VT^T p'
     uint4 *w2_ll;               // LLRED: ldt self-validating entries of w2
+    uint4 *ypart_ll;            // LLRED: the GEMV partials (layout of ypart) as self-validating entries
+    double *pcol2;              // LLRED: second buffer of the column being reduced (columns alternate between pcol and pcol2)
 };
 
 // All CTAs of the (cooperative, co-resident) grid: one arrival counter (red.release) that thread 0 of every CTA
@@ -175,6 +177,36 @@ __device__ __forceinline__ double sum_partials(const double *p, int ld, int S)
     return e;
 }
 
+// the same over self-validating LL entries (GEMV partials of a column, tag = its sequence number): the row owner polls
+// the partials of its rows instead of waiting at a grid barrier for ALL groups of the GEMV
+__device__ __forceinline__ double sum_partials_ll(const uint4 *p, int ld, int S, unsigned tag, unsigned *status)
+{
+    double e = 0.0;
+    int z = 0;
+    for (; z + 8 <= S; z += 8) {
+        double x[8];
+        bool ready[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const uint4 v = ld_volatile_v4(p + (size_t)(z + u) * ld);
+            ready[u] = (v.y == tag && v.w == tag);
+            x[u] = __longlong_as_double((long long)(((unsigned long long)v.z << 32) | v.x));
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u++)
+            if (!ready[u]) x[u] = ll_load(p + (size_t)(z + u) * ld, tag, status);
+        e += ((x[0] + x[1]) + (x[2] + x[3])) + ((x[4] + x[5]) + (x[6] + x[7]));
+    }
+    for (; z + 4 <= S; z += 4) {
+        double x[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) x[u] = ll_load(p + (size_t)(z + u) * ld, tag, status);
+        e += (x[0] + x[1]) + (x[2] + x[3]);
+    }
+    for (; z < S; z++) e += ll_load(p + (size_t)z * ld, tag, status);
+    return e;
+}
+
 // Column-wise dots of one CTA: out[t] = sum over the CTA's rows of M(r, t) * p(r) for t in [tb, tb+NC), t < tmax.
 // One warp; NC columns x NS sub-tiles = 32 independent loads are in flight per lane. p(r) comes from shared
 // memory (pv[sub*32 + lane], zero for rows >= m). Result: see transpose_reduce8 / transpose_reduce32.
@@ -290,8 +322,14 @@ __device__ __noinline__ double fused_rescale_x(double *pcol, const double *V, in
     return t_first < j ? sum_over_ctas(colpart + t_first, ldt, nblk, lane) : 0.0;
 }
 
-// LLRED: the reduction w2 = sum over CTAs of VT^T p' travels as self-validating LL entries (partials -> reducing warps ->
-// every CTA), which removes the two grid barriers around phase A'. Opt-in (STARNEIG_B200_FUSED_LL=1) until timed on a B200.
+// LLRED: one grid barrier per column instead of four. (1) The reduction w2 = sum over CTAs of VT^T p' travels as
+// self-validating LL entries (partials -> reducing warps -> every CTA): no barriers around phase A'. (2) The GEMV
+// partials are LL entries too: the owner of a row polls the partials of its rows instead of waiting for ALL groups of
+// the GEMV at a grid barrier, so a CTA whose producers are done starts the next column while the slowest GEMV groups
+// are still streaming. What the dropped barriers also ordered is handled explicitly: the column being reduced
+// alternates between two buffers (a fast CTA writes p' of column j+1 while a slow one still forms v from p'' of column
+// j), and tau / beta / scale of the previous column come from the CTA's own shared-memory copy. The barrier after
+// phase R stays (the GEMV reads p'' of all rows). Opt-in (STARNEIG_B200_FUSED_LL=1) until timed on a B200.
 template <bool DIST, bool LLRED>
 __global__ void __launch_bounds__(FUSED_THREADS, 1) k_panel_fused(FusedArgs f)
 {
@@ -329,6 +367,9 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_panel_fused(FusedArgs f)
         const int jm1 = j - 1;
         double *acol = f.pan + (size_t)j * f.ldpan;
         const int NW = max(1, (j + 31) >> 5);
+        // the column being reduced: p', then p'' (LLRED: columns alternate between two buffers)
+        double *const pc_cur = (LLRED && (j & 1)) ? f.pcol2 : a.pcol;
+        const double *const pc_prev = (LLRED && !(j & 1)) ? f.pcol2 : a.pcol;
 
         if (j > 0) {
             // ================= phase A: finish column j-1, start column j =================
@@ -336,8 +377,9 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_panel_fused(FusedArgs f)
             // GEMV of column j-1 was streaming (`red`); what is left on the critical path is y itself.
             const int NWa = max(1, (jm1 + 31) >> 5);
             const bool do_update = j < f.w;
-            const double tau = __ldcg(&a.scal[jm1].tau), beta_prev = __ldcg(&a.scal[jm1].beta),
-                         scale_prev = __ldcg(&a.scal[jm1].scale);
+            // LLRED: no grid barrier since R' of column j-1, where every CTA derived these scalars itself (scal_sh)
+            const double tau = LLRED ? scal_sh[0] : __ldcg(&a.scal[jm1].tau), beta_prev = LLRED ? scal_sh[1] : __ldcg(&a.scal[jm1].beta),
+                         scale_prev = LLRED ? scal_sh[2] : __ldcg(&a.scal[jm1].scale);
             double *acol_prev = f.pan + (size_t)jm1 * f.ldpan;
             {
                 // y(r) of the CTA's rows: sum of the local GEMV partials of column j-1 (fixed order); on P GPUs the
@@ -352,7 +394,10 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_panel_fused(FusedArgs f)
                     const int r = row0 + rr;
                     const int rb = (r + gs.skip) >> 8;
                     double sum = 0.0;
-                    if (nloc_prev > 0) sum = sum_partials(a.ypart + r, a.ldp, gp.last_group(rb) - gp.first_group(rb) + 1);
+                    if (nloc_prev > 0) {
+                        const int S = gp.last_group(rb) - gp.first_group(rb) + 1;
+                        sum = LLRED ? sum_partials_ll(f.ypart_ll + r, a.ldp, S, epoch, f.x.status) : sum_partials(a.ypart + r, a.ldp, S);
+                    }
                     if (DIST) {
                         const size_t slot = ((size_t)par * f.x.P + f.x.g) * a.ldp + r;
                         for (int d = 1; d < f.x.P; d++) ll_store((uint4 *)f.x.inbox[(f.x.g + d) % f.x.P] + slot, sum, epoch);
@@ -391,7 +436,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_panel_fused(FusedArgs f)
                 const bool valid = r < m;
                 double pp = 0.0;
                 if (valid) {
-                    const double pprev = a.pcol[r];
+                    const double pprev = pc_prev[r];
                     const double ac = do_update ? acol[r] : 0.0;
                     const double D3 = ysm[sub * 32 + lane];
                     const double *rd = red + (size_t)sub * 3 * NWa * 32 + lane;
@@ -407,7 +452,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_panel_fused(FusedArgs f)
                     a.VT[(size_t)jm1 * ld + r] = tau * (vr - D2);        // VT(:,j-1) = V * T(:,j-1)
                     if (do_update) {
                         pp = ac - (D1 + ynew);                           // prepare_column: p - Y V(j-1,:)^T, V(j-1,j-1) = 1
-                        a.pcol[r] = pp;
+                        pc_cur[r] = pp;
                     }
                 }
                 pv[sub * 32 + lane] = pp;
@@ -461,13 +506,13 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_panel_fused(FusedArgs f)
                 const bool valid = r < m;
                 double xx = 0.0;
                 if (valid) {
-                    double pp = j > 0 ? a.pcol[r] : acol[r];
+                    double pp = j > 0 ? pc_cur[r] : acol[r];
                     if (j > 0) {
                         double D = 0.0;
                         for (int q = 0; q < NW; q++) D += red[((size_t)sub * NW + q) * 32 + lane];
                         pp -= D;
                     }
-                    a.pcol[r] = pp;
+                    pc_cur[r] = pp;
                     if (r < j) acol[r] = pp;            // final entries of H above the sub-diagonal
                     if (r == j) a.scal[j].alpha = pp;
                     if (r > j) xx = pp;
@@ -506,7 +551,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_panel_fused(FusedArgs f)
                 if (b == 0) { a.scal[j].tau = tau; a.scal[j].beta = beta; a.scal[j].scale = scale; }
             }
             if (rf.xmul != 1.0) {       // denormal-range column
-                zsum = fused_rescale_x(a.pcol, a.V, ld, a.colpart, a.ldt, m, nsub, f.gbar, gen, pv, j, rf.xmul, t_first);
+                zsum = fused_rescale_x(pc_cur, a.V, ld, a.colpart, a.ldt, m, nsub, f.gbar, gen, pv, j, rf.xmul, t_first);
                 gen += 2 * G;
             }
             if (t_first < j && lane == 0) a.s[t_first] = fma(scale, zsum, vjt);
@@ -553,7 +598,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_panel_fused(FusedArgs f)
                         group_barrier(1 + vb, 128);          // previous chunk's vs fully consumed
                         for (int k = vt; k < nk; k += 128) {
                             const int kk = f.cm.l2g(lc0 + k0 + k) - gc0;
-                            vs[k] = (kk == 0) ? 1.0 : __ldcg(a.pcol + j + kk) * scale;
+                            vs[k] = (kk == 0) ? 1.0 : __ldcg(pc_cur + j + kk) * scale;
                         }
                         group_barrier(1 + vb, 128);
                         if (rows_ok) {
@@ -596,10 +641,17 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_panel_fused(FusedArgs f)
                         }
                     }
                     if (rows_ok) {
-                        double *yp = a.ypart + (size_t)(v - gq.first_group(rb)) * a.ldp;
+                        const size_t slot = (size_t)(v - gq.first_group(rb)) * a.ldp;
                         const int r = rp - gs.skip;
-                        if (r >= 0) yp[r] = acc.x;
-                        if (r + 1 < m) yp[r + 1] = acc.y;
+                        if (LLRED) {
+                            const unsigned tagc = f.x.epoch + j;
+                            if (r >= 0) ll_store(f.ypart_ll + slot + r, acc.x, tagc);
+                            if (r + 1 < m) ll_store(f.ypart_ll + slot + r + 1, acc.y, tagc);
+                        } else {
+                            double *yp = a.ypart + slot;
+                            if (r >= 0) yp[r] = acc.x;
+                            if (r + 1 < m) yp[r + 1] = acc.y;
+                        }
                     }
                     it += cend - cbeg;
                 }
@@ -655,7 +707,9 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_panel_fused(FusedArgs f)
                     rd[0] = d0; rd[NWn * 32] = d1; rd[2 * NWn * 32] = d2;
                 }
             }
-            grid_barrier(f.gbar, gen);
+            // LLRED: no grid barrier here -- phase A polls the LL-tagged partials of its own rows, and its first
+            // __syncthreads orders the look-ahead results (`red`) of this CTA
+            if (!LLRED) grid_barrier(f.gbar, gen);
             if (timer) { t_mark = globaltimer_ns(); t_gemv += t_mark; }
         }
     }

@@ -9,8 +9,9 @@
 // their kernels really run concurrently and talk through "peer" memory (plain host memory) with the same
 // acquire/release and LL protocols as on NVLink.
 // Checks the hardware does not make: a pass in which every live fiber is blocked on a barrier that cannot complete is
-// reported as a deadlock (mismatched barrier counts); CUSIM_SHUFFLE=seed resumes the fibers in a random order to shake
-// out ordering assumptions; fresh "device" and shared memory is filled with NaN patterns.
+// reported as a deadlock (mismatched barrier counts); CUSIM_SHUFFLE=seed resumes the fibers in a random order and
+// CUSIM_SKEW=N lets some blocks of a cooperative grid lag far behind the others, to shake out ordering assumptions;
+// fresh "device" and shared memory is filled with NaN patterns.
 #include <cuda_runtime.h>
 #include <sys/mman.h>
 #include <algorithm>
@@ -199,6 +200,8 @@ void run_grid(dim3 grid, dim3 block, size_t smem_bytes, bool cooperative, const 
     const size_t batch = cooperative ? nblocks : 1;
     static const char *shuffle_env = getenv("CUSIM_SHUFFLE");
     static const char *timeout_env = getenv("CUSIM_TIMEOUT");
+    static const char *skew_env = getenv("CUSIM_SKEW");
+    const unsigned skew = skew_env ? (unsigned)atoi(skew_env) : 0u;
     const double timeout_s = timeout_env ? atof(timeout_env) : 120.0;
     std::mt19937 rng(shuffle_env ? (unsigned)atoi(shuffle_env) : 0u);
     s.body = &body;
@@ -238,6 +241,9 @@ void run_grid(dim3 grid, dim3 block, size_t smem_bytes, bool cooperative, const 
             for (size_t k : order) {
                 Fiber &f = s.fibers[k];
                 if (f.st == DONE) continue;
+                // CUSIM_SKEW=N: block c of a cooperative grid only runs in one pass out of 1 + c % N, so some blocks
+                // lag far behind the others (exposes missing ordering between a fast and a slow block)
+                if (skew > 1 && batch > 1 && (rng() % (1u + (unsigned)(k / nthreads) % skew)) != 0u) { resumed = true; continue; }
                 if (f.st == BLOCKED) {
                     if (*f.wait_ptr == f.wait_val) continue;
                     f.st = RUN;

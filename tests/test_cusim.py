@@ -255,3 +255,44 @@ def test_sim_dgemm_kinds(sim, simlib, opt, monkeypatch):
                 assert np.abs(c[:m] - want).max() <= 50 * k * U * np.abs(want).max(), (ta, tb, m, n, k, offa, offb)
     finally:
         sim.starneig_node_finalize()
+
+
+_PANEL_CHILD = r"""
+import sys, os
+sys.path.insert(0, %r)
+import numpy as np
+import starneig_b200 as sn
+from starneig_b200 import api, _lib
+from oracle.oracle import Oracle
+lib = api._handle = _lib.load(%r)
+n, w = int(sys.argv[1]), int(sys.argv[2])
+A0, Q0, ld = Oracle().fullpos(n, 2019)
+def panel(env):
+    os.environ.update(env)
+    sn.starneig_node_init(-1, 1, sn.STARNEIG_NO_MESSAGES)
+    A = A0.copy(order="F")
+    ldw = (n + 15) // 16 * 16
+    V = np.full((ldw, w), np.nan, order="F"); Y = V.copy(order="F"); VT = V.copy(order="F"); tau = np.zeros(w)
+    ret = lib.starneig_b200_panel(n, 0, n, w, A.ctypes.data, ld, V.ctypes.data, Y.ctypes.data, VT.ctypes.data, ldw, tau.ctypes.data)
+    sn.starneig_node_finalize()
+    for k in env: os.environ.pop(k)
+    assert ret == 0
+    return A[:n, :w].copy(), V[:n - 1].copy(), Y[:n - 1].copy(), VT[:n - 1].copy(), tau
+ref = panel({})
+got = panel({"STARNEIG_B200_FUSED_LL": "1"})
+assert all(np.isfinite(x).all() for x in got)
+assert all(np.array_equal(a, b) for a, b in zip(ref, got)), "LL variant differs from the default kernel"
+print("OK")
+""" % (ROOT, SIM_LIB)
+
+
+@pytest.mark.parametrize("sms,skew,seed", [(4, 4, 1), (6, 5, 2), (3, 3, 4)])
+def test_sim_ll_variant_with_lagging_blocks(simlib, sms, skew, seed):
+    """One panel of a 600 x 600 matrix (three 256-row blocks of GEMV partials) with the LL variant of the persistent kernel
+    (one grid barrier per column instead of four) while some blocks of the grid are scheduled far less often than the
+    others: a fast block runs into the next column while a slow one is still forming v for its part of the GEMV. With a
+    single column buffer this schedule corrupts the result (that is how the two-buffer scheme was validated); V, Y, VT,
+    tau and the panel columns must be bitwise those of the default kernel."""
+    r = subprocess.run(["python", "-c", _PANEL_CHILD, "600", "12"], capture_output=True, text=True, timeout=600,
+                       env=dict(os.environ, CUSIM_SMS=str(sms), CUSIM_SKEW=str(skew), CUSIM_SHUFFLE=str(seed)))
+    assert r.returncode == 0 and r.stdout.strip().endswith("OK"), r.stdout[-1000:] + r.stderr[-2000:]
