@@ -177,6 +177,20 @@ __device__ __forceinline__ double sum_partials(const double *p, int ld, int S)
     return e;
 }
 
+// waits, with back-off, until an LL entry carries `tag` (used by ONE lane per warp before its rows are summed, so that
+// thousands of threads do not hammer L2 with polls while the stragglers of the GEMV are still streaming)
+__device__ __forceinline__ void ll_wait(const uint4 *src, unsigned tag, unsigned *status)
+{
+    long long t0 = 0;
+    for (;;) {
+        const uint4 e = ld_volatile_v4(src);
+        if (e.y == tag && e.w == tag) return;
+        if (t0 == 0) { t0 = clock64(); if (*(volatile unsigned *)status != 0u) return; }
+        else if (clock64() - t0 > 8000000000ll) { atomicExch(status, 2u); return; }
+        __nanosleep(200);
+    }
+}
+
 // the same over self-validating LL entries (GEMV partials of a column, tag = its sequence number): the row owner polls
 // the partials of its rows instead of waiting at a grid barrier for ALL groups of the GEMV
 __device__ __forceinline__ double sum_partials_ll(const uint4 *p, int ld, int S, unsigned tag, unsigned *status)
@@ -390,6 +404,13 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_panel_fused(FusedArgs f)
                 gp.per = max(FUSED_MINSEG, (int)(((long long)gs.RB * nloc_prev + G * FUSED_VB - 1) / (G * FUSED_VB)));
                 const unsigned epoch = f.x.epoch + jm1;
                 const int par = epoch & 1;
+                if (LLRED && nloc_prev > 0) {
+                    // one lane per warp waits for the partial of the warp's first row that is written last (the group
+                    // that first finishes the previous row block): the others are then there or about to be
+                    const int rr0 = tid & ~31;
+                    if (lane == 0 && rr0 < rows_here) ll_wait(f.ypart_ll + row0 + rr0, epoch, f.x.status);
+                    __syncwarp();
+                }
                 for (int rr = tid; rr < rows_here; rr += FUSED_THREADS) {
                     const int r = row0 + rr;
                     const int rb = (r + gs.skip) >> 8;
@@ -479,6 +500,10 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_panel_fused(FusedArgs f)
 
         // ================= phase R: p'' = p' - V w2; ||x||^2, z = V^T x =================
         {
+            if (LLRED && j > 0) {       // one polling lane per warp (see phase A)
+                if (lane == 0 && (tid & ~31) < j) ll_wait(f.w2_ll + (tid & ~31), f.x.epoch + j, f.x.status);
+                __syncwarp();
+            }
             for (int t = tid; t < j; t += FUSED_THREADS)
                 w2_sh[t] = LLRED ? ll_load(f.w2_ll + t, f.x.epoch + j, f.x.status) : __ldcg(a.w2 + t);
             __syncthreads();

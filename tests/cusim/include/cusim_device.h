@@ -83,6 +83,12 @@ template <class T> static inline T __shfl_xor_sync(unsigned, T v, int lane_mask)
     memcpy(&r, all[(::cusim::g_thread->lane ^ (unsigned)lane_mask) & 31], sizeof(T));
     return r;
 }
+static inline void __syncwarp()
+{
+    alignas(16) unsigned char all[32][16];
+    const int mine = 0;
+    ::cusim::warp_exchange(&mine, sizeof(int), all);
+}
 static inline int __any_sync(unsigned, int pred)
 {
     alignas(16) unsigned char all[32][16];
