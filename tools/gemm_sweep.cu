@@ -184,6 +184,11 @@ int main(int argc, char **argv)
         RUN(false, false, 2, 4, 4, 4, 4, 2, 1);     // 64 x 128, 256 threads
         RUN(false, false, 4, 4, 4, 4, 3, 1, 1);     // 128 x 128, 512 threads, 1 CTA/SM
         RUN(false, false, 4, 2, 8, 4, 3, 1, 1);     // 256 x 64, 256 threads
+        RUN(false, false, 4, 2, 4, 8, 3, 1, 1);     // 128 x 128, 8 warps of 32 x 64, 3 stages: the shape of cuBLAS's cutlass_80_tensorop_d884gemm_128x128_16x3
+        RUN(false, false, 4, 2, 4, 8, 4, 1, 1);
+        RUNO(2, false, false, 4, 2, 4, 8, 3, 1, 1);
+        RUNO(3, false, false, 4, 2, 4, 8, 3, 1, 1);
+        RUNO(3, false, false, 2, 4, 8, 4, 4, 1, 1);
     }
     {   // ---- TN: W(m-w x w) = A(m x m-w)^T VT(m x w)
         Shape s{'t', m - w, w, m};
