@@ -250,7 +250,8 @@ struct Rank {
     int fused = 1;                          // 1: one persistent kernel per panel (panel_fused.cuh); 0: three kernels per column
     int fused_ctas = 0;                     // grid of the fused kernel (number of SMs; fewer when ranks share a device)
     int gemm_opt = 0;                       // loader options of the DMMA kernels (GemmOpt<1..3>), 0: the default kernels
-    int fused_ll = 0;                       // 1: fused panel kernel with the LL-entry w2 reduction (two grid barriers fewer per column)
+    int fused_ll = 0;                       // 1: fused panel kernel with LL-entry reductions (one grid barrier per column instead of four)
+    int fused_even_rows = 0;                // 1: fused panel kernel: rows spread over all CTAs (changes the grouping of the partial sums)
     std::vector<cudaEvent_t> events;        // phase events: 4 per panel
     std::vector<cudaEvent_t> gemv_events;   // 4 per timed column (profile level 2)
     size_t gemv_events_used = 0;
@@ -283,6 +284,8 @@ struct Rank {
         if (e) gemm_opt = atoi(e) & 3;
         e = getenv("STARNEIG_B200_FUSED_LL");
         if (e) fused_ll = atoi(e);
+        e = getenv("STARNEIG_B200_FUSED_EVEN_ROWS");
+        if (e) fused_even_rows = atoi(e);
         e = getenv("STARNEIG_B200_OVERLAP");
         if (e) overlap = atoi(e);
         e = getenv("STARNEIG_B200_OVERLAP_CTAS");
@@ -526,6 +529,13 @@ struct Rank {
             memset(&f, 0, sizeof(f));
             f.a = pa; f.w = w; f.i = i; f.pan = pan; f.ldpan = ldpan; f.Aloc = A_loc; f.lda = ldA; f.cm = cm; f.lc_end = lc_end;
             f.nsub = std::max(1, ceil_div(m, 32 * ctas));
+            f.rpc = 32 * f.nsub;
+            if (fused_even_rows) {
+                // every CTA of the grid owns rows (m = 19999 on 148 SMs: 136 rows each instead of 160 rows on 125 CTAs):
+                // the level-2 phases stream V, Y, VT from L2 at a per-SM rate, so idle SMs are lost bandwidth
+                f.rpc = std::max(8, round_up(ceil_div(m, ctas), 8));
+                f.nsub = ceil_div(f.rpc, 32);
+            }
             f.gbar = ws.gbar; f.timers = ws.timers;
             f.x = x;
             f.x.epoch = y_epoch + 1;

@@ -43,6 +43,7 @@ struct FusedArgs {
     ColMap cm;
     int lc_end;                 // local index one past the last local column of the reduced block
     int nsub;                   // 32-row sub-tiles per CTA
+    int rpc;                    // rows owned by a CTA (<= 32 * nsub; the last sub-tile of a CTA may be partial)
     unsigned *gbar;             // grid barrier counter, zero at launch
     unsigned long long *timers; // ns on CTA 0: [0] GEMV phases, [1] whole kernel, [2..5] phases A, A', R, R' (each incl. its barrier)
     Xchg x;                     // x.epoch = sequence number of the panel's first column (tags of all LL entries); rest DIST only
@@ -318,20 +319,21 @@ struct FusedSmem {
 // column. Kept out of line: it must not cost the common path registers. Returns the z entry of this warp.
 // (All arguments by value: taking the address of the kernel's parameter block or of `gen` would move them to local memory.)
 // The caller advances its barrier generation by two barriers.
-__device__ __noinline__ double fused_rescale_x(double *pcol, const double *V, int ld, double *colpart, int ldt, int m, int nsub,
+__device__ __noinline__ double fused_rescale_x(double *pcol, const double *V, int ld, double *colpart, int ldt, int m, int nsub, int rpc,
                                                unsigned *gbar, unsigned gen, double *pv, int j, double xmul, int t_first)
 {
     const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
     const int b = blockIdx.x;
-    const int row0 = b * nsub * 32;
-    const int rows_here = max(0, min(nsub * 32, m - row0));
-    const int nblk = (m + nsub * 32 - 1) / (nsub * 32);
+    const int row0 = b * rpc;
+    const int row_end = min(m, row0 + rpc);
+    const int rows_here = max(0, row_end - row0);
+    const int nblk = (m + rpc - 1) / rpc;
     grid_barrier(gbar, gen);                // nobody reads the old z partials any more
     for (int rr = tid; rr < rows_here; rr += FUSED_THREADS)
         if (row0 + rr > j) pcol[row0 + rr] *= xmul;
     for (int rr = tid; rr < nsub * 32; rr += FUSED_THREADS) pv[rr] *= xmul;
     __syncthreads();
-    if (j > 0) coldots_all(V, ld, j, row0, m, nsub, pv, wp, FUSED_WARPS, lane, colpart + (size_t)b * ldt);
+    if (j > 0) coldots_all(V, ld, j, row0, row_end, nsub, pv, wp, FUSED_WARPS, lane, colpart + (size_t)b * ldt);
     grid_barrier(gbar, gen);
     return t_first < j ? sum_over_ctas(colpart + t_first, ldt, nblk, lane) : 0.0;
 }
@@ -352,9 +354,11 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_panel_fused(FusedArgs f)
     const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
     const int m = a.m, ld = a.ld, nsub = f.nsub;
     const int G = gridDim.x, b = blockIdx.x;
-    const int row0 = b * nsub * 32;
-    const int rows_here = max(0, min(nsub * 32, m - row0));
-    const int nblk = (m + nsub * 32 - 1) / (nsub * 32);         // CTAs that own rows
+    // CTA b owns rows [row0, row_end): rpc rows (rpc = 32 * nsub, or fewer so that every CTA of the grid owns rows)
+    const int row0 = b * f.rpc;
+    const int row_end = min(m, row0 + f.rpc);
+    const int rows_here = max(0, row_end - row0);
+    const int nblk = (m + f.rpc - 1) / f.rpc;                   // CTAs that own rows
     const FusedSmem L(f.w, nsub);
     double *const vs_all = sh + L.vs, *const s_sh = sh + L.s, *const vrow_sh = sh + L.vrow, *const w2_sh = sh + L.w2;
     double *const red = sh + L.red, *const pv = sh + L.pv, *const ysm = sh + L.ysm, *const sqred = sh + L.sqred;
@@ -454,7 +458,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_panel_fused(FusedArgs f)
             // ---- per-row epilogue, one warp per sub-tile
             for (int sub = wp; sub < nsub; sub += FUSED_WARPS) {
                 const int r = row0 + sub * 32 + lane;
-                const bool valid = r < m;
+                const bool valid = r < row_end;
                 double pp = 0.0;
                 if (valid) {
                     const double pprev = pc_prev[r];
@@ -483,7 +487,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_panel_fused(FusedArgs f)
 
             // ---- w2part[t] = sum over the CTA's rows of VT(r,t) * p'(r), t < j (column j-1 was stored just above)
             const unsigned tag = f.x.epoch + j;
-            coldots_all(a.VT, ld, j, row0, m, nsub, pv, wp, FUSED_WARPS, lane, a.colpart + (size_t)b * a.ldt,
+            coldots_all(a.VT, ld, j, row0, row_end, nsub, pv, wp, FUSED_WARPS, lane, a.colpart + (size_t)b * a.ldt,
                         LLRED ? f.w2part_ll + (size_t)b * a.ldt : nullptr, tag);
             if (!LLRED) grid_barrier(f.gbar, gen);
             SB_PHASE_MARK(0);
@@ -512,7 +516,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_panel_fused(FusedArgs f)
                 for (int item = wp; item < nsub * NW; item += FUSED_WARPS) {
                     const int sub = item / NW, g = item - sub * NW, t0 = g * 32;
                     const int r = row0 + sub * 32 + lane;
-                    const bool valid = r < m;
+                    const bool valid = r < row_end;
                     const double *Vr = a.V + (size_t)t0 * ld + r;
                     double v32[32];
 #pragma unroll
@@ -528,7 +532,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_panel_fused(FusedArgs f)
             sq.clear();
             for (int sub = wp; sub < nsub; sub += FUSED_WARPS) {
                 const int r = row0 + sub * 32 + lane;
-                const bool valid = r < m;
+                const bool valid = r < row_end;
                 double xx = 0.0;
                 if (valid) {
                     double pp = j > 0 ? pc_cur[r] : acol[r];
@@ -550,7 +554,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_panel_fused(FusedArgs f)
             if (__any_sync(0xffffffffu, sq.big != 0.0 || sq.sml != 0.0)) { sq.big = warp_sum(sq.big); sq.sml = warp_sum(sq.sml); }
             if (lane == 0) { sqred[wp] = sq.med; sqred[FUSED_WARPS + wp] = sq.big; sqred[2 * FUSED_WARPS + wp] = sq.sml; }
             __syncthreads();
-            if (j > 0) coldots_all(a.V, ld, j, row0, m, nsub, pv, wp, FUSED_WARPS, lane, a.colpart + (size_t)b * a.ldt);
+            if (j > 0) coldots_all(a.V, ld, j, row0, row_end, nsub, pv, wp, FUSED_WARPS, lane, a.colpart + (size_t)b * a.ldt);
             if (tid < 3) {
                 double sum = 0.0;
                 for (int q = 0; q < FUSED_WARPS; q++) sum += sqred[tid * FUSED_WARPS + q];
@@ -576,7 +580,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_panel_fused(FusedArgs f)
                 if (b == 0) { a.scal[j].tau = tau; a.scal[j].beta = beta; a.scal[j].scale = scale; }
             }
             if (rf.xmul != 1.0) {       // denormal-range column
-                zsum = fused_rescale_x(pc_cur, a.V, ld, a.colpart, a.ldt, m, nsub, f.gbar, gen, pv, j, rf.xmul, t_first);
+                zsum = fused_rescale_x(pc_cur, a.V, ld, a.colpart, a.ldt, m, nsub, f.rpc, f.gbar, gen, pv, j, rf.xmul, t_first);
                 gen += 2 * G;
             }
             if (t_first < j && lane == 0) a.s[t_first] = fma(scale, zsum, vjt);
@@ -689,7 +693,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_panel_fused(FusedArgs f)
                     // evicted by the streaming GEMVs: pull the CTA's rows of it towards L2 now, phase A reads them on
                     // the critical path (one 128-byte line per thread)
                     const int r = row0 + 16 * xt;
-                    if (16 * xt < rows_here && r < m) prefetch_l2(f.pan + (size_t)(j + 1) * f.ldpan + r);
+                    if (16 * xt < rows_here) prefetch_l2(f.pan + (size_t)(j + 1) * f.ldpan + r);
                 }
                 gen2 += G;
                 if (xt == 0) while ((int)(ld_acquire_gpu(bar2) - gen2) < 0) { }
@@ -703,7 +707,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_panel_fused(FusedArgs f)
                 for (int item = xw; item < nsub * NWn; item += FUSED_WARPS - FUSED_GEMV_WARPS) {
                     const int sub = item / NWn, g = item - sub * NWn, t0 = g * 32;
                     const int r = row0 + sub * 32 + lane;
-                    const bool valid = r < m;
+                    const bool valid = r < row_end;
                     double d0 = 0.0, d1 = 0.0, d2 = 0.0;
                     const double *VTr = a.VT + (size_t)t0 * ld + r;
                     const double *Yr = a.Y + (size_t)t0 * ld + r;

@@ -133,6 +133,16 @@ def test_sim_ll_reduction_variant(sim, ora, gpus, n, pw, sms):
     assert np.array_equal(A, A1) and np.array_equal(Q, Q1)
 
 
+@pytest.mark.parametrize("gpus,n,pw,sms,ll", [(1, 131, 24, 4, 0), (1, 131, 24, 5, 1), (1, 100, 16, 7, 1), (2, 96, 16, 3, 1), (1, 47, 16, 4, 0)])
+def test_sim_even_rows_variant(sim, ora, gpus, n, pw, sms, ll):
+    """persistent panel kernel with the panel rows spread over ALL CTAs of the grid (STARNEIG_B200_FUSED_EVEN_ROWS=1; the
+    last 32-row sub-tile of a CTA is partial) instead of whole sub-tiles on fewer CTAs: another grouping of the partial
+    sums, so parity with the oracle (not bitwise equality with the default)"""
+    with _Env(STARNEIG_B200_COL_BLOCK=8, CUSIM_SMS=sms, STARNEIG_B200_FUSED_EVEN_ROWS=1, STARNEIG_B200_FUSED_LL=ll):
+        _, _, st = _reduce(sim, ora, n, pw, gpus=gpus)
+    assert st["fused_panels"] == st["panels"]
+
+
 @pytest.mark.parametrize("opt", [1, 2, 3])
 def test_sim_gemm_loader_options(sim, ora, opt):
     """DMMA kernels with the loader options of dgemm.cuh (1: cp.async of the next stage between the DMMAs, 2: 16-byte
