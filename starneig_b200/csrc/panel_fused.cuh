@@ -17,9 +17,12 @@
 //   R'  DLARFG scalars (every CTA, identical), s = scale*z + V(j,:)  (one warp per entry)
 //   G   trailing GEMV partials, perfectly balanced 1-D split of (row block, column) items over all
 //       128-thread groups of the grid                                    -> grid barrier
-// Row ownership: CTA b owns rows [b*32*nsub, (b+1)*32*nsub) of the panel in every phase except G, so V, Y,
+// Row ownership: CTA b owns rows [b*rpc, (b+1)*rpc) of the panel in every phase except G (rpc = 32*nsub, or --
+// STARNEIG_B200_FUSED_EVEN_ROWS -- the smallest multiple of 8 that spreads the rows over all CTAs), so V, Y,
 // VT columns are written and re-read by the same SM; everything that crosses CTAs inside the launch (pcol, s,
 // w2, partials, scalars, row j of V) is read with ld.global.cg.
+// Variant LLRED (STARNEIG_B200_FUSED_LL, see the comment at the kernel): the barriers after A, A' and G are
+// replaced by self-validating LL entries (w2 partials, w2, GEMV partials); only the barrier after R remains.
 #pragma once
 #include "panel.cuh"
 
