@@ -252,6 +252,7 @@ struct Rank {
     int gemm_opt = 0;                       // loader options of the DMMA kernels (GemmOpt<1..3>), 0: the default kernels
     int fused_ll = 0;                       // 1: fused panel kernel with LL-entry reductions (one grid barrier per column instead of four)
     int fused_even_rows = 0;                // 1: fused panel kernel: rows spread over all CTAs (changes the grouping of the partial sums)
+    int fused_r = 0;                        // 1 (with fused_ll): phase R of the fused kernel reads its slab of V once instead of twice
     std::vector<cudaEvent_t> events;        // phase events: 4 per panel
     std::vector<cudaEvent_t> gemv_events;   // 4 per timed column (profile level 2)
     size_t gemv_events_used = 0;
@@ -286,6 +287,8 @@ struct Rank {
         if (e) fused_ll = atoi(e);
         e = getenv("STARNEIG_B200_FUSED_EVEN_ROWS");
         if (e) fused_even_rows = atoi(e);
+        e = getenv("STARNEIG_B200_FUSED_R");
+        if (e) fused_r = atoi(e);
         e = getenv("STARNEIG_B200_OVERLAP");
         if (e) overlap = atoi(e);
         e = getenv("STARNEIG_B200_OVERLAP_CTAS");
@@ -530,6 +533,7 @@ struct Rank {
             f.a = pa; f.w = w; f.i = i; f.pan = pan; f.ldpan = ldpan; f.Aloc = A_loc; f.lda = ldA; f.cm = cm; f.lc_end = lc_end;
             f.nsub = std::max(1, ceil_div(m, 32 * ctas));
             f.rpc = 32 * f.nsub;
+            f.fuse_r = fused_ll && fused_r;
             if (fused_even_rows) {
                 // every CTA of the grid owns rows (m = 19999 on 148 SMs: 136 rows each instead of 160 rows on 125 CTAs):
                 // the level-2 phases stream V, Y, VT from L2 at a per-SM rate, so idle SMs are lost bandwidth

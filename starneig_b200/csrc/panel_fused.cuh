@@ -47,6 +47,7 @@ struct FusedArgs {
     int lc_end;                 // local index one past the last local column of the reduced block
     int nsub;                   // 32-row sub-tiles per CTA
     int rpc;                    // rows owned by a CTA (<= 32 * nsub; the last sub-tile of a CTA may be partial)
+    int fuse_r;                 // LLRED only: phase R streams the CTA's slab of V once instead of twice
     unsigned *gbar;             // grid barrier counter, zero at launch
     unsigned long long *timers; // ns on CTA 0: [0] GEMV phases, [1] whole kernel, [2..5] phases A, A', R, R' (each incl. its barrier)
     Xchg x;                     // x.epoch = sequence number of the panel's first column (tags of all LL entries); rest DIST only
@@ -341,6 +342,75 @@ __device__ __noinline__ double fused_rescale_x(double *pcol, const double *V, in
     return t_first < j ? sum_over_ctas(colpart + t_first, ldt, nblk, lane) : 0.0;
 }
 
+// Phase R of the persistent kernel with ONE pass over the CTA's slab of V instead of two (variant LLRED + fuse_r): a warp
+// keeps its 32 x 16 tile in registers between d = V w2 (row-wise, summed over the column groups through shared memory)
+// and z = V^T x (column-wise, transpose-reduce over the 32 rows). A round covers SPR complete sub-tiles (all NW2 column
+// groups each); needs j <= 16 * FUSED_WARPS. Writes p'' (pc_cur, the H entries above the sub-diagonal, alpha), x (pv), the
+// per-warp sums of squares (sqred) and the CTA's partial of z (zpart). Out of line: its register tile must not compete
+// with the rest of the kernel for the 96 registers of a thread.
+__device__ __noinline__ void fused_reflector_pass(const double *V, int ld, int j, int row0, int row_end, int nsub, double *pc_cur,
+                                                  double *acol, double *alpha_out, const double *w2_sh, double *red, double *pv,
+                                                  double *sqred, double *zpart)
+{
+    const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
+    const int NW2 = (j + 15) >> 4;
+    const int SPR = max(1, min(nsub, FUSED_WARPS / NW2));
+    double *const zred = red + (size_t)SPR * NW2 * 32;
+    const int g = wp % NW2, so = wp / NW2, t0 = g * 16;
+    const bool tile_warp = wp < NW2 * SPR;
+    double zl = 0.0;
+    SumSq sq;
+    sq.clear();
+    for (int sub0 = 0; sub0 < nsub; sub0 += SPR) {
+        const int sub = sub0 + so;
+        const bool active = tile_warp && sub < nsub;
+        const int r = row0 + sub * 32 + lane;
+        const bool valid = active && r < row_end;
+        double v16[16];
+        double pold = 0.0;
+        if (active) {
+            const double *Vr = V + (size_t)t0 * ld + r;
+#pragma unroll
+            for (int q = 0; q < 16; q++) v16[q] = (valid && t0 + q < j) ? Vr[(size_t)q * ld] : 0.0;
+            if (valid) pold = pc_cur[r];
+            double d = 0.0;
+#pragma unroll
+            for (int q = 0; q < 16; q++) d = fma(v16[q], w2_sh[min(t0 + q, j - 1)], d);
+            red[((size_t)so * NW2 + g) * 32 + lane] = d;
+        }
+        __syncthreads();
+        if (active) {
+            double D = 0.0;
+            for (int q = 0; q < NW2; q++) D += red[((size_t)so * NW2 + q) * 32 + lane];
+            const double pp = pold - D;
+            const double xx = (valid && r > j) ? pp : 0.0;
+            if (g == 0) {       // one warp per sub-tile stores the column and sums the squares
+                if (valid) {
+                    pc_cur[r] = pp;
+                    if (r < j) acol[r] = pp;            // final entries of H above the sub-diagonal
+                    if (r == j) *alpha_out = pp;
+                }
+                sq.add(xx);
+                pv[sub * 32 + lane] = xx;
+            }
+#pragma unroll
+            for (int q = 0; q < 16; q++) v16[q] *= xx;
+            zl += transpose_reduce16(v16, lane);        // lane l: sum over the tile's rows of V(r, t0 + (l & 15)) x(r)
+        }
+        __syncthreads();        // `red` is reused by the next round
+    }
+    if (tile_warp && lane < 16) zred[((size_t)so * NW2 + g) * 16 + lane] = zl;
+    sq.med = warp_sum(sq.med);
+    if (__any_sync(0xffffffffu, sq.big != 0.0 || sq.sml != 0.0)) { sq.big = warp_sum(sq.big); sq.sml = warp_sum(sq.sml); }
+    if (lane == 0) { sqred[wp] = sq.med; sqred[FUSED_WARPS + wp] = sq.big; sqred[2 * FUSED_WARPS + wp] = sq.sml; }
+    __syncthreads();
+    if (wp < NW2 && lane < 16 && t0 + lane < j) {
+        double zsum = 0.0;
+        for (int q = 0; q < SPR; q++) zsum += zred[((size_t)q * NW2 + g) * 16 + lane];
+        zpart[t0 + lane] = zsum;
+    }
+}
+
 // LLRED: one grid barrier per column instead of four. (1) The reduction w2 = sum over CTAs of VT^T p' travels as
 // self-validating LL entries (partials -> reducing warps -> every CTA): no barriers around phase A'. (2) The GEMV
 // partials are LL entries too: the owner of a row polls the partials of its rows instead of waiting for ALL groups of
@@ -514,6 +584,12 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_panel_fused(FusedArgs f)
             for (int t = tid; t < j; t += FUSED_THREADS)
                 w2_sh[t] = LLRED ? ll_load(f.w2_ll + t, f.x.epoch + j, f.x.status) : __ldcg(a.w2 + t);
             __syncthreads();
+            // one pass over V needs a warp per 16-column group of a sub-tile: columns j <= 16 * FUSED_WARPS
+            const bool fuse_r = LLRED && f.fuse_r && j > 0 && j <= 16 * FUSED_WARPS;
+            if (fuse_r) {
+                fused_reflector_pass(a.V, ld, j, row0, row_end, nsub, pc_cur, acol, &a.scal[j].alpha, w2_sh, red, pv, sqred,
+                                     a.colpart + (size_t)b * a.ldt);
+            } else {
             if (j > 0) {
                 // d(r) = V(r, :j) w2: 32x32 tiles, 32 loads in flight per lane
                 for (int item = wp; item < nsub * NW; item += FUSED_WARPS) {
@@ -558,6 +634,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_panel_fused(FusedArgs f)
             if (lane == 0) { sqred[wp] = sq.med; sqred[FUSED_WARPS + wp] = sq.big; sqred[2 * FUSED_WARPS + wp] = sq.sml; }
             __syncthreads();
             if (j > 0) coldots_all(a.V, ld, j, row0, row_end, nsub, pv, wp, FUSED_WARPS, lane, a.colpart + (size_t)b * a.ldt);
+            }
             if (tid < 3) {
                 double sum = 0.0;
                 for (int q = 0; q < FUSED_WARPS; q++) sum += sqred[tid * FUSED_WARPS + q];

@@ -143,6 +143,16 @@ def test_sim_even_rows_variant(sim, ora, gpus, n, pw, sms, ll):
     assert st["fused_panels"] == st["panels"]
 
 
+@pytest.mark.parametrize("gpus,n,pw,sms,even", [(1, 131, 24, 4, 0), (1, 100, 16, 1, 0), (1, 150, 40, 7, 1), (2, 96, 16, 3, 1), (1, 60, 16, 5, 0)])
+def test_sim_single_pass_reflector_variant(sim, ora, gpus, n, pw, sms, even):
+    """LL variant whose phase R streams the CTA's slab of V once (the 32 x 32 tile stays in registers between d = V w2 and
+    z = V^T x) instead of twice (STARNEIG_B200_FUSED_R=1): z is summed in another order, so parity with the oracle"""
+    with _Env(STARNEIG_B200_COL_BLOCK=8, CUSIM_SMS=sms, STARNEIG_B200_FUSED_LL=1, STARNEIG_B200_FUSED_R=1,
+              STARNEIG_B200_FUSED_EVEN_ROWS=even):
+        _, _, st = _reduce(sim, ora, n, pw, gpus=gpus)
+    assert st["fused_panels"] == st["panels"]
+
+
 @pytest.mark.parametrize("opt", [1, 2, 3])
 def test_sim_gemm_loader_options(sim, ora, opt):
     """DMMA kernels with the loader options of dgemm.cuh (1: cp.async of the next stage between the DMMAs, 2: 16-byte

@@ -60,7 +60,8 @@ if mode == "denormal":
     assert np.abs(Q[:n] - Q2[:n]).max() <= 1e-5
 elif mode == "even_rows":
     A0, Q0, ld = ora.fullpos(n, 2019)
-    A, Q = run(A0, Q0, ld, {"STARNEIG_B200_FUSED_EVEN_ROWS": "1", "STARNEIG_B200_FUSED_LL": sys.argv[4]})
+    A, Q = run(A0, Q0, ld, {"STARNEIG_B200_FUSED_EVEN_ROWS": "1", "STARNEIG_B200_FUSED_LL": sys.argv[4],
+                            "STARNEIG_B200_FUSED_R": sys.argv[4]})
     A2, Q2 = A0.copy(order="F"), Q0.copy(order="F")
     assert ora.hessenberg_port(n, A2, ld, Q2, ld, 0, n, pw) == 0
     assert np.abs(A[:n] - A2[:n]).max() <= 200 * n * U * max(1.0, np.abs(A2[:n]).max())
@@ -100,5 +101,6 @@ def test_optin_variant_is_bitwise_equal_to_the_default(switch):
 @pytest.mark.skipif(not OPTIN, reason="opt-in kernel variant: set STARNEIG_TEST_OPTIN=1 (tools/r2_visit1.sh does)")
 @pytest.mark.parametrize("ll", [0, 1])
 def test_optin_even_rows_variant(ll):
-    # another grouping of the partial sums: parity with the oracle, not bitwise equality with the default
+    # another grouping of the partial sums (ll = 1: also the single-pass phase R): parity with the oracle, not bitwise
+    # equality with the default
     _child("even_rows", 1500, 200, ll)
