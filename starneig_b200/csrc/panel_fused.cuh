@@ -48,6 +48,7 @@ struct FusedArgs {
     int nsub;                   // 32-row sub-tiles per CTA
     int rpc;                    // rows owned by a CTA (<= 32 * nsub; the last sub-tile of a CTA may be partial)
     int fuse_r;                 // LLRED only: phase R streams the CTA's slab of V once instead of twice
+    int pf_cols;                // columns of its first GEMV item chunk that a group prefetches into L2 ahead of phase G (0: off)
     unsigned *gbar;             // grid barrier counter, zero at launch
     unsigned long long *timers; // ns on CTA 0: [0] GEMV phases, [1] whole kernel, [2..5] phases A, A', R, R' (each incl. its barrier)
     Xchg x;                     // x.epoch = sequence number of the panel's first column (tags of all LL entries); rest DIST only
@@ -461,6 +462,28 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_panel_fused(FusedArgs f)
         // the column being reduced: p', then p'' (LLRED: columns alternate between two buffers)
         double *const pc_cur = (LLRED && (j & 1)) ? f.pcol2 : a.pcol;
         const double *const pc_prev = (LLRED && !(j & 1)) ? f.pcol2 : a.pcol;
+
+        if (f.pf_cols > 0 && j < f.w && wp < FUSED_GEMV_WARPS) {
+            // HBM is idle while the level-2 phases of this column work out of L2 (~20 us): every GEMV group pulls the
+            // first pf_cols columns of its first (row block, column range) chunk of THIS column's GEMV into L2 now, so
+            // that phase G starts from L2 instead of waiting for HBM. A hint only: nothing depends on it.
+            const int lc0 = f.cm.lower(f.i + j + 1), nloc = f.lc_end - lc0;
+            const long long items = (long long)gs.RB * nloc;
+            const int per = max(FUSED_MINSEG, (int)((items + G * FUSED_VB - 1) / (G * FUSED_VB)));
+            const int vb = tid >> 7, vt = tid & 127;
+            const long long it = (long long)(vb * G + b) * per;
+            if (it < items) {
+                const int rb = (int)(it / nloc);
+                const int cbeg = (int)(it - (long long)rb * nloc);
+                const int cend = (int)min((long long)nloc, cbeg + min((long long)per, items - it));
+                const int kend = min(cend, cbeg + f.pf_cols);
+                const int rp = rb * 256 + (vt & 15) * 16;        // 16 lines of 128 bytes cover the 256 rows of the block
+                if (rp < m + gs.skip) {
+                    const double *Ap = f.Aloc + (size_t)lc0 * f.lda + f.i + 1 - gs.skip + rp;
+                    for (int k = cbeg + (vt >> 4); k < kend; k += 8) prefetch_l2(Ap + (size_t)k * f.lda);
+                }
+            }
+        }
 
         if (j > 0) {
             // ================= phase A: finish column j-1, start column j =================

@@ -16,6 +16,8 @@
 #include <sys/mman.h>
 #include <algorithm>
 #include <chrono>
+#include <map>
+#include <mutex>
 #include <cstdio>
 #include <cstdlib>
 #include <random>
@@ -299,6 +301,20 @@ cudaError_t cudaDeviceGetAttribute(int *v, cudaDeviceAttr a, int)
 }
 cudaError_t cudaDeviceGetStreamPriorityRange(int *lo, int *hi) { *lo = 0; *hi = -5; return cudaSuccess; }
 cudaError_t cudaDeviceEnablePeerAccess(int, unsigned) { return cudaSuccess; }
+namespace {
+std::mutex alloc_mutex;
+std::map<uintptr_t, size_t> alloc_map;      // base -> bytes as requested by the caller
+}
+namespace cusim {
+bool inside_device_allocation(const void *p, size_t bytes)
+{
+    std::lock_guard<std::mutex> lock(alloc_mutex);
+    auto it = alloc_map.upper_bound((uintptr_t)p);
+    if (it == alloc_map.begin()) return false;
+    --it;
+    return (uintptr_t)p + bytes <= it->first + it->second;
+}
+}
 cudaError_t cusimMalloc(void **p, size_t bytes)
 {
     const size_t rounded = (bytes + 255) / 256 * 256 + 256;
@@ -306,9 +322,16 @@ cudaError_t cusimMalloc(void **p, size_t bytes)
     if (!q) return cudaErrorMemoryAllocation;
     memset(q, 0xff, rounded);       // NaN doubles, 0xffffffff flags: nothing may rely on fresh memory being zero
     *p = q;
+    std::lock_guard<std::mutex> lock(alloc_mutex);
+    alloc_map[(uintptr_t)q] = bytes;
     return cudaSuccess;
 }
-cudaError_t cudaFree(void *p) { free(p); return cudaSuccess; }
+cudaError_t cudaFree(void *p)
+{
+    if (p) { std::lock_guard<std::mutex> lock(alloc_mutex); alloc_map.erase((uintptr_t)p); }
+    free(p);
+    return cudaSuccess;
+}
 cudaError_t cudaMemset(void *p, int v, size_t bytes) { memset(p, v, bytes); return cudaSuccess; }
 cudaError_t cudaMemsetAsync(void *p, int v, size_t bytes, cudaStream_t) { memset(p, v, bytes); return cudaSuccess; }
 cudaError_t cudaMemcpy(void *d, const void *s, size_t bytes, cudaMemcpyKind) { memmove(d, s, bytes); return cudaSuccess; }

@@ -77,6 +77,8 @@ template <class F> static inline cudaError_t cudaFuncGetAttributes(cudaFuncAttri
 template <class F> static inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int *n, F, int, size_t) { *n = 2; return cudaSuccess; }
 
 namespace cusim {
+// true if [p, p + bytes) lies inside a live cusimMalloc block (CUSIM_CHECK_PREFETCH: prefetch addresses are validated)
+bool inside_device_allocation(const void *p, size_t bytes);
 // what a CUDA thread knows about itself (threadIdx, blockIdx, ... are macros over this, cusim_device.h)
 struct ThreadCtx {
     uint3 t_idx, b_idx;

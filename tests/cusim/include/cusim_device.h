@@ -140,7 +140,12 @@ static inline void st_volatile_v4(uint4 *p, uint4 e)
 }
 static inline void group_barrier(int id, int nthreads) { ::cusim::named_barrier(id, nthreads); }
 static inline unsigned long long globaltimer_ns() { return ::cusim::now_ns(); }
-static inline void prefetch_l2(const void *) {}
+// a hint on the device; here (CUSIM_CHECK_PREFETCH=1) the address must at least lie inside a device allocation
+static inline void prefetch_l2(const void *p)
+{
+    static const bool check = getenv("CUSIM_CHECK_PREFETCH") != nullptr;
+    if (check && !::cusim::inside_device_allocation(p, 8)) { fprintf(stderr, "cusim: prefetch outside every device allocation\n"); abort(); }
+}
 static inline void cp_async8(void *smem_dst, const void *gmem_src, bool valid)
 {
     if (valid) memcpy(smem_dst, gmem_src, 8);

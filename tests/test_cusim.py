@@ -316,3 +316,30 @@ def test_sim_ll_variant_with_lagging_blocks(simlib, sms, skew, seed):
     r = subprocess.run(["python", "-c", _PANEL_CHILD, "600", "12"], capture_output=True, text=True, timeout=600,
                        env=dict(os.environ, CUSIM_SMS=str(sms), CUSIM_SKEW=str(skew), CUSIM_SHUFFLE=str(seed)))
     assert r.returncode == 0 and r.stdout.strip().endswith("OK"), r.stdout[-1000:] + r.stderr[-2000:]
+
+
+def test_sim_gemv_prefetch_addresses(simlib):
+    """STARNEIG_B200_GEMV_PREFETCH: during the level-2 phases of a column every GEMV group prefetches the head of its share
+    of that column's GEMV into L2. A hint on the device (nothing to compare); here every prefetch address is checked
+    against the live device allocations, for one and two ranks, with and without the LL variant."""
+    child = (
+        "import sys, os, numpy as np; sys.path.insert(0, %r)\n"
+        "import starneig_b200 as sn\n"
+        "from starneig_b200 import api, _lib\n"
+        "from oracle.oracle import Oracle\n"
+        "api._handle = _lib.load(%r)\n"
+        "ora = Oracle()\n"
+        "for gpus, n, pw in ((1, 131, 24), (2, 300, 100), (1, 47, 16)):\n"
+        "    A0, Q0, ld = ora.fullpos(n, 2019)\n"
+        "    A, Q = A0.copy(order='F'), Q0.copy(order='F')\n"
+        "    sn.starneig_node_init(-1, gpus, sn.STARNEIG_NO_MESSAGES)\n"
+        "    conf = sn.starneig_hessenberg_init_conf(); conf.panel_width = pw\n"
+        "    assert sn.starneig_SEP_SM_Hessenberg_expert(conf, n, 0, n, A, ld, Q, ld) == 0\n"
+        "    sn.starneig_node_finalize()\n"
+        "    assert ora.hessenberg_form_violations(n, A, ld) == 0 and ora.residual_u(n, Q, ld, A, ld, A0, ld) < 500\n"
+        "print('OK')\n") % (ROOT, SIM_LIB)
+    for ll in ("0", "1"):
+        r = subprocess.run(["python", "-c", child], capture_output=True, text=True, timeout=600,
+                           env=dict(os.environ, CUSIM_CHECK_PREFETCH="1", STARNEIG_B200_GEMV_PREFETCH="40", STARNEIG_B200_FUSED_LL=ll,
+                                    STARNEIG_B200_COL_BLOCK="8", CUSIM_SMS="2"))
+        assert r.returncode == 0 and r.stdout.strip().endswith("OK"), r.stdout[-1000:] + r.stderr[-2000:]
