@@ -254,6 +254,7 @@ struct Rank {
     int fused_even_rows = 0;                // 1: fused panel kernel: rows spread over all CTAs (changes the grouping of the partial sums)
     int fused_r = 0;                        // 1 (with fused_ll): phase R of the fused kernel reads its slab of V once instead of twice
     int gemv_prefetch = 0;                  // fused kernel: columns (2 KB each) per GEMV group pulled into L2 during the level-2 phases
+    int gemv_prefetch_mb = 96;              // L2 budget shared by V, Y, VT of the panel and the prefetched data
     std::vector<cudaEvent_t> events;        // phase events: 4 per panel
     std::vector<cudaEvent_t> gemv_events;   // 4 per timed column (profile level 2)
     size_t gemv_events_used = 0;
@@ -292,6 +293,8 @@ struct Rank {
         if (e) fused_r = atoi(e);
         e = getenv("STARNEIG_B200_GEMV_PREFETCH");
         if (e && atoi(e) >= 0) gemv_prefetch = atoi(e);
+        e = getenv("STARNEIG_B200_GEMV_PREFETCH_MB");
+        if (e && atoi(e) >= 0) gemv_prefetch_mb = atoi(e);
         e = getenv("STARNEIG_B200_OVERLAP");
         if (e) overlap = atoi(e);
         e = getenv("STARNEIG_B200_OVERLAP_CTAS");
@@ -538,6 +541,7 @@ struct Rank {
             f.rpc = 32 * f.nsub;
             f.fuse_r = fused_ll && fused_r;
             f.pf_cols = gemv_prefetch;
+            f.pf_budget = (long long)gemv_prefetch_mb << 20;
             if (fused_even_rows) {
                 // every CTA of the grid owns rows (m = 19999 on 148 SMs: 136 rows each instead of 160 rows on 125 CTAs):
                 // the level-2 phases stream V, Y, VT from L2 at a per-SM rate, so idle SMs are lost bandwidth

@@ -49,6 +49,7 @@ struct FusedArgs {
     int rpc;                    // rows owned by a CTA (<= 32 * nsub; the last sub-tile of a CTA may be partial)
     int fuse_r;                 // LLRED only: phase R streams the CTA's slab of V once instead of twice
     int pf_cols;                // columns of its first GEMV item chunk that a group prefetches into L2 ahead of phase G (0: off)
+    long long pf_budget;        // bytes of L2 that V, Y, VT (3 * 8 * m * j at column j) and the prefetched data may fill together
     unsigned *gbar;             // grid barrier counter, zero at launch
     unsigned long long *timers; // ns on CTA 0: [0] GEMV phases, [1] whole kernel, [2..5] phases A, A', R, R' (each incl. its barrier)
     Xchg x;                     // x.epoch = sequence number of the panel's first column (tags of all LL entries); rest DIST only
@@ -476,7 +477,9 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_panel_fused(FusedArgs f)
                 const int rb = (int)(it / nloc);
                 const int cbeg = (int)(it - (long long)rb * nloc);
                 const int cend = (int)min((long long)nloc, cbeg + min((long long)per, items - it));
-                const int kend = min(cend, cbeg + f.pf_cols);
+                // leave L2 to the level-2 working set first: V, Y, VT of the panel so far
+                const long long room = (f.pf_budget - 24ll * m * j) / (2048ll * G * FUSED_VB);
+                const int kend = min(cend, cbeg + (int)max(0ll, min((long long)f.pf_cols, room)));
                 const int rp = rb * 256 + (vt & 15) * 16;        // 16 lines of 128 bytes cover the 256 rows of the block
                 if (rp < m + gs.skip) {
                     const double *Ap = f.Aloc + (size_t)lc0 * f.lda + f.i + 1 - gs.skip + rp;
