@@ -255,6 +255,8 @@ struct Rank {
     int fused_r = 0;                        // 1 (with fused_ll): phase R of the fused kernel reads its slab of V once instead of twice
     int gemv_prefetch = 0;                  // fused kernel: columns (2 KB each) per GEMV group pulled into L2 during the level-2 phases
     int gemv_prefetch_mb = 96;              // L2 budget shared by V, Y, VT of the panel and the prefetched data
+    int gemv_resident_kb = 0;               // fused kernel: KB of the trailing matrix (its last local columns) kept in L2 across the
+                                            // columns of a panel ("evict last" loads), 0: everything streams
     std::vector<cudaEvent_t> events;        // phase events: 4 per panel
     std::vector<cudaEvent_t> gemv_events;   // 4 per timed column (profile level 2)
     size_t gemv_events_used = 0;
@@ -293,6 +295,8 @@ struct Rank {
         if (e) fused_r = atoi(e);
         e = getenv("STARNEIG_B200_GEMV_PREFETCH");
         if (e && atoi(e) >= 0) gemv_prefetch = atoi(e);
+        e = getenv("STARNEIG_B200_GEMV_RESIDENT_KB");
+        if (e && atoi(e) >= 0) gemv_resident_kb = atoi(e);
         e = getenv("STARNEIG_B200_GEMV_PREFETCH_MB");
         if (e && atoi(e) >= 0) gemv_prefetch_mb = atoi(e);
         e = getenv("STARNEIG_B200_OVERLAP");
@@ -542,6 +546,11 @@ struct Rank {
             f.fuse_r = fused_ll && fused_r;
             f.pf_cols = gemv_prefetch;
             f.pf_budget = (long long)gemv_prefetch_mb << 20;
+            {   // the last local columns, all of them right of the panel so that every GEMV of the panel reads them
+                const long long want = ((long long)gemv_resident_kb << 10) / (8ll * std::max(m, 1));
+                const int res_cols = (int)std::min<long long>(want, std::max(0, lc_end - cm.lower(i + w)));
+                f.res_lc0 = res_cols > 0 ? lc_end - res_cols : lc_end + 1;
+            }
             if (fused_even_rows) {
                 // every CTA of the grid owns rows (m = 19999 on 148 SMs: 136 rows each instead of 160 rows on 125 CTAs):
                 // the level-2 phases stream V, Y, VT from L2 at a per-SM rate, so idle SMs are lost bandwidth

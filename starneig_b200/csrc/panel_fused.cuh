@@ -49,6 +49,8 @@ struct FusedArgs {
     int rpc;                    // rows owned by a CTA (<= 32 * nsub; the last sub-tile of a CTA may be partial)
     int fuse_r;                 // LLRED only: phase R streams the CTA's slab of V once instead of twice
     int pf_cols;                // columns of its first GEMV item chunk that a group prefetches into L2 ahead of phase G (0: off)
+    int res_lc0;                // local columns >= res_lc0 are read with the "keep in L2" policy (the same columns in every GEMV
+                                // of the panel); >= lc_end: none
     long long pf_budget;        // bytes of L2 that V, Y, VT (3 * 8 * m * j at column j) and the prefetched data may fill together
     unsigned *gbar;             // grid barrier counter, zero at launch
     unsigned long long *timers; // ns on CTA 0: [0] GEMV phases, [1] whole kernel, [2..5] phases A, A', R, R' (each incl. its barrier)
@@ -318,6 +320,48 @@ struct FusedSmem {
         total = o;
     }
 };
+
+// One chunk (nk columns, vs = the matching entries of v) of a thread's GEMV rows, read with the "keep in L2" policy: the
+// columns the host marked resident (FusedArgs::res_lc0) are part of every GEMV of the panel, so after the first column
+// they come from L2 instead of HBM. Same arithmetic in the same order as the streaming loop of phase G.
+__device__ __forceinline__ void gemv_chunk_resident(const double *P0, size_t step, int nk, const double *vs, double2 &acc,
+                                                    unsigned long long policy)
+{
+    constexpr int U = 8;
+    double2 cur[U], nxt[U];
+    int k = 0;
+    if (nk >= U) {
+#pragma unroll
+        for (int u = 0; u < U; u++) cur[u] = ld_l2_keep((const double2 *)(P0 + u * step), policy);
+        const double *Pn = P0 + U * step;
+        for (; k + 2 * U <= nk; k += U) {
+#pragma unroll
+            for (int u = 0; u < U; u++) nxt[u] = ld_l2_keep((const double2 *)(Pn + u * step), policy);
+            Pn += U * step;
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const double vk = vs[k + u];
+                acc.x = fma(cur[u].x, vk, acc.x);
+                acc.y = fma(cur[u].y, vk, acc.y);
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++) cur[u] = nxt[u];
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const double vk = vs[k + u];
+            acc.x = fma(cur[u].x, vk, acc.x);
+            acc.y = fma(cur[u].y, vk, acc.y);
+        }
+        k += U;
+    }
+    for (; k < nk; k++) {
+        const double vk = vs[k];
+        const double2 xx = ld_l2_keep((const double2 *)(P0 + (size_t)k * step), policy);
+        acc.x = fma(xx.x, vk, acc.x);
+        acc.y = fma(xx.y, vk, acc.y);
+    }
+}
 
 // LAPACK's DLARFG rescaling branch inside the persistent kernel (a column in the denormal range; every CTA takes it
 // together): the row owners multiply x by 2^969 before anybody forms v = x * scale, and z = V^T x is taken again from the
@@ -720,6 +764,8 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_panel_fused(FusedArgs f)
                 long long it = (long long)v * gq.per;
                 const long long it_end = min(items, it + gq.per);
                 const int mp = m + gs.skip;
+                const int ks = f.res_lc0 - lc0;         // first resident column relative to lc0 (>= nloc: none)
+                const unsigned long long keep_policy = f.res_lc0 < f.lc_end ? l2_policy_evict_last() : 0ull;
                 while (it < it_end) {
                     const int rb = (int)(it / nloc);
                     const int cbeg = (int)(it - (long long)rb * nloc);
@@ -728,15 +774,21 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_panel_fused(FusedArgs f)
                     const bool rows_ok = rp < mp;
                     double2 acc = make_double2(0.0, 0.0);
                     const double *Ap = f.Aloc + (size_t)lc0 * f.lda + f.i + 1 - gs.skip + rp;
-                    for (int k0 = cbeg; k0 < cend; k0 += FUSED_KC) {
-                        const int nk = min(FUSED_KC, cend - k0);
+                    for (int k0 = cbeg, nk = 0; k0 < cend; k0 += nk) {
+                        nk = min(FUSED_KC, cend - k0);
+                        // columns >= ks are resident in L2 for the whole panel (read with another load policy): a chunk
+                        // is either streamed or resident
+                        const bool resident = k0 >= ks;
+                        if (!resident && k0 + nk > ks) nk = ks - k0;
                         group_barrier(1 + vb, 128);          // previous chunk's vs fully consumed
                         for (int k = vt; k < nk; k += 128) {
                             const int kk = f.cm.l2g(lc0 + k0 + k) - gc0;
                             vs[k] = (kk == 0) ? 1.0 : __ldcg(pc_cur + j + kk) * scale;
                         }
                         group_barrier(1 + vb, 128);
-                        if (rows_ok) {
+                        if (rows_ok && resident) {
+                            gemv_chunk_resident(Ap + (size_t)k0 * f.lda, (size_t)f.lda, nk, vs, acc, keep_policy);
+                        } else if (rows_ok) {
                             constexpr int U = 8;
                             const size_t step = (size_t)f.lda;
                             const double *P0 = Ap + (size_t)k0 * step;

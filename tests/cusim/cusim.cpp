@@ -45,6 +45,16 @@ extern "C" void cusim_switch(void **save_sp, void *load_sp);
 namespace cusim {
 
 thread_local ThreadCtx *g_thread = nullptr;
+unsigned long long g_keep_loads = 0, g_prefetches = 0;
+namespace {
+struct StatsAtExit {
+    ~StatsAtExit()
+    {
+        if (getenv("CUSIM_STATS"))
+            fprintf(stderr, "cusim: %llu loads with the keep-in-L2 policy, %llu L2 prefetches\n", g_keep_loads, g_prefetches);
+    }
+} stats_at_exit;
+}
 
 namespace {
 constexpr size_t STACK_BYTES = 96 * 1024;

@@ -119,6 +119,8 @@ static inline size_t min(size_t a, size_t b) { return a < b ? a : b; }
 static inline size_t max(size_t a, size_t b) { return a > b ? a : b; }
 using std::fma; using std::sqrt; using std::fabs; using std::hypot; using std::copysign; using std::fmin; using std::fmax;
 
+namespace cusim { extern unsigned long long g_keep_loads, g_prefetches; }     // CUSIM_STATS=1 prints them at exit
+
 namespace sb200 {
 // ---- the primitives of common.cuh ----------------------------------------------------------------------------
 static inline unsigned ld_acquire_gpu(const unsigned *p) { ::cusim::poll_yield(); return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
@@ -140,10 +142,13 @@ static inline void st_volatile_v4(uint4 *p, uint4 e)
 }
 static inline void group_barrier(int id, int nthreads) { ::cusim::named_barrier(id, nthreads); }
 static inline unsigned long long globaltimer_ns() { return ::cusim::now_ns(); }
+static inline unsigned long long l2_policy_evict_last() { return 0ull; }
+static inline double2 ld_l2_keep(const double2 *p, unsigned long long) { __atomic_fetch_add(&::cusim::g_keep_loads, 1ull, __ATOMIC_RELAXED); return __ldcg(p); }
 // a hint on the device; here (CUSIM_CHECK_PREFETCH=1) the address must at least lie inside a device allocation
 static inline void prefetch_l2(const void *p)
 {
     static const bool check = getenv("CUSIM_CHECK_PREFETCH") != nullptr;
+    __atomic_fetch_add(&::cusim::g_prefetches, 1ull, __ATOMIC_RELAXED);
     if (check && !::cusim::inside_device_allocation(p, 8)) { fprintf(stderr, "cusim: prefetch outside every device allocation\n"); abort(); }
 }
 static inline void cp_async8(void *smem_dst, const void *gmem_src, bool valid)

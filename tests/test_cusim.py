@@ -318,6 +318,18 @@ def test_sim_ll_variant_with_lagging_blocks(simlib, sms, skew, seed):
     assert r.returncode == 0 and r.stdout.strip().endswith("OK"), r.stdout[-1000:] + r.stderr[-2000:]
 
 
+@pytest.mark.parametrize("gpus,n,pw,kb,ll", [(1, 131, 24, 3, 0), (1, 131, 24, 100, 1), (2, 96, 16, 5, 0)])
+def test_sim_gemv_resident_columns(sim, ora, gpus, n, pw, kb, ll):
+    """STARNEIG_B200_GEMV_RESIDENT_KB: the last local columns of the trailing matrix are read with a keep-in-L2 load policy
+    (they are part of every GEMV of the panel), the rest streams; a chunk of a group's columns is split where the two
+    meet. Same sums in the same order => bitwise the same H and Q"""
+    with _Env(STARNEIG_B200_COL_BLOCK=8, CUSIM_SMS=3):
+        A, Q, _ = _reduce(sim, ora, n, pw, gpus=gpus)
+        with _Env(STARNEIG_B200_GEMV_RESIDENT_KB=kb, STARNEIG_B200_FUSED_LL=ll):
+            A1, Q1, _ = _reduce(sim, ora, n, pw, gpus=gpus)
+    assert np.array_equal(A, A1) and np.array_equal(Q, Q1)
+
+
 def test_sim_gemv_prefetch_addresses(simlib):
     """STARNEIG_B200_GEMV_PREFETCH: during the level-2 phases of a column every GEMV group prefetches the head of its share
     of that column's GEMV into L2. A hint on the device (nothing to compare); here every prefetch address is checked

@@ -17,6 +17,7 @@ run_bench() {   # label, extra env..., device arm only unless label = bench
 run_bench bench STARNEIG_BENCH_N=20000
 run_bench ll STARNEIG_BENCH_N=20000 STARNEIG_B200_FUSED_LL=1 STARNEIG_B200_FUSED_EVEN_ROWS=1 STARNEIG_B200_FUSED_R=1
 run_bench llpf STARNEIG_BENCH_N=20000 STARNEIG_B200_FUSED_LL=1 STARNEIG_B200_FUSED_EVEN_ROWS=1 STARNEIG_B200_FUSED_R=1 STARNEIG_B200_GEMV_PREFETCH=32
+run_bench llres STARNEIG_BENCH_N=20000 STARNEIG_B200_FUSED_LL=1 STARNEIG_B200_FUSED_EVEN_ROWS=1 STARNEIG_B200_FUSED_R=1 STARNEIG_B200_GEMV_RESIDENT_KB=30720 STARNEIG_B200_GEMV_PREFETCH=16
 run_bench pw192 STARNEIG_BENCH_N=20000 STARNEIG_B200_AUTO_PANEL_WIDTH=192
 run_bench cb32 STARNEIG_BENCH_N=20000 STARNEIG_B200_COL_BLOCK=32
 run_bench overlap STARNEIG_BENCH_N=20000 STARNEIG_B200_OVERLAP=1 STARNEIG_B200_OVERLAP_CTAS=132
