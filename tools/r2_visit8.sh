@@ -1,8 +1,8 @@
 #!/bin/bash
 # Round-2 multi-GPU visit (gpurun --gpus N, N = 8 by default; charged N x the box time, so every step is bounded):
-# the bench line at N GPUs (n = 20000, BASELINE configs[2]), n = 50000 sharded over the N GPUs with the invariants
-# evaluated on rank 0's GPU (configs[3]), and two cheap variants of the n = 20000 run (narrower panel: the replicated
-# level-2 work per column shrinks with it; deferred updates overlapped) through the device-resident arm only.
+# the bench line at N GPUs (n = 20000, BASELINE configs[2]); the opt-in variants of DESIGN.md section 4.2b at N GPUs through
+# the device-resident arm inside one process group (tools/dist_sweep.py); n = 50000 sharded over the N GPUs with the
+# invariants evaluated on rank 0's GPU (configs[3]).
 # usage: gpurun --gpus 8 --timeout 600 -- bash tools/r2_visit8.sh 8
 N=${1:-8}
 mkdir -p gpurun_out
@@ -15,12 +15,11 @@ run_bench() {   # label, extra env..., device arm only unless label = bench
     echo "$label exit $?"; cat gpurun_out/n${N}_$label.json; grep -v "^\*\|OMP_NUM\|^$" gpurun_out/n${N}_$label.err | tail -4
 }
 run_bench bench STARNEIG_BENCH_N=20000
-run_bench ll STARNEIG_BENCH_N=20000 STARNEIG_B200_FUSED_LL=1 STARNEIG_B200_FUSED_EVEN_ROWS=1 STARNEIG_B200_FUSED_R=1
-run_bench llpf STARNEIG_BENCH_N=20000 STARNEIG_B200_FUSED_LL=1 STARNEIG_B200_FUSED_EVEN_ROWS=1 STARNEIG_B200_FUSED_R=1 STARNEIG_B200_GEMV_PREFETCH=32
-run_bench llres STARNEIG_BENCH_N=20000 STARNEIG_B200_FUSED_LL=1 STARNEIG_B200_FUSED_EVEN_ROWS=1 STARNEIG_B200_FUSED_R=1 STARNEIG_B200_GEMV_RESIDENT_KB=30720 STARNEIG_B200_GEMV_PREFETCH=16
-run_bench pw192 STARNEIG_BENCH_N=20000 STARNEIG_B200_AUTO_PANEL_WIDTH=192
-run_bench cb32 STARNEIG_BENCH_N=20000 STARNEIG_B200_COL_BLOCK=32
-run_bench overlap STARNEIG_BENCH_N=20000 STARNEIG_B200_OVERLAP=1 STARNEIG_B200_OVERLAP_CTAS=132
+# the variants through ONE process group (tools/dist_sweep.py): ~5 s each instead of a process start-up each
+ALLIN="FUSED_LL=1,FUSED_R=1,FUSED_EVEN_ROWS=1"
+(STARNEIG_BENCH_N=20000 STARNEIG_SWEEP=";FUSED_LL=1;$ALLIN;$ALLIN,GEMV_PREFETCH=32;$ALLIN,GEMV_RESIDENT_KB=30720,GEMV_PREFETCH=16;$ALLIN,GEMV_RESIDENT_KB=30720,GEMV_PREFETCH=16,COL_BLOCK=32;$ALLIN,GEMV_RESIDENT_KB=30720,GEMV_PREFETCH=16,AUTO_PANEL_WIDTH=192;OVERLAP=1,OVERLAP_CTAS=132" \
+    timeout 280 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29514 \
+    tools/dist_sweep.py 2>&1 | grep -v "^\*\|OMP_NUM\|^$" | tail -12) | tee gpurun_out/dist_sweep_gpus$N.log
 (STARNEIG_BENCH_N=50000 timeout 280 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29513 \
     tools/big_check_dist.py 2>&1 | grep -v "^\*\|OMP_NUM\|^$" | tail -6) | tee gpurun_out/big_n50000_gpus$N.log
 ls -la gpurun_out | tail -12
