@@ -66,6 +66,14 @@ using GemmNTfat   = GemmConfig<false, false, 2, 4, 8, 4, 4, 1>;     // 128 x 128
 using GemmNN13fat = GemmConfig<false, true,  8, 1, 2, 13, 4, 1>;    // 128 x 104
 using GemmNN12fat = GemmConfig<false, true,  8, 1, 2, 12, 4, 1>;    // 128 x  96
 
+// "Slim" variants for the co-resident overlap (STARNEIG_B200_OVERLAP=2): 64 x 64 tiles, 128 threads, <= 170 registers, so
+// that one such CTA fits next to the 64-register build of the persistent panel kernel on the same SM (24576 registers and
+// >= 76 KB of shared memory are left) and the deferred DMMA work runs in the shadow of the HBM-bound column loop on ALL
+// SMs -- the panel kernel needs every SM to saturate HBM (per-SM bandwidth limit), so giving SMs away does not pay
+// (profiles/r1_s5_overlap_sweep.txt).
+using GemmNTslim = GemmConfig<false, false, 2, 2, 4, 4, 4, 3>;      // 64 x 64
+using GemmNNslim = GemmConfig<false, true,  4, 1, 2, 8, 4, 3>;      // 64 x 64, W = X VT
+
 static const size_t PANEL_SMEM_MAX = 200 * 1024;
 constexpr int PANEL_RING = 3;           // V / VT buffer sets: the deferred updates may lag two panels behind
 
@@ -74,6 +82,7 @@ static void prepare_device_functions()
 {
     GemmNT::prepare(); GemmTN13::prepare(); GemmTN12::prepare(); GemmNN13::prepare(); GemmNN12::prepare();
     GemmNTfat::prepare(); GemmNN13fat::prepare(); GemmNN12fat::prepare();
+    GemmNTslim::prepare(); GemmNNslim::prepare();
     GemmOpt<1>::prepare(); GemmOpt<2>::prepare(); GemmOpt<3>::prepare();
     SB_CUDA(cudaFuncSetAttribute(k_col_finish_update<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM_MAX));
     SB_CUDA(cudaFuncSetAttribute(k_col_finish_update<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM_MAX));
@@ -95,6 +104,8 @@ static void prepare_device_functions()
     SB_CUDA(cudaFuncSetAttribute((k_panel_fused<true, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM_MAX));
     SB_CUDA(cudaFuncSetAttribute((k_panel_fused<false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM_MAX));
     SB_CUDA(cudaFuncSetAttribute((k_panel_fused<true, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM_MAX));
+    SB_CUDA(cudaFuncSetAttribute((k_panel_fused<false, true, 1024>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM_MAX));
+    SB_CUDA(cudaFuncSetAttribute((k_panel_fused<true, true, 1024>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM_MAX));
 }
 
 struct Stats : starneig_b200_stats {};
@@ -229,6 +240,8 @@ struct Rank {
     cudaEvent_t ev_panel[PANEL_RING] = {}, ev_side[PANEL_RING] = {};
     cudaStream_t copy = nullptr;            // host staging that overlaps the reduction (Q upload, write-back of finished columns)
     cudaEvent_t ev_q_up = nullptr, ev_cols_final = nullptr;
+    // 2: like 1, but co-resident: the panel kernel keeps all SMs (64-register build), the deferred GEMMs use slim tiles that
+    //    fit next to it on the same SM. Untimed so far.
     // 1: deferred updates run on `side`, concurrently with the next column loops. Off by default: measured on B200 at
     // n = 20000 (profiles/r1_s5_overlap_sweep.txt) the concurrent DMMA GEMMs cost the HBM-bound column loops far more
     // (GEMV phases 6335 -> 3850-4540 GB/s) than the 770 ms of deferred work they hide: 5334 ms without, 6216-6854 ms with.
@@ -380,9 +393,11 @@ struct Rank {
         cudaStream_t st = on_side ? side : stream;
         double *wpart = on_side ? ws.Wpart_side : ws.Wpart;
         stats.gemm_flops += 2.0 * M * N * (double)K;
-        const bool fat = on_side && side_fat;
+        const bool slim = on_side && overlap == 2;
+        const bool fat = on_side && side_fat && !slim;
         if (kind == GEMM_NT) {
-            if (fat) GemmNTfat::launch(st, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, 1, K, 0);
+            if (slim)     GemmNTslim::launch(st, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, 1, K, 0);
+            else if (fat) GemmNTfat::launch(st, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, 1, K, 0);
             else switch (gemm_opt) {
                 case 1:  GemmOpt<1>::NT::launch(st, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, 1, K, 0); break;
                 case 2:  GemmOpt<2>::NT::launch(st, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, 1, K, 0); break;
@@ -395,6 +410,7 @@ struct Rank {
         // skinny output (N = panel width): pick the column tile with the least padding, split K if the
         // grid would not fill the GPU twice
         int bn = (ceil_div(N, 96) * 96 <= ceil_div(N, 104) * 104) ? 96 : 104;
+        if (slim && kind == GEMM_NN) bn = 64;
         // 2 CTAs per SM are resident; split K so that the grid is >= ~8 waves (tail quantisation < ~6 %)
         int tiles = ceil_div(M, fat ? 128 : 64) * ceil_div(N, bn);
         int splits = 1;
@@ -410,7 +426,9 @@ struct Rank {
         size_t stride = splits > 1 ? (size_t)ldc * N : 0;
         double b = splits > 1 ? 0.0 : beta;
 #define SB_SKINNY(CFG) CFG::launch(st, M, N, K, alpha, A, lda, B, ldb, b, out, ldc, splits, klen, stride)
-        if (kind == GEMM_NN && fat) {
+        if (kind == GEMM_NN && slim) {
+            SB_SKINNY(GemmNNslim);
+        } else if (kind == GEMM_NN && fat) {
             if (bn == 96) SB_SKINNY(GemmNN12fat); else SB_SKINNY(GemmNN13fat);
         } else if (kind == GEMM_TN) {
             switch (gemm_opt) {
@@ -543,7 +561,7 @@ struct Rank {
             f.a = pa; f.w = w; f.i = i; f.pan = pan; f.ldpan = ldpan; f.Aloc = A_loc; f.lda = ldA; f.cm = cm; f.lc_end = lc_end;
             f.nsub = std::max(1, ceil_div(m, 32 * ctas));
             f.rpc = 32 * f.nsub;
-            f.fuse_r = fused_ll && fused_r;
+            f.fuse_r = (fused_ll || overlap == 2) && fused_r;
             f.pf_cols = gemv_prefetch;
             f.pf_budget = (long long)gemv_prefetch_mb << 20;
             {   // the last local columns, all of them right of the panel so that every GEMV of the panel reads them
@@ -565,7 +583,9 @@ struct Rank {
             if (smem <= PANEL_SMEM_MAX) {
                 y_epoch += w;
                 SB_CUDA(cudaMemsetAsync(ws.gbar, 0, 1024 * sizeof(unsigned), st));
-                if (P > 1 && fused_ll) SB_LAUNCH_COOP((k_panel_fused<true, true>), ctas, FUSED_THREADS, smem, st, f);
+                if (overlap == 2 && P > 1) SB_LAUNCH_COOP((k_panel_fused<true, true, 1024>), ctas, FUSED_THREADS, smem, st, f);
+                else if (overlap == 2)     SB_LAUNCH_COOP((k_panel_fused<false, true, 1024>), ctas, FUSED_THREADS, smem, st, f);
+                else if (P > 1 && fused_ll) SB_LAUNCH_COOP((k_panel_fused<true, true>), ctas, FUSED_THREADS, smem, st, f);
                 else if (P > 1)        SB_LAUNCH_COOP((k_panel_fused<true, false>), ctas, FUSED_THREADS, smem, st, f);
                 else if (fused_ll)     SB_LAUNCH_COOP((k_panel_fused<false, true>), ctas, FUSED_THREADS, smem, st, f);
                 else                   SB_LAUNCH_COOP((k_panel_fused<false, false>), ctas, FUSED_THREADS, smem, st, f);
@@ -708,7 +728,8 @@ struct Rank {
             if (ovl && panel >= PANEL_RING) SB_CUDA(cudaStreamWaitEvent(st, ev_side[slot], 0));
             if (lvl >= 1) SB_CUDA(cudaEventRecord(phase_event(2 + 6 * panel + 0), st));
             const int pl0 = cm.lower(i), pl1 = cm.lower(i + w);
-            const int ctas = (ovl && side_pending > 0) ? panel_ctas(m, w, n, qrows, i) : fused_ctas;
+            // overlap == 2: the deferred GEMMs share the SMs with the (64-register) panel kernel, which keeps all of them
+            const int ctas = (ovl && overlap != 2 && side_pending > 0) ? panel_ctas(m, w, n, qrows, i) : fused_ctas;
             if (P == 1) {
                 panel_factor(cm, i, end, w, A, ldA, A + (size_t)i * ldA + i + 1, ldA, V, ws.Y, VT, ld, ctas);
             } else {
@@ -788,7 +809,7 @@ struct Rank {
         SB_CUDA(cudaStreamSynchronize(st));
         SB_CUDA(cudaStreamSynchronize(side));
         SB_CUDA(cudaGetLastError());
-        if (P == 1 && fused_ll) {
+        if (P == 1 && (fused_ll || overlap == 2)) {
             unsigned status = 0;
             SB_CUDA(cudaMemcpy(&status, ws.counter + 3, sizeof(status), cudaMemcpyDeviceToHost));
             if (status != 0) fatal("a wait inside the persistent panel kernel timed out", __FILE__, __LINE__);

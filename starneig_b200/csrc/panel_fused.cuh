@@ -324,10 +324,10 @@ struct FusedSmem {
 // One chunk (nk columns, vs = the matching entries of v) of a thread's GEMV rows, read with the "keep in L2" policy: the
 // columns the host marked resident (FusedArgs::res_lc0) are part of every GEMV of the panel, so after the first column
 // they come from L2 instead of HBM. Same arithmetic in the same order as the streaming loop of phase G.
+template <int U>
 __device__ __forceinline__ void gemv_chunk_resident(const double *P0, size_t step, int nk, const double *vs, double2 &acc,
                                                     unsigned long long policy)
 {
-    constexpr int U = 8;
     double2 cur[U], nxt[U];
     int k = 0;
     if (nk >= U) {
@@ -465,9 +465,14 @@ __device__ __noinline__ void fused_reflector_pass(const double *V, int ld, int j
 // alternates between two buffers (a fast CTA writes p' of column j+1 while a slow one still forms v from p'' of column
 // j), and tau / beta / scale of the previous column come from the CTA's own shared-memory copy. The barrier after
 // phase R stays (the GEMV reads p'' of all rows). Opt-in (STARNEIG_B200_FUSED_LL=1) until timed on a B200.
-template <bool DIST, bool LLRED>
-__global__ void __launch_bounds__(FUSED_THREADS, 1) k_panel_fused(FusedArgs f)
+// MAXT: the thread count the register allocation is sized for. FUSED_THREADS (640): 96 registers per thread, the CTA owns
+// the register file of its SM. 1024: 64 registers per thread (the launch still uses 640 threads), which leaves 24576
+// registers of the SM to a co-resident 128-thread DMMA CTA of the deferred updates (engine.cuh, overlap with slim tiles).
+template <bool DIST, bool LLRED, int MAXT = FUSED_THREADS>
+__global__ void __launch_bounds__(MAXT, 1) k_panel_fused(FusedArgs f)
 {
+    // 16-byte loads in flight per GEMV thread: U columns being accumulated + U being fetched (64-register variant: 4 + 4)
+    constexpr int GEMV_U = MAXT > FUSED_THREADS ? 4 : 8;
     SB_DYNAMIC_SMEM(double, sh);
     const PanelArgs &a = f.a;
     const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
@@ -787,9 +792,9 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_panel_fused(FusedArgs f)
                         }
                         group_barrier(1 + vb, 128);
                         if (rows_ok && resident) {
-                            gemv_chunk_resident(Ap + (size_t)k0 * f.lda, (size_t)f.lda, nk, vs, acc, keep_policy);
+                            gemv_chunk_resident<GEMV_U>(Ap + (size_t)k0 * f.lda, (size_t)f.lda, nk, vs, acc, keep_policy);
                         } else if (rows_ok) {
-                            constexpr int U = 8;
+                            constexpr int U = GEMV_U;
                             const size_t step = (size_t)f.lda;
                             const double *P0 = Ap + (size_t)k0 * step;
                             double2 cur[U], nxt[U];

@@ -330,6 +330,18 @@ def test_sim_gemv_resident_columns(sim, ora, gpus, n, pw, kb, ll):
     assert np.array_equal(A, A1) and np.array_equal(Q, Q1)
 
 
+@pytest.mark.parametrize("gpus,n,pw,sms,extra", [(1, 131, 24, 4, {}), (1, 200, 70, 3, {"STARNEIG_B200_FUSED_R": 1, "STARNEIG_B200_FUSED_EVEN_ROWS": 1}),
+                                                  (2, 120, 16, 2, {})])
+def test_sim_coresident_overlap_mode(sim, ora, gpus, n, pw, sms, extra):
+    """STARNEIG_B200_OVERLAP=2: deferred Q / top-row updates on the side stream with the slim (64 x 64, <= 170 registers)
+    DMMA tiles, next to the 64-register build of the persistent panel kernel (LL variant, 4 + 4 loads in flight per GEMV
+    thread). The emulator executes streams in program order, so this pins the launch sequence, the V / VT ring and the slim
+    kernels -- not the concurrency."""
+    with _Env(STARNEIG_B200_COL_BLOCK=8, CUSIM_SMS=sms, STARNEIG_B200_OVERLAP=2, **extra):
+        _, _, st = _reduce(sim, ora, n, pw, gpus=gpus)
+    assert st["fused_panels"] == st["panels"] and st["overlap"] == 1
+
+
 def test_sim_gemv_prefetch_addresses(simlib):
     """STARNEIG_B200_GEMV_PREFETCH: during the level-2 phases of a column every GEMV group prefetches the head of its share
     of that column's GEMV into L2. A hint on the device (nothing to compare); here every prefetch address is checked

@@ -58,10 +58,11 @@ if mode == "denormal":
     assert ora.orthogonality_u(n, Q, ld) <= 500
     assert np.abs(A[:n] - A2[:n]).max() <= 1e-5 * np.abs(A2[:n]).max()
     assert np.abs(Q[:n] - Q2[:n]).max() <= 1e-5
-elif mode == "even_rows":
+elif mode in ("even_rows", "overlap2"):
     A0, Q0, ld = ora.fullpos(n, 2019)
-    A, Q = run(A0, Q0, ld, {"STARNEIG_B200_FUSED_EVEN_ROWS": "1", "STARNEIG_B200_FUSED_LL": sys.argv[4],
-                            "STARNEIG_B200_FUSED_R": sys.argv[4]})
+    env = ({"STARNEIG_B200_OVERLAP": "2"} if mode == "overlap2" else
+           {"STARNEIG_B200_FUSED_EVEN_ROWS": "1", "STARNEIG_B200_FUSED_LL": sys.argv[4], "STARNEIG_B200_FUSED_R": sys.argv[4]})
+    A, Q = run(A0, Q0, ld, env)
     A2, Q2 = A0.copy(order="F"), Q0.copy(order="F")
     assert ora.hessenberg_port(n, A2, ld, Q2, ld, 0, n, pw) == 0
     assert np.abs(A[:n] - A2[:n]).max() <= 200 * n * U * max(1.0, np.abs(A2[:n]).max())
@@ -97,6 +98,13 @@ def test_denormal_range_takes_dlarfg_rescaling_branch(fused):
                                     "STARNEIG_B200_GEMV_RESIDENT_KB=4096"])
 def test_optin_variant_is_bitwise_equal_to_the_default(switch):
     _child("variant", 1500, 200, switch)
+
+
+@pytest.mark.skipif(not OPTIN, reason="opt-in kernel variant: set STARNEIG_TEST_OPTIN=1 (tools/r2_visit1.sh does)")
+@pytest.mark.skipif(not OPTIN, reason="opt-in kernel variant: set STARNEIG_TEST_OPTIN=1 (tools/r2_visit1.sh does)")
+def test_optin_coresident_overlap():
+    # deferred updates next to the 64-register panel kernel on the same SMs (slim tiles, other split-K): parity with the oracle
+    _child("overlap2", 1500, 200, 0)
 
 
 @pytest.mark.skipif(not OPTIN, reason="opt-in kernel variant: set STARNEIG_TEST_OPTIN=1 (tools/r2_visit1.sh does)")

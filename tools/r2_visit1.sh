@@ -9,7 +9,7 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gp
 (timeout 150 tools/bin/gemm_sweep 20000 2 3 2>&1) > gpurun_out/gemm_sweep_p2.txt; tail -50 gpurun_out/gemm_sweep_p2.txt
 (timeout 100 tools/bin/gemm_sweep 20000 40 3 2>&1) > gpurun_out/gemm_sweep_p40.txt
 : > gpurun_out/sweep.log
-for cfg in "" "FUSED_LL=1" "FUSED_EVEN_ROWS=1" "FUSED_LL=1,FUSED_EVEN_ROWS=1" "FUSED_LL=1,FUSED_R=1" "FUSED_LL=1,FUSED_R=1,FUSED_EVEN_ROWS=1" "GEMV_RESIDENT_KB=20480" "GEMV_RESIDENT_KB=40960" "GEMV_RESIDENT_KB=20480,GEMV_PREFETCH=16" "GEMV_PREFETCH=16" "GEMV_PREFETCH=32" "GEMV_PREFETCH=64" "FUSED_LL=1,FUSED_R=1,FUSED_EVEN_ROWS=1,GEMV_PREFETCH=32" "GEMM_OPT=1" "GEMM_OPT=2" "GEMM_OPT=3" "AUTO_PANEL_WIDTH=256" "AUTO_PANEL_WIDTH=192" "AUTO_PANEL_WIDTH=384" "FUSED_LL=1,FUSED_R=1,FUSED_EVEN_ROWS=1,GEMM_OPT=2,AUTO_PANEL_WIDTH=256"; do
+for cfg in "" "FUSED_LL=1" "FUSED_EVEN_ROWS=1" "FUSED_LL=1,FUSED_EVEN_ROWS=1" "FUSED_LL=1,FUSED_R=1" "FUSED_LL=1,FUSED_R=1,FUSED_EVEN_ROWS=1" "GEMV_RESIDENT_KB=20480" "GEMV_RESIDENT_KB=40960" "GEMV_RESIDENT_KB=20480,GEMV_PREFETCH=16" "GEMV_PREFETCH=16" "GEMV_PREFETCH=32" "GEMV_PREFETCH=64" "FUSED_LL=1,FUSED_R=1,FUSED_EVEN_ROWS=1,GEMV_PREFETCH=32" "OVERLAP=2" "OVERLAP=2,FUSED_R=1,FUSED_EVEN_ROWS=1,GEMV_PREFETCH=16" "GEMM_OPT=1" "GEMM_OPT=2" "GEMM_OPT=3" "AUTO_PANEL_WIDTH=256" "AUTO_PANEL_WIDTH=192" "AUTO_PANEL_WIDTH=384" "FUSED_LL=1,FUSED_R=1,FUSED_EVEN_ROWS=1,GEMM_OPT=2,AUTO_PANEL_WIDTH=256"; do
     timeout 90 python tools/sweep.py 20000 "$cfg" 2>&1 | grep -v "zeros below" | tee -a gpurun_out/sweep.log
 done
 timeout 300 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench exit $?"
