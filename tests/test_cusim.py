@@ -342,6 +342,13 @@ def test_sim_coresident_overlap_mode(sim, ora, gpus, n, pw, sms, extra):
     assert st["fused_panels"] == st["panels"] and st["overlap"] == 1
 
 
+def test_sim_side_stream_overlap_mode(sim, ora):
+    """STARNEIG_B200_OVERLAP=1 (round-1 variant: deferred updates on the side stream, fat tiles, panel kernel on fewer CTAs)"""
+    with _Env(CUSIM_SMS=6, STARNEIG_B200_OVERLAP=1, STARNEIG_B200_OVERLAP_CTAS=4):
+        _, _, st = _reduce(sim, ora, 150, 24)
+    assert st["overlap"] == 1
+
+
 def test_sim_gemv_prefetch_addresses(simlib):
     """STARNEIG_B200_GEMV_PREFETCH: during the level-2 phases of a column every GEMV group prefetches the head of its share
     of that column's GEMV into L2. A hint on the device (nothing to compare); here every prefetch address is checked

@@ -58,9 +58,9 @@ if mode == "denormal":
     assert ora.orthogonality_u(n, Q, ld) <= 500
     assert np.abs(A[:n] - A2[:n]).max() <= 1e-5 * np.abs(A2[:n]).max()
     assert np.abs(Q[:n] - Q2[:n]).max() <= 1e-5
-elif mode in ("even_rows", "overlap2"):
+elif mode in ("even_rows", "overlap"):
     A0, Q0, ld = ora.fullpos(n, 2019)
-    env = ({"STARNEIG_B200_OVERLAP": "2"} if mode == "overlap2" else
+    env = ({"STARNEIG_B200_OVERLAP": sys.argv[4]} if mode == "overlap" else
            {"STARNEIG_B200_FUSED_EVEN_ROWS": "1", "STARNEIG_B200_FUSED_LL": sys.argv[4], "STARNEIG_B200_FUSED_R": sys.argv[4]})
     A, Q = run(A0, Q0, ld, env)
     A2, Q2 = A0.copy(order="F"), Q0.copy(order="F")
@@ -102,9 +102,11 @@ def test_optin_variant_is_bitwise_equal_to_the_default(switch):
 
 @pytest.mark.skipif(not OPTIN, reason="opt-in kernel variant: set STARNEIG_TEST_OPTIN=1 (tools/r2_visit1.sh does)")
 @pytest.mark.skipif(not OPTIN, reason="opt-in kernel variant: set STARNEIG_TEST_OPTIN=1 (tools/r2_visit1.sh does)")
-def test_optin_coresident_overlap():
-    # deferred updates next to the 64-register panel kernel on the same SMs (slim tiles, other split-K): parity with the oracle
-    _child("overlap2", 1500, 200, 0)
+@pytest.mark.parametrize("mode", [1, 2])
+def test_optin_overlapped_deferred_updates(mode):
+    # deferred updates on the side stream, concurrent with the next column loops. 1: the panel kernel gives SMs away (fat
+    # tiles); 2: next to the 64-register panel kernel on the same SMs (slim tiles). Other split-K: parity with the oracle
+    _child("overlap", 1500, 200, mode)
 
 
 @pytest.mark.skipif(not OPTIN, reason="opt-in kernel variant: set STARNEIG_TEST_OPTIN=1 (tools/r2_visit1.sh does)")
