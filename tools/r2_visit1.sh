@@ -9,9 +9,14 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gp
 (timeout 150 tools/bin/gemm_sweep 20000 2 3 2>&1) > gpurun_out/gemm_sweep_p2.txt; tail -50 gpurun_out/gemm_sweep_p2.txt
 (timeout 100 tools/bin/gemm_sweep 20000 40 3 2>&1) > gpurun_out/gemm_sweep_p40.txt
 : > gpurun_out/sweep.log
-for cfg in "" "FUSED_LL=1" "FUSED_EVEN_ROWS=1" "FUSED_LL=1,FUSED_EVEN_ROWS=1" "FUSED_LL=1,FUSED_R=1" "FUSED_LL=1,FUSED_R=1,FUSED_EVEN_ROWS=1" "GEMV_RESIDENT_KB=20480" "GEMV_RESIDENT_KB=40960" "GEMV_RESIDENT_KB=20480,GEMV_PREFETCH=16" "GEMV_PREFETCH=16" "GEMV_PREFETCH=32" "GEMV_PREFETCH=64" "FUSED_LL=1,FUSED_R=1,FUSED_EVEN_ROWS=1,GEMV_PREFETCH=32" "OVERLAP=2" "OVERLAP=2,FUSED_R=1,FUSED_EVEN_ROWS=1,GEMV_PREFETCH=16" "GEMM_OPT=1" "GEMM_OPT=2" "GEMM_OPT=3" "AUTO_PANEL_WIDTH=256" "AUTO_PANEL_WIDTH=192" "AUTO_PANEL_WIDTH=384" "FUSED_LL=1,FUSED_R=1,FUSED_EVEN_ROWS=1,GEMM_OPT=2,AUTO_PANEL_WIDTH=256"; do
-    timeout 90 python tools/sweep.py 20000 "$cfg" 2>&1 | grep -v "zeros below" | tee -a gpurun_out/sweep.log
-done
+# all configurations in one process (tools/sweep.py); if a variant faults, the rest is repeated one process each
+CFGS=("" "FUSED_LL=1" "FUSED_EVEN_ROWS=1" "FUSED_LL=1,FUSED_EVEN_ROWS=1" "FUSED_LL=1,FUSED_R=1" "FUSED_LL=1,FUSED_R=1,FUSED_EVEN_ROWS=1" "GEMV_RESIDENT_KB=20480" "GEMV_RESIDENT_KB=40960" "GEMV_RESIDENT_KB=20480,GEMV_PREFETCH=16" "GEMV_PREFETCH=16" "GEMV_PREFETCH=32" "GEMV_PREFETCH=64" "FUSED_LL=1,FUSED_R=1,FUSED_EVEN_ROWS=1,GEMV_PREFETCH=32" "OVERLAP=2" "OVERLAP=2,FUSED_R=1,FUSED_EVEN_ROWS=1,GEMV_PREFETCH=16" "GEMM_OPT=1" "GEMM_OPT=2" "GEMM_OPT=3" "AUTO_PANEL_WIDTH=256" "AUTO_PANEL_WIDTH=192" "AUTO_PANEL_WIDTH=384" "FUSED_LL=1,FUSED_R=1,FUSED_EVEN_ROWS=1,GEMM_OPT=2,AUTO_PANEL_WIDTH=256")
+timeout 600 python tools/sweep.py 20000 "${CFGS[@]}" 2>&1 | tee -a gpurun_out/sweep.log
+DONE=$(grep -c "device_ms" gpurun_out/sweep.log)
+if [ "$DONE" -lt "${#CFGS[@]}" ]; then
+    echo "sweep stopped after $DONE configurations: running the others isolated (skipping the one that stopped it)" | tee -a gpurun_out/sweep.log
+    timeout 600 python tools/sweep.py 20000 --isolate "${CFGS[@]:$((DONE + 1))}" 2>&1 | tee -a gpurun_out/sweep.log
+fi
 timeout 300 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench exit $?"
 cat gpurun_out/bench.json; tail -3 gpurun_out/bench.err
 timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/launches_bench_n20000.csv \
