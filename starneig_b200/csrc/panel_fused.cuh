@@ -543,6 +543,13 @@ __global__ void __launch_bounds__(MAXT, 1) k_panel_fused(FusedArgs f)
             // GEMV of column j-1 was streaming (`red`); what is left on the critical path is y itself.
             const int NWa = max(1, (jm1 + 31) >> 5);
             const bool do_update = j < f.w;
+            // LLRED: the epilogue's inputs that do not depend on the GEMV (p'' of column j-1 and column j of the panel, own
+            // rows) are fetched before the wait for the GEMV partials instead of after it (one L2 round trip less)
+            double pre_p = 0.0, pre_a = 0.0;
+            if (LLRED && wp < nsub) {
+                const int r = row0 + wp * 32 + lane;
+                if (r < row_end) { pre_p = pc_prev[r]; pre_a = do_update ? acol[r] : 0.0; }
+            }
             // LLRED: no grid barrier since R' of column j-1, where every CTA derived these scalars itself (scal_sh)
             const double tau = LLRED ? scal_sh[0] : __ldcg(&a.scal[jm1].tau), beta_prev = LLRED ? scal_sh[1] : __ldcg(&a.scal[jm1].beta),
                          scale_prev = LLRED ? scal_sh[2] : __ldcg(&a.scal[jm1].scale);
@@ -609,8 +616,9 @@ __global__ void __launch_bounds__(MAXT, 1) k_panel_fused(FusedArgs f)
                 const bool valid = r < row_end;
                 double pp = 0.0;
                 if (valid) {
-                    const double pprev = pc_prev[r];
-                    const double ac = do_update ? acol[r] : 0.0;
+                    const bool pre = LLRED && sub == wp;
+                    const double pprev = pre ? pre_p : pc_prev[r];
+                    const double ac = pre ? pre_a : (do_update ? acol[r] : 0.0);
                     const double D3 = ysm[sub * 32 + lane];
                     const double *rd = red + (size_t)sub * 3 * NWa * 32 + lane;
                     double D0 = 0.0, D1 = 0.0, D2 = 0.0;
