@@ -266,6 +266,7 @@ struct Rank {
     int fused_ll = 0;                       // 1: fused panel kernel with LL-entry reductions (one grid barrier per column instead of four)
     int fused_even_rows = 0;                // 1: fused panel kernel: rows spread over all CTAs (changes the grouping of the partial sums)
     int fused_r = 0;                        // 1 (with fused_ll): phase R of the fused kernel reads its slab of V once instead of twice
+    int gemv_kc = FUSED_KC;                 // fused kernel: columns of v staged per GEMV group at a time
     int gemv_prefetch = 0;                  // fused kernel: columns (2 KB each) per GEMV group pulled into L2 during the level-2 phases
     int gemv_prefetch_mb = 96;              // L2 budget shared by V, Y, VT of the panel and the prefetched data
     int gemv_resident_kb = 0;               // fused kernel: KB of the trailing matrix (its last local columns) kept in L2 across the
@@ -306,6 +307,8 @@ struct Rank {
         if (e) fused_even_rows = atoi(e);
         e = getenv("STARNEIG_B200_FUSED_R");
         if (e) fused_r = atoi(e);
+        e = getenv("STARNEIG_B200_GEMV_KC");
+        if (e && atoi(e) >= 64) gemv_kc = std::min(4096, atoi(e) / 8 * 8);
         e = getenv("STARNEIG_B200_GEMV_PREFETCH");
         if (e && atoi(e) >= 0) gemv_prefetch = atoi(e);
         e = getenv("STARNEIG_B200_GEMV_RESIDENT_KB");
@@ -579,7 +582,9 @@ struct Rank {
             f.x = x;
             f.x.epoch = y_epoch + 1;
             f.w2part_ll = ws.w2part_ll; f.w2_ll = ws.w2_ll; f.ypart_ll = ws.ypart_ll; f.pcol2 = ws.pcol2;
-            const size_t smem = fused_smem_bytes(w, f.nsub);
+            f.kc = gemv_kc;
+            size_t smem = fused_smem_bytes(w, f.nsub, f.kc);
+            if (smem > PANEL_SMEM_MAX) { f.kc = FUSED_KC; smem = fused_smem_bytes(w, f.nsub, f.kc); }
             if (smem <= PANEL_SMEM_MAX) {
                 y_epoch += w;
                 SB_CUDA(cudaMemsetAsync(ws.gbar, 0, 1024 * sizeof(unsigned), st));

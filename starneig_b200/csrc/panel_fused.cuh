@@ -32,7 +32,7 @@ constexpr int FUSED_THREADS = 640;
 constexpr int FUSED_WARPS = FUSED_THREADS / 32;
 constexpr int FUSED_MAX_NB = 512;
 constexpr int FUSED_VB = 4;                          // 128-thread GEMV groups per CTA (warps 0..15); warps 16..19 look ahead
-constexpr int FUSED_KC = 512;                        // columns of v staged per group at a time
+constexpr int FUSED_KC = 512;                        // columns of v staged per group at a time (default; FusedArgs::kc)
 constexpr int FUSED_MINSEG = 16;                     // fewest (row block, column) items per group
 
 struct FusedArgs {
@@ -48,6 +48,7 @@ struct FusedArgs {
     int nsub;                   // 32-row sub-tiles per CTA
     int rpc;                    // rows owned by a CTA (<= 32 * nsub; the last sub-tile of a CTA may be partial)
     int fuse_r;                 // LLRED only: phase R streams the CTA's slab of V once instead of twice
+    int kc;                     // columns of v a GEMV group stages in shared memory at a time (each refill drains its load pipeline)
     int pf_cols;                // columns of its first GEMV item chunk that a group prefetches into L2 ahead of phase G (0: off)
     int res_lc0;                // local columns >= res_lc0 are read with the "keep in L2" policy (the same columns in every GEMV
                                 // of the panel); >= lc_end: none
@@ -303,12 +304,12 @@ constexpr int FUSED_SHADOW_THREADS = FUSED_THREADS - 32 * FUSED_GEMV_WARPS;     
 // shared-memory layout (doubles), fixed for the whole launch
 struct FusedSmem {
     int vs, s, vrow, w2, red, pv, ysm, sqred, scal, total;
-    __host__ __device__ FusedSmem(int w, int nsub)
+    __host__ __device__ FusedSmem(int w, int nsub, int kc = FUSED_KC)
     {
         const int NW = (w + 31) / 32 > 1 ? (w + 31) / 32 : 1;
         const int wp8 = (w + 8) / 8 * 8;
         int o = 0;
-        vs = o;    o += FUSED_VB * FUSED_KC;
+        vs = o;    o += FUSED_VB * kc;
         s = o;     o += wp8;
         vrow = o;  o += wp8;
         w2 = o;    o += wp8;
@@ -483,7 +484,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_panel_fused(FusedArgs f)
     const int row_end = min(m, row0 + f.rpc);
     const int rows_here = max(0, row_end - row0);
     const int nblk = (m + f.rpc - 1) / f.rpc;                   // CTAs that own rows
-    const FusedSmem L(f.w, nsub);
+    const FusedSmem L(f.w, nsub, f.kc);
     double *const vs_all = sh + L.vs, *const s_sh = sh + L.s, *const vrow_sh = sh + L.vrow, *const w2_sh = sh + L.w2;
     double *const red = sh + L.red, *const pv = sh + L.pv, *const ysm = sh + L.ysm, *const sqred = sh + L.sqred;
     unsigned gen = 0, gen2 = 0;
@@ -773,7 +774,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_panel_fused(FusedArgs f)
                 // groups are spread over the CTAs first (group v lives on CTA v % G), so that a GEMV smaller than the
                 // grid still touches every SM
                 const int v = vb * G + b;
-                double *vs = vs_all + vb * FUSED_KC;
+                double *vs = vs_all + vb * f.kc;
                 long long it = (long long)v * gq.per;
                 const long long it_end = min(items, it + gq.per);
                 const int mp = m + gs.skip;
@@ -788,7 +789,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_panel_fused(FusedArgs f)
                     double2 acc = make_double2(0.0, 0.0);
                     const double *Ap = f.Aloc + (size_t)lc0 * f.lda + f.i + 1 - gs.skip + rp;
                     for (int k0 = cbeg, nk = 0; k0 < cend; k0 += nk) {
-                        nk = min(FUSED_KC, cend - k0);
+                        nk = min(f.kc, cend - k0);
                         // columns >= ks are resident in L2 for the whole panel (read with another load policy): a chunk
                         // is either streamed or resident
                         const bool resident = k0 >= ks;
@@ -922,6 +923,6 @@ __global__ void __launch_bounds__(MAXT, 1) k_panel_fused(FusedArgs f)
 }
 
 // dynamic shared memory of k_panel_fused for a panel of w columns with nsub sub-tiles per CTA
-static inline size_t fused_smem_bytes(int w, int nsub) { return (size_t)FusedSmem(w, nsub).total * sizeof(double); }
+static inline size_t fused_smem_bytes(int w, int nsub, int kc = FUSED_KC) { return (size_t)FusedSmem(w, nsub, kc).total * sizeof(double); }
 
 } // namespace sb200

@@ -322,10 +322,11 @@ def test_sim_ll_variant_with_lagging_blocks(simlib, sms, skew, seed):
 def test_sim_gemv_resident_columns(sim, ora, gpus, n, pw, kb, ll):
     """STARNEIG_B200_GEMV_RESIDENT_KB: the last local columns of the trailing matrix are read with a keep-in-L2 load policy
     (they are part of every GEMV of the panel), the rest streams; a chunk of a group's columns is split where the two
-    meet. Same sums in the same order => bitwise the same H and Q"""
+    meet. Also STARNEIG_B200_GEMV_KC (columns of v staged per group at a time: 64 = many refills, 2048 = few).
+    Same sums in the same order => bitwise the same H and Q"""
     with _Env(STARNEIG_B200_COL_BLOCK=8, CUSIM_SMS=3):
         A, Q, _ = _reduce(sim, ora, n, pw, gpus=gpus)
-        with _Env(STARNEIG_B200_GEMV_RESIDENT_KB=kb, STARNEIG_B200_FUSED_LL=ll):
+        with _Env(STARNEIG_B200_GEMV_RESIDENT_KB=kb, STARNEIG_B200_FUSED_LL=ll, STARNEIG_B200_GEMV_KC=(64 if kb == 3 else 2048)):
             A1, Q1, _ = _reduce(sim, ora, n, pw, gpus=gpus)
     assert np.array_equal(A, A1) and np.array_equal(Q, Q1)
 
