@@ -452,6 +452,8 @@ def run_ours(args):
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"Hessenberg reduction with Q, random dense FP64 n={n} (BASELINE.json configs[2] at {world} GPU{'s' if world > 1 else ''})",
                    "n": n, "panel_width": sn.default_panel_width(n), "ld": ld,
+                   # engine switches taken from the environment (none: the defaults of DESIGN.md section 4)
+                   "switches": {k: v for k, v in sorted(os.environ.items()) if k.startswith("STARNEIG_B200_")},
                    "l2": "inputs (A, Q: 2 x %.1f GB) are larger than the 126 MB L2; no explicit flush" % (n * ld * 8 / 1e9),
                    "parallelism": "1 GPU" if world == 1 else
                    f"{world} GPUs, one process each: A 1-D block-cyclic by columns (block 64), Q by row slabs; per-column GEMV "
