@@ -451,7 +451,7 @@ def run_ours(args):
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"Hessenberg reduction with Q, random dense FP64 n={n} (BASELINE.json configs[2] at {world} GPU{'s' if world > 1 else ''})",
-                   "n": n, "panel_width": sn.default_panel_width(n), "ld": ld,
+                   "n": n, "panel_width": int(st["panel_width"]), "ld": ld,
                    # engine switches taken from the environment (none: the defaults of DESIGN.md section 4)
                    "switches": {k: v for k, v in sorted(os.environ.items()) if k.startswith("STARNEIG_B200_")},
                    "l2": "inputs (A, Q: 2 x %.1f GB) are larger than the 126 MB L2; no explicit flush" % (n * ld * 8 / 1e9),
