@@ -215,6 +215,16 @@ def test_sim_eight_ranks(sim, ora):
     assert st["ranks"] == 8 and st["fused_panels"] == st["panels"]
 
 
+@pytest.mark.parametrize("gpus,n,cb,allin", [(4, 9, 8, 0), (4, 20, 16, 1), (2, 5, 8, 1), (8, 40, 8, 1)])
+def test_sim_ranks_with_few_or_no_columns(sim, ora, gpus, n, cb, allin):
+    """matrices smaller than one round of column blocks: some ranks own one block, some nothing at all; default kernels and
+    the opt-in variants together (LL reductions, single-pass phase R, even rows)"""
+    extra = dict(STARNEIG_B200_FUSED_LL=1, STARNEIG_B200_FUSED_R=1, STARNEIG_B200_FUSED_EVEN_ROWS=1) if allin else {}
+    with _Env(STARNEIG_B200_COL_BLOCK=cb, CUSIM_SMS=2, CUSIM_DEVICES=8, **extra):
+        _, _, st = _reduce(sim, ora, n, 8, gpus=gpus)
+    assert st["ranks"] == gpus
+
+
 def test_sim_multi_rank_unfused(sim, ora):
     with _Env(STARNEIG_B200_COL_BLOCK=8, STARNEIG_B200_FUSED_PANEL=0):
         _, _, st = _reduce(sim, ora, 72, 16, gpus=2)
