@@ -59,6 +59,16 @@ struct Shard {
 // The copies only overlap when the host buffers are page-locked (caller-pinned or registered for the call by
 // ScopedPin); with pageable memory cudaMemcpy2DAsync blocks the calling thread, so everything stays in
 // order on the compute stream: upload, reduce, download.
+// columns of `width` bytes between pitched buffers; one flat copy when both sides are contiguous (the usual case:
+// ld == n on the host and n a multiple of 16), so that the DMA engine sees one transfer instead of one per column
+static void copy_columns(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width, size_t ncols,
+                         cudaMemcpyKind kind, cudaStream_t st)
+{
+    if (ncols == 0 || width == 0) return;
+    if (dpitch == width && spitch == width) SB_CUDA(cudaMemcpyAsync(dst, src, width * ncols, kind, st));
+    else SB_CUDA(cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, ncols, kind, st));
+}
+
 struct HostStage : StageHook {
     const Rank &r; Shard &sh;
     const int n; double *const A; const int ldA; double *const Q; const int ldQ;
@@ -79,8 +89,8 @@ struct HostStage : StageHook {
             const int nc = std::min(std::min(cb - off, l1 - l0), n - gc);
             if (nc <= 0) break;
             double *d = sh.A + (size_t)l0 * sh.ldA, *h = A + (size_t)gc * ldA;
-            if (to_device) SB_CUDA(cudaMemcpy2DAsync(d, (size_t)sh.ldA * 8, h, (size_t)ldA * 8, (size_t)n * 8, nc, kind, st));
-            else           SB_CUDA(cudaMemcpy2DAsync(h, (size_t)ldA * 8, d, (size_t)sh.ldA * 8, (size_t)n * 8, nc, kind, st));
+            if (to_device) copy_columns(d, (size_t)sh.ldA * 8, h, (size_t)ldA * 8, (size_t)n * 8, nc, kind, st);
+            else           copy_columns(h, (size_t)ldA * 8, d, (size_t)sh.ldA * 8, (size_t)n * 8, nc, kind, st);
             l0 += nc;
         }
     }
@@ -90,8 +100,8 @@ struct HostStage : StageHook {
         if (sh.qrows <= 0 || c1 <= c0) return;
         const cudaMemcpyKind kind = to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
         double *d = sh.Q + (size_t)c0 * sh.ldQ, *h = Q + (size_t)c0 * ldQ + sh.q0;
-        if (to_device) SB_CUDA(cudaMemcpy2DAsync(d, (size_t)sh.ldQ * 8, h, (size_t)ldQ * 8, (size_t)sh.qrows * 8, c1 - c0, kind, st));
-        else           SB_CUDA(cudaMemcpy2DAsync(h, (size_t)ldQ * 8, d, (size_t)sh.ldQ * 8, (size_t)sh.qrows * 8, c1 - c0, kind, st));
+        if (to_device) copy_columns(d, (size_t)sh.ldQ * 8, h, (size_t)ldQ * 8, (size_t)sh.qrows * 8, c1 - c0, kind, st);
+        else           copy_columns(h, (size_t)ldQ * 8, d, (size_t)sh.ldQ * 8, (size_t)sh.qrows * 8, c1 - c0, kind, st);
     }
     void upload()
     {
