@@ -96,6 +96,11 @@ __device__ __forceinline__ double2 ld_l2_keep(const double2 *p, unsigned long lo
     return v;
 }
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// bulk variant (TMA engine): `bytes` (multiple of 16) from a 16-byte aligned address with ONE instruction
+__device__ __forceinline__ void prefetch_l2_bulk(const void *p, unsigned bytes)
+{
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
 // 8-byte asynchronous global -> shared copy; !valid: the 8 destination bytes are zero-filled (src-size 0)
 __device__ __forceinline__ void cp_async8(void *smem_dst, const void *gmem_src, bool valid)
 {

@@ -268,6 +268,8 @@ struct Rank {
     int fused_r = 0;                        // 1 (with fused_ll): phase R of the fused kernel reads its slab of V once instead of twice
     int gemv_kc = FUSED_KC;                 // fused kernel: columns of v staged per GEMV group at a time
     int gemv_prefetch = 0;                  // fused kernel: columns (2 KB each) per GEMV group pulled into L2 during the level-2 phases
+    int gemv_prefetch_bulk = 0;             // 1: bulk (TMA) prefetch instructions
+    int ll_sleep = 200;                     // ns between polls of the LL waits
     int gemv_prefetch_mb = 96;              // L2 budget shared by V, Y, VT of the panel and the prefetched data
     int gemv_resident_kb = 0;               // fused kernel: KB of the trailing matrix (its last local columns) kept in L2 across the
                                             // columns of a panel ("evict last" loads), 0: everything streams
@@ -313,6 +315,10 @@ struct Rank {
         if (e && atoi(e) >= 0) gemv_prefetch = atoi(e);
         e = getenv("STARNEIG_B200_GEMV_RESIDENT_KB");
         if (e && atoi(e) >= 0) gemv_resident_kb = atoi(e);
+        e = getenv("STARNEIG_B200_GEMV_PREFETCH_BULK");
+        if (e) gemv_prefetch_bulk = atoi(e);
+        e = getenv("STARNEIG_B200_LL_SLEEP");
+        if (e && atoi(e) >= 0) ll_sleep = atoi(e);
         e = getenv("STARNEIG_B200_GEMV_PREFETCH_MB");
         if (e && atoi(e) >= 0) gemv_prefetch_mb = atoi(e);
         e = getenv("STARNEIG_B200_OVERLAP");
@@ -566,6 +572,8 @@ struct Rank {
             f.rpc = 32 * f.nsub;
             f.fuse_r = (fused_ll || overlap == 2) && fused_r;
             f.pf_cols = gemv_prefetch;
+            f.pf_bulk = gemv_prefetch_bulk;
+            f.ll_sleep = ll_sleep;
             f.pf_budget = (long long)gemv_prefetch_mb << 20;
             {   // the last local columns, all of them right of the panel so that every GEMV of the panel reads them
                 const long long want = ((long long)gemv_resident_kb << 10) / (8ll * std::max(m, 1));

@@ -50,6 +50,8 @@ struct FusedArgs {
     int fuse_r;                 // LLRED only: phase R streams the CTA's slab of V once instead of twice
     int kc;                     // columns of v a GEMV group stages in shared memory at a time (each refill drains its load pipeline)
     int pf_cols;                // columns of its first GEMV item chunk that a group prefetches into L2 ahead of phase G (0: off)
+    int pf_bulk;                // 1: the prefetch uses one bulk (TMA) instruction per column and group instead of 16 line prefetches
+    int ll_sleep;               // LLRED: nanoseconds the polling lanes sleep between polls (0: spin)
     int res_lc0;                // local columns >= res_lc0 are read with the "keep in L2" policy (the same columns in every GEMV
                                 // of the panel); >= lc_end: none
     long long pf_budget;        // bytes of L2 that V, Y, VT (3 * 8 * m * j at column j) and the prefetched data may fill together
@@ -189,7 +191,7 @@ __device__ __forceinline__ double sum_partials(const double *p, int ld, int S)
 
 // waits, with back-off, until an LL entry carries `tag` (used by ONE lane per warp before its rows are summed, so that
 // thousands of threads do not hammer L2 with polls while the stragglers of the GEMV are still streaming)
-__device__ __forceinline__ void ll_wait(const uint4 *src, unsigned tag, unsigned *status)
+__device__ __forceinline__ void ll_wait(const uint4 *src, unsigned tag, unsigned *status, int sleep_ns = 200)
 {
     long long t0 = 0;
     for (;;) {
@@ -197,7 +199,7 @@ __device__ __forceinline__ void ll_wait(const uint4 *src, unsigned tag, unsigned
         if (e.y == tag && e.w == tag) return;
         if (t0 == 0) { t0 = clock64(); if (*(volatile unsigned *)status != 0u) return; }
         else if (clock64() - t0 > 8000000000ll) { atomicExch(status, 2u); return; }
-        __nanosleep(200);
+        if (sleep_ns > 0) __nanosleep(sleep_ns);
     }
 }
 
@@ -530,10 +532,18 @@ __global__ void __launch_bounds__(MAXT, 1) k_panel_fused(FusedArgs f)
                 // leave L2 to the level-2 working set first: V, Y, VT of the panel so far
                 const long long room = (f.pf_budget - 24ll * m * j) / (2048ll * G * FUSED_VB);
                 const int kend = min(cend, cbeg + (int)max(0ll, min((long long)f.pf_cols, room)));
+                if (f.pf_bulk) {
+                    // one bulk prefetch per column: the 256 rows of the row block (fewer at the matrix end), 16-byte granular
+                    const int rows = min(256, m + gs.skip - rb * 256) & ~1;
+                    const double *Ap = f.Aloc + (size_t)lc0 * f.lda + f.i + 1 - gs.skip + rb * 256;
+                    if (rows > 0)
+                        for (int k = cbeg + vt; k < kend; k += 128) prefetch_l2_bulk(Ap + (size_t)k * f.lda, (unsigned)rows * 8u);
+                } else {
                 const int rp = rb * 256 + (vt & 15) * 16;        // 16 lines of 128 bytes cover the 256 rows of the block
                 if (rp < m + gs.skip) {
                     const double *Ap = f.Aloc + (size_t)lc0 * f.lda + f.i + 1 - gs.skip + rp;
                     for (int k = cbeg + (vt >> 4); k < kend; k += 8) prefetch_l2(Ap + (size_t)k * f.lda);
+                }
                 }
             }
         }
@@ -568,7 +578,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_panel_fused(FusedArgs f)
                     // one lane per warp waits for the partial of the warp's first row that is written last (the group
                     // that first finishes the previous row block): the others are then there or about to be
                     const int rr0 = tid & ~31;
-                    if (lane == 0 && rr0 < rows_here) ll_wait(f.ypart_ll + row0 + rr0, epoch, f.x.status);
+                    if (lane == 0 && rr0 < rows_here) ll_wait(f.ypart_ll + row0 + rr0, epoch, f.x.status, f.ll_sleep);
                     __syncwarp();
                 }
                 for (int rr = tid; rr < rows_here; rr += FUSED_THREADS) {
@@ -662,7 +672,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_panel_fused(FusedArgs f)
         // ================= phase R: p'' = p' - V w2; ||x||^2, z = V^T x =================
         {
             if (LLRED && j > 0) {       // one polling lane per warp (see phase A)
-                if (lane == 0 && (tid & ~31) < j) ll_wait(f.w2_ll + (tid & ~31), f.x.epoch + j, f.x.status);
+                if (lane == 0 && (tid & ~31) < j) ll_wait(f.w2_ll + (tid & ~31), f.x.epoch + j, f.x.status, f.ll_sleep);
                 __syncwarp();
             }
             for (int t = tid; t < j; t += FUSED_THREADS)

@@ -151,6 +151,13 @@ static inline void prefetch_l2(const void *p)
     __atomic_fetch_add(&::cusim::g_prefetches, 1ull, __ATOMIC_RELAXED);
     if (check && !::cusim::inside_device_allocation(p, 8)) { fprintf(stderr, "cusim: prefetch outside every device allocation\n"); abort(); }
 }
+static inline void prefetch_l2_bulk(const void *p, unsigned bytes)
+{
+    static const bool check = getenv("CUSIM_CHECK_PREFETCH") != nullptr;
+    __atomic_fetch_add(&::cusim::g_prefetches, 1ull, __ATOMIC_RELAXED);
+    if ((((uintptr_t)p) & 15) || (bytes & 15) || bytes == 0) { fprintf(stderr, "cusim: misaligned bulk prefetch\n"); abort(); }
+    if (check && !::cusim::inside_device_allocation(p, bytes)) { fprintf(stderr, "cusim: bulk prefetch outside every device allocation\n"); abort(); }
+}
 static inline void cp_async8(void *smem_dst, const void *gmem_src, bool valid)
 {
     if (valid) memcpy(smem_dst, gmem_src, 8);

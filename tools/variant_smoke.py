@@ -14,6 +14,8 @@ U = 2.0 ** -52
 VARIANTS = ["", "FUSED_LL=1", "FUSED_LL=1,FUSED_R=1", "FUSED_EVEN_ROWS=1", "FUSED_LL=1,FUSED_R=1,FUSED_EVEN_ROWS=1", "GEMV_KC=2048",
             "GEMV_PREFETCH=32", "GEMV_RESIDENT_KB=20480", "OVERLAP=2", "GEMM_OPT=1", "GEMM_OPT=2", "GEMM_OPT=3",
             "FUSED_LL=1,FUSED_R=1,FUSED_EVEN_ROWS=1,GEMV_KC=2048,GEMV_PREFETCH=32,GEMV_RESIDENT_KB=20480"]
+if os.environ.get("VARIANTS"):
+    VARIANTS = os.environ["VARIANTS"].split(";")
 BITWISE = {"FUSED_LL=1", "GEMV_KC=2048", "GEMV_PREFETCH=32", "GEMV_RESIDENT_KB=20480", "GEMM_OPT=1", "GEMM_OPT=2", "GEMM_OPT=3"}
 
 
@@ -37,22 +39,23 @@ def run(n, pw, A0, Q0, ld, cfg):
 
 
 t0 = time.time()
-n, pw = n_check, 200
-A0, Q0, ld = ora.fullpos(n, 2019)
-A2, Q2 = A0.copy(order="F"), Q0.copy(order="F")
-ora.set_threads(os.cpu_count() or 1)
-ora.hessenberg_port(n, A2, ld, Q2, ld, 0, n, pw)
-Ad, Qd, _ = run(n, pw, A0, Q0, ld, "")
-for cfg in VARIANTS:
-    try:
-        A, Q, st = run(n, pw, A0, Q0, ld, cfg)
-        eh = np.abs(A[:n] - A2[:n]).max() / np.abs(A2[:n]).max() / (n * U)
-        eq = np.abs(Q[:n] - Q2[:n]).max() / (n * U)
-        bit = np.array_equal(A, Ad) and np.array_equal(Q, Qd)
-        ok = eh <= 200 and eq <= 200 and ora.hessenberg_form_violations(n, A, ld) == 0 and (bit or cfg not in BITWISE)
-        print(f"check n={n} [{cfg or 'default':88s}] {'ok ' if ok else 'BAD'} |dH|/(n u max|H|) {eh:6.2f} |dQ|/(n u) {eq:6.2f} bitwise_equal_to_default {bit}", flush=True)
-    except Exception as e:                      # noqa: BLE001
-        print(f"check n={n} [{cfg}] EXCEPTION {e!r}", flush=True)
+if n_check > 0:
+  n, pw = n_check, 200
+  A0, Q0, ld = ora.fullpos(n, 2019)
+  A2, Q2 = A0.copy(order="F"), Q0.copy(order="F")
+  ora.set_threads(os.cpu_count() or 1)
+  ora.hessenberg_port(n, A2, ld, Q2, ld, 0, n, pw)
+  Ad, Qd, _ = run(n, pw, A0, Q0, ld, "")
+  for cfg in VARIANTS:
+      try:
+          A, Q, st = run(n, pw, A0, Q0, ld, cfg)
+          eh = np.abs(A[:n] - A2[:n]).max() / np.abs(A2[:n]).max() / (n * U)
+          eq = np.abs(Q[:n] - Q2[:n]).max() / (n * U)
+          bit = np.array_equal(A, Ad) and np.array_equal(Q, Qd)
+          ok = eh <= 200 and eq <= 200 and ora.hessenberg_form_violations(n, A, ld) == 0 and (bit or cfg not in BITWISE)
+          print(f"check n={n} [{cfg or 'default':88s}] {'ok ' if ok else 'BAD'} |dH|/(n u max|H|) {eh:6.2f} |dQ|/(n u) {eq:6.2f} bitwise_equal_to_default {bit}", flush=True)
+      except Exception as e:                      # noqa: BLE001
+          print(f"check n={n} [{cfg}] EXCEPTION {e!r}", flush=True)
 print(f"checks done after {time.time() - t0:.1f} s", flush=True)
 
 n, pw = n_time, -1
