@@ -263,7 +263,8 @@ struct Rank {
     int fused = 1;                          // 1: one persistent kernel per panel (panel_fused.cuh); 0: three kernels per column
     int fused_ctas = 0;                     // grid of the fused kernel (number of SMs; fewer when ranks share a device)
     int gemm_opt = 0;                       // loader options of the DMMA kernels (GemmOpt<1..3>), 0: the default kernels
-    int fused_ll = 0;                       // 1: fused panel kernel with LL-entry reductions (one grid barrier per column instead of four)
+    int fused_ll = 0;                       // 1: fused panel kernel with LL-entry reductions (one grid barrier per column instead of four);
+                                            // 2: LL entries for the GEMV partials only (three barriers: w2 keeps barrier-reduce-barrier)
     int fused_even_rows = 0;                // 1: fused panel kernel: rows spread over all CTAs (changes the grouping of the partial sums)
     int fused_r = 0;                        // 1 (with fused_ll): phase R of the fused kernel reads its slab of V once instead of twice
     int gemv_kc = FUSED_KC;                 // fused kernel: columns of v staged per GEMV group at a time
@@ -574,9 +575,13 @@ struct Rank {
             f.pf_cols = gemv_prefetch;
             f.pf_bulk = gemv_prefetch_bulk;
             f.ll_sleep = ll_sleep;
+            f.ll_w2 = fused_ll == 1 || (overlap == 2 && fused_ll != 2);
             f.pf_budget = (long long)gemv_prefetch_mb << 20;
             {   // the last local columns, all of them right of the panel so that every GEMV of the panel reads them
-                const long long want = ((long long)gemv_resident_kb << 10) / (8ll * std::max(m, 1));
+                // at most what the L2 budget leaves next to V, Y, VT of a full panel (they come first: the level-2 phases
+                // are latency-bound and read them three times per column)
+                const long long room = std::max(0ll, ((long long)gemv_prefetch_mb << 20) - 24ll * m * w);
+                const long long want = std::min(room, (long long)gemv_resident_kb << 10) / (8ll * std::max(m, 1));
                 const int res_cols = (int)std::min<long long>(want, std::max(0, lc_end - cm.lower(i + w)));
                 f.res_lc0 = res_cols > 0 ? lc_end - res_cols : lc_end + 1;
             }

@@ -51,6 +51,9 @@ struct FusedArgs {
     int kc;                     // columns of v a GEMV group stages in shared memory at a time (each refill drains its load pipeline)
     int pf_cols;                // columns of its first GEMV item chunk that a group prefetches into L2 ahead of phase G (0: off)
     int pf_bulk;                // 1: the prefetch uses one bulk (TMA) instruction per column and group instead of 16 line prefetches
+    int ll_w2;                  // LLRED: 1 = the w2 reduction travels as LL entries too; 0 = only the GEMV partials do, w2 keeps its
+                                // two grid barriers (first B200 timing, n = 6000: the LL-polled w2 path is ~2.8 us per column SLOWER
+                                // than barrier-reduce-barrier, the LL GEMV partials ~1.5 us per column faster)
     int ll_sleep;               // LLRED: nanoseconds the polling lanes sleep between polls (0: spin)
     int res_lc0;                // local columns >= res_lc0 are read with the "keep in L2" policy (the same columns in every GEMV
                                 // of the panel); >= lc_end: none
@@ -654,29 +657,35 @@ __global__ void __launch_bounds__(MAXT, 1) k_panel_fused(FusedArgs f)
 
             // ---- w2part[t] = sum over the CTA's rows of VT(r,t) * p'(r), t < j (column j-1 was stored just above)
             const unsigned tag = f.x.epoch + j;
-            coldots_all(a.VT, ld, j, row0, row_end, nsub, pv, wp, FUSED_WARPS, lane, a.colpart + (size_t)b * a.ldt,
-                        LLRED ? f.w2part_ll + (size_t)b * a.ldt : nullptr, tag);
-            if (!LLRED) grid_barrier(f.gbar, gen);
+            const bool llw2 = LLRED && f.ll_w2;
+            // LLRED without LL entries for w2: the per-CTA partials of w2 still need a buffer of their own -- with no grid
+            // barrier after the GEMV a fast CTA is here while a slow one still reads the z partials of the previous
+            // column from colpart in its phase R'. (The LL buffer is idle in that mode: used as plain doubles.)
+            double *const w2part = LLRED ? (double *)f.w2part_ll : a.colpart;
+            coldots_all(a.VT, ld, j, row0, row_end, nsub, pv, wp, FUSED_WARPS, lane, w2part + (size_t)b * a.ldt,
+                        llw2 ? f.w2part_ll + (size_t)b * a.ldt : nullptr, tag);
+            if (!llw2) grid_barrier(f.gbar, gen);
             SB_PHASE_MARK(0);
 
             // ================= A': w2[t] = sum over CTAs (one warp per entry) =================
             for (int t = b * FUSED_WARPS + wp; t < j; t += G * FUSED_WARPS) {
-                const double acc = LLRED ? sum_over_ctas_ll(f.w2part_ll + t, a.ldt, nblk, lane, tag, f.x.status)
-                                         : sum_over_ctas(a.colpart + t, a.ldt, nblk, lane);
-                if (lane == 0) { if (LLRED) ll_store(f.w2_ll + t, acc, tag); else a.w2[t] = acc; }
+                const double acc = llw2 ? sum_over_ctas_ll(f.w2part_ll + t, a.ldt, nblk, lane, tag, f.x.status)
+                                        : sum_over_ctas(w2part + t, a.ldt, nblk, lane);
+                if (lane == 0) { if (llw2) ll_store(f.w2_ll + t, acc, tag); else a.w2[t] = acc; }
             }
-            if (!LLRED) grid_barrier(f.gbar, gen);
+            if (!llw2) grid_barrier(f.gbar, gen);
             SB_PHASE_MARK(1);
         }
 
         // ================= phase R: p'' = p' - V w2; ||x||^2, z = V^T x =================
         {
-            if (LLRED && j > 0) {       // one polling lane per warp (see phase A)
+            const bool llw2_r = LLRED && f.ll_w2;
+            if (llw2_r && j > 0) {      // one polling lane per warp (see phase A)
                 if (lane == 0 && (tid & ~31) < j) ll_wait(f.w2_ll + (tid & ~31), f.x.epoch + j, f.x.status, f.ll_sleep);
                 __syncwarp();
             }
             for (int t = tid; t < j; t += FUSED_THREADS)
-                w2_sh[t] = LLRED ? ll_load(f.w2_ll + t, f.x.epoch + j, f.x.status) : __ldcg(a.w2 + t);
+                w2_sh[t] = llw2_r ? ll_load(f.w2_ll + t, f.x.epoch + j, f.x.status) : __ldcg(a.w2 + t);
             __syncthreads();
             // one pass over V needs a warp per 16-column group of a sub-tile: columns j <= 16 * FUSED_WARPS
             const bool fuse_r = LLRED && f.fuse_r && j > 0 && j <= 16 * FUSED_WARPS;

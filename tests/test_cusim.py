@@ -121,13 +121,14 @@ def test_sim_unfused_single_rank(sim, ora, n, pw):
     assert st["fused_panels"] == 0
 
 
+@pytest.mark.parametrize("llmode", [1, 2])
 @pytest.mark.parametrize("gpus,n,pw,sms", [(1, 131, 24, 4), (1, 90, 16, 1), (2, 96, 16, 2)])
-def test_sim_ll_reduction_variant(sim, ora, gpus, n, pw, sms):
+def test_sim_ll_reduction_variant(sim, ora, gpus, n, pw, sms, llmode):
     """persistent panel kernel with the w2 reduction carried by self-validating LL entries instead of two grid barriers
     (STARNEIG_B200_FUSED_LL=1): same partial sums in the same order => bitwise the same H and Q"""
     with _Env(STARNEIG_B200_COL_BLOCK=8, CUSIM_SMS=sms):
         A, Q, _ = _reduce(sim, ora, n, pw, gpus=gpus)
-        with _Env(STARNEIG_B200_FUSED_LL=1):
+        with _Env(STARNEIG_B200_FUSED_LL=llmode):
             A1, Q1, st = _reduce(sim, ora, n, pw, gpus=gpus)
     assert st["fused_panels"] == st["panels"]
     assert np.array_equal(A, A1) and np.array_equal(Q, Q1)
@@ -309,22 +310,24 @@ def panel(env):
     assert ret == 0
     return A[:n, :w].copy(), V[:n - 1].copy(), Y[:n - 1].copy(), VT[:n - 1].copy(), tau
 ref = panel({})
-got = panel({"STARNEIG_B200_FUSED_LL": "1"})
+got = panel({"STARNEIG_B200_FUSED_LL": os.environ.get("LLMODE", "1")})
 assert all(np.isfinite(x).all() for x in got)
 assert all(np.array_equal(a, b) for a, b in zip(ref, got)), "LL variant differs from the default kernel"
 print("OK")
 """ % (ROOT, SIM_LIB)
 
 
+@pytest.mark.parametrize("llmode", [1, 2])
 @pytest.mark.parametrize("sms,skew,seed", [(4, 4, 1), (6, 5, 2), (3, 3, 4)])
-def test_sim_ll_variant_with_lagging_blocks(simlib, sms, skew, seed):
+def test_sim_ll_variant_with_lagging_blocks(simlib, sms, skew, seed, llmode):
     """One panel of a 600 x 600 matrix (three 256-row blocks of GEMV partials) with the LL variant of the persistent kernel
     (one grid barrier per column instead of four) while some blocks of the grid are scheduled far less often than the
     others: a fast block runs into the next column while a slow one is still forming v for its part of the GEMV. With a
     single column buffer this schedule corrupts the result (that is how the two-buffer scheme was validated); V, Y, VT,
-    tau and the panel columns must be bitwise those of the default kernel."""
+    tau and the panel columns must be bitwise those of the default kernel. llmode 2: LL entries for the GEMV partials only
+    (w2 keeps its grid barriers and gets a partial buffer of its own)."""
     r = subprocess.run(["python", "-c", _PANEL_CHILD, "600", "12"], capture_output=True, text=True, timeout=600,
-                       env=dict(os.environ, CUSIM_SMS=str(sms), CUSIM_SKEW=str(skew), CUSIM_SHUFFLE=str(seed)))
+                       env=dict(os.environ, CUSIM_SMS=str(sms), CUSIM_SKEW=str(skew), CUSIM_SHUFFLE=str(seed), LLMODE=str(llmode)))
     assert r.returncode == 0 and r.stdout.strip().endswith("OK"), r.stdout[-1000:] + r.stderr[-2000:]
 
 

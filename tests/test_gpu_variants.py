@@ -93,7 +93,7 @@ def test_denormal_range_takes_dlarfg_rescaling_branch(fused):
 
 
 @pytest.mark.skipif(not OPTIN, reason="opt-in kernel variant: set STARNEIG_TEST_OPTIN=1 (tools/r2_visit1.sh does)")
-@pytest.mark.parametrize("switch", ["STARNEIG_B200_FUSED_LL=1", "STARNEIG_B200_GEMM_OPT=1", "STARNEIG_B200_GEMM_OPT=2",
+@pytest.mark.parametrize("switch", ["STARNEIG_B200_FUSED_LL=1", "STARNEIG_B200_FUSED_LL=2", "STARNEIG_B200_GEMM_OPT=1", "STARNEIG_B200_GEMM_OPT=2",
                                     "STARNEIG_B200_GEMM_OPT=3", "STARNEIG_B200_GEMV_PREFETCH=32",
                                     "STARNEIG_B200_GEMV_RESIDENT_KB=4096", "STARNEIG_B200_GEMV_KC=2048"])
 def test_optin_variant_is_bitwise_equal_to_the_default(switch):

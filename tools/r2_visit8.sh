@@ -16,8 +16,8 @@ run_bench() {   # label, extra env..., device arm only unless label = bench
 }
 run_bench bench STARNEIG_BENCH_N=20000
 # the variants through ONE process group (tools/dist_sweep.py): ~5 s each instead of a process start-up each
-ALLIN="FUSED_LL=1,FUSED_R=1,FUSED_EVEN_ROWS=1,GEMV_KC=2048"
-(STARNEIG_BENCH_N=20000 STARNEIG_SWEEP=";FUSED_LL=1;$ALLIN;$ALLIN,GEMV_PREFETCH=32;$ALLIN,GEMV_RESIDENT_KB=30720,GEMV_PREFETCH=16;$ALLIN,GEMV_RESIDENT_KB=30720,GEMV_PREFETCH=16,COL_BLOCK=32;$ALLIN,GEMV_RESIDENT_KB=30720,GEMV_PREFETCH=16,AUTO_PANEL_WIDTH=192;OVERLAP=2;$ALLIN,OVERLAP=2,GEMV_PREFETCH=16" \
+BEST="GEMV_RESIDENT_KB=40960,GEMM_OPT=1"          # the winners of the n = 6000 timings
+(STARNEIG_BENCH_N=20000 STARNEIG_SWEEP=";$BEST;$BEST,FUSED_LL=2;$BEST,FUSED_LL=2,COL_BLOCK=32;$BEST,FUSED_LL=2,AUTO_PANEL_WIDTH=192;$BEST,FUSED_LL=1;$BEST,GEMV_PREFETCH=32,GEMV_PREFETCH_BULK=1;$BEST,OVERLAP=2" \
     timeout 280 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29514 \
     tools/dist_sweep.py 2>&1 | grep -v "^\*\|OMP_NUM\|^$" | tail -12) | tee gpurun_out/dist_sweep_gpus$N.log
 (STARNEIG_BENCH_N=50000 timeout 280 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29513 \
