@@ -10,7 +10,7 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gp
 (timeout 100 tools/bin/gemm_sweep 20000 40 3 2>&1) > gpurun_out/gemm_sweep_p40.txt
 : > gpurun_out/sweep.log
 # all configurations in one process (tools/sweep.py); if a variant faults, the rest is repeated one process each
-CFGS=("" "GEMM_OPT=1" "GEMV_RESIDENT_KB=20480" "GEMV_RESIDENT_KB=40960" "GEMV_RESIDENT_KB=81920" "GEMV_RESIDENT_KB=40960,GEMM_OPT=1" "GEMV_KC=2048" "GEMV_RESIDENT_KB=40960,GEMM_OPT=1,GEMV_KC=2048" "FUSED_LL=2" "FUSED_LL=2,GEMV_RESIDENT_KB=40960,GEMM_OPT=1,GEMV_KC=2048" "FUSED_LL=1" "GEMV_PREFETCH=32,GEMV_PREFETCH_BULK=1" "OVERLAP=2" "OVERLAP=2,GEMV_RESIDENT_KB=40960" "FUSED_EVEN_ROWS=1" "FUSED_LL=1,FUSED_R=1" "GEMM_OPT=2" "GEMM_OPT=3" "AUTO_PANEL_WIDTH=256" "AUTO_PANEL_WIDTH=384")
+CFGS=("" "GEMM_OPT=1" "GEMV_RESIDENT_KB=20480" "GEMV_RESIDENT_KB=40960" "GEMV_RESIDENT_KB=81920,GEMV_PREFETCH_MB=112" "GEMV_RESIDENT_KB=40960,GEMM_OPT=1" "GEMV_KC=2048" "GEMV_RESIDENT_KB=40960,GEMM_OPT=1,GEMV_KC=2048" "FUSED_LL=2" "FUSED_LL=2,GEMV_RESIDENT_KB=40960,GEMM_OPT=1,GEMV_KC=2048" "FUSED_LL=1" "GEMV_PREFETCH=32,GEMV_PREFETCH_BULK=1" "OVERLAP=2" "OVERLAP=2,GEMV_RESIDENT_KB=40960" "FUSED_EVEN_ROWS=1" "FUSED_LL=1,FUSED_R=1" "GEMM_OPT=2" "GEMM_OPT=3" "AUTO_PANEL_WIDTH=256" "AUTO_PANEL_WIDTH=384")
 timeout 600 python tools/sweep.py 20000 "${CFGS[@]}" 2>&1 | tee -a gpurun_out/sweep.log
 DONE=$(grep -c "device_ms" gpurun_out/sweep.log)
 if [ "$DONE" -lt "${#CFGS[@]}" ]; then

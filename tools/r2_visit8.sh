@@ -17,7 +17,7 @@ run_bench() {   # label, extra env..., device arm only unless label = bench
 run_bench bench STARNEIG_BENCH_N=20000
 # the variants through ONE process group (tools/dist_sweep.py): ~5 s each instead of a process start-up each
 BEST="GEMV_RESIDENT_KB=40960,GEMM_OPT=1"          # the winners of the n = 6000 timings
-(STARNEIG_BENCH_N=20000 STARNEIG_SWEEP=";$BEST;$BEST,FUSED_LL=2;$BEST,FUSED_LL=2,COL_BLOCK=32;$BEST,FUSED_LL=2,AUTO_PANEL_WIDTH=192;$BEST,FUSED_LL=1;$BEST,GEMV_PREFETCH=32,GEMV_PREFETCH_BULK=1;$BEST,OVERLAP=2" \
+(STARNEIG_BENCH_N=20000 STARNEIG_SWEEP=";$BEST;$BEST,FUSED_LL=2;$BEST,FUSED_LL=2,COL_BLOCK=32;$BEST,FUSED_LL=2,AUTO_PANEL_WIDTH=192;$BEST,FUSED_LL=1;$BEST,GEMV_PREFETCH=32,GEMV_PREFETCH_BULK=1;GEMV_RESIDENT_KB=81920,GEMV_PREFETCH_MB=112,GEMM_OPT=1,FUSED_LL=2;$BEST,OVERLAP=2" \
     timeout 280 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29514 \
     tools/dist_sweep.py 2>&1 | grep -v "^\*\|OMP_NUM\|^$" | tail -12) | tee gpurun_out/dist_sweep_gpus$N.log
 (STARNEIG_BENCH_N=50000 timeout 280 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29513 \
