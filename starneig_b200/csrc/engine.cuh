@@ -577,13 +577,10 @@ struct Rank {
             f.ll_sleep = ll_sleep;
             f.ll_w2 = fused_ll == 1 || (overlap == 2 && fused_ll != 2);
             f.pf_budget = (long long)gemv_prefetch_mb << 20;
-            {   // the last local columns, all of them right of the panel so that every GEMV of the panel reads them
-                // at most what the L2 budget leaves next to V, Y, VT of a full panel (they come first: the level-2 phases
-                // are latency-bound and read them three times per column)
-                const long long room = std::max(0ll, ((long long)gemv_prefetch_mb << 20) - 24ll * m * w);
-                const long long want = std::min(room, (long long)gemv_resident_kb << 10) / (8ll * std::max(m, 1));
-                const int res_cols = (int)std::min<long long>(want, std::max(0, lc_end - cm.lower(i + w)));
-                f.res_lc0 = res_cols > 0 ? lc_end - res_cols : lc_end + 1;
+            {   // the last local columns, all of them right of the panel so that every GEMV of the panel reads them; how many
+                // of them are kept at a given column is decided in the kernel from the L2 budget (pf_budget)
+                const long long want = ((long long)gemv_resident_kb << 10) / (8ll * std::max(m, 1));
+                f.res_cols = (int)std::min<long long>(want, std::max(0, lc_end - cm.lower(i + w)));
             }
             if (fused_even_rows) {
                 // every CTA of the grid owns rows (m = 19999 on 148 SMs: 136 rows each instead of 160 rows on 125 CTAs):

@@ -55,8 +55,9 @@ struct FusedArgs {
                                 // two grid barriers (first B200 timing, n = 6000: the LL-polled w2 path is ~2.8 us per column SLOWER
                                 // than barrier-reduce-barrier, the LL GEMV partials ~1.5 us per column faster)
     int ll_sleep;               // LLRED: nanoseconds the polling lanes sleep between polls (0: spin)
-    int res_lc0;                // local columns >= res_lc0 are read with the "keep in L2" policy (the same columns in every GEMV
-                                // of the panel); >= lc_end: none
+    int res_cols;               // at most this many local columns (the last ones: they are part of every GEMV of the panel) are read
+                                // with the "keep in L2" policy; at column j as many of them as pf_budget leaves next to V, Y, VT
+                                // of the panel so far (24 m j bytes). 0: everything streams
     long long pf_budget;        // bytes of L2 that V, Y, VT (3 * 8 * m * j at column j) and the prefetched data may fill together
     unsigned *gbar;             // grid barrier counter, zero at launch
     unsigned long long *timers; // ns on CTA 0: [0] GEMV phases, [1] whole kernel, [2..5] phases A, A', R, R' (each incl. its barrier)
@@ -328,7 +329,7 @@ struct FusedSmem {
 };
 
 // One chunk (nk columns, vs = the matching entries of v) of a thread's GEMV rows, read with the "keep in L2" policy: the
-// columns the host marked resident (FusedArgs::res_lc0) are part of every GEMV of the panel, so after the first column
+// columns the host marked resident (FusedArgs::res_cols) are part of every GEMV of the panel, so after the first column
 // they come from L2 instead of HBM. Same arithmetic in the same order as the streaming loop of phase G.
 template <int U>
 __device__ __forceinline__ void gemv_chunk_resident(const double *P0, size_t step, int nk, const double *vs, double2 &acc,
@@ -797,8 +798,11 @@ __global__ void __launch_bounds__(MAXT, 1) k_panel_fused(FusedArgs f)
                 long long it = (long long)v * gq.per;
                 const long long it_end = min(items, it + gq.per);
                 const int mp = m + gs.skip;
-                const int ks = f.res_lc0 - lc0;         // first resident column relative to lc0 (>= nloc: none)
-                const unsigned long long keep_policy = f.res_lc0 < f.lc_end ? l2_policy_evict_last() : 0ull;
+                // resident columns of this column's GEMV: the set shrinks as V, Y, VT of the panel grow (a line that is
+                // read with the streaming policy again gives its place up)
+                const int res_now = (int)max(0ll, min((long long)f.res_cols, (f.pf_budget - 24ll * m * j) / (8ll * max(m, 1))));
+                const int ks = f.lc_end - res_now - lc0;    // first resident column relative to lc0 (>= nloc: none)
+                const unsigned long long keep_policy = res_now > 0 ? l2_policy_evict_last() : 0ull;
                 while (it < it_end) {
                     const int rb = (int)(it / nloc);
                     const int cbeg = (int)(it - (long long)rb * nloc);
