@@ -103,6 +103,30 @@ __device__ __forceinline__ double ll_load(const uint4 *src, unsigned tag, unsign
     return __longlong_as_double((long long)(((unsigned long long)e.z << 32) | e.x));
 }
 
+// `count` (<= N) LL entries p[u * stride], polled TOGETHER until every one of them carries `tag`: a poll round costs one L2
+// round trip whatever the number of entries (polling them one after the other costs one round trip EACH -- the first B200
+// timing of the LL variant lost ~3 us per column that way). Entries u >= count give 0.
+template <int N>
+__device__ __forceinline__ void ll_load_batch(const uint4 *p, size_t stride, int count, unsigned tag, unsigned *status, double (&x)[N])
+{
+    long long t0 = 0;
+    for (;;) {
+        uint4 e[N];
+#pragma unroll
+        for (int u = 0; u < N; u++) e[u] = ld_volatile_v4(p + (size_t)min(u, max(count - 1, 0)) * stride);
+        bool all = true;
+#pragma unroll
+        for (int u = 0; u < N; u++) {
+            const bool ok = u >= count || (e[u].y == tag && e[u].w == tag);
+            all = all && ok;
+            x[u] = u < count ? __longlong_as_double((long long)(((unsigned long long)e[u].z << 32) | e[u].x)) : 0.0;
+        }
+        if (all || count <= 0) return;
+        if (t0 == 0) { t0 = clock64(); if (*(volatile unsigned *)status != 0u) return; }
+        else if (clock64() - t0 > 8000000000ll) { atomicExch(status, 2u); return; }
+    }
+}
+
 // sum over the CTAs that own rows (nblk <= 32*5) of part[bb*ldt], fixed order, by one warp: the (up to) five loads
 // of a lane are independent
 __device__ __forceinline__ double sum_over_ctas(const double *part, size_t ldt, int nblk, int lane)
@@ -126,21 +150,11 @@ __device__ __forceinline__ double sum_over_ctas_ll(const uint4 *part, size_t ldt
 {
     double acc = 0.0;
     for (int b0 = 0; b0 < nblk; b0 += 160) {
+        // this lane's entries b0 + lane + 32 u (u < 5) lie 32 * ldt apart
+        const int first = b0 + lane;
+        const int count = first < nblk ? min(5, (nblk - first + 31) / 32) : 0;
         double x[5];
-        bool ready[5];
-#pragma unroll
-        for (int u = 0; u < 5; u++) {       // first pass: all loads in flight together
-            const int bb = b0 + lane + 32 * u;
-            x[u] = 0.0; ready[u] = true;
-            if (bb < nblk) {
-                const uint4 e = ld_volatile_v4(part + (size_t)bb * ldt);
-                ready[u] = (e.y == tag && e.w == tag);
-                x[u] = __longlong_as_double((long long)(((unsigned long long)e.z << 32) | e.x));
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < 5; u++)
-            if (!ready[u]) x[u] = ll_load(part + (size_t)(b0 + lane + 32 * u) * ldt, tag, status);
+        ll_load_batch<5>(part + (size_t)min(first, nblk - 1) * ldt, 32 * ldt, count, tag, status, x);
         acc += ((x[0] + x[1]) + (x[2] + x[3])) + x[4];
     }
     return warp_sum(acc);
@@ -211,29 +225,23 @@ __device__ __forceinline__ void ll_wait(const uint4 *src, unsigned tag, unsigned
 // the partials of its rows instead of waiting at a grid barrier for ALL groups of the GEMV
 __device__ __forceinline__ double sum_partials_ll(const uint4 *p, int ld, int S, unsigned tag, unsigned *status)
 {
+    // same order of additions as sum_partials; every batch is polled as a whole
     double e = 0.0;
     int z = 0;
+    double x[8];
     for (; z + 8 <= S; z += 8) {
-        double x[8];
-        bool ready[8];
-#pragma unroll
-        for (int u = 0; u < 8; u++) {
-            const uint4 v = ld_volatile_v4(p + (size_t)(z + u) * ld);
-            ready[u] = (v.y == tag && v.w == tag);
-            x[u] = __longlong_as_double((long long)(((unsigned long long)v.z << 32) | v.x));
-        }
-#pragma unroll
-        for (int u = 0; u < 8; u++)
-            if (!ready[u]) x[u] = ll_load(p + (size_t)(z + u) * ld, tag, status);
+        ll_load_batch<8>(p + (size_t)z * ld, (size_t)ld, 8, tag, status, x);
         e += ((x[0] + x[1]) + (x[2] + x[3])) + ((x[4] + x[5]) + (x[6] + x[7]));
     }
-    for (; z + 4 <= S; z += 4) {
-        double x[4];
+    if (z < S) {
+        const int rem = S - z;          // 1 .. 7: one more poll round for all of them
+        ll_load_batch<8>(p + (size_t)z * ld, (size_t)ld, rem, tag, status, x);
+        const int u0 = rem >= 4 ? 4 : 0;
+        if (rem >= 4) e += (x[0] + x[1]) + (x[2] + x[3]);
 #pragma unroll
-        for (int u = 0; u < 4; u++) x[u] = ll_load(p + (size_t)(z + u) * ld, tag, status);
-        e += (x[0] + x[1]) + (x[2] + x[3]);
+        for (int q = 0; q < 8; q++)
+            if (q >= u0 && q < rem) e += x[q];
     }
-    for (; z < S; z++) e += ll_load(p + (size_t)z * ld, tag, status);
     return e;
 }
 
@@ -594,31 +602,17 @@ __global__ void __launch_bounds__(MAXT, 1) k_panel_fused(FusedArgs f)
                         sum = LLRED ? sum_partials_ll(f.ypart_ll + r, a.ldp, S, epoch, f.x.status) : sum_partials(a.ypart + r, a.ldp, S);
                     }
                     if (DIST) {
+                        // all-reduce over the ranks: the rank's sum goes to every inbox (the own one included, so that all
+                        // P entries of a row are polled alike and together), the P contributions are added in rank order
                         const size_t slot = ((size_t)par * f.x.P + f.x.g) * a.ldp + r;
-                        for (int d = 1; d < f.x.P; d++) ll_store((uint4 *)f.x.inbox[(f.x.g + d) % f.x.P] + slot, sum, epoch);
+                        for (int d = 0; d < f.x.P; d++) ll_store((uint4 *)f.x.inbox[(f.x.g + d) % f.x.P] + slot, sum, epoch);
                         const uint4 *in = (const uint4 *)f.x.inbox[f.x.g] + (size_t)par * f.x.P * a.ldp + r;
-                        // first pass: all P entries in flight at once; stragglers are polled individually
                         double val[MAX_RANKS];
-                        bool ready[MAX_RANKS];
-#pragma unroll
-                        for (int q = 0; q < MAX_RANKS; q++) {
-                            ready[q] = true; val[q] = 0.0;
-                            if (q < f.x.P && q != f.x.g) {
-                                const uint4 e = ld_volatile_v4(in + (size_t)q * a.ldp);
-                                ready[q] = (e.y == epoch && e.w == epoch);
-                                val[q] = __longlong_as_double((long long)(((unsigned long long)e.z << 32) | e.x));
-                            }
-                        }
-                        const double own = sum;
+                        ll_load_batch<MAX_RANKS>(in, (size_t)a.ldp, f.x.P, epoch, f.x.status, val);
                         sum = 0.0;
 #pragma unroll
-                        for (int q = 0; q < MAX_RANKS; q++) {
-                            if (q < f.x.P) {
-                                double xq = (q == f.x.g) ? own : val[q];
-                                if (!ready[q]) xq = ll_load(in + (size_t)q * a.ldp, epoch, f.x.status);
-                                sum += xq;
-                            }
-                        }
+                        for (int q = 0; q < MAX_RANKS; q++)
+                            if (q < f.x.P) sum += val[q];
                     }
                     ysm[rr] = sum;
                 }
