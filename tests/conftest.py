@@ -52,3 +52,40 @@ GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
 
 def golden_cases():
     return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz") and not f.startswith("prand"))
+
+
+# Structured inputs in which DLARFG meets x = 0 (tau = 0, H = I: reference src/hessenberg/cpu.c:140, LAPACK dlarfg's early
+# return) in some or all columns, plus the shape the Schur stage's AED step hands to the Hessenberg reduction
+# (src/schur/core.c:893-929: a deflation window = upper triangular + a spike in its first column). `entrywise` says whether
+# H and Q may be compared entry by entry with another backward-stable reduction: the spike window has exactly zero
+# sub-diagonal entries in H, so H and Q are not uniquely determined to working precision (the reference port and LAPACK
+# differ by 1e7 * n * u on it) and only the invariants are checked.
+STRUCTURED = ["zero", "identity", "upper_triangular", "already_hessenberg", "zero_columns", "block_triangular", "aed_spike"]
+
+
+def structured_input(ora, name, n, seed=7):
+    import numpy as np
+    A0, Q0, ld = ora.full(n, seed)
+    A = A0.copy(order="F")
+    entrywise = True
+    if name == "zero":
+        A[:n] = 0.0
+    elif name == "identity":
+        A[:n] = np.eye(n)
+    elif name == "upper_triangular":
+        A[:n] = np.triu(A0[:n])
+    elif name == "already_hessenberg":
+        A[:n] = np.triu(A0[:n], -1)
+    elif name == "zero_columns":
+        A[:n, min(3, n - 1)] = 0.0
+        A[:n, n // 2] = 0.0
+        A[min(5, n):n, min(10, n - 1)] = 0.0
+    elif name == "block_triangular":
+        A[n // 2:n, :n // 2] = 0.0
+    elif name == "aed_spike":
+        A[:n] = np.triu(A0[:n])
+        A[1:3 * n // 4, 0] = A0[1:3 * n // 4, 1]
+        entrywise = False
+    else:
+        raise ValueError(name)
+    return A, Q0, ld, entrywise

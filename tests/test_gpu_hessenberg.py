@@ -16,7 +16,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import GOLDEN_DIR, golden_cases
+from conftest import GOLDEN_DIR, STRUCTURED, golden_cases, structured_input
 
 pytestmark = pytest.mark.gpu
 U = 2.0 ** -52
@@ -79,6 +79,32 @@ def test_partial_reduction(node, ora, n):
     A2, Q2 = A0.copy(order="F"), Q0.copy(order="F")
     ora.hessenberg_port(n, A2, ld, Q2, ld, begin, end, 16)
     _check_entrywise(n, A, Q, A2, Q2)
+
+
+# x = 0 in DLARFG (tau = 0, H = I: reference src/hessenberg/cpu.c:140) in every / some columns, and the deflation
+# window the Schur stage's AED step hands to the Hessenberg reduction (src/schur/core.c:893-929); see tests/conftest.py
+@pytest.mark.parametrize("name", STRUCTURED)
+@pytest.mark.parametrize("n,pw,end", [(300, 45, 300), (333, 64, 250)])
+def test_structured_inputs(node, ora, name, n, pw, end):
+    A0, Q0, ld, entrywise = structured_input(ora, name, n)
+    A0[end:n, :end] = 0.0       # a partial reduction is a similarity only if nothing lies below the reduced block
+    A, Q = A0.copy(order="F"), Q0.copy(order="F")
+    assert _run(node, n, A, ld, Q, 0, end, pw=pw) == 0
+    assert np.isfinite(A[:n]).all() and np.isfinite(Q[:n]).all()
+    assert np.count_nonzero(np.tril(A[:end, :end], -2)) == 0
+    A2, Q2 = A0.copy(order="F"), Q0.copy(order="F")
+    assert ora.hessenberg_port(n, A2, ld, Q2, ld, 0, end, pw) == 0
+    if entrywise:
+        _check_entrywise(n, A, Q, A2, Q2)
+    else:
+        assert np.array_equal(A[:n] == 0.0, A2[:n] == 0.0)
+    if np.any(A0[:n]):
+        res = ora.residual_u(n, Q, ld, A, ld, A0, ld)
+        assert res <= 500, res
+    orth = ora.orthogonality_u(n, Q, ld)
+    assert orth <= 500, orth
+    if name in ("zero", "identity", "upper_triangular", "already_hessenberg"):
+        assert np.array_equal(A, A0)            # nothing to do: the matrix comes back bit for bit
 
 
 def test_simple_interface_wide_ld_and_general_q(node, ora):
