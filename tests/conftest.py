@@ -89,3 +89,36 @@ def structured_input(ora, name, n, seed=7):
     else:
         raise ValueError(name)
     return A, Q0, ld, entrywise
+
+
+def aed_window_check(sn, ora, n, end, pw, gpus=None):
+    """The Schur stage's AED client (reference src/schur/core.c:893-929): a deflation window (upper triangular + spike,
+    only [0, end) reduced) whose transformations are accumulated into a non-identity local Q. Invariants only (see
+    STRUCTURED): exact Hessenberg form inside the block, untouched zeros below it, Q orthogonal, Q H Q^T = Q0 A0 Q0^T,
+    and the same exact-zero pattern as the reference port. `gpus`: initialise / finalise the node here (emulator tests)."""
+    import numpy as np
+    u = 2.0 ** -52
+    A0, _, ld, _ = structured_input(ora, "aed_spike", n)
+    A0[end:n, :end] = 0.0
+    Qr, _ = np.linalg.qr(np.random.default_rng(3).standard_normal((n, n)))
+    Q0 = np.zeros((ld, n), order="F")
+    Q0[:n] = Qr
+    A, Q = A0.copy(order="F"), Q0.copy(order="F")
+    if gpus is not None:
+        sn.starneig_node_init(sn.STARNEIG_USE_ALL, gpus, sn.STARNEIG_NO_MESSAGES)
+    try:
+        conf = sn.starneig_hessenberg_init_conf()
+        conf.panel_width = pw
+        assert sn.starneig_SEP_SM_Hessenberg_expert(conf, n, 0, end, A, ld, Q, ld) == 0
+    finally:
+        if gpus is not None:
+            sn.starneig_node_finalize()
+    A2, Q2 = A0.copy(order="F"), Q0.copy(order="F")
+    assert ora.hessenberg_port(n, A2, ld, Q2, ld, 0, end, pw) == 0
+    assert np.isfinite(A[:n]).all() and np.isfinite(Q[:n]).all()
+    assert np.count_nonzero(np.tril(A[:end, :end], -2)) == 0 and np.count_nonzero(A[end:n, :end]) == 0
+    assert np.array_equal(A[:n] == 0.0, A2[:n] == 0.0)
+    assert ora.orthogonality_u(n, Q, ld) <= 500
+    res = np.linalg.norm(Q[:n] @ A[:n] @ Q[:n].T - Qr @ A0[:n] @ Qr.T) / np.linalg.norm(A0[:n]) / u
+    assert res <= 500, res
+    assert np.array_equal(A[n:], A0[n:]) and np.array_equal(Q[n:], Q0[n:])      # padding rows untouched

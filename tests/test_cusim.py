@@ -18,7 +18,7 @@ import subprocess
 import numpy as np
 import pytest
 
-from conftest import STRUCTURED, structured_input
+from conftest import STRUCTURED, aed_window_check, structured_input
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SIM_DIR = os.path.join(ROOT, "tests", "cusim")
@@ -214,6 +214,12 @@ def test_sim_structured_inputs(sim, ora, name, gpus, n, pw, end, fused):
     assert np.count_nonzero(np.tril(A[:end, :end], -2)) == 0
     if name in ("zero", "identity", "upper_triangular", "already_hessenberg"):
         assert np.array_equal(A, A0)            # nothing to do: tau = 0 everywhere, the matrix comes back bit for bit
+
+
+# the AED client accumulates into its local (non-identity) Q: Q <- Q0 U, so Q H Q^T = Q0 A0 Q0^T
+@pytest.mark.parametrize("gpus,n,end,pw", [(1, 60, 45, 16), (2, 64, 48, 16)])
+def test_sim_aed_window_with_general_q(sim, ora, gpus, n, end, pw):
+    aed_window_check(sim, ora, n, end, pw, gpus)
 
 
 def test_sim_padded_leading_dimension(sim, ora):

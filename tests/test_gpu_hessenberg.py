@@ -16,7 +16,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import GOLDEN_DIR, STRUCTURED, golden_cases, structured_input
+from conftest import GOLDEN_DIR, STRUCTURED, aed_window_check, golden_cases, structured_input
 
 pytestmark = pytest.mark.gpu
 U = 2.0 ** -52
@@ -105,6 +105,10 @@ def test_structured_inputs(node, ora, name, n, pw, end):
     assert orth <= 500, orth
     if name in ("zero", "identity", "upper_triangular", "already_hessenberg"):
         assert np.array_equal(A, A0)            # nothing to do: the matrix comes back bit for bit
+
+
+def test_aed_window_with_general_q(node, ora):
+    aed_window_check(node, ora, 400, 300, 64)
 
 
 def test_simple_interface_wide_ld_and_general_q(node, ora):
