@@ -153,6 +153,11 @@ class SharedHostMatrices:
             os.unlink(self.path)
 
 
+def workload_name(n, gpus):
+    """`config.workload` of both arms (ours and --impl reference)"""
+    return f"Hessenberg reduction with Q, random dense FP64 n={n} (BASELINE.json configs[2] at {gpus} GPU{'s' if gpus > 1 else ''})"
+
+
 def cpu_reference_run(n, threads):
     """One reduction with the reference's CPU implementation on a fullpos matrix; returns (seconds, kind)."""
     from oracle.oracle import Oracle, Reference
@@ -198,7 +203,8 @@ def run_reference_arm(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"Hessenberg reduction with Q, random dense FP64, n={args.n}", "sample_n": n},
+        # same workload name and size as our arm's line; `sample_n` is the bounded sample a step actually reduces
+        "config": {"workload": workload_name(args.n, args.gpus), "n": args.n, "sample_n": n},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -450,7 +456,7 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"Hessenberg reduction with Q, random dense FP64 n={n} (BASELINE.json configs[2] at {world} GPU{'s' if world > 1 else ''})",
+        "config": {"workload": workload_name(n, world),
                    "n": n, "panel_width": int(st["panel_width"]), "ld": ld,
                    # engine switches taken from the environment (none: the defaults of DESIGN.md section 4)
                    "switches": {k: v for k, v in sorted(os.environ.items()) if k.startswith("STARNEIG_B200_")},
