@@ -19,6 +19,15 @@ if [ "$DONE" -lt "${#CFGS[@]}" ]; then
 fi
 timeout 300 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench exit $?"
 cat gpurun_out/bench.json; tail -3 gpurun_out/bench.err
+# the fastest correct configuration of the sweep, as a full bench line of its own (saves a second visit): the
+# candidate for the new defaults
+BEST=$(python tools/best_of_sweep.py gpurun_out/sweep.log)
+echo "best of sweep: '${BEST}'" | tee -a gpurun_out/sweep.log
+if [ -n "$BEST" ]; then
+    (IFS=','; for kv in $BEST; do export "STARNEIG_B200_$kv"; done
+     timeout 300 python bench.py --no-cpu > gpurun_out/bench_best.json 2> gpurun_out/bench_best.err; echo "bench (best) exit $?")
+    cat gpurun_out/bench_best.json; tail -3 gpurun_out/bench_best.err
+fi
 timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/launches_bench_n20000.csv \
     python bench.py --steps 1 --warmup 0 --no-cpu --no-e2e > gpurun_out/ncu_list.log 2>&1; echo "ncu list exit $?"
 timeout 200 ncu --set full --clock-control none --import-source on -k regex:dgemm_kernel --launch-skip 8 -c 8 -o gpurun_out/dgemm_full -f \
