@@ -16,7 +16,7 @@ import sys
 import numpy as np
 import pytest
 
-from conftest import ROOT
+from conftest import ROOT, structured_input
 
 pytestmark = pytest.mark.gpu
 U = 2.0 ** -52
@@ -118,6 +118,18 @@ def test_threads_match_single_gpu_and_repeat(team, ora):
     assert np.abs(outs[0][0][:n] - A1[:n]).max() <= 50 * n * U * np.abs(A1[:n]).max()
     assert np.abs(outs[0][1][:n] - Q1[:n]).max() <= 50 * n * U
     assert np.array_equal(outs[0][0][:n] == 0.0, A1[:n] == 0.0)
+
+
+# columns in which DLARFG meets x = 0 (tau = 0) while the GEMV sums of all ranks are exchanged (tests/conftest.py)
+@pytest.mark.parametrize("name", ["upper_triangular", "zero_columns", "block_triangular"])
+@pytest.mark.parametrize("P", [2, 4])
+def test_threads_structured_inputs(team, ora, P, name):
+    n, pw = 200, 24
+    sn = team(P)
+    A0, Q0, ld, _ = structured_input(ora, name, n)
+    A, Q = A0.copy(order="F"), Q0.copy(order="F")
+    assert _run(sn, n, A, ld, Q, pw=pw) == 0
+    _check(ora, n, A, Q, A0, Q0, ld, pw=pw)
 
 
 @pytest.mark.parametrize("world", [2, 4])
