@@ -220,3 +220,12 @@ def test_invariants_at_larger_size(node, ora, n):
     _check_invariants(ora, n, A, Q, A0, ld)
     assert abs(np.trace(A[:n]) - np.trace(A0[:n])) <= 100 * n * U * abs(np.trace(A0[:n]))
     assert abs(np.linalg.norm(A[:n]) - np.linalg.norm(A0[:n])) <= 100 * n * U * np.linalg.norm(A0[:n])
+
+
+# the largest case of the reference's ctest matrix (test/CMakeLists.txt:366-406: n = 3569, odd, panel widths 303 / 410)
+@pytest.mark.parametrize("n,pw", [(3569, 410)])
+def test_invariants_reference_ctest_size(node, ora, n, pw):
+    A0, Q0, ld = ora.fullpos(n, 2019)
+    A, Q = A0.copy(order="F"), Q0.copy(order="F")
+    assert _run(node, n, A, ld, Q, pw=pw) == 0
+    _check_invariants(ora, n, A, Q, A0, ld)
