@@ -222,6 +222,20 @@ def test_sim_aed_window_with_general_q(sim, ora, gpus, n, end, pw):
     aed_window_check(sim, ora, n, end, pw, gpus)
 
 
+# BASELINE.json configs[4] at emulator size: this path's H -> dhseqr (stand-in for starneig_SEP_SM_Schur) against the
+# all-CPU chain (reference port -> dhseqr), eigenvalues within 1e-10 * ||A||
+@pytest.mark.parametrize("gpus", [1, 2])
+def test_sim_downstream_eigenvalues(sim, ora, gpus):
+    n = 150
+    A0, Q0, ld = ora.full(n, 12)
+    A, _, _ = _reduce(sim, ora, n, 24, gpus=gpus, given=(A0, Q0, ld))
+    A2, Q2 = A0.copy(order="F"), Q0.copy(order="F")
+    assert ora.hessenberg_port(n, A2, ld, Q2, ld, 0, n, 24) == 0
+    ev, ev_cpu = ora.eigenvalues(n, A, ld), ora.eigenvalues(n, A2, ld)
+    d = np.abs(ev[:, None] - ev_cpu[None, :]).min(axis=1)
+    assert d.max() <= 1e-10 * np.linalg.norm(A0[:n])
+
+
 def test_sim_padded_leading_dimension(sim, ora):
     _reduce(sim, ora, 50, 16, ld_extra=6)
 
