@@ -15,8 +15,14 @@ from starneig_b200 import api, _lib
 from oracle.oracle import Oracle
 api._handle = _lib.load(%r)
 ora = Oracle()
-n, pw, gpus = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])
-A0, Q0, ld = ora.fullpos(n, 2019)
+sys.path.insert(0, %r)
+from conftest import structured_input
+n, pw, gpus, kind = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3]), sys.argv[4]
+entrywise = True
+if kind == "fullpos":
+    A0, Q0, ld = ora.fullpos(n, 2019)
+else:       # tau = 0 columns, AED deflation window (tests/conftest.py)
+    A0, Q0, ld, entrywise = structured_input(ora, kind, n)
 A, Q = A0.copy(order="F"), Q0.copy(order="F")
 sn.starneig_node_init(-1, gpus, sn.STARNEIG_NO_MESSAGES)
 conf = sn.starneig_hessenberg_init_conf(); conf.panel_width = pw
@@ -25,13 +31,16 @@ sn.starneig_node_finalize()
 A2, Q2 = A0.copy(order="F"), Q0.copy(order="F")
 ora.hessenberg_port(n, A2, ld, Q2, ld, 0, n, pw)
 u = 2.0 ** -52
-assert np.abs(A[:n] - A2[:n]).max() <= 200 * n * u * max(1.0, np.abs(A2[:n]).max())
-assert np.abs(Q[:n] - Q2[:n]).max() <= 200 * n * u
+if entrywise:
+    assert np.abs(A[:n] - A2[:n]).max() <= 200 * n * u * max(1.0, np.abs(A2[:n]).max())
+    assert np.abs(Q[:n] - Q2[:n]).max() <= 200 * n * u
+assert np.array_equal(A[:n] == 0.0, A2[:n] == 0.0)
 assert ora.hessenberg_form_violations(n, A, ld) == 0
-assert ora.residual_u(n, Q, ld, A, ld, A0, ld) <= 500 and ora.orthogonality_u(n, Q, ld) <= 500
+assert (not np.any(A0[:n]) or ora.residual_u(n, Q, ld, A, ld, A0, ld) <= 500) and ora.orthogonality_u(n, Q, ld) <= 500
 print("OK")
-''' % (ROOT, SIM_LIB)
+''' % (ROOT, SIM_LIB, os.path.join(ROOT, "tests"))
 
+KINDS = ["zero", "identity", "upper_triangular", "already_hessenberg", "zero_columns", "block_triangular", "aed_spike"]
 random.seed(int(sys.argv[1]) if len(sys.argv) > 1 else 1)
 t_end = time.time() + (float(sys.argv[2]) if len(sys.argv) > 2 else 240.0)
 bad = runs = 0
@@ -55,10 +64,11 @@ while time.time() < t_end:
     if random.random() < 0.3: env["CUSIM_SKEW"] = str(random.choice([2, 3, 5]))
     for k, v in sw.items():
         env["STARNEIG_B200_" + k] = str(v)
-    r = subprocess.run([sys.executable, "-c", CHILD, str(n), str(pw), str(P)], env=env, capture_output=True, text=True, timeout=900)
+    kind = random.choice(["fullpos", "fullpos"] + KINDS) if n >= 12 else "fullpos"
+    r = subprocess.run([sys.executable, "-c", CHILD, str(n), str(pw), str(P), kind], env=env, capture_output=True, text=True, timeout=900)
     runs += 1
     if r.returncode != 0 or not r.stdout.strip().endswith("OK"):
         bad += 1
-        print("FAIL", dict(P=P, n=n, pw=pw), sw, {k: v for k, v in env.items() if k.startswith("CUSIM")}, r.stderr[-400:], flush=True)
+        print("FAIL", dict(P=P, n=n, pw=pw, kind=kind), sw, {k: v for k, v in env.items() if k.startswith("CUSIM")}, r.stderr[-400:], flush=True)
 print("runs", runs, "failures", bad)
 sys.exit(1 if bad else 0)
