@@ -49,8 +49,21 @@ struct starneig_b200_stats {
                               * w2 reduction (A'), reflector (R), scalars + s (R') */
     int overlap;             /* 1: the Q / top-row updates ran on the side stream, overlapped with the column loops */
     double side_tail_ms;     /* end of the last trailing update -> end of the call (what the deferred updates still add) */
+    int panel_width_used;    /* panel width of the reduction (the requested one unless it exceeds what the panel kernels'
+                              * shared-memory layout holds: > 1024 columns, or a narrower limit for n > ~70000) */
 };
 void starneig_b200_get_stats(struct starneig_b200_stats *stats);
+
+/* Largest supported matrix order (two n x n FP64 matrices of this order exceed one B200's memory anyway); the
+ * entry points return STARNEIG_INVALID_ARGUMENTS beyond it instead of overrunning a workspace. */
+#define STARNEIG_B200_MAX_N 131056
+
+/* Host-only arithmetic (no GPU needed): the workspace plan for an n x n reduction with the given panel width
+ * (< 0: reference default) on `ranks` GPUs. out[0] = panel width that would be used, out[1] = dynamic shared memory
+ * (bytes) of the persistent panel kernel for the first panel (0: it does not fit, the per-column kernels run),
+ * out[2] = capacity of the GEMV partial-sum buffer (doubles), out[3] = largest number of doubles any column of the
+ * per-column path would write into it. Returns 0, or STARNEIG_INVALID_ARGUMENTS if n is not supported. */
+int starneig_b200_plan_check(int n, int panel_width, int ranks, long long out[4]);
 
 /* 0: no extra events; 1: per-panel phase events (default); 2: additionally time every 8th GEMV launch;
  * 3: time every GEMV launch */

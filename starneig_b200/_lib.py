@@ -32,6 +32,7 @@ class Stats(ctypes.Structure):
         ("ranks", ctypes.c_int), ("fused_panels", ctypes.c_int), ("fused_kernel_ms", ctypes.c_double),
         ("fused_phase_ms", ctypes.c_double * 4),
         ("overlap", ctypes.c_int), ("side_tail_ms", ctypes.c_double),
+        ("panel_width_used", ctypes.c_int),
     ]
 
     def as_dict(self):
@@ -92,4 +93,6 @@ def load(path=None):
     lib.starneig_b200_dist_hessenberg_host.argtypes = [i, i, i, i, vp, i, vp, i]
     lib.starneig_b200_dist_hessenberg_host.restype = i
     lib.starneig_b200_dist_finalize.restype = None
+    lib.starneig_b200_plan_check.argtypes = [i, i, i, ctypes.POINTER(ctypes.c_longlong)]
+    lib.starneig_b200_plan_check.restype = i
     return lib

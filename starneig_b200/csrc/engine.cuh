@@ -108,6 +108,47 @@ static void prepare_device_functions()
     SB_CUDA(cudaFuncSetAttribute((k_panel_fused<true, true, 1024>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM_MAX));
 }
 
+struct GemvPlan { int skip, RB, S, kc; const double *A0; };
+
+// Largest matrix order the path is laid out for: the exchanged GEMV result has at most RB_MAX row blocks of 256 rows
+// (panel.cuh) and the per-column kernels stage at most 2048 columns of v per block. Two FP64 n x n matrices of this order
+// (137 GB each) exceed the memory of one B200 anyway; the entry points reject larger n instead of overrunning a buffer.
+constexpr int SB_MAX_N = RB_MAX * 256 - 16;
+
+// Capacity (doubles) of the GEMV partial-sum buffer for matrices up to order n:
+//   * persistent panel kernel: every 128-thread group of the grid owns one slice per row block it touches:
+//     at most (groups / RB + 2) slices of ldp <= 256 RB + 16 doubles, groups <= 148 * FUSED_VB = 592;
+//   * per-column kernels (plan_gemv_for): S <= ceil(n / 2048) + 1 column chunks of ldp = roundup(m + 2, 16) doubles when
+//     one wave of blocks cannot cover the matrix with shorter chunks (n > ~47000).
+static inline size_t ypart_doubles(int n)
+{
+    const size_t ldp = (size_t)round_up(n + 2, 16);
+    const size_t fused = (size_t)2 * 148 * 12 * 256 + 4 * ldp;
+    const size_t unfused = ((size_t)ceil_div(n, 2048) + 2) * ldp;
+    return std::max(fused, unfused);
+}
+
+// Decomposition of the per-column GEMV over rows [0, m) x ncols local columns: row blocks of 256 (padded) rows times S
+// column chunks of kc <= 2048 columns, sized so that the grid is at most one full wave of `slots` resident blocks --
+// or, for matrices too large for that, as few chunks as the 2048-column staging buffer allows. Pure host arithmetic
+// (unit-tested through starneig_b200_plan_check). Returns S = 0 if the partial sums would not fit `ypart_cap` doubles.
+static inline GemvPlan plan_gemv_for(int slots, int skip, int m, int ncols, int ldp, size_t ypart_cap)
+{
+    GemvPlan p;
+    p.skip = skip; p.A0 = nullptr;
+    const int mp = m + skip;
+    p.RB = ceil_div(mp, 256);
+    int S = std::max(1, slots / std::max(p.RB, 1));
+    int kc = ceil_div(std::max(ncols, 1), S);
+    kc = std::max(kc, 16);
+    kc = std::min(round_up(kc, 4), 2048);
+    S = std::max(1, ceil_div(ncols, kc));
+    while ((size_t)S * ldp > ypart_cap && kc < 2048) { kc = std::min(2048, kc * 2); S = std::max(1, ceil_div(ncols, kc)); }
+    p.kc = kc;
+    p.S = (size_t)S * ldp > ypart_cap ? 0 : S;
+    return p;
+}
+
 struct Stats : starneig_b200_stats {};
 
 // private workspace of a rank
@@ -174,7 +215,7 @@ struct Workspace {
         Wpart = alloc<double>(wpart_cap);
         Wpart_side = alloc<double>(wpart_cap);
         pcol = alloc<double>(ldv);
-        ypart_cap = (size_t)2 * 148 * 12 * 256 + 4 * (size_t)ldv;
+        ypart_cap = ypart_doubles(n);
         ypart = alloc<double>(ypart_cap);
         ypart_ll = alloc<uint4>(ypart_cap);
         SB_CUDA(cudaMemset(ypart_ll, 0, ypart_cap * sizeof(uint4)));
@@ -218,7 +259,28 @@ struct ArenaLayout {
     }
 };
 
-struct GemvPlan { int skip, RB, S, kc; const double *A0; };
+// Widest panel <= nb whose row-block kernels fit their shared-memory layout for a panel of m rows on `ctas` CTAs: both
+// panel paths keep 3-4 partial vectors per owned row and 32 panel columns in shared memory, so for very large matrices
+// (n > ~70000 at the reference's default width) the panel is narrowed -- the same reduction with another blocking, as
+// for panels wider than PANEL_MAX_NB. Returns 0 if not even 32 columns fit (cannot happen for m <= SB_MAX_N).
+static inline int fit_panel_width(int m, int nb, int ctas, bool fused)
+{
+    for (int w = nb; w >= 8; w = (w > 32 ? std::max(32, (w - 8) / 8 * 8) : w - 8)) {
+        const bool try_fused = fused && w <= FUSED_MAX_NB;
+        if (try_fused) {
+            const int nsub = std::max(1, ceil_div(m, 32 * std::max(ctas, 1)));
+            if (fused_smem_bytes(std::min(w, std::max(m, 1)), nsub, FUSED_KC) <= PANEL_SMEM_MAX) return w;
+        } else {
+            const int nsub = std::max(1, ceil_div(m, 32 * PANEL_MAX_BLOCKS));
+            const int NW = std::max(1, ceil_div(w, 32));
+            const int RS = std::max(1, std::min(nsub, (NW <= 16 ? 16 : 32) / NW));
+            const size_t smem_fu = (size_t)(2 * w + nsub * 4 * NW * 32 + 2 * nsub * 32 + (RS + 3) * NW * 32) * sizeof(double);
+            if (smem_fu <= PANEL_SMEM_MAX) return w;
+        }
+        if (w <= 32) break;
+    }
+    return 0;
+}
 
 // Host staging hooks of a reduction (host-pointer API, hessenberg.cu): the upload of Q hides behind the first
 // column loop and finished columns travel back while the next panels are factorised.
@@ -487,18 +549,10 @@ struct Rank {
             SB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_col_gemv<false>, GEMV_THREADS, 2048 * sizeof(double)));
             gemv_slots = std::max(1, occ) * sms;
         }
-        GemvPlan p;
-        p.skip = (int)(((uintptr_t)base / sizeof(double)) & 1);
-        p.A0 = base - p.skip;
-        int mp = m + p.skip;
-        p.RB = ceil_div(mp, 256);
-        int S = std::max(1, gemv_slots / p.RB);
-        int kc = ceil_div(std::max(ncols, 1), S);
-        kc = std::max(kc, 16);
-        kc = std::min(round_up(kc, 4), 2048);
-        S = std::max(1, ceil_div(ncols, kc));
-        while ((size_t)S * ldp > ws.ypart_cap && kc < 2048) { kc *= 2; S = std::max(1, ceil_div(ncols, kc)); }
-        p.kc = kc; p.S = S;
+        const int skip = (int)(((uintptr_t)base / sizeof(double)) & 1);
+        GemvPlan p = plan_gemv_for(gemv_slots, skip, m, ncols, ldp, ws.ypart_cap);
+        if (p.S == 0) fatal("matrix too large for the GEMV partial-sum buffer", __FILE__, __LINE__);
+        p.A0 = base - skip;
         return p;
     }
 
@@ -706,6 +760,12 @@ struct Rank {
         SB_CUDA(cudaSetDevice(device));
         cudaStream_t st = stream;
         nb = std::min(nb, PANEL_MAX_NB);      // wider panels are split; the result only differs in rounding
+        if (end - begin > 1) {
+            const int fit = fit_panel_width(end - begin - 1, nb, fused_ctas, fused != 0);
+            if (fit == 0) fatal("matrix too large for the panel kernels' shared-memory layout", __FILE__, __LINE__);
+            nb = fit;
+        }
+        stats.panel_width_used = nb;
         ws.ensure(n, nb, P > 1);
         if (P > 1 && (arena == nullptr || n > al.n_cap || nb > al.nb_cap))
             fatal("internal error: exchange arena not prepared", __FILE__, __LINE__);

@@ -350,6 +350,7 @@ starneig_error_t starneig_b200_hessenberg_device(int n, int begin, int end, int 
     if (dQ == NULL) return -7;
     if (ldQ < n || (ldQ & 1) || ((uintptr_t)dQ & 15)) return -8;
     if (!starneig_node_initialized()) return STARNEIG_NOT_INITIALIZED;
+    if (n > SB_MAX_N) return STARNEIG_INVALID_ARGUMENTS;
     if (panel_width < 0) panel_width = default_panel_width(n);
     if (panel_width < 8) return STARNEIG_INVALID_CONFIGURATION;
     if (!have_gpu()) return STARNEIG_GENERIC_ERROR;
@@ -392,6 +393,11 @@ starneig_error_t starneig_SEP_SM_Hessenberg_expert(struct starneig_hessenberg_co
     if (Q == NULL) return -7;
     if (ldQ < n) return -8;
     if (!starneig_node_initialized()) return STARNEIG_NOT_INITIALIZED;
+    if (n > SB_MAX_N) {
+        fprintf(stderr, "[starneig][error] Matrices larger than %d x %d are not supported by the CUDA Hessenberg path. Exiting...\n",
+                SB_MAX_N, SB_MAX_N);
+        return STARNEIG_INVALID_ARGUMENTS;
+    }
 
     int nb = 0;
     starneig_error_t ret = resolve_conf(conf, n, &nb);
@@ -477,7 +483,7 @@ extern "C" __attribute__((visibility("default")))
 int starneig_b200_dist_init(int world, int rank, int n_max, int panel_width_max, void *handle_out)
 {
     if (!starneig_node_initialized()) return STARNEIG_NOT_INITIALIZED;
-    if (world < 1 || world > MAX_RANKS || rank < 0 || rank >= world || n_max < 1) return STARNEIG_INVALID_ARGUMENTS;
+    if (world < 1 || world > MAX_RANKS || rank < 0 || rank >= world || n_max < 1 || n_max > SB_MAX_N) return STARNEIG_INVALID_ARGUMENTS;
     if (!have_gpu()) return STARNEIG_GENERIC_ERROR;
     if (g_dist) { g_dist_shard.release(); g_dist->close(); delete g_dist; g_dist = nullptr; }
     int dev = 0;
@@ -542,6 +548,7 @@ starneig_error_t starneig_b200_dist_hessenberg_device(int n, int begin, int end,
     int q0, q1;
     q_row_range(r.P, r.g, n, &q0, &q1);
     if (ldQ < q1 - q0 || (ldQ & 1) || ((uintptr_t)dQ_loc & 15)) return -8;
+    if (n > SB_MAX_N) return STARNEIG_INVALID_ARGUMENTS;
     if (panel_width < 0) panel_width = default_panel_width(n);
     if (panel_width < 8) return STARNEIG_INVALID_CONFIGURATION;
     if (r.P > 1 && (n > r.al.n_cap || std::min(panel_width, PANEL_MAX_NB) > r.al.nb_cap)) return STARNEIG_INVALID_ARGUMENTS;
@@ -566,6 +573,7 @@ starneig_error_t starneig_b200_dist_hessenberg_host(int n, int begin, int end, i
     if (ldA < n) return -6;
     if (Q == NULL) return -7;
     if (ldQ < n) return -8;
+    if (n > SB_MAX_N) return STARNEIG_INVALID_ARGUMENTS;
     if (panel_width < 0) panel_width = default_panel_width(n);
     if (panel_width < 8) return STARNEIG_INVALID_CONFIGURATION;
     if (r.P > 1 && (n > r.al.n_cap || std::min(panel_width, PANEL_MAX_NB) > r.al.nb_cap)) return STARNEIG_INVALID_ARGUMENTS;
@@ -585,6 +593,45 @@ extern "C" __attribute__((visibility("default")))
 void starneig_b200_dist_finalize(void)
 {
     if (g_dist) { g_dist_shard.release(); g_dist->close(); delete g_dist; g_dist = nullptr; }
+}
+
+// host-only: the workspace plan of a reduction (see include/starneig_b200.h); lets the CPU test suite check the buffer
+// bounds of both panel paths for every size up to STARNEIG_B200_MAX_N without a GPU
+extern "C" __attribute__((visibility("default")))
+int starneig_b200_plan_check(int n, int panel_width, int ranks, long long out[4])
+{
+    static_assert(STARNEIG_B200_MAX_N == SB_MAX_N, "header and engine disagree on the largest supported order");
+    if (n < 1 || n > SB_MAX_N || ranks < 1 || ranks > MAX_RANKS) return STARNEIG_INVALID_ARGUMENTS;
+    if (panel_width < 0) panel_width = default_panel_width(n);
+    if (panel_width < 8) return STARNEIG_INVALID_CONFIGURATION;
+    const int ctas = 148, slots = 148 * 8;      // a B200: one persistent CTA per SM; k_col_gemv: 8 resident blocks per SM
+    int nb = std::min(panel_width, PANEL_MAX_NB);
+    const int m0 = n - 1;
+    if (m0 >= 1) nb = fit_panel_width(m0, nb, ctas, true);
+    if (nb == 0) return STARNEIG_INVALID_ARGUMENTS;
+    const int w = std::max(1, std::min(nb, m0));
+    const int nsub = std::max(1, ceil_div(std::max(m0, 1), 32 * ctas));
+    const size_t smem = nb <= FUSED_MAX_NB ? fused_smem_bytes(w, nsub, FUSED_KC) : 0;
+    const size_t cap = ypart_doubles(n);
+    // per-column path: the first panel has the longest columns; a rank's share of the trailing columns
+    long long worst = 0;
+    const int ldp = round_up(m0 + 2, 16);
+    for (int j = 0; j < w; j++) {
+        const int ncols = ceil_div(std::max(m0 - j, 0), ranks) + 64;
+        for (int skip = 0; skip < 2; skip++) {
+            const GemvPlan gp = plan_gemv_for(slots, skip, m0, std::min(ncols, n), ldp, cap);
+            if (gp.S == 0) return STARNEIG_INVALID_ARGUMENTS;
+            worst = std::max(worst, (long long)gp.S * ldp);
+        }
+    }
+    // persistent kernel: slices of a group per row block (see ypart_doubles)
+    if (smem > 0 && smem <= PANEL_SMEM_MAX) {
+        const int RB = ceil_div(m0 + 1, 256);
+        const long long groups = (long long)ctas * FUSED_VB;
+        worst = std::max(worst, (groups / std::max(RB, 1) + 2) * (long long)ldp);
+    }
+    out[0] = nb; out[1] = (smem > 0 && smem <= PANEL_SMEM_MAX) ? (long long)smem : 0; out[2] = (long long)cap; out[3] = worst;
+    return 0;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -139,3 +139,28 @@ def test_product_never_touches_the_oracle():
     if os.path.exists(driver):
         needed = subprocess.run(["readelf", "-d", driver], capture_output=True, text=True).stdout
         assert "liboracle" not in needed.lower() and "libstarneig_ref" not in needed.lower()
+
+
+def test_workspace_plan_bounds_up_to_the_largest_supported_order(sn):
+    """Host-only arithmetic of both panel paths (starneig_b200_plan_check): for every size up to STARNEIG_B200_MAX_N the
+    GEMV partial sums of any column fit the buffer that is allocated for them, a panel width that fits the panel
+    kernels' shared memory is found (narrower than the reference default beyond n ~ 70000), and larger n is rejected."""
+    import ctypes
+    lib = sn.lib()
+    out = (ctypes.c_longlong * 4)()
+    MAX_N = 131056
+    sizes = [1, 2, 9, 300, 4000, 20000, 46000, 47500, 50000, 60000, 75000, 76001, 80000, 100000, 120000, MAX_N]
+    for n in sizes:
+        for ranks in (1, 2, 8):
+            for pw in (-1, 64, 512, 1024):
+                assert lib.starneig_b200_plan_check(n, pw, ranks, out) == 0, (n, ranks, pw)
+                used, smem, cap, worst = out[0], out[1], out[2], out[3]
+                assert 8 <= used <= 1024 and (pw < 0 or used <= max(pw, 8))
+                assert smem <= 200 * 1024
+                assert worst <= cap, (n, ranks, pw, worst, cap)
+    # the reference default survives wherever the persistent kernel's layout holds it
+    assert lib.starneig_b200_plan_check(20000, -1, 1, out) == 0 and out[0] == 312 and out[1] > 0
+    assert lib.starneig_b200_plan_check(50000, -1, 8, out) == 0 and out[0] == 368 and out[1] > 0
+    assert lib.starneig_b200_plan_check(100000, -1, 1, out) == 0 and out[0] < sn.default_panel_width(100000)
+    assert lib.starneig_b200_plan_check(MAX_N + 1, -1, 1, out) == 4          # STARNEIG_INVALID_ARGUMENTS
+    assert lib.starneig_b200_plan_check(0, -1, 1, out) == 4

@@ -25,9 +25,12 @@ def test_reference_arm_line():
     assert j["impl"] == "reference" and j["n_gpus"] == 1 and j["steps"] == 2 and j["warmup"] == 1
     assert j["unit"] == "GFLOP/s" and j["higher_is_better"] is True and j["dtype"] == "f64" and j["vs_baseline"] is None
     assert j["value"] > 0 and j["ms_per_step"] > 0
-    assert "n=20000" in j["config"]["workload"] and j["config"]["sample_n"] == 300
+    # `config` is the dict our arm prints too (bench.shared_config); the bounded sample is named outside it
+    assert j["config"] == {"workload": j["config"]["workload"], "n": 20000} and "n=20000" in j["config"]["workload"]
+    assert j["sample_n"] == 300
     cb = j["cpu_baseline"]
     assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == j["value"] and cb["sample"]
+    assert cb["lapack"]["value"] > 0 and "dgehrd" in cb["lapack"]["what"]
     assert j["e2e"] == {"value": j["value"], "unit": j["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 

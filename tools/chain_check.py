@@ -5,7 +5,10 @@ built in this image, so LAPACK dhseqr from the same OpenBLAS stands in for starn
     CPU chain:  the reference's own Hessenberg sources (oracle/_ref; else the oracle port)  ->  dhseqr  ->  eigenvalues
 Acceptance (BASELINE.json): every eigenvalue of the GPU chain has a partner of the CPU chain within 1e-10 * ||A||_F.
 Matrix: the reference example's generator (examples/sep_sm_full_chain.c:65-75), entries uniform in [-1, 1].
-usage: chain_check.py [n] (default 4000; n = 10000 needs ~10 min of host time for the two dhseqr runs)"""
+usage: chain_check.py [n] [--cpu-only] [--save-cpu FILE | --load-cpu FILE]
+       (default n = 4000; n = 10000 needs ~10 min of host time for the two dhseqr runs. --save-cpu stores the eigenvalues of
+       the CPU chain (with --cpu-only: on a machine without a GPU), --load-cpu reads them back instead of re-running the CPU
+       chain, so that the GPU box only pays for its own half: tests/golden/chain_n10000_cpu_eigs.npz was made that way.)"""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -13,6 +16,8 @@ from oracle.oracle import Oracle, Reference
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 4000
 cpu_only = "--cpu-only" in sys.argv
+save_cpu = sys.argv[sys.argv.index("--save-cpu") + 1] if "--save-cpu" in sys.argv else None
+load_cpu = sys.argv[sys.argv.index("--load-cpu") + 1] if "--load-cpu" in sys.argv else None
 ora = Oracle()
 cores = os.cpu_count() or 1
 ora.set_threads(cores)
@@ -34,20 +39,29 @@ def nearest_gap(ev_a, ev_b):
     return worst
 
 
-t0 = time.time()
-A2, Q2 = A0.copy(order="F"), Q0.copy(order="F")
-if Reference.available():
-    ref = Reference(); ref.set_threads(cores); ref.set_workers(1)
-    assert ref.hessenberg(n, A2, ld, Q2, ld) == 0
-    kind = "reference sources (oracle/_ref)"
+if load_cpu:
+    saved = np.load(load_cpu)
+    assert int(saved["n"]) == n and abs(float(saved["normA"]) - float(normA)) <= 1e-12 * float(normA), "the saved CPU chain belongs to another matrix"
+    ev_cpu = saved["eigenvalues"]
+    print(f"n {n}  CPU chain: eigenvalues loaded from {load_cpu} ({str(saved['how'])})", flush=True)
 else:
-    assert ora.hessenberg_port(n, A2, ld, Q2, ld) == 0
-    kind = "oracle port"
-t_cpu_h = time.time() - t0
-t0 = time.time()
-ev_cpu = ora.eigenvalues(n, A2, ld)
-t_cpu_s = time.time() - t0
-print(f"n {n} cores {cores}  CPU chain: Hessenberg [{kind}] {t_cpu_h:.1f} s, dhseqr {t_cpu_s:.1f} s", flush=True)
+    t0 = time.time()
+    A2, Q2 = A0.copy(order="F"), Q0.copy(order="F")
+    if Reference.available():
+        ref = Reference(); ref.set_threads(cores); ref.set_workers(1)
+        assert ref.hessenberg(n, A2, ld, Q2, ld) == 0
+        kind = "reference sources (oracle/_ref)"
+    else:
+        assert ora.hessenberg_port(n, A2, ld, Q2, ld) == 0
+        kind = "oracle port"
+    t_cpu_h = time.time() - t0
+    t0 = time.time()
+    ev_cpu = ora.eigenvalues(n, A2, ld)
+    t_cpu_s = time.time() - t0
+    how = f"Hessenberg [{kind}] {t_cpu_h:.1f} s, dhseqr {t_cpu_s:.1f} s, {cores} cores"
+    print(f"n {n} cores {cores}  CPU chain: {how}", flush=True)
+    if save_cpu:
+        np.savez_compressed(save_cpu, n=n, normA=normA, eigenvalues=ev_cpu, how=how)
 if cpu_only:
     sys.exit(0)
 
