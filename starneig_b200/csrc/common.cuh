@@ -52,6 +52,18 @@ __device__ __forceinline__ void red_release_gpu_add(unsigned *p, unsigned v)
 {
     asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+// 64-bit variants: an arrival counter (low word) that carries grid-wide vote counts in its high word, so that the
+// thread that polls the barrier learns the outcome of the vote with the same load
+__device__ __forceinline__ unsigned long long ld_acquire_gpu_u64(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void red_release_gpu_add_u64(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
 __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned *p)
 {
     unsigned v;

@@ -173,7 +173,7 @@ template <bool AK, bool BKM, int WM, int WN, int MB, int NB, int STAGES, int MIN
 __global__ void __launch_bounds__(WM * WN * 32, MINB)
 dgemm_kernel(int M, int N, int K, double alpha, const double *__restrict__ A, int lda,
              const double *__restrict__ B, int ldb, double beta, double *__restrict__ C, int ldc,
-             int klen, size_t split_stride)
+             int klen, size_t split_stride, int raster)
 {
     constexpr int BM = WM * MB * 8, BN = WN * NB * 8, NT = WM * WN * 32;
     constexpr bool ILV = (OPT & GEMM_OPT_ILV) != 0;
@@ -186,7 +186,10 @@ dgemm_kernel(int M, int N, int K, double alpha, const double *__restrict__ A, in
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = warp % WM, wn = warp / WM;
     const int g = lane >> 2, t = lane & 3;
-    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    // raster 1 (skinny outputs): consecutive CTAs are the column tiles of ONE row tile, so the long operand's tile is read
+    // from DRAM once and from L2 by the others (with rows fastest the re-read came a whole wave later: ncu showed 3x the
+    // algorithmic DRAM traffic on W = A^T VT)
+    const int m0 = (raster ? blockIdx.y : blockIdx.x) * BM, n0 = (raster ? blockIdx.x : blockIdx.y) * BN;
     const int kbeg = blockIdx.z * klen;
     const int kend = min(K, kbeg + klen);
     const int ktiles = max(0, (kend - kbeg + GEMM_BK - 1) / GEMM_BK);
@@ -299,12 +302,16 @@ dgemm_kernel(int M, int N, int K, double alpha, const double *__restrict__ A, in
         for (int i = 0; i < MB; i++)
 #pragma unroll
             for (int e = 0; e < 2; e++)
-                old[i][e] = (use_beta && col + e < N && rbase + i * 8 < M) ? Cc[(size_t)e * ldc + i * 8] : 0.0;
+                old[i][e] = (use_beta && col + e < N && rbase + i * 8 < M) ? __ldcs(Cc + (size_t)e * ldc + i * 8) : 0.0;
 #pragma unroll
         for (int i = 0; i < MB; i++)
 #pragma unroll
             for (int e = 0; e < 2; e++)
-                if (col + e < N && rbase + i * 8 < M) Cc[(size_t)e * ldc + i * 8] = fma(alpha, acc[i][j][e], beta * old[i][e]);
+                if (col + e < N && rbase + i * 8 < M) {
+                    // a read-modify-write pass over C streams through L2 once (evict first): the operands stay resident
+                    const double val = fma(alpha, acc[i][j][e], beta * old[i][e]);
+                    if (use_beta) __stcs(Cc + (size_t)e * ldc + i * 8, val); else Cc[(size_t)e * ldc + i * 8] = val;
+                }
     }
 }
 
@@ -330,11 +337,11 @@ struct GemmConfig {
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
     }
     static void launch(cudaStream_t st, int M, int N, int K, double alpha, const double *A, int lda, const double *B,
-                       int ldb, double beta, double *C, int ldc, int splits, int klen, size_t split_stride)
+                       int ldb, double beta, double *C, int ldc, int splits, int klen, size_t split_stride, int raster = 0)
     {
-        dim3 grid(ceil_div(M, BM), ceil_div(N, BN), splits);
+        dim3 grid(raster ? ceil_div(N, BN) : ceil_div(M, BM), raster ? ceil_div(M, BM) : ceil_div(N, BN), splits);
         SB_LAUNCH((dgemm_kernel<AK, BKM, WM, WN, MB, NB, STAGES, MINB, OPT>), grid, NT, SMEM, st, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc,
-                  klen, split_stride);
+                  klen, split_stride, raster);
     }
 };
 

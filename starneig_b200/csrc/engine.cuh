@@ -41,23 +41,15 @@ namespace sb200 {
 // ---------------------------------------------------------------------------------------------
 // GEMM dispatch
 // ---------------------------------------------------------------------------------------------
-// <A K-major, B K-major, warps along M, warps along N, 8-row blocks per warp, 8-col blocks per warp, stages, CTAs/SM>
-using GemmNT   = GemmConfig<false, false, 2, 2, 8, 4, 4, 2>;     // 128 x  64, 128 threads: rank-nb updates
-using GemmTN13 = GemmConfig<true,  true,  4, 1, 2, 13, 4, 2>;    //  64 x 104, W = A^T VT
-using GemmTN12 = GemmConfig<true,  true,  4, 1, 2, 12, 4, 2>;    //  64 x  96
-using GemmNN13 = GemmConfig<false, true,  4, 1, 2, 13, 4, 2>;    //  64 x 104, W = A VT
-using GemmNN12 = GemmConfig<false, true,  4, 1, 2, 12, 4, 2>;    //  64 x  96
-// The same tiles with the loader options of dgemm.cuh (OPT bit 0: the next stage's cp.async spread between the DMMAs;
-// bit 1: 16-byte cp.async where the operand is aligned). Opt-in (STARNEIG_B200_GEMM_OPT=1|2|3) until they have been
-// timed on a B200 against the default kernels (tools/gemm_sweep.cu).
-template <int OPT> struct GemmOpt {
-    using NT   = GemmConfig<false, false, 2, 2, 8, 4, 4, 2, OPT>;
-    using TN13 = GemmConfig<true,  true,  4, 1, 2, 13, 4, 2, OPT>;
-    using TN12 = GemmConfig<true,  true,  4, 1, 2, 12, 4, 2, OPT>;
-    using NN13 = GemmConfig<false, true,  4, 1, 2, 13, 4, 2, OPT>;
-    using NN12 = GemmConfig<false, true,  4, 1, 2, 12, 4, 2, OPT>;
-    static void prepare() { NT::prepare(); TN13::prepare(); TN12::prepare(); NN13::prepare(); NN12::prepare(); }
-};
+// <A K-major, B K-major, warps along M, warps along N, 8-row blocks per warp, 8-col blocks per warp, stages, CTAs/SM, OPT>
+// Defaults from the tile sweep against cuBLAS on the exact shapes (tools/gemm_sweep.cu, profiles/r2_v1_gemm_sweep_p2.txt;
+// cuBLAS: NT 33.2, TN 34.8, NN 34.0 TFLOP/s): NT with the next stage's cp.async spread between the DMMAs (OPT bit 0:
+// 28.2 -> 31.6 TFLOP/s); the skinny products with a 3-stage ring instead of 4 (TN 22.5 -> 30.7, NN 30.9 -> 32.2).
+using GemmNT   = GemmConfig<false, false, 2, 2, 8, 4, 4, 2, 1>;  // 128 x  64, 128 threads: rank-nb updates
+using GemmTN13 = GemmConfig<true,  true,  4, 1, 2, 13, 3, 2>;    //  64 x 104, W = A^T VT
+using GemmTN12 = GemmConfig<true,  true,  4, 1, 2, 12, 3, 2>;    //  64 x  96
+using GemmNN13 = GemmConfig<false, true,  4, 1, 2, 13, 3, 2>;    //  64 x 104, W = A VT
+using GemmNN12 = GemmConfig<false, true,  4, 1, 2, 12, 3, 2>;    //  64 x  96
 // "Fat" variants for the side stream: 256 threads x ~200 registers fill the register file of an SM, so a CTA owns
 // its SM exclusively. When it retires the SM is completely free and the (higher-priority, equally SM-exclusive)
 // persistent panel kernel can claim it at once; with the 2-CTAs-per-SM variants an SM never drains while the
@@ -65,14 +57,6 @@ template <int OPT> struct GemmOpt {
 using GemmNTfat   = GemmConfig<false, false, 2, 4, 8, 4, 4, 1>;     // 128 x 128
 using GemmNN13fat = GemmConfig<false, true,  8, 1, 2, 13, 4, 1>;    // 128 x 104
 using GemmNN12fat = GemmConfig<false, true,  8, 1, 2, 12, 4, 1>;    // 128 x  96
-
-// "Slim" variants for the co-resident overlap (STARNEIG_B200_OVERLAP=2): 64 x 64 tiles, 128 threads, <= 170 registers, so
-// that one such CTA fits next to the 64-register build of the persistent panel kernel on the same SM (24576 registers and
-// >= 76 KB of shared memory are left) and the deferred DMMA work runs in the shadow of the HBM-bound column loop on ALL
-// SMs -- the panel kernel needs every SM to saturate HBM (per-SM bandwidth limit), so giving SMs away does not pay
-// (profiles/r1_s5_overlap_sweep.txt).
-using GemmNTslim = GemmConfig<false, false, 2, 2, 4, 4, 4, 3>;      // 64 x 64
-using GemmNNslim = GemmConfig<false, true,  4, 1, 2, 8, 4, 3>;      // 64 x 64, W = X VT
 
 static const size_t PANEL_SMEM_MAX = 200 * 1024;
 constexpr int PANEL_RING = 3;           // V / VT buffer sets: the deferred updates may lag two panels behind
@@ -82,8 +66,6 @@ static void prepare_device_functions()
 {
     GemmNT::prepare(); GemmTN13::prepare(); GemmTN12::prepare(); GemmNN13::prepare(); GemmNN12::prepare();
     GemmNTfat::prepare(); GemmNN13fat::prepare(); GemmNN12fat::prepare();
-    GemmNTslim::prepare(); GemmNNslim::prepare();
-    GemmOpt<1>::prepare(); GemmOpt<2>::prepare(); GemmOpt<3>::prepare();
     SB_CUDA(cudaFuncSetAttribute(k_col_finish_update<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM_MAX));
     SB_CUDA(cudaFuncSetAttribute(k_col_finish_update<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM_MAX));
     SB_CUDA(cudaFuncSetAttribute(k_col_reflector<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM_MAX));
@@ -100,12 +82,8 @@ static void prepare_device_functions()
     SB_CUDA(cudaFuncGetAttributes(&fa, k_sum_peers));
     SB_CUDA(cudaFuncGetAttributes(&fa, k_barrier));
     SB_CUDA(cudaFuncGetAttributes(&fa, splitk_reduce_kernel));
-    SB_CUDA(cudaFuncSetAttribute((k_panel_fused<false, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM_MAX));
-    SB_CUDA(cudaFuncSetAttribute((k_panel_fused<true, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM_MAX));
-    SB_CUDA(cudaFuncSetAttribute((k_panel_fused<false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM_MAX));
-    SB_CUDA(cudaFuncSetAttribute((k_panel_fused<true, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM_MAX));
-    SB_CUDA(cudaFuncSetAttribute((k_panel_fused<false, true, 1024>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM_MAX));
-    SB_CUDA(cudaFuncSetAttribute((k_panel_fused<true, true, 1024>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM_MAX));
+    SB_CUDA(cudaFuncSetAttribute(k_panel_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM_MAX));
+    SB_CUDA(cudaFuncSetAttribute(k_panel_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM_MAX));
 }
 
 struct GemvPlan { int skip, RB, S, kc; const double *A0; };
@@ -167,10 +145,8 @@ struct Workspace {
     double *s = nullptr, *w2 = nullptr, *colpart = nullptr, *sqpart = nullptr;
     ColScal *scal = nullptr;
     unsigned *counter = nullptr;
-    uint4 *w2part_ll = nullptr, *w2_ll = nullptr;       // LL entries of the w2 reduction (fused kernel, LLRED)
-    uint4 *ypart_ll = nullptr;                          // LL entries of the GEMV partials (fused kernel, LLRED)
-    double *pcol2 = nullptr;                            // second column buffer (fused kernel, LLRED)
     unsigned *gbar = nullptr;                   // grid barrier counter of the fused panel kernel
+    unsigned long long *rbar = nullptr;         // its per-column arrival words (barrier after phase R + the vote on `linear`)
     unsigned long long *timers = nullptr;       // device-side phase timers of the fused panel kernel (ns)
     std::vector<void *> allocs;
 
@@ -186,15 +162,6 @@ struct Workspace {
         for (void *p : allocs) cudaFree(p);
         allocs.clear();
         n_cap = nb_cap = 0;
-        w2part_ll = w2_ll = ypart_ll = nullptr;
-    }
-    // the column sequence numbers restart (new exchange arena): no stale LL entry may carry a tag that will be reused
-    void reset_ll()
-    {
-        if (!w2part_ll) return;
-        SB_CUDA(cudaMemset(w2part_ll, 0, (size_t)nbp * PANEL_LDB * sizeof(uint4)));
-        SB_CUDA(cudaMemset(w2_ll, 0, nbp * sizeof(uint4)));
-        SB_CUDA(cudaMemset(ypart_ll, 0, ypart_cap * sizeof(uint4)));
     }
     void ensure(int n, int nb, bool dist)
     {
@@ -217,20 +184,14 @@ struct Workspace {
         pcol = alloc<double>(ldv);
         ypart_cap = ypart_doubles(n);
         ypart = alloc<double>(ypart_cap);
-        ypart_ll = alloc<uint4>(ypart_cap);
-        SB_CUDA(cudaMemset(ypart_ll, 0, ypart_cap * sizeof(uint4)));
-        pcol2 = alloc<double>(ldv);
         s = alloc<double>(nbp); w2 = alloc<double>(nbp);
         colpart = alloc<double>((size_t)nbp * PANEL_LDB);
         sqpart = alloc<double>(3 * PANEL_LDB);
         scal = alloc<ColScal>(nbp);
         counter = alloc<unsigned>(4);
         SB_CUDA(cudaMemset(counter, 0, 4 * sizeof(unsigned)));
-        w2part_ll = alloc<uint4>((size_t)nbp * PANEL_LDB);
-        w2_ll = alloc<uint4>(nbp);
-        SB_CUDA(cudaMemset(w2part_ll, 0, (size_t)nbp * PANEL_LDB * sizeof(uint4)));       // tag 0 is never used
-        SB_CUDA(cudaMemset(w2_ll, 0, nbp * sizeof(uint4)));
         gbar = alloc<unsigned>(1024);
+        rbar = alloc<unsigned long long>(FUSED_MAX_NB + 8);
         timers = alloc<unsigned long long>(8);
         SB_CUDA(cudaMemset(timers, 0, 8 * sizeof(unsigned long long)));
     }
@@ -253,7 +214,7 @@ struct ArenaLayout {
         off_rbcount = o;  o = align(o + RB_MAX * sizeof(unsigned));
         off_yflag = o;    o = align(o + (size_t)2 * P * RB_MAX * sizeof(unsigned));
         off_inbox = o;    o = align(o + (size_t)2 * P * ldp * 16);      // 16-byte LL entries (fused kernel) or doubles
-        off_pan = o;      o = align(o + (size_t)ldv * nbp * sizeof(double));
+        off_pan = o;      o = align(o + (size_t)ldv * (nbp + 8) * sizeof(double));    // the panel and the column right of it
         off_wx = o;       o = align(o + (size_t)ldv * nbp * sizeof(double));
         bytes = o;
     }
@@ -302,8 +263,6 @@ struct Rank {
     cudaEvent_t ev_panel[PANEL_RING] = {}, ev_side[PANEL_RING] = {};
     cudaStream_t copy = nullptr;            // host staging that overlaps the reduction (Q upload, write-back of finished columns)
     cudaEvent_t ev_q_up = nullptr, ev_cols_final = nullptr;
-    // 2: like 1, but co-resident: the panel kernel keeps all SMs (64-register build), the deferred GEMMs use slim tiles that
-    //    fit next to it on the same SM. Untimed so far.
     // 1: deferred updates run on `side`, concurrently with the next column loops. Off by default: measured on B200 at
     // n = 20000 (profiles/r1_s5_overlap_sweep.txt) the concurrent DMMA GEMMs cost the HBM-bound column loops far more
     // (GEMV phases 6335 -> 3850-4540 GB/s) than the 770 ms of deferred work they hide: 5334 ms without, 6216-6854 ms with.
@@ -324,16 +283,9 @@ struct Rank {
     int gemv_slots = 0;                     // resident k_col_gemv blocks on the whole GPU (one wave)
     int fused = 1;                          // 1: one persistent kernel per panel (panel_fused.cuh); 0: three kernels per column
     int fused_ctas = 0;                     // grid of the fused kernel (number of SMs; fewer when ranks share a device)
-    int gemm_opt = 0;                       // loader options of the DMMA kernels (GemmOpt<1..3>), 0: the default kernels
-    int fused_ll = 0;                       // 1: fused panel kernel with LL-entry reductions (one grid barrier per column instead of four);
-                                            // 2: LL entries for the GEMV partials only (three barriers: w2 keeps barrier-reduce-barrier)
-    int fused_even_rows = 0;                // 1: fused panel kernel: rows spread over all CTAs (changes the grouping of the partial sums)
-    int fused_r = 0;                        // 1 (with fused_ll): phase R of the fused kernel reads its slab of V once instead of twice
-    int gemv_kc = FUSED_KC;                 // fused kernel: columns of v staged per GEMV group at a time
-    int gemv_prefetch = 0;                  // fused kernel: columns (2 KB each) per GEMV group pulled into L2 during the level-2 phases
-    int gemv_prefetch_bulk = 0;             // 1: bulk (TMA) prefetch instructions
-    int ll_sleep = 200;                     // ns between polls of the LL waits
-    int gemv_prefetch_mb = 96;              // L2 budget shared by V, Y, VT of the panel and the prefetched data
+    int gemv_kc = FUSED_KC;                 // fused kernel: columns of v staged per GEMV group at a time (2048 timed: no gain)
+    int gemv_linear = 1;                    // fused kernel: the GEMV streams against the unscaled x (FusedArgs::linear)
+    int l2_budget_mb = 96;                  // L2 budget shared by V, Y, VT of the panel and the resident columns
     int gemv_resident_kb = 0;               // fused kernel: KB of the trailing matrix (its last local columns) kept in L2 across the
                                             // columns of a panel ("evict last" loads), 0: everything streams
     std::vector<cudaEvent_t> events;        // phase events: 4 per panel
@@ -364,26 +316,14 @@ struct Rank {
         SB_CUDA(cudaDeviceGetAttribute(&fused_ctas, cudaDevAttrMultiProcessorCount, device));
         e = getenv("STARNEIG_B200_FUSED_CTAS");
         if (e && atoi(e) >= 1) fused_ctas = std::min(fused_ctas, atoi(e));
-        e = getenv("STARNEIG_B200_GEMM_OPT");
-        if (e) gemm_opt = atoi(e) & 3;
-        e = getenv("STARNEIG_B200_FUSED_LL");
-        if (e) fused_ll = atoi(e);
-        e = getenv("STARNEIG_B200_FUSED_EVEN_ROWS");
-        if (e) fused_even_rows = atoi(e);
-        e = getenv("STARNEIG_B200_FUSED_R");
-        if (e) fused_r = atoi(e);
         e = getenv("STARNEIG_B200_GEMV_KC");
         if (e && atoi(e) >= 64) gemv_kc = std::min(4096, atoi(e) / 8 * 8);
-        e = getenv("STARNEIG_B200_GEMV_PREFETCH");
-        if (e && atoi(e) >= 0) gemv_prefetch = atoi(e);
+        e = getenv("STARNEIG_B200_GEMV_LINEAR");
+        if (e) gemv_linear = atoi(e);
         e = getenv("STARNEIG_B200_GEMV_RESIDENT_KB");
         if (e && atoi(e) >= 0) gemv_resident_kb = atoi(e);
-        e = getenv("STARNEIG_B200_GEMV_PREFETCH_BULK");
-        if (e) gemv_prefetch_bulk = atoi(e);
-        e = getenv("STARNEIG_B200_LL_SLEEP");
-        if (e && atoi(e) >= 0) ll_sleep = atoi(e);
-        e = getenv("STARNEIG_B200_GEMV_PREFETCH_MB");
-        if (e && atoi(e) >= 0) gemv_prefetch_mb = atoi(e);
+        e = getenv("STARNEIG_B200_L2_BUDGET_MB");
+        if (e && atoi(e) >= 0) l2_budget_mb = atoi(e);
         e = getenv("STARNEIG_B200_OVERLAP");
         if (e) overlap = atoi(e);
         e = getenv("STARNEIG_B200_OVERLAP_CTAS");
@@ -437,7 +377,6 @@ struct Rank {
         for (int s = 0; s < P; s++) peer[s] = nullptr;
         peer[g] = arena;
         bar_epoch = 0; y_epoch = 0;
-        ws.reset_ll();
         return true;
     }
     template <typename T> T *at(int s, size_t off) const { return (T *)(peer[s] + off); }
@@ -465,24 +404,16 @@ struct Rank {
         cudaStream_t st = on_side ? side : stream;
         double *wpart = on_side ? ws.Wpart_side : ws.Wpart;
         stats.gemm_flops += 2.0 * M * N * (double)K;
-        const bool slim = on_side && overlap == 2;
-        const bool fat = on_side && side_fat && !slim;
+        const bool fat = on_side && side_fat;
         if (kind == GEMM_NT) {
-            if (slim)     GemmNTslim::launch(st, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, 1, K, 0);
-            else if (fat) GemmNTfat::launch(st, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, 1, K, 0);
-            else switch (gemm_opt) {
-                case 1:  GemmOpt<1>::NT::launch(st, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, 1, K, 0); break;
-                case 2:  GemmOpt<2>::NT::launch(st, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, 1, K, 0); break;
-                case 3:  GemmOpt<3>::NT::launch(st, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, 1, K, 0); break;
-                default: GemmNT::launch(st, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, 1, K, 0);
-            }
+            if (fat) GemmNTfat::launch(st, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, 1, K, 0);
+            else     GemmNT::launch(st, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, 1, K, 0);
             stats.kernel_launches++;
             return;
         }
         // skinny output (N = panel width): pick the column tile with the least padding, split K if the
         // grid would not fill the GPU twice
         int bn = (ceil_div(N, 96) * 96 <= ceil_div(N, 104) * 104) ? 96 : 104;
-        if (slim && kind == GEMM_NN) bn = 64;
         // 2 CTAs per SM are resident; split K so that the grid is >= ~8 waves (tail quantisation < ~6 %)
         int tiles = ceil_div(M, fat ? 128 : 64) * ceil_div(N, bn);
         int splits = 1;
@@ -497,25 +428,13 @@ struct Rank {
         double *out = splits > 1 ? wpart : C;
         size_t stride = splits > 1 ? (size_t)ldc * N : 0;
         double b = splits > 1 ? 0.0 : beta;
-#define SB_SKINNY(CFG) CFG::launch(st, M, N, K, alpha, A, lda, B, ldb, b, out, ldc, splits, klen, stride)
-        if (kind == GEMM_NN && slim) {
-            SB_SKINNY(GemmNNslim);
-        } else if (kind == GEMM_NN && fat) {
+#define SB_SKINNY(CFG) CFG::launch(st, M, N, K, alpha, A, lda, B, ldb, b, out, ldc, splits, klen, stride, 1)
+        if (kind == GEMM_NN && fat) {
             if (bn == 96) SB_SKINNY(GemmNN12fat); else SB_SKINNY(GemmNN13fat);
         } else if (kind == GEMM_TN) {
-            switch (gemm_opt) {
-                case 1:  if (bn == 96) SB_SKINNY(GemmOpt<1>::TN12); else SB_SKINNY(GemmOpt<1>::TN13); break;
-                case 2:  if (bn == 96) SB_SKINNY(GemmOpt<2>::TN12); else SB_SKINNY(GemmOpt<2>::TN13); break;
-                case 3:  if (bn == 96) SB_SKINNY(GemmOpt<3>::TN12); else SB_SKINNY(GemmOpt<3>::TN13); break;
-                default: if (bn == 96) SB_SKINNY(GemmTN12); else SB_SKINNY(GemmTN13);
-            }
+            if (bn == 96) SB_SKINNY(GemmTN12); else SB_SKINNY(GemmTN13);
         } else {
-            switch (gemm_opt) {
-                case 1:  if (bn == 96) SB_SKINNY(GemmOpt<1>::NN12); else SB_SKINNY(GemmOpt<1>::NN13); break;
-                case 2:  if (bn == 96) SB_SKINNY(GemmOpt<2>::NN12); else SB_SKINNY(GemmOpt<2>::NN13); break;
-                case 3:  if (bn == 96) SB_SKINNY(GemmOpt<3>::NN12); else SB_SKINNY(GemmOpt<3>::NN13); break;
-                default: if (bn == 96) SB_SKINNY(GemmNN12); else SB_SKINNY(GemmNN13);
-            }
+            if (bn == 96) SB_SKINNY(GemmNN12); else SB_SKINNY(GemmNN13);
         }
 #undef SB_SKINNY
         stats.kernel_launches++;
@@ -625,39 +544,25 @@ struct Rank {
             f.a = pa; f.w = w; f.i = i; f.pan = pan; f.ldpan = ldpan; f.Aloc = A_loc; f.lda = ldA; f.cm = cm; f.lc_end = lc_end;
             f.nsub = std::max(1, ceil_div(m, 32 * ctas));
             f.rpc = 32 * f.nsub;
-            f.fuse_r = (fused_ll || overlap == 2) && fused_r;
-            f.pf_cols = gemv_prefetch;
-            f.pf_bulk = gemv_prefetch_bulk;
-            f.ll_sleep = ll_sleep;
-            f.ll_w2 = fused_ll == 1 || (overlap == 2 && fused_ll != 2);
-            f.pf_budget = (long long)gemv_prefetch_mb << 20;
+            f.l2_budget = (long long)l2_budget_mb << 20;
             {   // the last local columns, all of them right of the panel so that every GEMV of the panel reads them; how many
-                // of them are kept at a given column is decided in the kernel from the L2 budget (pf_budget)
+                // of them are kept at a given column is decided in the kernel from the L2 budget
                 const long long want = ((long long)gemv_resident_kb << 10) / (8ll * std::max(m, 1));
                 f.res_cols = (int)std::min<long long>(want, std::max(0, lc_end - cm.lower(i + w)));
             }
-            if (fused_even_rows) {
-                // every CTA of the grid owns rows (m = 19999 on 148 SMs: 136 rows each instead of 160 rows on 125 CTAs):
-                // the level-2 phases stream V, Y, VT from L2 at a per-SM rate, so idle SMs are lost bandwidth
-                f.rpc = std::max(8, round_up(ceil_div(m, ctas), 8));
-                f.nsub = ceil_div(f.rpc, 32);
-            }
-            f.gbar = ws.gbar; f.timers = ws.timers;
+            f.gbar = ws.gbar; f.rbar = ws.rbar; f.timers = ws.timers;
+            f.linear = gemv_linear;
             f.x = x;
             f.x.epoch = y_epoch + 1;
-            f.w2part_ll = ws.w2part_ll; f.w2_ll = ws.w2_ll; f.ypart_ll = ws.ypart_ll; f.pcol2 = ws.pcol2;
             f.kc = gemv_kc;
             size_t smem = fused_smem_bytes(w, f.nsub, f.kc);
             if (smem > PANEL_SMEM_MAX) { f.kc = FUSED_KC; smem = fused_smem_bytes(w, f.nsub, f.kc); }
             if (smem <= PANEL_SMEM_MAX) {
                 y_epoch += w;
                 SB_CUDA(cudaMemsetAsync(ws.gbar, 0, 1024 * sizeof(unsigned), st));
-                if (overlap == 2 && P > 1) SB_LAUNCH_COOP((k_panel_fused<true, true, 1024>), ctas, FUSED_THREADS, smem, st, f);
-                else if (overlap == 2)     SB_LAUNCH_COOP((k_panel_fused<false, true, 1024>), ctas, FUSED_THREADS, smem, st, f);
-                else if (P > 1 && fused_ll) SB_LAUNCH_COOP((k_panel_fused<true, true>), ctas, FUSED_THREADS, smem, st, f);
-                else if (P > 1)        SB_LAUNCH_COOP((k_panel_fused<true, false>), ctas, FUSED_THREADS, smem, st, f);
-                else if (fused_ll)     SB_LAUNCH_COOP((k_panel_fused<false, true>), ctas, FUSED_THREADS, smem, st, f);
-                else                   SB_LAUNCH_COOP((k_panel_fused<false, false>), ctas, FUSED_THREADS, smem, st, f);
+                SB_CUDA(cudaMemsetAsync(ws.rbar, 0, (FUSED_MAX_NB + 8) * sizeof(unsigned long long), st));
+                if (P > 1) SB_LAUNCH_COOP(k_panel_fused<true>, ctas, FUSED_THREADS, smem, st, f);
+                else       SB_LAUNCH_COOP(k_panel_fused<false>, ctas, FUSED_THREADS, smem, st, f);
                 stats.kernel_launches++;
                 stats.fused_panels++;
                 for (int j = 0; j < w; j++) {
@@ -803,15 +708,16 @@ struct Rank {
             if (ovl && panel >= PANEL_RING) SB_CUDA(cudaStreamWaitEvent(st, ev_side[slot], 0));
             if (lvl >= 1) SB_CUDA(cudaEventRecord(phase_event(2 + 6 * panel + 0), st));
             const int pl0 = cm.lower(i), pl1 = cm.lower(i + w);
-            // overlap == 2: the deferred GEMMs share the SMs with the (64-register) panel kernel, which keeps all of them
-            const int ctas = (ovl && overlap != 2 && side_pending > 0) ? panel_ctas(m, w, n, qrows, i) : fused_ctas;
+            const int ctas = (ovl && side_pending > 0) ? panel_ctas(m, w, n, qrows, i) : fused_ctas;
             if (P == 1) {
                 panel_factor(cm, i, end, w, A, ldA, A + (size_t)i * ldA + i + 1, ldA, V, ws.Y, VT, ld, ctas);
             } else {
                 // gather the panel on every rank; the first barrier protects Pan and Wx of the previous panel
                 barrier();
-                if (pl1 > pl0) {
-                    SB_LAUNCH(k_panel_push, dim3(ceil_div(m, 1024), pl1 - pl0), 256, 0, st, cm, i, pl0, m, A, ldA, panp, al.ldv);
+                // (the column right of the panel travels too: the row owners add it to the linear GEMV of the last column)
+                const int pl1x = cm.lower(std::min(i + w + 1, end));
+                if (pl1x > pl0) {
+                    SB_LAUNCH(k_panel_push, dim3(ceil_div(m, 1024), pl1x - pl0), 256, 0, st, cm, i, pl0, m, A, ldA, panp, al.ldv);
                     stats.kernel_launches++;
                 }
                 barrier();
@@ -884,11 +790,6 @@ struct Rank {
         SB_CUDA(cudaStreamSynchronize(st));
         SB_CUDA(cudaStreamSynchronize(side));
         SB_CUDA(cudaGetLastError());
-        if (P == 1 && (fused_ll || overlap == 2)) {
-            unsigned status = 0;
-            SB_CUDA(cudaMemcpy(&status, ws.counter + 3, sizeof(status), cudaMemcpyDeviceToHost));
-            if (status != 0) fatal("a wait inside the persistent panel kernel timed out", __FILE__, __LINE__);
-        }
         if (P > 1) {
             unsigned status = 0;
             SB_CUDA(cudaMemcpy(&status, at<unsigned>(g, al.off_status), sizeof(status), cudaMemcpyDeviceToHost));

@@ -13,16 +13,18 @@
 //   A   finish column j-1 (V, Y, VT columns, H entries of the panel column), right-update column j,
 //       partial w2 = VT^T p'                                            -> grid barrier
 //   A'  w2 = sum of the partials (one warp per entry, fixed order)       -> grid barrier
-//   R   p'' = p' - V w2, partial ||x||^2 and z = V^T x                   -> grid barrier
-//   R'  DLARFG scalars (every CTA, identical), s = scale*z + V(j,:)  (one warp per entry)
+//   R   p'' = p' - V w2, partial ||x||^2 and z = V^T x                   -> grid barrier (+ vote: linear column?)
+//   R'  DLARFG scalars, s = scale*z + V(j,:)  (one warp per entry). Linear column (the usual case): look-ahead warps
+//       only, off the critical path -- the GEMV warps are already streaming against the unscaled x (FusedArgs::linear)
 //   G   trailing GEMV partials, perfectly balanced 1-D split of (row block, column) items over all
 //       128-thread groups of the grid                                    -> grid barrier
-// Row ownership: CTA b owns rows [b*rpc, (b+1)*rpc) of the panel in every phase except G (rpc = 32*nsub, or --
-// STARNEIG_B200_FUSED_EVEN_ROWS -- the smallest multiple of 8 that spreads the rows over all CTAs), so V, Y,
+// Row ownership: CTA b owns rows [b*rpc, (b+1)*rpc) of the panel in every phase except G (rpc = 32*nsub), so V, Y,
 // VT columns are written and re-read by the same SM; everything that crosses CTAs inside the launch (pcol, s,
 // w2, partials, scalars, row j of V) is read with ld.global.cg.
-// Variant LLRED (STARNEIG_B200_FUSED_LL, see the comment at the kernel): the barriers after A, A' and G are
-// replaced by self-validating LL entries (w2 partials, w2, GEMV partials); only the barrier after R remains.
+// (Round 1 carried opt-in variants of this kernel -- LL-entry reductions instead of grid barriers, a single-pass phase R,
+// rows spread over all CTAs, L2 prefetch of the GEMV's head, a 64-register build for co-resident DMMA tiles. All of them
+// were timed on B200 at n = 6000 and n = 20000 and lost to this kernel (profiles/r2_v1_switch_sweep_n20000.txt,
+// profiles/r1_s8_variant_smoke*_n6000.log); they were removed in round 2.)
 #pragma once
 #include "panel.cuh"
 
@@ -46,26 +48,26 @@ struct FusedArgs {
     ColMap cm;
     int lc_end;                 // local index one past the last local column of the reduced block
     int nsub;                   // 32-row sub-tiles per CTA
-    int rpc;                    // rows owned by a CTA (<= 32 * nsub; the last sub-tile of a CTA may be partial)
-    int fuse_r;                 // LLRED only: phase R streams the CTA's slab of V once instead of twice
+    int rpc;                    // rows owned by a CTA (32 * nsub)
     int kc;                     // columns of v a GEMV group stages in shared memory at a time (each refill drains its load pipeline)
-    int pf_cols;                // columns of its first GEMV item chunk that a group prefetches into L2 ahead of phase G (0: off)
-    int pf_bulk;                // 1: the prefetch uses one bulk (TMA) instruction per column and group instead of 16 line prefetches
-    int ll_w2;                  // LLRED: 1 = the w2 reduction travels as LL entries too; 0 = only the GEMV partials do, w2 keeps its
-                                // two grid barriers (first B200 timing, n = 6000: the LL-polled w2 path is ~2.8 us per column SLOWER
-                                // than barrier-reduce-barrier, the LL GEMV partials ~1.5 us per column faster)
-    int ll_sleep;               // LLRED: nanoseconds the polling lanes sleep between polls (0: spin)
     int res_cols;               // at most this many local columns (the last ones: they are part of every GEMV of the panel) are read
-                                // with the "keep in L2" policy; at column j as many of them as pf_budget leaves next to V, Y, VT
+                                // with the "keep in L2" policy; at column j as many of them as l2_budget leaves next to V, Y, VT
                                 // of the panel so far (24 m j bytes). 0: everything streams
-    long long pf_budget;        // bytes of L2 that V, Y, VT (3 * 8 * m * j at column j) and the prefetched data may fill together
+    long long l2_budget;        // bytes of L2 that V, Y, VT (3 * 8 * m * j at column j) and the resident columns may fill together
     unsigned *gbar;             // grid barrier counter, zero at launch
+    unsigned long long *rbar;   // one arrival word per panel column for the barrier that ends phase R, zero at launch: arrivals in
+                                // the low 32 bits, and above them how many CTAs saw a medium-range (bits 32-47) / a huge (bits
+                                // 48-63) entry in their part of x -- the grid-wide vote that decides `linear` for the column
+    int linear;                 // 1: GEMV linearity. v = (1, scale x), so A v = A(:, c+1) + scale (A(:, c+2:) x): the GEMV
+                                // streams against the UNSCALED x as soon as x is complete (the barrier after phase R) while the
+                                // look-ahead warps alone derive beta, tau, scale and s = V^T v; the row owner forms
+                                // y(r) = A(r, c+1) + scale g(r) when it sums the partials. Takes phase R' (two dependent L2
+                                // round trips, a division and a square root per column) off the critical path. Only for columns
+                                // whose x has a medium-range entry and no huge one (so that neither the DLARFG rescaling branch
+                                // nor an overflow of A x can occur); other columns (zero x: tau = 0, denormal or huge
+                                // entries) take the sequential path.
     unsigned long long *timers; // ns on CTA 0: [0] GEMV phases, [1] whole kernel, [2..5] phases A, A', R, R' (each incl. its barrier)
-    Xchg x;                     // x.epoch = sequence number of the panel's first column (tags of all LL entries); rest DIST only
-    uint4 *w2part_ll;           // LLRED: PANEL_LDB x ldt self-validating per-CTA partials of w2 = VT^T p'
-    uint4 *w2_ll;               // LLRED: ldt self-validating entries of w2
-    uint4 *ypart_ll;            // LLRED: the GEMV partials (layout of ypart) as self-validating entries
-    double *pcol2;              // LLRED: second buffer of the column being reduced (columns alternate between pcol and pcol2)
+    Xchg x;                     // DIST: x.epoch = sequence number of the panel's first column (tags of the LL entries of the exchange)
 };
 
 // All CTAs of the (cooperative, co-resident) grid: one arrival counter (red.release) that thread 0 of every CTA
@@ -90,19 +92,6 @@ __device__ __forceinline__ void ll_store(uint4 *dst, double v, unsigned tag)
     const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
     st_volatile_v4(dst, make_uint4((unsigned)bits, tag, (unsigned)(bits >> 32), tag));
 }
-__device__ __forceinline__ double ll_load(const uint4 *src, unsigned tag, unsigned *status)
-{
-    uint4 e;
-    long long t0 = 0;
-    for (;;) {
-        e = ld_volatile_v4(src);
-        if (e.y == tag && e.w == tag) break;
-        if (t0 == 0) { t0 = clock64(); if (*(volatile unsigned *)status != 0u) break; }
-        else if (clock64() - t0 > 8000000000ll) { atomicExch(status, 2u); break; }
-    }
-    return __longlong_as_double((long long)(((unsigned long long)e.z << 32) | e.x));
-}
-
 // `count` (<= N) LL entries p[u * stride], polled TOGETHER until every one of them carries `tag`: a poll round costs one L2
 // round trip whatever the number of entries (polling them one after the other costs one round trip EACH -- the first B200
 // timing of the LL variant lost ~3 us per column that way). Entries u >= count give 0.
@@ -139,22 +128,6 @@ __device__ __forceinline__ double sum_over_ctas(const double *part, size_t ldt, 
             const int bb = b0 + lane + 32 * u;
             x[u] = bb < nblk ? __ldcg(part + (size_t)bb * ldt) : 0.0;
         }
-        acc += ((x[0] + x[1]) + (x[2] + x[3])) + x[4];
-    }
-    return warp_sum(acc);
-}
-
-// the same over self-validating LL entries (tag = sequence number of the column): no grid barrier between the CTAs that
-// write the partials and the warp that sums them -- the reader polls until every entry carries the tag
-__device__ __forceinline__ double sum_over_ctas_ll(const uint4 *part, size_t ldt, int nblk, int lane, unsigned tag, unsigned *status)
-{
-    double acc = 0.0;
-    for (int b0 = 0; b0 < nblk; b0 += 160) {
-        // this lane's entries b0 + lane + 32 u (u < 5) lie 32 * ldt apart
-        const int first = b0 + lane;
-        const int count = first < nblk ? min(5, (nblk - first + 31) / 32) : 0;
-        double x[5];
-        ll_load_batch<5>(part + (size_t)min(first, nblk - 1) * ldt, 32 * ldt, count, tag, status, x);
         acc += ((x[0] + x[1]) + (x[2] + x[3])) + x[4];
     }
     return warp_sum(acc);
@@ -207,44 +180,6 @@ __device__ __forceinline__ double sum_partials(const double *p, int ld, int S)
     return e;
 }
 
-// waits, with back-off, until an LL entry carries `tag` (used by ONE lane per warp before its rows are summed, so that
-// thousands of threads do not hammer L2 with polls while the stragglers of the GEMV are still streaming)
-__device__ __forceinline__ void ll_wait(const uint4 *src, unsigned tag, unsigned *status, int sleep_ns = 200)
-{
-    long long t0 = 0;
-    for (;;) {
-        const uint4 e = ld_volatile_v4(src);
-        if (e.y == tag && e.w == tag) return;
-        if (t0 == 0) { t0 = clock64(); if (*(volatile unsigned *)status != 0u) return; }
-        else if (clock64() - t0 > 8000000000ll) { atomicExch(status, 2u); return; }
-        if (sleep_ns > 0) __nanosleep(sleep_ns);
-    }
-}
-
-// the same over self-validating LL entries (GEMV partials of a column, tag = its sequence number): the row owner polls
-// the partials of its rows instead of waiting at a grid barrier for ALL groups of the GEMV
-__device__ __forceinline__ double sum_partials_ll(const uint4 *p, int ld, int S, unsigned tag, unsigned *status)
-{
-    // same order of additions as sum_partials; every batch is polled as a whole
-    double e = 0.0;
-    int z = 0;
-    double x[8];
-    for (; z + 8 <= S; z += 8) {
-        ll_load_batch<8>(p + (size_t)z * ld, (size_t)ld, 8, tag, status, x);
-        e += ((x[0] + x[1]) + (x[2] + x[3])) + ((x[4] + x[5]) + (x[6] + x[7]));
-    }
-    if (z < S) {
-        const int rem = S - z;          // 1 .. 7: one more poll round for all of them
-        ll_load_batch<8>(p + (size_t)z * ld, (size_t)ld, rem, tag, status, x);
-        const int u0 = rem >= 4 ? 4 : 0;
-        if (rem >= 4) e += (x[0] + x[1]) + (x[2] + x[3]);
-#pragma unroll
-        for (int q = 0; q < 8; q++)
-            if (q >= u0 && q < rem) e += x[q];
-    }
-    return e;
-}
-
 // Column-wise dots of one CTA: out[t] = sum over the CTA's rows of M(r, t) * p(r) for t in [tb, tb+NC), t < tmax.
 // One warp; NC columns x NS sub-tiles = 32 independent loads are in flight per lane. p(r) comes from shared
 // memory (pv[sub*32 + lane], zero for rows >= m). Result: see transpose_reduce8 / transpose_reduce32.
@@ -291,8 +226,7 @@ __device__ __forceinline__ double transpose_reduce16(double (&v)[16], int lane)
 
 // partial column dots of the CTA -> colpart[b][t], t < tmax; warps [0, T) share the column batches
 __device__ __forceinline__ void coldots_all(const double *__restrict__ M, int ld, int tmax, int row0, int m, int nsub,
-                                            const double *pv, int wp, int T, int lane, double *out,
-                                            uint4 *out_ll = nullptr, unsigned tag = 0u)
+                                            const double *pv, int wp, int T, int lane, double *out)
 {
     if (nsub >= 3) {
         for (int tb = 8 * wp; tb < tmax; tb += 8 * T) {
@@ -300,14 +234,14 @@ __device__ __forceinline__ void coldots_all(const double *__restrict__ M, int ld
             coldots<8, 4>(M, ld, tb, tmax, row0, m, nsub, pv, lane, acc);
             const double xx = transpose_reduce8(acc, lane);
             const int t = tb + (lane >> 2);
-            if ((lane & 3) == 0 && t < tmax) { if (out_ll) ll_store(out_ll + t, xx, tag); else out[t] = xx; }
+            if ((lane & 3) == 0 && t < tmax) out[t] = xx;
         }
     } else {
         for (int tb = 16 * wp; tb < tmax; tb += 16 * T) {
             double acc[16];
             coldots<16, 2>(M, ld, tb, tmax, row0, m, nsub, pv, lane, acc);
             const double xx = transpose_reduce16(acc, lane);
-            if (lane < 16 && tb + lane < tmax) { if (out_ll) ll_store(out_ll + tb + lane, xx, tag); else out[tb + lane] = xx; }
+            if (lane < 16 && tb + lane < tmax) out[tb + lane] = xx;
         }
     }
 }
@@ -403,91 +337,12 @@ __device__ __noinline__ double fused_rescale_x(double *pcol, const double *V, in
     return t_first < j ? sum_over_ctas(colpart + t_first, ldt, nblk, lane) : 0.0;
 }
 
-// Phase R of the persistent kernel with ONE pass over the CTA's slab of V instead of two (variant LLRED + fuse_r): a warp
-// keeps its 32 x 16 tile in registers between d = V w2 (row-wise, summed over the column groups through shared memory)
-// and z = V^T x (column-wise, transpose-reduce over the 32 rows). A round covers SPR complete sub-tiles (all NW2 column
-// groups each); needs j <= 16 * FUSED_WARPS. Writes p'' (pc_cur, the H entries above the sub-diagonal, alpha), x (pv), the
-// per-warp sums of squares (sqred) and the CTA's partial of z (zpart). Out of line: its register tile must not compete
-// with the rest of the kernel for the 96 registers of a thread.
-__device__ __noinline__ void fused_reflector_pass(const double *V, int ld, int j, int row0, int row_end, int nsub, double *pc_cur,
-                                                  double *acol, double *alpha_out, const double *w2_sh, double *red, double *pv,
-                                                  double *sqred, double *zpart)
+// The kernel. 640 threads x 96 registers: the CTA owns the register file of its SM (one CTA per SM, cooperative launch).
+template <bool DIST>
+__global__ void __launch_bounds__(FUSED_THREADS, 1) k_panel_fused(FusedArgs f)
 {
-    const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
-    const int NW2 = (j + 15) >> 4;
-    const int SPR = max(1, min(nsub, FUSED_WARPS / NW2));
-    double *const zred = red + (size_t)SPR * NW2 * 32;
-    const int g = wp % NW2, so = wp / NW2, t0 = g * 16;
-    const bool tile_warp = wp < NW2 * SPR;
-    double zl = 0.0;
-    SumSq sq;
-    sq.clear();
-    for (int sub0 = 0; sub0 < nsub; sub0 += SPR) {
-        const int sub = sub0 + so;
-        const bool active = tile_warp && sub < nsub;
-        const int r = row0 + sub * 32 + lane;
-        const bool valid = active && r < row_end;
-        double v16[16];
-        double pold = 0.0;
-        if (active) {
-            const double *Vr = V + (size_t)t0 * ld + r;
-#pragma unroll
-            for (int q = 0; q < 16; q++) v16[q] = (valid && t0 + q < j) ? Vr[(size_t)q * ld] : 0.0;
-            if (valid) pold = pc_cur[r];
-            double d = 0.0;
-#pragma unroll
-            for (int q = 0; q < 16; q++) d = fma(v16[q], w2_sh[min(t0 + q, j - 1)], d);
-            red[((size_t)so * NW2 + g) * 32 + lane] = d;
-        }
-        __syncthreads();
-        if (active) {
-            double D = 0.0;
-            for (int q = 0; q < NW2; q++) D += red[((size_t)so * NW2 + q) * 32 + lane];
-            const double pp = pold - D;
-            const double xx = (valid && r > j) ? pp : 0.0;
-            if (g == 0) {       // one warp per sub-tile stores the column and sums the squares
-                if (valid) {
-                    pc_cur[r] = pp;
-                    if (r < j) acol[r] = pp;            // final entries of H above the sub-diagonal
-                    if (r == j) *alpha_out = pp;
-                }
-                sq.add(xx);
-                pv[sub * 32 + lane] = xx;
-            }
-#pragma unroll
-            for (int q = 0; q < 16; q++) v16[q] *= xx;
-            zl += transpose_reduce16(v16, lane);        // lane l: sum over the tile's rows of V(r, t0 + (l & 15)) x(r)
-        }
-        __syncthreads();        // `red` is reused by the next round
-    }
-    if (tile_warp && lane < 16) zred[((size_t)so * NW2 + g) * 16 + lane] = zl;
-    sq.med = warp_sum(sq.med);
-    if (__any_sync(0xffffffffu, sq.big != 0.0 || sq.sml != 0.0)) { sq.big = warp_sum(sq.big); sq.sml = warp_sum(sq.sml); }
-    if (lane == 0) { sqred[wp] = sq.med; sqred[FUSED_WARPS + wp] = sq.big; sqred[2 * FUSED_WARPS + wp] = sq.sml; }
-    __syncthreads();
-    if (wp < NW2 && lane < 16 && t0 + lane < j) {
-        double zsum = 0.0;
-        for (int q = 0; q < SPR; q++) zsum += zred[((size_t)q * NW2 + g) * 16 + lane];
-        zpart[t0 + lane] = zsum;
-    }
-}
-
-// LLRED: one grid barrier per column instead of four. (1) The reduction w2 = sum over CTAs of VT^T p' travels as
-// self-validating LL entries (partials -> reducing warps -> every CTA): no barriers around phase A'. (2) The GEMV
-// partials are LL entries too: the owner of a row polls the partials of its rows instead of waiting for ALL groups of
-// the GEMV at a grid barrier, so a CTA whose producers are done starts the next column while the slowest GEMV groups
-// are still streaming. What the dropped barriers also ordered is handled explicitly: the column being reduced
-// alternates between two buffers (a fast CTA writes p' of column j+1 while a slow one still forms v from p'' of column
-// j), and tau / beta / scale of the previous column come from the CTA's own shared-memory copy. The barrier after
-// phase R stays (the GEMV reads p'' of all rows). Opt-in (STARNEIG_B200_FUSED_LL=1) until timed on a B200.
-// MAXT: the thread count the register allocation is sized for. FUSED_THREADS (640): 96 registers per thread, the CTA owns
-// the register file of its SM. 1024: 64 registers per thread (the launch still uses 640 threads), which leaves 24576
-// registers of the SM to a co-resident 128-thread DMMA CTA of the deferred updates (engine.cuh, overlap with slim tiles).
-template <bool DIST, bool LLRED, int MAXT = FUSED_THREADS>
-__global__ void __launch_bounds__(MAXT, 1) k_panel_fused(FusedArgs f)
-{
-    // 16-byte loads in flight per GEMV thread: U columns being accumulated + U being fetched (64-register variant: 4 + 4)
-    constexpr int GEMV_U = MAXT > FUSED_THREADS ? 4 : 8;
+    // 16-byte loads in flight per GEMV thread: U columns being accumulated + U being fetched
+    constexpr int GEMV_U = 8;
     SB_DYNAMIC_SMEM(double, sh);
     const PanelArgs &a = f.a;
     const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
@@ -502,6 +357,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_panel_fused(FusedArgs f)
     double *const vs_all = sh + L.vs, *const s_sh = sh + L.s, *const vrow_sh = sh + L.vrow, *const w2_sh = sh + L.w2;
     double *const red = sh + L.red, *const pv = sh + L.pv, *const ysm = sh + L.ysm, *const sqred = sh + L.sqred;
     unsigned gen = 0, gen2 = 0;
+    bool lin = false, lin_prev = false;     // the GEMV of this / of the previous column runs (ran) against the unscaled x
     unsigned *const bar2 = f.gbar + 32;         // arrival counter "s of this column is complete" (look-ahead warps only)
     unsigned long long t_gemv = 0, t_begin = 0, t_ph[4] = {0, 0, 0, 0}, t_mark = 0;
     const bool timer = (b == 0 && tid == 0);
@@ -511,8 +367,14 @@ __global__ void __launch_bounds__(MAXT, 1) k_panel_fused(FusedArgs f)
     // GEMV geometry that does not depend on the column
     GemvSplit gs;
     {
-        const double *base = f.Aloc + (size_t)f.i + 1;      // parity of the row offset decides the alignment
-        gs.skip = (int)(((uintptr_t)base / sizeof(double)) & 1);
+        // Row blocks start on a 128-byte line of the matrix (up to 15 rows above the panel's first row; those rows are
+        // read and dropped), so that a warp's 512 contiguous bytes of a column are four whole lines: measured on B200,
+        // blocks that start mid-line (panels at i = 8 mod 16, every other panel of the default width 312) stream 4 % slower.
+        // Needs columns that all start on a line (128-byte aligned storage, leading dimension a multiple of 16);
+        // otherwise only the 16-byte alignment of the loads is kept (parity of the row offset).
+        const double *base = f.Aloc + (size_t)f.i + 1;
+        const bool lines = ((uintptr_t)f.Aloc & 127) == 0 && (f.lda & 15) == 0;
+        gs.skip = (int)(((uintptr_t)base / sizeof(double)) & (lines ? 15 : 1));
         gs.RB = (m + gs.skip + 255) >> 8;
     }
     double *const scal_sh = sh + L.scal;    // tau, beta, scale of the current column
@@ -522,43 +384,11 @@ __global__ void __launch_bounds__(MAXT, 1) k_panel_fused(FusedArgs f)
 
     for (int j = 0; j <= f.w; j++) {
         const int jm1 = j - 1;
+        lin_prev = lin;
         double *acol = f.pan + (size_t)j * f.ldpan;
         const int NW = max(1, (j + 31) >> 5);
-        // the column being reduced: p', then p'' (LLRED: columns alternate between two buffers)
-        double *const pc_cur = (LLRED && (j & 1)) ? f.pcol2 : a.pcol;
-        const double *const pc_prev = (LLRED && !(j & 1)) ? f.pcol2 : a.pcol;
-
-        if (f.pf_cols > 0 && j < f.w && wp < FUSED_GEMV_WARPS) {
-            // HBM is idle while the level-2 phases of this column work out of L2 (~20 us): every GEMV group pulls the
-            // first pf_cols columns of its first (row block, column range) chunk of THIS column's GEMV into L2 now, so
-            // that phase G starts from L2 instead of waiting for HBM. A hint only: nothing depends on it.
-            const int lc0 = f.cm.lower(f.i + j + 1), nloc = f.lc_end - lc0;
-            const long long items = (long long)gs.RB * nloc;
-            const int per = max(FUSED_MINSEG, (int)((items + G * FUSED_VB - 1) / (G * FUSED_VB)));
-            const int vb = tid >> 7, vt = tid & 127;
-            const long long it = (long long)(vb * G + b) * per;
-            if (it < items) {
-                const int rb = (int)(it / nloc);
-                const int cbeg = (int)(it - (long long)rb * nloc);
-                const int cend = (int)min((long long)nloc, cbeg + min((long long)per, items - it));
-                // leave L2 to the level-2 working set first: V, Y, VT of the panel so far
-                const long long room = (f.pf_budget - 24ll * m * j) / (2048ll * G * FUSED_VB);
-                const int kend = min(cend, cbeg + (int)max(0ll, min((long long)f.pf_cols, room)));
-                if (f.pf_bulk) {
-                    // one bulk prefetch per column: the 256 rows of the row block (fewer at the matrix end), 16-byte granular
-                    const int rows = min(256, m + gs.skip - rb * 256) & ~1;
-                    const double *Ap = f.Aloc + (size_t)lc0 * f.lda + f.i + 1 - gs.skip + rb * 256;
-                    if (rows > 0)
-                        for (int k = cbeg + vt; k < kend; k += 128) prefetch_l2_bulk(Ap + (size_t)k * f.lda, (unsigned)rows * 8u);
-                } else {
-                const int rp = rb * 256 + (vt & 15) * 16;        // 16 lines of 128 bytes cover the 256 rows of the block
-                if (rp < m + gs.skip) {
-                    const double *Ap = f.Aloc + (size_t)lc0 * f.lda + f.i + 1 - gs.skip + rp;
-                    for (int k = cbeg + (vt >> 4); k < kend; k += 8) prefetch_l2(Ap + (size_t)k * f.lda);
-                }
-                }
-            }
-        }
+        double *const pc_cur = a.pcol;              // the column being reduced: p', then p''
+        const double *const pc_prev = a.pcol;
 
         if (j > 0) {
             // ================= phase A: finish column j-1, start column j =================
@@ -566,16 +396,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_panel_fused(FusedArgs f)
             // GEMV of column j-1 was streaming (`red`); what is left on the critical path is y itself.
             const int NWa = max(1, (jm1 + 31) >> 5);
             const bool do_update = j < f.w;
-            // LLRED: the epilogue's inputs that do not depend on the GEMV (p'' of column j-1 and column j of the panel, own
-            // rows) are fetched before the wait for the GEMV partials instead of after it (one L2 round trip less)
-            double pre_p = 0.0, pre_a = 0.0;
-            if (LLRED && wp < nsub) {
-                const int r = row0 + wp * 32 + lane;
-                if (r < row_end) { pre_p = pc_prev[r]; pre_a = do_update ? acol[r] : 0.0; }
-            }
-            // LLRED: no grid barrier since R' of column j-1, where every CTA derived these scalars itself (scal_sh)
-            const double tau = LLRED ? scal_sh[0] : __ldcg(&a.scal[jm1].tau), beta_prev = LLRED ? scal_sh[1] : __ldcg(&a.scal[jm1].beta),
-                         scale_prev = LLRED ? scal_sh[2] : __ldcg(&a.scal[jm1].scale);
+            const double tau = __ldcg(&a.scal[jm1].tau), beta_prev = __ldcg(&a.scal[jm1].beta), scale_prev = __ldcg(&a.scal[jm1].scale);
             double *acol_prev = f.pan + (size_t)jm1 * f.ldpan;
             {
                 // y(r) of the CTA's rows: sum of the local GEMV partials of column j-1 (fixed order); on P GPUs the
@@ -586,20 +407,13 @@ __global__ void __launch_bounds__(MAXT, 1) k_panel_fused(FusedArgs f)
                 gp.per = max(FUSED_MINSEG, (int)(((long long)gs.RB * nloc_prev + G * FUSED_VB - 1) / (G * FUSED_VB)));
                 const unsigned epoch = f.x.epoch + jm1;
                 const int par = epoch & 1;
-                if (LLRED && nloc_prev > 0) {
-                    // one lane per warp waits for the partial of the warp's first row that is written last (the group
-                    // that first finishes the previous row block): the others are then there or about to be
-                    const int rr0 = tid & ~31;
-                    if (lane == 0 && rr0 < rows_here) ll_wait(f.ypart_ll + row0 + rr0, epoch, f.x.status, f.ll_sleep);
-                    __syncwarp();
-                }
                 for (int rr = tid; rr < rows_here; rr += FUSED_THREADS) {
                     const int r = row0 + rr;
                     const int rb = (r + gs.skip) >> 8;
                     double sum = 0.0;
                     if (nloc_prev > 0) {
                         const int S = gp.last_group(rb) - gp.first_group(rb) + 1;
-                        sum = LLRED ? sum_partials_ll(f.ypart_ll + r, a.ldp, S, epoch, f.x.status) : sum_partials(a.ypart + r, a.ldp, S);
+                        sum = sum_partials(a.ypart + r, a.ldp, S);
                     }
                     if (DIST) {
                         // all-reduce over the ranks: the rank's sum goes to every inbox (the own one included, so that all
@@ -625,10 +439,13 @@ __global__ void __launch_bounds__(MAXT, 1) k_panel_fused(FusedArgs f)
                 const bool valid = r < row_end;
                 double pp = 0.0;
                 if (valid) {
-                    const bool pre = LLRED && sub == wp;
-                    const double pprev = pre ? pre_p : pc_prev[r];
-                    const double ac = pre ? pre_a : (do_update ? acol[r] : 0.0);
-                    const double D3 = ysm[sub * 32 + lane];
+                    const double pprev = pc_prev[r];
+                    const double ac = do_update ? acol[r] : 0.0;
+                    // the GEMV of column j-1 was linear: its partials are g = A(:, c+1:) x and column j of the panel (not
+                    // yet updated) is A(:, c), the column that belongs to the leading one of v
+                    double D3 = ysm[sub * 32 + lane];
+                    // (j == w: column i + w, the first one right of the panel; it exists -- the last panel ends at end - 2)
+                    if (lin_prev) D3 = fma(scale_prev, D3, do_update ? ac : acol[r]);
                     const double *rd = red + (size_t)sub * 3 * NWa * 32 + lane;
                     double D0 = 0.0, D1 = 0.0, D2 = 0.0;
                     for (int q = 0; q < NWa; q++) { D0 += rd[q * 32]; D1 += rd[(NWa + q) * 32]; D2 += rd[(2 * NWa + q) * 32]; }
@@ -651,43 +468,23 @@ __global__ void __launch_bounds__(MAXT, 1) k_panel_fused(FusedArgs f)
             __syncthreads();
 
             // ---- w2part[t] = sum over the CTA's rows of VT(r,t) * p'(r), t < j (column j-1 was stored just above)
-            const unsigned tag = f.x.epoch + j;
-            const bool llw2 = LLRED && f.ll_w2;
-            // LLRED without LL entries for w2: the per-CTA partials of w2 still need a buffer of their own -- with no grid
-            // barrier after the GEMV a fast CTA is here while a slow one still reads the z partials of the previous
-            // column from colpart in its phase R'. (The LL buffer is idle in that mode: used as plain doubles.)
-            double *const w2part = LLRED ? (double *)f.w2part_ll : a.colpart;
-            coldots_all(a.VT, ld, j, row0, row_end, nsub, pv, wp, FUSED_WARPS, lane, w2part + (size_t)b * a.ldt,
-                        llw2 ? f.w2part_ll + (size_t)b * a.ldt : nullptr, tag);
-            if (!llw2) grid_barrier(f.gbar, gen);
+            coldots_all(a.VT, ld, j, row0, row_end, nsub, pv, wp, FUSED_WARPS, lane, a.colpart + (size_t)b * a.ldt);
+            grid_barrier(f.gbar, gen);
             SB_PHASE_MARK(0);
 
             // ================= A': w2[t] = sum over CTAs (one warp per entry) =================
             for (int t = b * FUSED_WARPS + wp; t < j; t += G * FUSED_WARPS) {
-                const double acc = llw2 ? sum_over_ctas_ll(f.w2part_ll + t, a.ldt, nblk, lane, tag, f.x.status)
-                                        : sum_over_ctas(w2part + t, a.ldt, nblk, lane);
-                if (lane == 0) { if (llw2) ll_store(f.w2_ll + t, acc, tag); else a.w2[t] = acc; }
+                const double acc = sum_over_ctas(a.colpart + t, a.ldt, nblk, lane);
+                if (lane == 0) a.w2[t] = acc;
             }
-            if (!llw2) grid_barrier(f.gbar, gen);
+            grid_barrier(f.gbar, gen);
             SB_PHASE_MARK(1);
         }
 
         // ================= phase R: p'' = p' - V w2; ||x||^2, z = V^T x =================
         {
-            const bool llw2_r = LLRED && f.ll_w2;
-            if (llw2_r && j > 0) {      // one polling lane per warp (see phase A)
-                if (lane == 0 && (tid & ~31) < j) ll_wait(f.w2_ll + (tid & ~31), f.x.epoch + j, f.x.status, f.ll_sleep);
-                __syncwarp();
-            }
-            for (int t = tid; t < j; t += FUSED_THREADS)
-                w2_sh[t] = llw2_r ? ll_load(f.w2_ll + t, f.x.epoch + j, f.x.status) : __ldcg(a.w2 + t);
+            for (int t = tid; t < j; t += FUSED_THREADS) w2_sh[t] = __ldcg(a.w2 + t);
             __syncthreads();
-            // one pass over V needs a warp per 16-column group of a sub-tile: columns j <= 16 * FUSED_WARPS
-            const bool fuse_r = LLRED && f.fuse_r && j > 0 && j <= 16 * FUSED_WARPS;
-            if (fuse_r) {
-                fused_reflector_pass(a.V, ld, j, row0, row_end, nsub, pc_cur, acol, &a.scal[j].alpha, w2_sh, red, pv, sqred,
-                                     a.colpart + (size_t)b * a.ldt);
-            } else {
             if (j > 0) {
                 // d(r) = V(r, :j) w2: 32x32 tiles, 32 loads in flight per lane
                 for (int item = wp; item < nsub * NW; item += FUSED_WARPS) {
@@ -732,20 +529,36 @@ __global__ void __launch_bounds__(MAXT, 1) k_panel_fused(FusedArgs f)
             if (lane == 0) { sqred[wp] = sq.med; sqred[FUSED_WARPS + wp] = sq.big; sqred[2 * FUSED_WARPS + wp] = sq.sml; }
             __syncthreads();
             if (j > 0) coldots_all(a.V, ld, j, row0, row_end, nsub, pv, wp, FUSED_WARPS, lane, a.colpart + (size_t)b * a.ldt);
-            }
             if (tid < 3) {
                 double sum = 0.0;
                 for (int q = 0; q < FUSED_WARPS; q++) sum += sqred[tid * FUSED_WARPS + q];
                 a.sqpart[tid * PANEL_LDB + b] = sum;
             }
-            grid_barrier(f.gbar, gen);
+            // grid barrier on the column's own arrival word; the arrivals carry the vote on `linear`
+            __syncthreads();
+            if (tid == 0) {
+                bool any_med = false, any_big = false;
+                for (int q = 0; q < FUSED_WARPS; q++) {
+                    any_med = any_med || !(sqred[q] == 0.0);                      // NaN counts
+                    any_big = any_big || !(sqred[FUSED_WARPS + q] == 0.0);
+                }
+                red_release_gpu_add_u64(f.rbar + j, 1ull | (any_med ? 1ull << 32 : 0ull) | (any_big ? 1ull << 48 : 0ull));
+                unsigned long long seen;
+                while ((unsigned)((seen = ld_acquire_gpu_u64(f.rbar + j)) & 0xffffffffull) < (unsigned)G) { }
+                scal_sh[3] = (f.linear && ((seen >> 32) & 0xffffull) != 0ull && (seen >> 48) == 0ull) ? 1.0 : 0.0;
+            }
+            __syncthreads();
+            lin = scal_sh[3] != 0.0;
             SB_PHASE_MARK(2);
         }
 
         // ================= R': DLARFG scalars (every warp, identical), s = scale*z + V(j,:) =================
-        {
+        // `lin`: only the look-ahead warps run it (the GEMV warps are already streaming A against the unscaled x)
+        if (!lin || wp >= FUSED_GEMV_WARPS) {
             // every warp derives the scalars itself (no CTA-wide wait); the z entries it owns are loaded alongside
-            const int t_first = b * FUSED_WARPS + wp;
+            const int nwr = lin ? FUSED_WARPS - FUSED_GEMV_WARPS : FUSED_WARPS;
+            const int wpr = lin ? wp - FUSED_GEMV_WARPS : wp;
+            const int t_first = b * nwr + wpr;
             double zsum = 0.0, vjt = 0.0;
             if (t_first < j) { zsum = sum_over_ctas(a.colpart + t_first, a.ldt, nblk, lane); vjt = __ldcg(a.V + (size_t)t_first * ld + j); }
             double ssq[3];
@@ -753,29 +566,31 @@ __global__ void __launch_bounds__(MAXT, 1) k_panel_fused(FusedArgs f)
             const double alpha = __ldcg(&a.scal[j].alpha);
             const Reflector rf = dlarfg_scalars(alpha, ssq[0], ssq[1], ssq[2], m - j > 1);
             const double tau = rf.tau, beta = rf.beta, scale = rf.scale;
-            if (tid == 0) {
+            if (wpr == 0 && lane == 0) {
                 scal_sh[0] = tau; scal_sh[1] = beta; scal_sh[2] = scale;
                 if (b == 0) { a.scal[j].tau = tau; a.scal[j].beta = beta; a.scal[j].scale = scale; }
             }
-            if (rf.xmul != 1.0) {       // denormal-range column
+            if (rf.xmul != 1.0) {       // denormal-range column (never `lin`: all warps are here)
                 zsum = fused_rescale_x(pc_cur, a.V, ld, a.colpart, a.ldt, m, nsub, f.rpc, f.gbar, gen, pv, j, rf.xmul, t_first);
                 gen += 2 * G;
             }
             if (t_first < j && lane == 0) a.s[t_first] = fma(scale, zsum, vjt);
-            for (int t = t_first + G * FUSED_WARPS; t < j; t += G * FUSED_WARPS) {
+            for (int t = t_first + G * nwr; t < j; t += G * nwr) {
                 const double acc = sum_over_ctas(a.colpart + t, a.ldt, nblk, lane);
                 if (lane == 0) a.s[t] = fma(scale, acc, __ldcg(a.V + (size_t)t * ld + j));
             }
-            __syncthreads();
+            if (lin) group_barrier(5, FUSED_SHADOW_THREADS); else __syncthreads();
             // "my part of s is written": only the look-ahead warps wait for this, the GEMV starts at once
-            if (tid == 0) red_release_gpu_add(bar2, 1u);
+            if (wpr == 0 && lane == 0) red_release_gpu_add(bar2, 1u);
         }
 
         // ================= phase G: GEMV partials (warps 0..11) + look-ahead for column j+1 (warps 12..15) ==========
         {
             SB_PHASE_MARK(3);
             if (timer) t_gemv -= globaltimer_ns();
-            const double scale = scal_sh[2];
+            // `lin`: the GEMV runs against x itself; y(r) = A(r, c+1) + scale g(r) is formed by the row owner in phase A
+            const double scale = lin ? 1.0 : scal_sh[2];
+            const double v_first = lin ? 0.0 : 1.0;
             if (wp < FUSED_GEMV_WARPS) {
                 const int c = f.i + j;
                 const int lc0 = f.cm.lower(c + 1), nloc = f.lc_end - lc0;
@@ -794,7 +609,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_panel_fused(FusedArgs f)
                 const int mp = m + gs.skip;
                 // resident columns of this column's GEMV: the set shrinks as V, Y, VT of the panel grow (a line that is
                 // read with the streaming policy again gives its place up)
-                const int res_now = (int)max(0ll, min((long long)f.res_cols, (f.pf_budget - 24ll * m * j) / (8ll * max(m, 1))));
+                const int res_now = (int)max(0ll, min((long long)f.res_cols, (f.l2_budget - 24ll * m * j) / (8ll * max(m, 1))));
                 const int ks = f.lc_end - res_now - lc0;    // first resident column relative to lc0 (>= nloc: none)
                 const unsigned long long keep_policy = res_now > 0 ? l2_policy_evict_last() : 0ull;
                 while (it < it_end) {
@@ -814,7 +629,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_panel_fused(FusedArgs f)
                         group_barrier(1 + vb, 128);          // previous chunk's vs fully consumed
                         for (int k = vt; k < nk; k += 128) {
                             const int kk = f.cm.l2g(lc0 + k0 + k) - gc0;
-                            vs[k] = (kk == 0) ? 1.0 : __ldcg(pc_cur + j + kk) * scale;
+                            vs[k] = (kk == 0) ? v_first : __ldcg(pc_cur + j + kk) * scale;
                         }
                         group_barrier(1 + vb, 128);
                         if (rows_ok && resident) {
@@ -861,15 +676,9 @@ __global__ void __launch_bounds__(MAXT, 1) k_panel_fused(FusedArgs f)
                     if (rows_ok) {
                         const size_t slot = (size_t)(v - gq.first_group(rb)) * a.ldp;
                         const int r = rp - gs.skip;
-                        if (LLRED) {
-                            const unsigned tagc = f.x.epoch + j;
-                            if (r >= 0) ll_store(f.ypart_ll + slot + r, acc.x, tagc);
-                            if (r + 1 < m) ll_store(f.ypart_ll + slot + r + 1, acc.y, tagc);
-                        } else {
-                            double *yp = a.ypart + slot;
-                            if (r >= 0) yp[r] = acc.x;
-                            if (r + 1 < m) yp[r + 1] = acc.y;
-                        }
+                        double *yp = a.ypart + slot;
+                        if (r >= 0) yp[r] = acc.x;
+                        if (r + 1 >= 0 && r + 1 < m) yp[r + 1] = acc.y;
                     }
                     it += cend - cbeg;
                 }
@@ -877,13 +686,6 @@ __global__ void __launch_bounds__(MAXT, 1) k_panel_fused(FusedArgs f)
                 // ---- look-ahead for phase A of column j+1: D0 = Y(:, :j) s_j, D1 = Y(:, :j) V(j, :j)^T, D2 = VT(:, :j) s_j.
                 // None of them needs the GEMV result, so they run in the shadow of the HBM-bound GEMV.
                 const int xt = tid - 32 * FUSED_GEMV_WARPS, xw = wp - FUSED_GEMV_WARPS;
-                if (LLRED && j + 1 < f.w) {
-                    // The next panel column was last touched by the previous panel's trailing update and has long been
-                    // evicted by the streaming GEMVs: pull the CTA's rows of it towards L2 now, phase A reads them on
-                    // the critical path (one 128-byte line per thread)
-                    const int r = row0 + 16 * xt;
-                    if (16 * xt < rows_here) prefetch_l2(f.pan + (size_t)(j + 1) * f.ldpan + r);
-                }
                 gen2 += G;
                 if (xt == 0) while ((int)(ld_acquire_gpu(bar2) - gen2) < 0) { }
                 group_barrier(5, FUSED_SHADOW_THREADS);
@@ -925,9 +727,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_panel_fused(FusedArgs f)
                     rd[0] = d0; rd[NWn * 32] = d1; rd[2 * NWn * 32] = d2;
                 }
             }
-            // LLRED: no grid barrier here -- phase A polls the LL-tagged partials of its own rows, and its first
-            // __syncthreads orders the look-ahead results (`red`) of this CTA
-            if (!LLRED) grid_barrier(f.gbar, gen);
+            grid_barrier(f.gbar, gen);
             if (timer) { t_mark = globaltimer_ns(); t_gemv += t_mark; }
         }
     }

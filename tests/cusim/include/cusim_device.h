@@ -73,6 +73,7 @@ template <class T> static inline T __ldcg(const T *p)
     return v;
 }
 template <class T> static inline T __ldcs(const T *p) { return __ldcg(p); }
+template <class T> static inline void __stcs(T *p, T v) { *p = v; }
 
 template <class T> static inline T __shfl_xor_sync(unsigned, T v, int lane_mask)
 {
@@ -126,6 +127,8 @@ namespace sb200 {
 static inline unsigned ld_acquire_gpu(const unsigned *p) { ::cusim::poll_yield(); return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
 static inline unsigned ld_acquire_sys(const unsigned *p) { ::cusim::poll_yield(); return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
 static inline void red_release_gpu_add(unsigned *p, unsigned v) { __atomic_fetch_add(p, v, __ATOMIC_RELEASE); }
+static inline unsigned long long ld_acquire_gpu_u64(const unsigned long long *p) { ::cusim::poll_yield(); return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
+static inline void red_release_gpu_add_u64(unsigned long long *p, unsigned long long v) { __atomic_fetch_add(p, v, __ATOMIC_RELEASE); }
 static inline void st_release_sys(unsigned *p, unsigned v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
 // 16-byte entries: two 8-byte words, each accessed atomically (what the LL protocol assumes of the interconnect)
 static inline uint4 ld_volatile_v4(const uint4 *p)

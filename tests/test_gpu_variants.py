@@ -1,11 +1,8 @@
-"""GPU tests of code that had not yet run on a B200 when it was written (the last session of round 1 had no GPU time):
-the DLARFG rescaling branch of the default kernels and the opt-in kernel variants of DESIGN.md section 4.2b. All of it
-was stepped through the kernel-logic emulator (tests/test_cusim.py); here every case runs in its own process with a
-time-out, so that a fault or a hang in such code fails one test instead of taking the whole GPU suite with it.
-
-The opt-in variants (STARNEIG_B200_FUSED_LL, STARNEIG_B200_GEMM_OPT) are not on any default path; their tests run when
-STARNEIG_TEST_OPTIN=1 (tools/r2_visit1.sh sets it) and are skipped otherwise.
-"""
+"""GPU tests of the engine's switches and rare branches, each in its own process with a time-out (a fault or a hang fails
+one test instead of taking the whole GPU suite with it): the DLARFG rescaling branch, GEMV linearity against the
+sequential order of operations, the switches that must not change a single bit (resident GEMV columns, staging chunk),
+and the side-stream schedule of the deferred updates. All of it is also stepped through the kernel-logic emulator
+(tests/test_cusim.py)."""
 import os
 import subprocess
 import sys
@@ -14,7 +11,6 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-OPTIN = os.environ.get("STARNEIG_TEST_OPTIN", "0") == "1"
 
 CHILD = r'''
 import os, sys
@@ -58,10 +54,9 @@ if mode == "denormal":
     assert ora.orthogonality_u(n, Q, ld) <= 500
     assert np.abs(A[:n] - A2[:n]).max() <= 1e-5 * np.abs(A2[:n]).max()
     assert np.abs(Q[:n] - Q2[:n]).max() <= 1e-5
-elif mode in ("even_rows", "overlap"):
+elif mode in ("sequential_gemv", "overlap"):
     A0, Q0, ld = ora.fullpos(n, 2019)
-    env = ({"STARNEIG_B200_OVERLAP": sys.argv[4]} if mode == "overlap" else
-           {"STARNEIG_B200_FUSED_EVEN_ROWS": "1", "STARNEIG_B200_FUSED_LL": sys.argv[4], "STARNEIG_B200_FUSED_R": sys.argv[4]})
+    env = {"STARNEIG_B200_OVERLAP": sys.argv[4]} if mode == "overlap" else {"STARNEIG_B200_GEMV_LINEAR": "0"}
     A, Q = run(A0, Q0, ld, env)
     A2, Q2 = A0.copy(order="F"), Q0.copy(order="F")
     assert ora.hessenberg_port(n, A2, ld, Q2, ld, 0, n, pw) == 0
@@ -69,6 +64,11 @@ elif mode in ("even_rows", "overlap"):
     assert np.abs(Q[:n] - Q2[:n]).max() <= 200 * n * U
     assert ora.hessenberg_form_violations(n, A, ld) == 0
     assert ora.residual_u(n, Q, ld, A, ld, A0, ld) <= 500 and ora.orthogonality_u(n, Q, ld) <= 500
+    if mode == "sequential_gemv":
+        # ... and the default (linear) order of operations gives the same reduction up to where `scale` is applied
+        A1, Q1 = run(A0, Q0, ld, {})
+        assert np.abs(A[:n] - A1[:n]).max() <= 200 * n * U * max(1.0, np.abs(A1[:n]).max())
+        assert np.abs(Q[:n] - Q1[:n]).max() <= 200 * n * U and not np.array_equal(A, A1)
 else:
     # opt-in variant against the default kernels: same partial sums in the same order => bitwise the same H and Q
     key, val = sys.argv[4].split("=")
@@ -92,26 +92,17 @@ def test_denormal_range_takes_dlarfg_rescaling_branch(fused):
     _child("denormal", 333, 45, fused)
 
 
-@pytest.mark.skipif(not OPTIN, reason="opt-in kernel variant: set STARNEIG_TEST_OPTIN=1 (tools/r2_visit1.sh does)")
-@pytest.mark.parametrize("switch", ["STARNEIG_B200_FUSED_LL=1", "STARNEIG_B200_FUSED_LL=2", "STARNEIG_B200_GEMM_OPT=1", "STARNEIG_B200_GEMM_OPT=2",
-                                    "STARNEIG_B200_GEMM_OPT=3", "STARNEIG_B200_GEMV_PREFETCH=32",
-                                    "STARNEIG_B200_GEMV_RESIDENT_KB=4096", "STARNEIG_B200_GEMV_KC=2048"])
-def test_optin_variant_is_bitwise_equal_to_the_default(switch):
+@pytest.mark.parametrize("switch", ["STARNEIG_B200_GEMV_RESIDENT_KB=4096", "STARNEIG_B200_GEMV_KC=2048"])
+def test_switch_is_bitwise_equal_to_the_default(switch):
     _child("variant", 1500, 200, switch)
 
 
-@pytest.mark.skipif(not OPTIN, reason="opt-in kernel variant: set STARNEIG_TEST_OPTIN=1 (tools/r2_visit1.sh does)")
-@pytest.mark.skipif(not OPTIN, reason="opt-in kernel variant: set STARNEIG_TEST_OPTIN=1 (tools/r2_visit1.sh does)")
-@pytest.mark.parametrize("mode", [1, 2])
-def test_optin_overlapped_deferred_updates(mode):
-    # deferred updates on the side stream, concurrent with the next column loops. 1: the panel kernel gives SMs away (fat
-    # tiles); 2: next to the 64-register panel kernel on the same SMs (slim tiles). Other split-K: parity with the oracle
-    _child("overlap", 1500, 200, mode)
+def test_sequential_gemv_order_agrees_with_the_linear_default():
+    _child("sequential_gemv", 1500, 200, 0)
 
 
-@pytest.mark.skipif(not OPTIN, reason="opt-in kernel variant: set STARNEIG_TEST_OPTIN=1 (tools/r2_visit1.sh does)")
-@pytest.mark.parametrize("ll", [0, 1])
-def test_optin_even_rows_variant(ll):
-    # another grouping of the partial sums (ll = 1: also the single-pass phase R): parity with the oracle, not bitwise
-    # equality with the default
-    _child("even_rows", 1500, 200, ll)
+def test_side_stream_schedule_of_the_deferred_updates():
+    # deferred updates on the side stream, concurrent with the next column loops (the panel kernel gives SMs away, fat
+    # tiles). A measured loser on B200 (profiles/r1_s5_overlap_sweep.txt), kept as a schedule option. Other split-K: parity
+    # with the oracle, not bitwise equality
+    _child("overlap", 1500, 200, 1)

@@ -51,14 +51,10 @@ while time.time() < t_end:
     env = dict(os.environ, CUSIM_SMS=str(random.choice([1, 2, 3, 4, 6])), CUSIM_DEVICES="8", CUSIM_CHECK_PREFETCH="1",
                STARNEIG_B200_COL_BLOCK=str(random.choice([8, 16, 24])))
     sw = {}
-    if random.random() < 0.6: sw["FUSED_LL"] = random.choice([1, 2])
-    if random.random() < 0.5: sw["FUSED_R"] = 1
-    if random.random() < 0.5: sw["FUSED_EVEN_ROWS"] = 1
-    if random.random() < 0.4: sw["GEMV_PREFETCH"] = random.choice([1, 8, 40]); sw["GEMV_PREFETCH_BULK"] = random.choice([0, 1])
+    if random.random() < 0.3: sw["GEMV_LINEAR"] = 0
     if random.random() < 0.4: sw["GEMV_RESIDENT_KB"] = random.choice([1, 5, 30, 500])
     if random.random() < 0.4: sw["GEMV_KC"] = random.choice([64, 128, 2048])
-    if random.random() < 0.3: sw["GEMM_OPT"] = random.choice([1, 2, 3])
-    if random.random() < 0.25: sw["OVERLAP"] = random.choice([1, 2])
+    if random.random() < 0.25: sw["OVERLAP"] = 1
     if random.random() < 0.15: sw["FUSED_PANEL"] = 0
     if random.random() < 0.3: env["CUSIM_SHUFFLE"] = str(random.randint(1, 99))
     if random.random() < 0.3: env["CUSIM_SKEW"] = str(random.choice([2, 3, 5]))
