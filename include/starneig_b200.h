@@ -49,6 +49,7 @@ struct starneig_b200_stats {
                               * w2 reduction (A'), reflector (R), scalars + s (R') */
     int overlap;             /* 1: the Q / top-row updates ran on the side stream, overlapped with the column loops */
     double side_tail_ms;     /* end of the last trailing update -> end of the call (what the deferred updates still add) */
+    long long gemm_tma_launches, gemm_cpasync_launches;   /* DMMA kernel launches by kind of tile movement (dgemm_tma.cuh / dgemm.cuh) */
     int panel_width_used;    /* panel width of the reduction (the requested one unless it exceeds what the panel kernels'
                               * shared-memory layout holds: > 1024 columns, or a narrower limit for n > ~70000) */
 };

@@ -32,6 +32,7 @@ class Stats(ctypes.Structure):
         ("ranks", ctypes.c_int), ("fused_panels", ctypes.c_int), ("fused_kernel_ms", ctypes.c_double),
         ("fused_phase_ms", ctypes.c_double * 4),
         ("overlap", ctypes.c_int), ("side_tail_ms", ctypes.c_double),
+        ("gemm_tma_launches", ctypes.c_longlong), ("gemm_cpasync_launches", ctypes.c_longlong),
         ("panel_width_used", ctypes.c_int),
     ]
 

@@ -1,6 +1,9 @@
 // common.cuh -- shared helpers for the sm_100a Hessenberg kernels.
 #pragma once
 #include <cuda_runtime.h>
+#ifndef SB_CUSIM
+#include <cuda.h>               // CUtensorMap (types only: the encoder is resolved through cudaGetDriverEntryPoint)
+#endif
 #include <cstdio>
 #include <cstdlib>
 #include <cstdint>
@@ -134,6 +137,56 @@ __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double
 {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                  : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+// ---- TMA + mbarrier (dgemm_tma.cuh). A tensor map is a 128-byte descriptor made on the host and passed to the kernel as a
+// __grid_constant__ parameter; one thread issues a bulk tensor copy global -> shared memory that signals an mbarrier with
+// the number of bytes it delivered.
+typedef CUtensorMap SbTensorMap;
+#define SB_GRID_CONSTANT __grid_constant__
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+// first address >= p that is `align`-byte aligned in the shared window (TMA swizzle patterns are functions of the address)
+__device__ __forceinline__ double *sb_align_shared(double *p, unsigned align)
+{
+    const unsigned a = smem_u32(p);
+    return (double *)((char *)p + ((align - (a & (align - 1))) & (align - 1)));
+}
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+// makes the initialised barriers visible to the other threads' and the TMA engine's view of shared memory
+__device__ __forceinline__ void mbar_fence_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// blocks until the phase of the barrier with the given parity has completed
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
+{
+    asm volatile("{\n"
+                 ".reg .pred p;\n"
+                 "SB_MBAR_WAIT:\n"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+                 "@p bra SB_MBAR_DONE;\n"
+                 "bra SB_MBAR_WAIT;\n"
+                 "SB_MBAR_DONE:\n"
+                 "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// orders this thread's earlier generic-proxy accesses to shared memory before its later async-proxy (TMA) ones
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// box of the tensor map at coordinates (c0 = contiguous dimension, c1) -> shared memory; completes `bar` by the box's bytes
+__device__ __forceinline__ void tma_load_2d(void *smem_dst, const SbTensorMap *map, int c0, int c1, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(smem_u32(smem_dst)), "l"((unsigned long long)map), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
 }
 #endif
 

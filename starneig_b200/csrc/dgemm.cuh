@@ -329,6 +329,7 @@ __global__ void splitk_reduce_kernel(int rows, int cols, int splits, const doubl
 
 template <bool AK, bool BKM, int WM, int WN, int MB, int NB, int STAGES, int MINB, int OPT = 0>
 struct GemmConfig {
+    static constexpr bool IS_TMA = false;
     static constexpr int BM = WM * MB * 8, BN = WN * NB * 8, NT = WM * WN * 32;
     static constexpr size_t SMEM = (size_t)STAGES * (OperandTile<AK, BM>::SIZE + OperandTile<BKM, BN>::SIZE) * sizeof(double);
     static void prepare()

@@ -30,6 +30,7 @@
 #include "panel.cuh"
 #include "panel_fused.cuh"
 #include "dgemm.cuh"
+#include "dgemm_tma.cuh"
 #include <starneig_b200.h>
 #include <algorithm>
 #include <cmath>
@@ -50,6 +51,17 @@ using GemmTN13 = GemmConfig<true,  true,  4, 1, 2, 13, 3, 2>;    //  64 x 104, W
 using GemmTN12 = GemmConfig<true,  true,  4, 1, 2, 12, 3, 2>;    //  64 x  96
 using GemmNN13 = GemmConfig<false, true,  4, 1, 2, 13, 3, 2>;    //  64 x 104, W = A VT
 using GemmNN12 = GemmConfig<false, true,  4, 1, 2, 12, 3, 2>;    //  64 x  96
+// Tiles fed by the TMA engine (dgemm_tma.cuh: one thread issues bulk tensor copies into 128-byte-swizzled shared memory,
+// the warps run LDS + DMMA only). The defaults wherever a product can be framed for TMA (even leading dimensions; odd
+// operand offsets are handled by moving the frame); STARNEIG_B200_GEMM_TMA=0 selects the cp.async kernels. Tiles from
+// the sweep on the engine's shapes and operand parities (profiles/r2_v3_gemm_sweep_tma_p2.txt), TFLOP/s TMA / cuBLAS:
+// NT 64 x 64, 3 stages, 4 CTAs/SM: 33.2 / 33.2; TN 64 x 104, 3 stages: 34.6 / 34.7; NN 64 x 104, 3 stages: 34.4 / 34.0.
+using TmaNT   = GemmTmaConfig<false, false, 2, 2, 4, 4, 3, 4>;
+using TmaTN13 = GemmTmaConfig<true,  true,  4, 1, 2, 13, 3, 2>;
+using TmaTN12 = GemmTmaConfig<true,  true,  4, 1, 2, 12, 3, 2>;
+using TmaNN13 = GemmTmaConfig<false, true,  4, 1, 2, 13, 3, 2>;
+using TmaNN12 = GemmTmaConfig<false, true,  4, 1, 2, 12, 3, 2>;
+
 // "Fat" variants for the side stream: 256 threads x ~200 registers fill the register file of an SM, so a CTA owns
 // its SM exclusively. When it retires the SM is completely free and the (higher-priority, equally SM-exclusive)
 // persistent panel kernel can claim it at once; with the 2-CTAs-per-SM variants an SM never drains while the
@@ -66,6 +78,7 @@ static void prepare_device_functions()
 {
     GemmNT::prepare(); GemmTN13::prepare(); GemmTN12::prepare(); GemmNN13::prepare(); GemmNN12::prepare();
     GemmNTfat::prepare(); GemmNN13fat::prepare(); GemmNN12fat::prepare();
+    TmaNT::prepare(); TmaTN13::prepare(); TmaTN12::prepare(); TmaNN13::prepare(); TmaNN12::prepare();
     SB_CUDA(cudaFuncSetAttribute(k_col_finish_update<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM_MAX));
     SB_CUDA(cudaFuncSetAttribute(k_col_finish_update<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM_MAX));
     SB_CUDA(cudaFuncSetAttribute(k_col_reflector<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM_MAX));
@@ -284,6 +297,8 @@ struct Rank {
     int fused = 1;                          // 1: one persistent kernel per panel (panel_fused.cuh); 0: three kernels per column
     int fused_ctas = 0;                     // grid of the fused kernel (number of SMs; fewer when ranks share a device)
     int gemv_kc = FUSED_KC;                 // fused kernel: columns of v staged per GEMV group at a time (2048 timed: no gain)
+    int gemm_tma = 3;                       // DMMA kernels fed by the TMA engine (dgemm_tma.cuh): bit 0 = the rank-nb updates (NT),
+                                            // bit 1 = the skinny products (TN, NN); 0: the cp.async kernels (dgemm.cuh)
     int gemv_linear = 1;                    // fused kernel: the GEMV streams against the unscaled x (FusedArgs::linear)
     int l2_budget_mb = 96;                  // L2 budget shared by V, Y, VT of the panel and the resident columns
     int gemv_resident_kb = 0;               // fused kernel: KB of the trailing matrix (its last local columns) kept in L2 across the
@@ -318,6 +333,8 @@ struct Rank {
         if (e && atoi(e) >= 1) fused_ctas = std::min(fused_ctas, atoi(e));
         e = getenv("STARNEIG_B200_GEMV_KC");
         if (e && atoi(e) >= 64) gemv_kc = std::min(4096, atoi(e) / 8 * 8);
+        e = getenv("STARNEIG_B200_GEMM_TMA");
+        if (e) gemm_tma = atoi(e);
         e = getenv("STARNEIG_B200_GEMV_LINEAR");
         if (e) gemv_linear = atoi(e);
         e = getenv("STARNEIG_B200_GEMV_RESIDENT_KB");
@@ -397,8 +414,10 @@ struct Rank {
 
     // C = alpha*op(A)*op(B) + beta*C on the rank's stream; split-K through ws.Wpart for skinny outputs
     // (ws.Wpart_side when issued on the side stream)
+    // k_guard: see GemmTmaConfig::launch (an operand whose k runs over the panel's rows may start at an odd element; the
+    // engine's V / VT / Y buffers carry a zero row in front for that case)
     void gemm(GemmKind kind, int M, int N, int K, double alpha, const double *A, int lda,
-              const double *B, int ldb, double beta, double *C, int ldc, bool on_side = false)
+              const double *B, int ldb, double beta, double *C, int ldc, bool on_side = false, bool k_guard = false)
     {
         if (M < 1 || N < 1) return;
         cudaStream_t st = on_side ? side : stream;
@@ -407,7 +426,8 @@ struct Rank {
         const bool fat = on_side && side_fat;
         if (kind == GEMM_NT) {
             if (fat) GemmNTfat::launch(st, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, 1, K, 0);
-            else     GemmNT::launch(st, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, 1, K, 0);
+            else if ((gemm_tma & 1) && TmaNT::launch(st, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, 1, K, 0, 0, k_guard)) stats.gemm_tma_launches++;
+            else { GemmNT::launch(st, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, 1, K, 0); stats.gemm_cpasync_launches++; }
             stats.kernel_launches++;
             return;
         }
@@ -423,20 +443,25 @@ struct Rank {
             splits = std::min(splits, std::max(1, K / 512));
             while (splits > 1 && (size_t)splits * ldc * N > ws.wpart_cap) splits--;
         }
-        int klen = round_up(std::max(1, ceil_div(K, splits)), GEMM_BK);
-        splits = std::max(1, ceil_div(K, klen));
+        // (K + 1: a k frame moved by one element -- GemmTmaConfig::launch -- must still be covered by the slices)
+        int klen = round_up(std::max(1, ceil_div(K + 1, splits)), GEMM_BK);
+        splits = std::max(1, ceil_div(K + 1, klen));
         double *out = splits > 1 ? wpart : C;
         size_t stride = splits > 1 ? (size_t)ldc * N : 0;
         double b = splits > 1 ? 0.0 : beta;
 #define SB_SKINNY(CFG) CFG::launch(st, M, N, K, alpha, A, lda, B, ldb, b, out, ldc, splits, klen, stride, 1)
+#define SB_SKINNY_TMA(CFG) ((gemm_tma & 2) && CFG::launch(st, M, N, K, alpha, A, lda, B, ldb, b, out, ldc, splits, klen, stride, 1, k_guard))
         if (kind == GEMM_NN && fat) {
             if (bn == 96) SB_SKINNY(GemmNN12fat); else SB_SKINNY(GemmNN13fat);
         } else if (kind == GEMM_TN) {
-            if (bn == 96) SB_SKINNY(GemmTN12); else SB_SKINNY(GemmTN13);
+            if (bn == 96) { if (SB_SKINNY_TMA(TmaTN12)) stats.gemm_tma_launches++; else { SB_SKINNY(GemmTN12); stats.gemm_cpasync_launches++; } }
+            else          { if (SB_SKINNY_TMA(TmaTN13)) stats.gemm_tma_launches++; else { SB_SKINNY(GemmTN13); stats.gemm_cpasync_launches++; } }
         } else {
-            if (bn == 96) SB_SKINNY(GemmNN12); else SB_SKINNY(GemmNN13);
+            if (bn == 96) { if (SB_SKINNY_TMA(TmaNN12)) stats.gemm_tma_launches++; else { SB_SKINNY(GemmNN12); stats.gemm_cpasync_launches++; } }
+            else          { if (SB_SKINNY_TMA(TmaNN13)) stats.gemm_tma_launches++; else { SB_SKINNY(GemmNN13); stats.gemm_cpasync_launches++; } }
         }
 #undef SB_SKINNY
+#undef SB_SKINNY_TMA
         stats.kernel_launches++;
         if (splits > 1) {
             dim3 grid(ceil_div(M, 256), N);
@@ -636,7 +661,7 @@ struct Rank {
         const int chunk = (on_side && side_chunk > 0) ? side_chunk : rows;
         for (int r0 = 0; r0 < rows; r0 += chunk) {
             const int nr = std::min(chunk, rows - r0);
-            gemm(GEMM_NN, nr, w, m, 1.0, X + r0, ldx, VT, ld, 0.0, W + r0, ld, on_side);
+            gemm(GEMM_NN, nr, w, m, 1.0, X + r0, ldx, VT, ld, 0.0, W + r0, ld, on_side, true);
             gemm(GEMM_NT, nr, m, w, -1.0, W + r0, ld, V, ld, 1.0, X + r0, ldx, on_side);
         }
     }
@@ -703,7 +728,16 @@ struct Rank {
             const int w = std::min(nb, end - i - 1);
             const int m = end - i - 1;
             const int slot = panel % PANEL_RING;
-            double *V = ws.Vb[slot], *VT = ws.VTb[slot];
+            // V and VT of the panel are stored with the row parity of the panel's first row in A (row i + 1; A is 16-byte
+            // aligned with an even leading dimension), behind a zero guard row: the products over the panel's rows whose
+            // operands are both K-major (W = A^T VT) then agree on where 16-byte units start, and moving the k frame by one
+            // element for TMA adds a term that is zero (dgemm_tma.cuh)
+            const int par = (i + 1) & 1;
+            double *V = ws.Vb[slot] + par, *VT = ws.VTb[slot] + par;
+            if (par) {
+                SB_CUDA(cudaMemset2DAsync(ws.Vb[slot], (size_t)ld * sizeof(double), 0, sizeof(double), (size_t)w, st));
+                SB_CUDA(cudaMemset2DAsync(ws.VTb[slot], (size_t)ld * sizeof(double), 0, sizeof(double), (size_t)w, st));
+            }
             // the buffers of this slot were last read by the deferred updates of panel - PANEL_RING
             if (ovl && panel >= PANEL_RING) SB_CUDA(cudaStreamWaitEvent(st, ev_side[slot], 0));
             if (lvl >= 1) SB_CUDA(cudaEventRecord(phase_event(2 + 6 * panel + 0), st));
@@ -747,7 +781,7 @@ struct Rank {
             if (ntr > 0) {
                 double *Atr = A + (size_t)tl0 * ldA + i + 1;
                 gemm(GEMM_NT, m, ntr, w, -1.0, ws.Y, ld, Vg + (tl0 - cl0), ldg, 1.0, Atr, ldA);
-                gemm(GEMM_TN, ntr, w, m, 1.0, Atr, ldA, VT, ld, 0.0, ws.W, ld);
+                gemm(GEMM_TN, ntr, w, m, 1.0, Atr, ldA, VT, ld, 0.0, ws.W, ld, false, true);
                 gemm(GEMM_NT, m, ntr, w, -1.0, V, ld, ws.W, ld, 1.0, Atr, ldA);
             }
             if (lvl >= 1) SB_CUDA(cudaEventRecord(phase_event(2 + 6 * panel + 2), st));
@@ -773,7 +807,7 @@ struct Rank {
             if (end < n) {   // columns right of the reduced block (partial reduction)
                 const int xl0 = cm.lower(end), nx = cm.lower(n) - xl0;
                 double *X = A + (size_t)xl0 * ldA + i + 1;
-                gemm(GEMM_TN, nx, w, m, 1.0, X, ldA, VT, ld, 0.0, ws.W, ld);
+                gemm(GEMM_TN, nx, w, m, 1.0, X, ldA, VT, ld, 0.0, ws.W, ld, false, true);
                 gemm(GEMM_NT, m, nx, w, -1.0, V, ld, ws.W, ld, 1.0, X, ldA);
             }
             if (hook && panel == 0) hook->before_q(sq);

@@ -263,6 +263,8 @@ struct Team {
         for (int g = 1; g < P; g++) {
             stats.kernel_launches += ranks[g]->stats.kernel_launches;
             stats.gemm_flops += ranks[g]->stats.gemm_flops;
+            stats.gemm_tma_launches += ranks[g]->stats.gemm_tma_launches;
+            stats.gemm_cpasync_launches += ranks[g]->stats.gemm_cpasync_launches;
             stats.device_ms = std::max(stats.device_ms, ranks[g]->stats.device_ms);
         }
     }

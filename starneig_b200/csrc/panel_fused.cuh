@@ -536,16 +536,16 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_panel_fused(FusedArgs f)
             }
             // grid barrier on the column's own arrival word; the arrivals carry the vote on `linear`
             __syncthreads();
-            if (tid == 0) {
-                bool any_med = false, any_big = false;
-                for (int q = 0; q < FUSED_WARPS; q++) {
-                    any_med = any_med || !(sqred[q] == 0.0);                      // NaN counts
-                    any_big = any_big || !(sqred[FUSED_WARPS + q] == 0.0);
+            if (wp == 0) {
+                // lane q looks at the sums of warp q: !(x == 0) so that a NaN counts as an entry
+                const bool any_med = __any_sync(0xffffffffu, lane < FUSED_WARPS && !(sqred[min(lane, FUSED_WARPS - 1)] == 0.0));
+                const bool any_big = __any_sync(0xffffffffu, lane < FUSED_WARPS && !(sqred[FUSED_WARPS + min(lane, FUSED_WARPS - 1)] == 0.0));
+                if (lane == 0) {
+                    red_release_gpu_add_u64(f.rbar + j, 1ull | (any_med ? 1ull << 32 : 0ull) | (any_big ? 1ull << 48 : 0ull));
+                    unsigned long long seen;
+                    while ((unsigned)((seen = ld_acquire_gpu_u64(f.rbar + j)) & 0xffffffffull) < (unsigned)G) { }
+                    scal_sh[3] = (f.linear && ((seen >> 32) & 0xffffull) != 0ull && (seen >> 48) == 0ull) ? 1.0 : 0.0;
                 }
-                red_release_gpu_add_u64(f.rbar + j, 1ull | (any_med ? 1ull << 32 : 0ull) | (any_big ? 1ull << 48 : 0ull));
-                unsigned long long seen;
-                while ((unsigned)((seen = ld_acquire_gpu_u64(f.rbar + j)) & 0xffffffffull) < (unsigned)G) { }
-                scal_sh[3] = (f.linear && ((seen >> 32) & 0xffffull) != 0ull && (seen >> 48) == 0ull) ? 1.0 : 0.0;
             }
             __syncthreads();
             lin = scal_sh[3] != 0.0;

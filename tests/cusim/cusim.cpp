@@ -344,6 +344,11 @@ cudaError_t cudaFree(void *p)
 }
 cudaError_t cudaMemset(void *p, int v, size_t bytes) { memset(p, v, bytes); return cudaSuccess; }
 cudaError_t cudaMemsetAsync(void *p, int v, size_t bytes, cudaStream_t) { memset(p, v, bytes); return cudaSuccess; }
+cudaError_t cudaMemset2DAsync(void *p, size_t pitch, int v, size_t width, size_t height, cudaStream_t)
+{
+    for (size_t r = 0; r < height; r++) memset((char *)p + r * pitch, v, width);
+    return cudaSuccess;
+}
 cudaError_t cudaMemcpy(void *d, const void *s, size_t bytes, cudaMemcpyKind) { memmove(d, s, bytes); return cudaSuccess; }
 cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t bytes, cudaMemcpyKind, cudaStream_t) { memmove(d, s, bytes); return cudaSuccess; }
 cudaError_t cudaMemcpy2DAsync(void *d, size_t dpitch, const void *s, size_t spitch, size_t width, size_t height, cudaMemcpyKind, cudaStream_t)

@@ -53,6 +53,7 @@ template <class T> static inline cudaError_t cudaMalloc(T **p, size_t bytes) { r
 cudaError_t cudaFree(void *p);
 cudaError_t cudaMemset(void *p, int v, size_t bytes);
 cudaError_t cudaMemsetAsync(void *p, int v, size_t bytes, cudaStream_t st);
+cudaError_t cudaMemset2DAsync(void *p, size_t pitch, int v, size_t width, size_t height, cudaStream_t st);
 cudaError_t cudaMemcpy(void *d, const void *s, size_t bytes, cudaMemcpyKind k);
 cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t bytes, cudaMemcpyKind k, cudaStream_t st);
 cudaError_t cudaMemcpy2DAsync(void *d, size_t dpitch, const void *s, size_t spitch, size_t width, size_t height, cudaMemcpyKind k, cudaStream_t st);

@@ -174,6 +174,70 @@ static inline void cp_async16(void *smem_dst, const void *gmem_src, int src_byte
 }
 static inline void cp_async_commit() {}
 template <int N> static inline void cp_async_wait() {}
+// ---- TMA + mbarrier (dgemm_tma.cuh). The tensor map is a plain struct, the bulk tensor copy is performed at once by the
+// issuing thread (zero fill outside the tensor, 128-byte swizzle relative to the box start -- on the device the box starts
+// on a 1024-byte boundary, where the address-based pattern of the hardware is the same), and an mbarrier is
+// {phase : 1, pending arrivals : 15, arrival count : 16, pending bytes : 32} in its 8 bytes. The fibers of a CTA run on
+// one host thread, so no atomics are needed.
+struct alignas(64) SbTensorMap { const double *base; unsigned long long dim0, dim1, ld; unsigned box0, box1; char pad[80]; };
+#define SB_GRID_CONSTANT
+static inline void sb_make_tensor_map(SbTensorMap *map, const double *base, unsigned long long dim0, unsigned long long dim1,
+                                      unsigned long long ld, unsigned box0, unsigned box1)
+{
+    if (((uintptr_t)base & 15) != 0 || (ld & 1) != 0 || box0 * sizeof(double) != 128 || box1 > 256 || dim0 == 0 || dim1 == 0) {
+        fprintf(stderr, "cusim: invalid tensor map (base %p ld %llu box %u x %u)\n", (const void *)base, ld, box0, box1);
+        abort();
+    }
+    map->base = base; map->dim0 = dim0; map->dim1 = dim1; map->ld = ld; map->box0 = box0; map->box1 = box1;
+}
+static inline double *sb_align_shared(double *p, unsigned align) { return (double *)(((uintptr_t)p + align - 1) / align * align); }
+namespace mbar_bits {
+static inline unsigned phase(unsigned long long b) { return (unsigned)(b >> 63); }
+static inline unsigned pending(unsigned long long b) { return (unsigned)((b >> 48) & 0x7fff); }
+static inline unsigned count(unsigned long long b) { return (unsigned)((b >> 32) & 0xffff); }
+static inline int tx(unsigned long long b) { return (int)(unsigned)(b & 0xffffffffull); }
+static inline unsigned long long pack(unsigned ph, unsigned pend, unsigned cnt, int t)
+{
+    return ((unsigned long long)ph << 63) | ((unsigned long long)pend << 48) | ((unsigned long long)cnt << 32) | (unsigned)t;
+}
+static inline void settle(unsigned long long *bar)      // phase completes when no arrival and no byte is pending
+{
+    const unsigned long long b = *bar;
+    if (pending(b) == 0 && tx(b) == 0) *bar = pack(phase(b) ^ 1u, count(b), count(b), 0);
+}
+}
+static inline void mbar_init(unsigned long long *bar, unsigned count) { *bar = mbar_bits::pack(0, count, count, 0); }
+static inline void mbar_fence_init() {}
+static inline void fence_proxy_async() {}
+static inline void mbar_arrive_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+    const unsigned long long b = *bar;
+    if (mbar_bits::pending(b) == 0) { fprintf(stderr, "cusim: mbarrier arrival beyond its count\n"); abort(); }
+    *bar = mbar_bits::pack(mbar_bits::phase(b), mbar_bits::pending(b) - 1, mbar_bits::count(b), mbar_bits::tx(b) + (int)bytes);
+    mbar_bits::settle(bar);
+}
+static inline void mbar_arrive(unsigned long long *bar) { mbar_arrive_expect_tx(bar, 0u); }
+static inline void mbar_wait(unsigned long long *bar, unsigned parity)
+{
+    while (mbar_bits::phase(*(volatile unsigned long long *)bar) == parity) ::cusim::poll_yield();
+}
+static inline void tma_load_2d(void *smem_dst, const SbTensorMap *map, int c0, int c1, unsigned long long *bar)
+{
+    double *dst = (double *)smem_dst;
+    // the hardware addresses global memory in 16-byte units: an odd coordinate in the contiguous dimension traps
+    if (c0 & 1) { fprintf(stderr, "cusim: TMA box starts at an odd element of the contiguous dimension (c0 = %d)\n", c0); abort(); }
+    for (unsigned r = 0; r < map->box1; r++)
+        for (unsigned e = 0; e < map->box0; e++) {
+            const long long x0 = (long long)c0 + e, x1 = (long long)c1 + r;
+            const bool inside = x0 >= 0 && x1 >= 0 && (unsigned long long)x0 < map->dim0 && (unsigned long long)x1 < map->dim1;
+            dst[r * 16 + ((((e >> 1) ^ (r & 7)) << 1) | (e & 1))] = inside ? map->base[(size_t)x1 * map->ld + x0] : 0.0;
+        }
+    const unsigned long long b = *bar;
+    *bar = mbar_bits::pack(mbar_bits::phase(b), mbar_bits::pending(b), mbar_bits::count(b), mbar_bits::tx(b) - (int)(map->box0 * map->box1 * sizeof(double)));
+    mbar_bits::settle(bar);
+    ::cusim::poll_yield();
+}
+
 // mma.sync.m8n8k4.f64: lane l holds A[l/4][l%4], B[l%4][l/4] and C[l/4][2*(l%4) + {0,1}]; the products of one
 // output element are accumulated in ascending k with fused multiply-adds
 static inline void dmma884(double &c0, double &c1, double a, double b)

@@ -268,6 +268,20 @@ def test_sim_results_do_not_depend_on_the_schedule(sim, ora, simlib):
     assert np.array_equal(AQ[0], A1[:64]) and np.array_equal(AQ[1], Q1[:64])
 
 
+@pytest.mark.parametrize("gpus,n,pw", [(1, 131, 24), (1, 90, 35), (2, 96, 16)])
+def test_sim_all_updates_take_the_tma_kernels(sim, ora, gpus, n, pw):
+    """Every DMMA launch of a reduction is framed for the TMA kernels (dgemm_tma.cuh): the emulator is as strict as the
+    hardware about 16-byte box origins, panels start at odd and even rows, panel widths are odd and even -- only products
+    without a k extent (a rank that owns no column of the range) fall back to the cp.async kernels."""
+    with _Env(STARNEIG_B200_COL_BLOCK=8, CUSIM_SMS=2):
+        _, _, st = _reduce(sim, ora, n, pw, gpus=gpus)
+    assert st["gemm_tma_launches"] > 0
+    assert st["gemm_cpasync_launches"] == 0 or gpus > 1, st
+    with _Env(STARNEIG_B200_COL_BLOCK=8, CUSIM_SMS=2, STARNEIG_B200_GEMM_TMA=0):
+        _, _, st = _reduce(sim, ora, n, pw, gpus=gpus)
+    assert st["gemm_tma_launches"] == 0 and st["gemm_cpasync_launches"] > 0
+
+
 def test_sim_dgemm_kinds(sim, simlib):
     """the three operand layouts of the DMMA kernel (fragment layout of mma.m8n8k4 emulated lane by lane), edges, odd
     sizes, split-K; operands at 16-byte aligned and at odd (8-byte aligned) offsets"""

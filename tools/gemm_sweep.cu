@@ -9,10 +9,11 @@
 //   TN  W(m-w x w)  = A(m x m-w)^T VT(m x w)            trailing left update, a     GEMM_TN (+ split-K)
 //   NN  W(n x w)    = Q(n x m) VT(m x w)                Q / top-row update, a       GEMM_NN (+ split-K)
 // build: make -C tools            run: tools/bin/gemm_sweep [n] [panel] [reps]
-#include "../starneig_b200/csrc/dgemm.cuh"
+#include "../starneig_b200/csrc/dgemm_tma.cuh"
 #include <cublas_v2.h>
 #include <algorithm>
 #include <cmath>
+#include <cstring>
 #include <string>
 #include <vector>
 
@@ -52,14 +53,17 @@ __global__ void k_maxdiff(const double *a, const double *b, int rows, int cols, 
 
 // one timed configuration: `launch(splits, klen, stride, out)` issues the GEMM (and nothing else)
 template <class Cfg>
-static void run_config(const char *name, const Shape &s, Buffers &b, int reps, int splits_req, cudaStream_t st)
+static void run_config(const char *name, const Shape &s, Buffers &b, int reps, int splits_req, cudaStream_t st, int raster = 0)
 {
+    // GEMM_ONLY=substring: run only the configurations whose label contains it (one process per suspect configuration)
+    static const char *only = getenv("GEMM_ONLY");
+    if (only && !strstr(name, only)) return;
     Cfg::prepare();
     const bool nt = s.kind == 'T';
     int splits = nt ? 1 : std::max(1, splits_req);
-    int klen = round_up(std::max(1, ceil_div(s.K, splits)), GEMM_BK);
-    splits = std::max(1, ceil_div(s.K, klen));
-    while (splits > 1 && (size_t)splits * b.ldc * s.N > b.part_cap) { splits--; klen = round_up(ceil_div(s.K, splits), GEMM_BK); splits = ceil_div(s.K, klen); }
+    int klen = round_up(std::max(1, ceil_div(s.K + 1, splits)), GEMM_BK);
+    splits = std::max(1, ceil_div(s.K + 1, klen));
+    while (splits > 1 && (size_t)splits * b.ldc * s.N > b.part_cap) { splits--; klen = round_up(ceil_div(s.K + 1, splits), GEMM_BK); splits = ceil_div(s.K + 1, klen); }
     double *out = splits > 1 ? b.part : b.C;
     const size_t stride = splits > 1 ? (size_t)b.ldc * s.N : 0;
     const double alpha = nt ? -1.0 : 1.0, beta = nt ? 1.0 : 0.0;
@@ -70,7 +74,14 @@ static void run_config(const char *name, const Shape &s, Buffers &b, int reps, i
     for (int it = 0; it < reps + 1; it++) {
         if (nt) SB_CUDA(cudaMemcpyAsync(b.C, b.Cref + (size_t)b.ldc * s.N, (size_t)b.ldc * s.N * 8, cudaMemcpyDeviceToDevice, st));
         SB_CUDA(cudaEventRecord(e0, st));
-        Cfg::launch(st, s.M, s.N, s.K, alpha, b.A, b.lda, b.B, b.ldb, splits > 1 ? 0.0 : beta, out, b.ldc, splits, klen, stride);
+        if constexpr (Cfg::IS_TMA) {
+            // operands as the engine hands them over: zero guard in front of the K-major workspace operand (k_guard)
+            if (!Cfg::launch(st, s.M, s.N, s.K, alpha, b.A, b.lda, b.B, b.ldb, splits > 1 ? 0.0 : beta, out, b.ldc, splits, klen, stride, raster, true)) {
+                printf("  %-34s cannot be framed for TMA\n", name);
+                return;
+            }
+        } else
+            Cfg::launch(st, s.M, s.N, s.K, alpha, b.A, b.lda, b.B, b.ldb, splits > 1 ? 0.0 : beta, out, b.ldc, splits, klen, stride, raster);
         if (splits > 1) {
             dim3 grid(ceil_div(s.M, 256), s.N);
             splitk_reduce_kernel<<<grid, 256, 0, st>>>(s.M, s.N, splits, out, b.ldc, stride, b.C, b.ldc);
@@ -131,6 +142,14 @@ static void run_cublas(cublasHandle_t h, const Shape &s, Buffers &b, int reps, c
 #define RUNO(OPT, AK, BK_, WM, WN, MB, NB, ST, MINB, SPL)                                                              \
     run_config<GemmConfig<AK, BK_, WM, WN, MB, NB, ST, MINB, OPT>>(#WM "x" #WN " warps, " #MB "x" #NB " blocks, " #ST " st, " #MINB "/SM opt" #OPT, s, b, reps, SPL, st)
 #define RUNI(AK, BK_, WM, WN, MB, NB, ST, MINB, SPL) RUNO(1, AK, BK_, WM, WN, MB, NB, ST, MINB, SPL)
+// rasterised with the column tiles of one row tile next to each other (what the engine does for the skinny products)
+#define RUNR(OPT, AK, BK_, WM, WN, MB, NB, ST, MINB, SPL)                                                              \
+    run_config<GemmConfig<AK, BK_, WM, WN, MB, NB, ST, MINB, OPT>>(#WM "x" #WN " warps, " #MB "x" #NB " blocks, " #ST " st, " #MINB "/SM opt" #OPT " raster", s, b, reps, SPL, st, 1)
+// tiles moved by TMA (dgemm_tma.cuh); PW 1 = dedicated producer warp + empty barriers, 0 = thread 0 after a CTA barrier
+#define RUNK(KBOX, PW, AK, BK_, WM, WN, MB, NB, ST, MINB, SPL, RASTER)                                                 \
+    run_config<GemmTmaConfig<AK, BK_, WM, WN, MB, NB, ST, MINB, PW, KBOX>>("TMA kbox" #KBOX " pw" #PW " " #WM "x" #WN " warps, " #MB "x" #NB " blocks, " #ST " st, " #MINB "/SM r" #RASTER, s, b, reps, SPL, st, RASTER)
+#define RUNT(PW, AK, BK_, WM, WN, MB, NB, ST, MINB, SPL, RASTER)                                                       \
+    run_config<GemmTmaConfig<AK, BK_, WM, WN, MB, NB, ST, MINB, PW>>("TMA pw" #PW " " #WM "x" #WN " warps, " #MB "x" #NB " blocks, " #ST " st, " #MINB "/SM r" #RASTER, s, b, reps, SPL, st, RASTER)
 
 int main(int argc, char **argv)
 {
@@ -157,80 +176,78 @@ int main(int argc, char **argv)
     k_fill<<<1184, 256>>>(big, nbig, 1); k_fill<<<1184, 256>>>(sk1, nsk, 2); k_fill<<<1184, 256>>>(sk2, nsk, 3);
     SB_CUDA(cudaDeviceSynchronize());
     printf("gemm_sweep: n = %d, nb = %d, panel %d (i = %d, m = %d, w = %d)\n", n, nb, panel, i, m, w);
+    // the skinny operands play V / VT / Y: stored with the row parity of the panel in A, behind a zero guard row
+    const int par = (i + 1) & 1;
+    SB_CUDA(cudaMemset2D(sk1, (size_t)ld * 8, 0, 8, round_up(w, 8)));
+    SB_CUDA(cudaMemset2D(sk2, (size_t)ld * 8, 0, 8, round_up(w, 8)));
 
     {   // ---- NT: C(m x m-w) -= Y V^T
         Shape s{'T', m, m - w, w};
-        Buffers b{sk1, sk2 + w, out, ref, part, ld, ld, ld, part_cap};
+        Buffers b{sk1, sk2 + par + (w - 1), out + (size_t)w * ld + i + 1, ref, part, ld, ld, ld, part_cap};        // Y, rows w-1.. of V, C = A(i+1:, i+w:)
         k_fill<<<1184, 256>>>(ref + (size_t)ld * s.N, (size_t)ld * s.N, 4);     // pristine C
         printf("NT  C(%d x %d) -= A(%d x %d) B(%d x %d)^T\n", s.M, s.N, s.M, s.K, s.N, s.K);
         run_cublas(h, s, b, reps, st);
-        RUN(false, false, 2, 2, 8, 4, 4, 2, 1);     // product configuration (GemmNT)
-        RUNO(1, false, false, 2, 2, 8, 4, 4, 2, 1);     // product tile, interleaved cp.async (GemmOpt<1>::NT)
-        RUNO(2, false, false, 2, 2, 8, 4, 4, 2, 1);     // product tile, 16-byte cp.async where aligned (GemmOpt<2>::NT)
-        RUNO(3, false, false, 2, 2, 8, 4, 4, 2, 1);     // both
-        RUNO(2, false, false, 2, 4, 8, 4, 4, 1, 1);     // 128 x 128, 256 threads, 16-byte cp.async
-        RUNO(2, false, false, 4, 2, 4, 4, 4, 2, 1);     // 128 x 64, 256 threads, 2 CTAs/SM, 16-byte cp.async
-        RUN(false, false, 2, 4, 8, 4, 4, 1, 1);     // product side-stream configuration (GemmNTfat)
-        RUNI(false, false, 4, 2, 4, 4, 4, 2, 1);    // 128 x 64, 256 threads, 2 CTAs/SM, interleaved
-        RUNI(false, false, 2, 2, 4, 4, 4, 4, 1);    // 64 x 64, 4 CTAs/SM, interleaved
-        RUN(false, false, 2, 2, 8, 4, 3, 2, 1);
-        RUN(false, false, 2, 2, 8, 4, 5, 2, 1);
-        RUN(false, false, 2, 2, 4, 8, 4, 2, 1);
-        RUN(false, false, 4, 1, 4, 8, 4, 2, 1);
-        RUN(false, false, 2, 2, 4, 4, 4, 4, 1);     // 64 x 64, 4 CTAs/SM: 4 warps per sub-partition
-        RUN(false, false, 2, 2, 4, 4, 4, 3, 1);
-        RUN(false, false, 4, 2, 4, 4, 4, 2, 1);     // 128 x 64, 256 threads, 2 CTAs/SM
-        RUN(false, false, 4, 2, 4, 4, 3, 2, 1);
-        RUN(false, false, 2, 4, 4, 4, 4, 2, 1);     // 64 x 128, 256 threads
-        RUN(false, false, 4, 4, 4, 4, 3, 1, 1);     // 128 x 128, 512 threads, 1 CTA/SM
-        RUN(false, false, 4, 2, 8, 4, 3, 1, 1);     // 256 x 64, 256 threads
-        RUN(false, false, 4, 2, 4, 8, 3, 1, 1);     // 128 x 128, 8 warps of 32 x 64, 3 stages: the shape of cuBLAS's cutlass_80_tensorop_d884gemm_128x128_16x3
-        RUN(false, false, 4, 2, 4, 8, 4, 1, 1);
-        RUNO(2, false, false, 4, 2, 4, 8, 3, 1, 1);
-        RUNO(3, false, false, 4, 2, 4, 8, 3, 1, 1);
-        RUNO(3, false, false, 2, 4, 8, 4, 4, 1, 1);
+        RUNO(1, false, false, 2, 2, 8, 4, 4, 2, 1);     // cp.async product configuration (GemmNT: interleaved cp.async)
+        RUN(false, false, 2, 2, 4, 4, 4, 4, 1);         // 64 x 64, 4 CTAs/SM (best cp.async tile of the round-2 sweep)
+        RUNT(0, false, false, 2, 2, 8, 4, 4, 2, 1, 0);  // TMA product configuration (TmaNT)
+        RUNT(1, false, false, 2, 2, 8, 4, 4, 2, 1, 0);
+        RUNT(0, false, false, 2, 2, 8, 4, 3, 2, 1, 0);
+        RUNT(0, false, false, 2, 2, 4, 4, 4, 3, 1, 0);  // 64 x 64, 3 CTAs/SM
+        RUNT(0, false, false, 2, 2, 4, 4, 3, 4, 1, 0);  // 64 x 64, 4 CTAs/SM
+        RUNT(1, false, false, 2, 2, 4, 4, 4, 3, 1, 0);
+        RUNT(0, false, false, 2, 4, 8, 4, 4, 1, 1, 0);  // 128 x 128, 8 warps of 64 x 32, 1 CTA/SM
+        RUNT(1, false, false, 2, 4, 8, 4, 4, 1, 1, 0);
+        RUNT(1, false, false, 2, 4, 8, 4, 3, 1, 1, 0);
+        RUNT(1, false, false, 4, 2, 4, 8, 4, 1, 1, 0);  // 128 x 128, 8 warps of 32 x 64 (cuBLAS's d884gemm_128x128 shape)
+        RUNT(0, false, false, 4, 2, 4, 4, 4, 2, 1, 0);  // 128 x 64, 8 warps of 32 x 32, 2 CTAs/SM
     }
     {   // ---- TN: W(m-w x w) = A(m x m-w)^T VT(m x w)
         Shape s{'t', m - w, w, m};
-        Buffers b{big + (size_t)(i + w) * ld + i + 1, sk1, out, ref, part, ld, ld, ld, part_cap};
+        Buffers b{big + (size_t)(i + w) * ld + i + 1, sk1 + par, out, ref, part, ld, ld, ld, part_cap};
         printf("TN  W(%d x %d) = A(%d x %d)^T B(%d x %d)\n", s.M, s.N, s.K, s.M, s.K, s.N);
         run_cublas(h, s, b, reps, st);
         const int t13 = ceil_div(s.M, 64) * ceil_div(s.N, 104);
         const int spl = std::min(32, std::max(1, std::min(ceil_div(8 * 2 * 148, t13), s.K / 512)));
-        RUN(true, true, 4, 1, 2, 13, 4, 2, spl);    // product configuration (GemmTN13)
-        RUNO(1, true, true, 4, 1, 2, 13, 4, 2, spl);    // interleaved cp.async (GemmOpt<1>::TN13)
-        RUNO(2, true, true, 4, 1, 2, 13, 4, 2, spl);    // 16-byte cp.async where aligned
-        RUNO(3, true, true, 4, 1, 2, 13, 4, 2, spl);
-        RUN(true, true, 4, 1, 2, 13, 4, 2, 1);
-        RUN(true, true, 4, 1, 2, 13, 3, 2, spl);
-        RUN(true, true, 4, 1, 2, 13, 5, 2, spl);
-        RUN(true, true, 4, 1, 4, 13, 3, 1, spl);    // 128 x 104
-        RUN(true, true, 8, 1, 2, 13, 4, 1, spl);    // 128 x 104, 256 threads
-        RUN(true, true, 4, 2, 2, 7, 4, 2, spl);     // 64 x 112, 256 threads
-        RUN(true, true, 4, 2, 4, 5, 4, 1, spl);     // 128 x 80, 256 threads (w = 312 -> 4 x 80 = 320)
-        RUN(true, true, 4, 1, 2, 10, 4, 2, spl);    // 64 x 80
-        RUN(true, true, 4, 1, 2, 8, 4, 3, spl);     // 64 x 64 (w = 312 -> 5 x 64 = 320)
+        RUN(true, true, 4, 1, 2, 13, 3, 2, spl);        // cp.async product configuration (GemmTN13), rows fastest
+        RUNR(0, true, true, 4, 1, 2, 13, 3, 2, spl);    // ... as the engine launches it
+        RUNK(8, 0, true, true, 4, 1, 2, 13, 4, 2, spl, 1);  // K-major tiles in boxes of 8 rows
+        RUNK(8, 1, true, true, 4, 1, 2, 13, 4, 2, spl, 1);
+        RUNK(8, 0, true, true, 4, 1, 2, 13, 3, 2, spl, 1);
+        RUNK(8, 0, true, true, 4, 1, 2, 8, 4, 3, spl, 1);   // 64 x 64
+        RUNK(16, 0, true, true, 4, 1, 2, 8, 4, 3, spl, 1);
+        RUNK(64, 0, true, true, 4, 1, 2, 8, 4, 3, spl, 1);
+        RUNT(0, true, true, 4, 1, 2, 13, 4, 2, spl, 1); // TMA product configuration (TmaTN13)
+        RUNT(0, true, true, 4, 1, 2, 13, 4, 2, spl, 0);
+        RUNT(1, true, true, 4, 1, 2, 13, 4, 2, spl, 1);
+        RUNT(0, true, true, 4, 1, 2, 13, 3, 2, spl, 1);
+        RUNT(0, true, true, 4, 1, 2, 13, 5, 2, spl, 1);
+        RUNT(0, true, true, 4, 1, 2, 13, 4, 2, 1, 1);   // no split-K
+        RUNT(1, true, true, 8, 1, 2, 13, 4, 1, spl, 1); // 128 x 104, 8 warps
+        RUNT(0, true, true, 4, 1, 4, 13, 3, 1, spl, 1); // 128 x 104, 4 warps
+        RUNT(0, true, true, 4, 1, 2, 10, 4, 2, spl, 1); // 64 x 80
+        RUNT(0, true, true, 4, 1, 2, 8, 4, 3, spl, 1);  // 64 x 64
     }
     {   // ---- NN: W(n x w) = Q(n x m) VT(m x w)
         Shape s{'n', n, w, m};
-        Buffers b{big + (size_t)(i + 1) * ld, sk1, out, ref, part, ld, ld, ld, part_cap};
+        Buffers b{big + (size_t)(i + 1) * ld, sk1 + par, out, ref, part, ld, ld, ld, part_cap};
         printf("NN  W(%d x %d) = A(%d x %d) B(%d x %d)\n", s.M, s.N, s.M, s.K, s.K, s.N);
         run_cublas(h, s, b, reps, st);
         const int t13 = ceil_div(s.M, 64) * ceil_div(s.N, 104);
         const int spl = std::min(32, std::max(1, std::min(ceil_div(8 * 2 * 148, t13), s.K / 512)));
-        RUN(false, true, 4, 1, 2, 13, 4, 2, spl);   // product configuration (GemmNN13)
-        RUNO(1, false, true, 4, 1, 2, 13, 4, 2, spl);   // interleaved cp.async (GemmOpt<1>::NN13)
-        RUNO(2, false, true, 4, 1, 2, 13, 4, 2, spl);   // 16-byte cp.async where aligned
-        RUNO(3, false, true, 4, 1, 2, 13, 4, 2, spl);
-        RUNO(2, false, true, 8, 1, 2, 13, 4, 1, spl);   // 128 x 104, 256 threads, 16-byte cp.async
-        RUN(false, true, 4, 1, 2, 13, 4, 2, 1);
-        RUN(false, true, 8, 1, 2, 13, 4, 1, spl);   // product side-stream configuration (GemmNN13fat)
-        RUN(false, true, 4, 1, 2, 13, 3, 2, spl);
-        RUN(false, true, 4, 1, 4, 13, 3, 1, spl);   // 128 x 104, 128 threads
-        RUN(false, true, 4, 2, 4, 5, 4, 1, spl);    // 128 x 80, 256 threads
-        RUN(false, true, 4, 2, 2, 7, 4, 2, spl);    // 64 x 112, 256 threads
-        RUN(false, true, 4, 1, 2, 10, 4, 2, spl);   // 64 x 80
-        RUN(false, true, 4, 1, 2, 8, 4, 3, spl);    // 64 x 64
+        RUN(false, true, 4, 1, 2, 13, 3, 2, spl);       // cp.async product configuration (GemmNN13), rows fastest
+        RUNR(0, false, true, 4, 1, 2, 13, 3, 2, spl);   // ... as the engine launches it
+        RUNK(8, 0, false, true, 4, 1, 2, 13, 4, 2, spl, 1);
+        RUNK(8, 1, false, true, 4, 1, 2, 13, 4, 2, spl, 1);
+        RUNK(8, 0, false, true, 4, 1, 2, 13, 3, 2, spl, 1);
+        RUNK(8, 0, false, true, 4, 1, 2, 8, 4, 3, spl, 1);
+        RUNT(0, false, true, 4, 1, 2, 13, 4, 2, spl, 1);// TMA product configuration (TmaNN13)
+        RUNT(0, false, true, 4, 1, 2, 13, 4, 2, spl, 0);
+        RUNT(1, false, true, 4, 1, 2, 13, 4, 2, spl, 1);
+        RUNT(0, false, true, 4, 1, 2, 13, 3, 2, spl, 1);
+        RUNT(0, false, true, 4, 1, 2, 13, 5, 2, spl, 1);
+        RUNT(1, false, true, 8, 1, 2, 13, 4, 1, spl, 1);// 128 x 104, 8 warps
+        RUNT(0, false, true, 4, 1, 4, 13, 3, 1, spl, 1);// 128 x 104, 4 warps
+        RUNT(0, false, true, 4, 1, 2, 8, 4, 3, spl, 1); // 64 x 64
     }
     cublasDestroy(h);
     return 0;
