@@ -50,10 +50,40 @@ struct starneig_b200_stats {
     int overlap;             /* 1: the Q / top-row updates ran on the side stream, overlapped with the column loops */
     double side_tail_ms;     /* end of the last trailing update -> end of the call (what the deferred updates still add) */
     long long gemm_tma_launches, gemm_cpasync_launches;   /* DMMA kernel launches by kind of tile movement (dgemm_tma.cuh / dgemm.cuh) */
+    int staging_overlapped;  /* host API: 1 if the host buffers were page-locked from end to end, so that Q's upload and the
+                              * write-back of finished columns really overlapped the reduction (then h2d_ms is the upload of A
+                              * alone and d2h_ms what was left of the write-back when the reduction ended) */
     int panel_width_used;    /* panel width of the reduction (the requested one unless it exceeds what the panel kernels'
                               * shared-memory layout holds: > 1024 columns, or a narrower limit for n > ~70000) */
 };
 void starneig_b200_get_stats(struct starneig_b200_stats *stats);
+
+/* ---- chain hand-off: the Hessenberg stage in front of GPU-resident next stages ----
+ *
+ * starneig_b200_SEP_SM_Hessenberg_stage: as starneig_SEP_SM_Hessenberg (reference src/hessenberg/interface.c:170-185; same
+ * argument numbering for errors -1 .. -5), but H and Q are not copied back: they stay in the library's device buffers
+ * (*dH, *dQ: column-major, leading dimensions *lddH, *lddQ; valid until the next Hessenberg call on this library or
+ * starneig_node_finalize) for a next stage that runs on the GPU. Host A, Q are left untouched. One GPU.
+ * starneig_b200_stage_fetch copies them (either may be NULL) to host arrays when a later stage runs on the host after all.
+ *
+ * starneig_b200_SEP_SM_Reduce has the shape of starneig_SEP_SM_Reduce (reference src/common/combined.c:45-98: Hessenberg,
+ * Schur, optional Select + ReorderSchur; same argument numbering, -12 for an incomplete `next`) with the stages this
+ * library does not own supplied by the caller -- in a StarNEig build: starneig_SEP_SM_Schur, starneig_SEP_SM_Select,
+ * starneig_SEP_SM_ReorderSchur (reference src/include/starneig/sep_sm.h). A `schur_device` stage takes the DEVICE pointers
+ * of H and Q (no host round trip between the stages) and leaves the Schur form and the updated Q there. */
+struct starneig_b200_chain {
+    starneig_error_t (*schur)(int n, double H[], int ldH, double Q[], int ldQ, double real[], double imag[]);
+    starneig_error_t (*schur_device)(int n, double *dH, int lddH, double *dQ, int lddQ, double real[], double imag[]);
+    starneig_error_t (*select)(int n, double S[], int ldS, int (*predicate)(double real, double imag, void *arg), void *arg,
+                               int selected[], int *num_selected);
+    starneig_error_t (*reorder_schur)(int n, int selected[], double S[], int ldS, double Q[], int ldQ, double real[], double imag[]);
+};
+starneig_error_t starneig_b200_SEP_SM_Hessenberg_stage(int n, double A[], int ldA, double Q[], int ldQ,
+                                                       double **dH, int *lddH, double **dQ, int *lddQ);
+starneig_error_t starneig_b200_stage_fetch(int n, double A[], int ldA, double Q[], int ldQ);
+starneig_error_t starneig_b200_SEP_SM_Reduce(int n, double A[], int ldA, double Q[], int ldQ, double real[], double imag[],
+                                             int (*predicate)(double real, double imag, void *arg), void *arg,
+                                             int selected[], int *num_selected, const struct starneig_b200_chain *next);
 
 /* Largest supported matrix order (two n x n FP64 matrices of this order exceed one B200's memory anyway); the
  * entry points return STARNEIG_INVALID_ARGUMENTS beyond it instead of overrunning a workspace. */

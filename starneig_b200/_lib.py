@@ -33,11 +33,25 @@ class Stats(ctypes.Structure):
         ("fused_phase_ms", ctypes.c_double * 4),
         ("overlap", ctypes.c_int), ("side_tail_ms", ctypes.c_double),
         ("gemm_tma_launches", ctypes.c_longlong), ("gemm_cpasync_launches", ctypes.c_longlong),
-        ("panel_width_used", ctypes.c_int),
+        ("staging_overlapped", ctypes.c_int), ("panel_width_used", ctypes.c_int),
     ]
 
     def as_dict(self):
         return {name: (list(getattr(self, name)) if name == "fused_phase_ms" else getattr(self, name)) for name, _ in self._fields_}
+
+
+SCHUR_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
+                            ctypes.c_void_p, ctypes.c_void_p)
+PREDICATE_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_void_p)
+SELECT_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, PREDICATE_FN, ctypes.c_void_p,
+                             ctypes.c_void_p, ctypes.POINTER(ctypes.c_int))
+REORDER_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
+                              ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p)
+
+
+class Chain(ctypes.Structure):
+    """``struct starneig_b200_chain`` (include/starneig_b200.h): the next stages of a Reduce-shaped chain."""
+    _fields_ = [("schur", SCHUR_FN), ("schur_device", SCHUR_FN), ("select", SELECT_FN), ("reorder_schur", REORDER_FN)]
 
 
 def load(path=None):
@@ -94,6 +108,12 @@ def load(path=None):
     lib.starneig_b200_dist_hessenberg_host.argtypes = [i, i, i, i, vp, i, vp, i]
     lib.starneig_b200_dist_hessenberg_host.restype = i
     lib.starneig_b200_dist_finalize.restype = None
+    lib.starneig_b200_SEP_SM_Hessenberg_stage.argtypes = [i, vp, i, vp, i, ctypes.POINTER(vp), ip, ctypes.POINTER(vp), ip]
+    lib.starneig_b200_SEP_SM_Hessenberg_stage.restype = i
+    lib.starneig_b200_stage_fetch.argtypes = [i, vp, i, vp, i]
+    lib.starneig_b200_stage_fetch.restype = i
+    lib.starneig_b200_SEP_SM_Reduce.argtypes = [i, vp, i, vp, i, vp, vp, PREDICATE_FN, vp, vp, ip, ctypes.POINTER(Chain)]
+    lib.starneig_b200_SEP_SM_Reduce.restype = i
     lib.starneig_b200_plan_check.argtypes = [i, i, i, ctypes.POINTER(ctypes.c_longlong)]
     lib.starneig_b200_plan_check.restype = i
     return lib

@@ -109,6 +109,32 @@ def hessenberg_device(n, A, ldA, Q, ldQ, begin=0, end=None, panel_width=-1):
     return lib().starneig_b200_hessenberg_device(n, begin, end, panel_width, A.data_ptr(), ldA, Q.data_ptr(), ldQ)
 
 
+def hessenberg_stage(n, A, ldA, Q, ldQ):
+    """``starneig_b200_SEP_SM_Hessenberg_stage``: the Hessenberg stage of a chain whose next stage runs on the GPU. Host A, Q are
+    inputs only; returns (ret, dH, lddH, dQ, lddQ) with dH, dQ the device addresses (ints) of H and Q."""
+    dH, dQ = ctypes.c_void_p(), ctypes.c_void_p()
+    lddH, lddQ = ctypes.c_int(), ctypes.c_int()
+    ret = lib().starneig_b200_SEP_SM_Hessenberg_stage(n, _host_ptr(A), ldA, _host_ptr(Q), ldQ, ctypes.byref(dH), ctypes.byref(lddH),
+                                                      ctypes.byref(dQ), ctypes.byref(lddQ))
+    return ret, dH.value, lddH.value, dQ.value, lddQ.value
+
+
+def stage_fetch(n, A, ldA, Q, ldQ):
+    """``starneig_b200_stage_fetch``: H and Q of the last stage call -> host arrays (either may be None)."""
+    return lib().starneig_b200_stage_fetch(n, _host_ptr(A), ldA, _host_ptr(Q), ldQ)
+
+
+def starneig_b200_SEP_SM_Reduce(n, A, ldA, Q, ldQ, real, imag, chain, predicate=None, arg=None, selected=None):
+    """``starneig_b200_SEP_SM_Reduce`` (shape of the reference's starneig_SEP_SM_Reduce, src/common/combined.c:45-98).
+    `chain`: a ``_lib.Chain`` of ctypes callbacks for the stages this library does not own. Returns (ret, num_selected)."""
+    num = ctypes.c_int(0)
+    pred = predicate if predicate is not None else _lib.PREDICATE_FN()
+    sel = selected.ctypes.data if selected is not None else None
+    ret = lib().starneig_b200_SEP_SM_Reduce(n, _host_ptr(A), ldA, _host_ptr(Q), ldQ, real.ctypes.data, imag.ctypes.data, pred, arg, sel,
+                                            ctypes.byref(num), ctypes.byref(chain))
+    return ret, num.value
+
+
 def get_stats():
     st = Stats()
     lib().starneig_b200_get_stats(ctypes.byref(st))

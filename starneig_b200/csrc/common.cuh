@@ -96,20 +96,6 @@ __device__ __forceinline__ unsigned long long globaltimer_ns()
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
     return t;
 }
-// L2 residency control for data that is read again soon: a cache policy that marks lines "evict last" in L2, and a
-// 16-byte load that carries it (no L1 allocation). The rest of the streamed matrix is read with evict-first loads.
-__device__ __forceinline__ unsigned long long l2_policy_evict_last()
-{
-    unsigned long long policy;
-    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(policy));
-    return policy;
-}
-__device__ __forceinline__ double2 ld_l2_keep(const double2 *p, unsigned long long policy)
-{
-    double2 v;
-    asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v2.f64 {%0,%1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(policy));
-    return v;
-}
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 // bulk variant (TMA engine): `bytes` (multiple of 16) from a 16-byte aligned address with ONE instruction
 __device__ __forceinline__ void prefetch_l2_bulk(const void *p, unsigned bytes)

@@ -300,9 +300,6 @@ struct Rank {
     int gemm_tma = 3;                       // DMMA kernels fed by the TMA engine (dgemm_tma.cuh): bit 0 = the rank-nb updates (NT),
                                             // bit 1 = the skinny products (TN, NN); 0: the cp.async kernels (dgemm.cuh)
     int gemv_linear = 1;                    // fused kernel: the GEMV streams against the unscaled x (FusedArgs::linear)
-    int l2_budget_mb = 96;                  // L2 budget shared by V, Y, VT of the panel and the resident columns
-    int gemv_resident_kb = 0;               // fused kernel: KB of the trailing matrix (its last local columns) kept in L2 across the
-                                            // columns of a panel ("evict last" loads), 0: everything streams
     std::vector<cudaEvent_t> events;        // phase events: 4 per panel
     std::vector<cudaEvent_t> gemv_events;   // 4 per timed column (profile level 2)
     size_t gemv_events_used = 0;
@@ -337,10 +334,6 @@ struct Rank {
         if (e) gemm_tma = atoi(e);
         e = getenv("STARNEIG_B200_GEMV_LINEAR");
         if (e) gemv_linear = atoi(e);
-        e = getenv("STARNEIG_B200_GEMV_RESIDENT_KB");
-        if (e && atoi(e) >= 0) gemv_resident_kb = atoi(e);
-        e = getenv("STARNEIG_B200_L2_BUDGET_MB");
-        if (e && atoi(e) >= 0) l2_budget_mb = atoi(e);
         e = getenv("STARNEIG_B200_OVERLAP");
         if (e) overlap = atoi(e);
         e = getenv("STARNEIG_B200_OVERLAP_CTAS");
@@ -569,12 +562,6 @@ struct Rank {
             f.a = pa; f.w = w; f.i = i; f.pan = pan; f.ldpan = ldpan; f.Aloc = A_loc; f.lda = ldA; f.cm = cm; f.lc_end = lc_end;
             f.nsub = std::max(1, ceil_div(m, 32 * ctas));
             f.rpc = 32 * f.nsub;
-            f.l2_budget = (long long)l2_budget_mb << 20;
-            {   // the last local columns, all of them right of the panel so that every GEMV of the panel reads them; how many
-                // of them are kept at a given column is decided in the kernel from the L2 budget
-                const long long want = ((long long)gemv_resident_kb << 10) / (8ll * std::max(m, 1));
-                f.res_cols = (int)std::min<long long>(want, std::max(0, lc_end - cm.lower(i + w)));
-            }
             f.gbar = ws.gbar; f.rbar = ws.rbar; f.timers = ws.timers;
             f.linear = gemv_linear;
             f.x = x;
@@ -872,14 +859,21 @@ static inline void q_row_range(int P, int g, int n, int *q0, int *q1)
     *q1 = std::min(n, (g + 1) * per);
 }
 
-static inline int default_panel_width(int n)
+// The "automatic" panel width (conf->panel_width == STARNEIG_HESSENBERG_DEFAULT_PANEL_WIDTH). One GPU: the reference's
+// formula (src/hessenberg/interface.c:74-78: 312 at n = 20000; measured flat between 256 and 384 on B200). Several GPUs:
+// narrower, because the level-2 phases of a column (replicated on every rank, streaming V, Y, VT of the panel from L2) grow
+// with the panel width while a rank's share of everything else shrinks with the number of GPUs -- measured at n = 20000
+// (profiles/r2_v5_visit8b_panelwidth_by_gpus_overlap.log): 2 GPUs 256 (-0.6 %), 4 GPUs 192 (-3.7 %), 8 GPUs 192 (-6 %,
+// flat between 96 and 192). An explicit conf->panel_width is always taken as given.
+static inline int default_panel_width(int n, int P = 1)
 {
     // tuning aid (tools/sweep.py): another "automatic" width without touching the caller's configuration
     const char *e = getenv("STARNEIG_B200_AUTO_PANEL_WIDTH");
     if (e && atoi(e) >= 8) return atoi(e);
-    // reference src/hessenberg/interface.c:74-78
-    int w = (int)std::ceil((0.001875596476 * n + 273.5908216) / 8.0) * 8;
-    return std::max(64, w);
+    const double ref = 0.001875596476 * n + 273.5908216;
+    if (P >= 4) return std::max(64, (int)std::ceil(0.6 * ref / 16.0) * 16);
+    if (P >= 2) return std::max(64, (int)std::ceil(0.8 * ref / 16.0) * 16);
+    return std::max(64, (int)std::ceil(ref / 8.0) * 8);
 }
 
 } // namespace sb200

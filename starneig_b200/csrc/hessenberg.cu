@@ -11,9 +11,12 @@
 //                                            same engine; all cross-GPU traffic is NVLink peer stores/loads
 //                                            issued by the kernels themselves
 // There is no CPU implementation of this path: without a GPU every compute entry point fails loudly.
-#include "engine.cuh"
 #include <chrono>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <thread>
+#include "engine.cuh"
 
 namespace sb200 {
 
@@ -74,6 +77,7 @@ struct HostStage : StageHook {
     const int n; double *const A; const int ldA; double *const Q; const int ldQ;
     const bool overlap;
     const int cb;
+    bool writeback = true;              // false: H and Q stay on the device (starneig_b200_SEP_SM_Hessenberg_stage)
     int a_done = 0, q_done = 0;         // local columns of A / columns of Q already on their way back
 
     HostStage(const Rank &r_, Shard &sh_, int n_, double *A_, int ldA_, double *Q_, int ldQ_, bool overlap_)
@@ -131,7 +135,7 @@ struct HostStage : StageHook {
     }
     void panel_done(cudaStream_t s, int final_cols) override
     {
-        if (!overlap) return;
+        if (!overlap || !writeback) return;
         SB_CUDA(cudaEventRecord(r.ev_cols_final, s));
         SB_CUDA(cudaStreamWaitEvent(r.copy, r.ev_cols_final, 0));
         send_back(final_cols, r.copy);
@@ -139,6 +143,7 @@ struct HostStage : StageHook {
     // after the reduction (its streams are idle): whatever is still on the device
     void finish()
     {
+        if (!writeback) return;
         cudaStream_t st = overlap ? r.copy : r.stream;
         a_done = std::min(a_done, sh.ncols);
         copy_a(a_done, sh.ncols, false, st); a_done = sh.ncols;
@@ -147,24 +152,37 @@ struct HostStage : StageHook {
     }
 };
 
-static bool page_locked(const void *p)
+// the whole buffer [p, p + bytes) is page-locked (caller-pinned or registered by ScopedPin): probed at both ends, because a
+// registration that failed half-way (two buffers sharing a page of one malloc arena) leaves the first byte of the second
+// buffer inside the first one's registered range
+static bool page_locked(const void *p, size_t bytes)
 {
-    cudaPointerAttributes attr;
-    if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) { cudaGetLastError(); return false; }
-    return attr.type == cudaMemoryTypeHost;
+    auto probe = [](const void *q) {
+        cudaPointerAttributes attr;
+        if (cudaPointerGetAttributes(&attr, q) != cudaSuccess) { cudaGetLastError(); return false; }
+        return attr.type == cudaMemoryTypeHost;
+    };
+    return probe(p) && probe((const char *)p + (bytes > 0 ? bytes - 1 : 0));
 }
 
-struct HostTimes { double h2d_ms = 0, d2h_ms = 0; long long h2d_bytes = 0, d2h_bytes = 0; };
+struct HostTimes { double h2d_ms = 0, d2h_ms = 0; long long h2d_bytes = 0, d2h_bytes = 0; int overlapped = 0; };
 
 // upload, reduce, download on one rank (called on the rank's own host thread)
-static void run_rank_host(Rank &r, Shard &sh, int n, int begin, int end, int nb, double *A, int ldA, double *Q, int ldQ, HostTimes *ht)
+// `rendezvous` (several ranks): called between the upload and the first cross-GPU barrier kernel, so that a rank whose
+// upload takes seconds longer (pageable memory, a loaded host) does not run into the time-out of the device-side waits
+static void run_rank_host(Rank &r, Shard &sh, int n, int begin, int end, int nb, double *A, int ldA, double *Q, int ldQ, HostTimes *ht,
+                          bool writeback = true, const std::function<void()> *rendezvous = nullptr)
 {
     SB_CUDA(cudaSetDevice(r.device));
     const char *e = getenv("STARNEIG_B200_STAGE_OVERLAP");
-    const bool overlap = (e ? atoi(e) != 0 : true) && page_locked(A) && page_locked(Q);
+    const size_t bytesA = ((size_t)ldA * (n - 1) + n) * sizeof(double), bytesQ = ((size_t)ldQ * (n - 1) + n) * sizeof(double);
+    const bool overlap = (e ? atoi(e) != 0 : true) && page_locked(A, bytesA) && page_locked(Q, bytesQ);
     HostStage stage(r, sh, n, A, ldA, Q, ldQ, overlap);
+    stage.writeback = writeback;
+    ht->overlapped = overlap ? 1 : 0;
     double t1 = wall_ms();
     stage.upload();
+    if (rendezvous) (*rendezvous)();
     double t2 = wall_ms();
     r.reduce(n, begin, end, nb, sh.A, sh.ldA, sh.Q, sh.ldQ, sh.qrows, &stage);
     double t3 = wall_ms();
@@ -186,7 +204,13 @@ struct Team {
 
     void open(int P_)
     {
-        if (P == P_) return;
+        if (P == P_ && P_ == 1) {
+            // the single-rank engine lives on the device that was current when it was created: a caller that has switched
+            // devices since (torch.cuda.set_device) gets a new engine there instead of launches on foreign pointers
+            int cur = 0;
+            SB_CUDA(cudaGetDevice(&cur));
+            if (ranks[0]->device == cur) return;
+        } else if (P == P_) return;
         close();
         P = P_;
         int ndev = 0, cur = 0;
@@ -329,7 +353,7 @@ static starneig_error_t resolve_conf(struct starneig_hessenberg_conf const *conf
         return STARNEIG_INVALID_CONFIGURATION;
     }
     if (local.panel_width == STARNEIG_HESSENBERG_DEFAULT_PANEL_WIDTH) {
-        local.panel_width = default_panel_width(n);
+        local.panel_width = default_panel_width(n, std::min(std::max(starneig_node_get_gpus(), 1), MAX_RANKS));
         if (starneig_b200_node_messages_enabled())
             printf("[starneig][message] Setting panel width to %d.\n", local.panel_width);
     } else if (local.panel_width < 8) {
@@ -382,31 +406,35 @@ struct ScopedPin {
 };
 }
 
-extern "C" __attribute__((visibility("default")))
-starneig_error_t starneig_SEP_SM_Hessenberg_expert(struct starneig_hessenberg_conf *conf, int n, int begin, int end,
-                                                   double A[], int ldA, double Q[], int ldQ)
-{
-    // argument checks: reference src/hessenberg/interface.c:144-153
-    if (n < 1) return -2;
-    if (begin < 0) return -3;
-    if (n < end) return -4;
-    if (A == NULL) return -5;
-    if (ldA < n) return -6;
-    if (Q == NULL) return -7;
-    if (ldQ < n) return -8;
-    if (!starneig_node_initialized()) return STARNEIG_NOT_INITIALIZED;
-    if (n > SB_MAX_N) {
-        fprintf(stderr, "[starneig][error] Matrices larger than %d x %d are not supported by the CUDA Hessenberg path. Exiting...\n",
-                SB_MAX_N, SB_MAX_N);
-        return STARNEIG_INVALID_ARGUMENTS;
+namespace {
+// all host threads of a team arrive before any of them goes on (one use per call)
+struct ThreadRendezvous {
+    std::mutex m; std::condition_variable cv; int waiting = 0; const int count;
+    explicit ThreadRendezvous(int count_) : count(count_) {}
+    void arrive()
+    {
+        std::unique_lock<std::mutex> lk(m);
+        if (++waiting == count) cv.notify_all();
+        else cv.wait(lk, [this] { return waiting >= count; });
     }
+};
+}
 
+// the host-pointer call: upload, reduce, (writeback) download; `writeback == false` leaves H and Q in the library's device
+// buffers of rank 0 (single GPU only)
+static starneig_error_t hessenberg_host(struct starneig_hessenberg_conf *conf, int n, int begin, int end,
+                                        double A[], int ldA, double Q[], int ldQ, bool writeback)
+{
     int nb = 0;
     starneig_error_t ret = resolve_conf(conf, n, &nb);
     if (ret != STARNEIG_SUCCESS) return ret;
     if (!have_gpu()) return STARNEIG_GENERIC_ERROR;
 
     const int P = std::min(starneig_node_get_gpus(), MAX_RANKS);
+    if (!writeback && P != 1) {
+        fprintf(stderr, "[starneig][error] The device-resident Hessenberg stage runs on one GPU (node initialised with %d). Exiting...\n", P);
+        return STARNEIG_GENERIC_ERROR;
+    }
     g_team.open(P);
     g_team.reset_stats();
     double t0 = wall_ms();
@@ -425,19 +453,135 @@ starneig_error_t starneig_SEP_SM_Hessenberg_expert(struct starneig_hessenberg_co
     {
         ScopedPin pinA(A, ((size_t)ldA * (n - 1) + n) * sizeof(double), starneig_b200_node_pinning_enabled());
         ScopedPin pinQ(Q, ((size_t)ldQ * (n - 1) + n) * sizeof(double), starneig_b200_node_pinning_enabled());
+        ThreadRendezvous uploaded(P);
+        const std::function<void()> rendezvous = [&uploaded] { uploaded.arrive(); };
         g_team.run([&](int g) {
-            run_rank_host(*g_team.ranks[g], g_team.shards[g], n, begin, end, nb, A, ldA, Q, ldQ, &ht[g]);
+            run_rank_host(*g_team.ranks[g], g_team.shards[g], n, begin, end, nb, A, ldA, Q, ldQ, &ht[g], writeback,
+                          P > 1 ? &rendezvous : nullptr);
         });
     }
     g_team.collect_stats(n, begin, end, nb);
+    g_team.stats.staging_overlapped = 1;
     for (int g = 0; g < P; g++) {
         g_team.stats.h2d_ms = std::max(g_team.stats.h2d_ms, ht[g].h2d_ms);
         g_team.stats.d2h_ms = std::max(g_team.stats.d2h_ms, ht[g].d2h_ms);
         g_team.stats.h2d_bytes += ht[g].h2d_bytes;
-        g_team.stats.d2h_bytes += ht[g].d2h_bytes;
+        g_team.stats.d2h_bytes += writeback ? ht[g].d2h_bytes : 0;
+        g_team.stats.staging_overlapped = std::min(g_team.stats.staging_overlapped, ht[g].overlapped);
     }
     g_team.stats.wall_ms = wall_ms() - t0;
     return STARNEIG_SUCCESS;
+}
+
+extern "C" __attribute__((visibility("default")))
+starneig_error_t starneig_SEP_SM_Hessenberg_expert(struct starneig_hessenberg_conf *conf, int n, int begin, int end,
+                                                   double A[], int ldA, double Q[], int ldQ)
+{
+    // argument checks: reference src/hessenberg/interface.c:144-153
+    if (n < 1) return -2;
+    if (begin < 0) return -3;
+    if (n < end) return -4;
+    if (A == NULL) return -5;
+    if (ldA < n) return -6;
+    if (Q == NULL) return -7;
+    if (ldQ < n) return -8;
+    if (!starneig_node_initialized()) return STARNEIG_NOT_INITIALIZED;
+    if (n > SB_MAX_N) {
+        fprintf(stderr, "[starneig][error] Matrices larger than %d x %d are not supported by the CUDA Hessenberg path. Exiting...\n",
+                SB_MAX_N, SB_MAX_N);
+        return STARNEIG_INVALID_ARGUMENTS;
+    }
+    return hessenberg_host(conf, n, begin, end, A, ldA, Q, ldQ, true);
+}
+
+// ---------------------------------------------------------------------------------------------
+// chain hand-off: the Hessenberg stage of starneig_SEP_SM_Reduce with H and Q left on the device
+// ---------------------------------------------------------------------------------------------
+static int g_stage_n = 0;       // order of the matrices the last stage call left on the device (0: none)
+
+extern "C" __attribute__((visibility("default")))
+starneig_error_t starneig_b200_SEP_SM_Hessenberg_stage(int n, double A[], int ldA, double Q[], int ldQ,
+                                                       double **dH, int *lddH, double **dQ, int *lddQ)
+{
+    // same argument numbering as starneig_SEP_SM_Hessenberg (reference src/hessenberg/interface.c:175-184)
+    if (n < 1) return -1;
+    if (A == NULL) return -2;
+    if (ldA < n) return -3;
+    if (Q == NULL) return -4;
+    if (ldQ < n) return -5;
+    if (dH == NULL || lddH == NULL) return -6;
+    if (dQ == NULL || lddQ == NULL) return -8;
+    if (!starneig_node_initialized()) return STARNEIG_NOT_INITIALIZED;
+    if (n > SB_MAX_N) return STARNEIG_INVALID_ARGUMENTS;
+    g_stage_n = 0;
+    starneig_error_t ret = hessenberg_host(NULL, n, 0, n, A, ldA, Q, ldQ, false);
+    if (ret != STARNEIG_SUCCESS) return ret;
+    *dH = g_team.shards[0].A; *lddH = g_team.shards[0].ldA;
+    *dQ = g_team.shards[0].Q; *lddQ = g_team.shards[0].ldQ;
+    g_stage_n = n;
+    return STARNEIG_SUCCESS;
+}
+
+extern "C" __attribute__((visibility("default")))
+starneig_error_t starneig_b200_stage_fetch(int n, double A[], int ldA, double Q[], int ldQ)
+{
+    if (n < 1 || n != g_stage_n) return -1;
+    if (A != NULL && ldA < n) return -3;
+    if (Q != NULL && ldQ < n) return -5;
+    if (!starneig_node_initialized() || g_team.P != 1) return STARNEIG_NOT_INITIALIZED;
+    Rank &r = *g_team.ranks[0];
+    Shard &sh = g_team.shards[0];
+    SB_CUDA(cudaSetDevice(r.device));
+    if (A) copy_columns(A, (size_t)ldA * 8, sh.A, (size_t)sh.ldA * 8, (size_t)n * 8, n, cudaMemcpyDeviceToHost, r.stream);
+    if (Q) copy_columns(Q, (size_t)ldQ * 8, sh.Q, (size_t)sh.ldQ * 8, (size_t)n * 8, n, cudaMemcpyDeviceToHost, r.stream);
+    SB_CUDA(cudaStreamSynchronize(r.stream));
+    return STARNEIG_SUCCESS;
+}
+
+// The shape of starneig_SEP_SM_Reduce (reference src/common/combined.c:45-98) with this library's Hessenberg stage in
+// front of caller-supplied next stages: the stages that take device pointers (`schur_device`) see H and Q where the
+// Hessenberg stage left them, without a trip through host memory; host stages get them fetched first.
+extern "C" __attribute__((visibility("default")))
+starneig_error_t starneig_b200_SEP_SM_Reduce(int n, double A[], int ldA, double Q[], int ldQ, double real[], double imag[],
+                                             int (*predicate)(double real, double imag, void *arg), void *arg,
+                                             int selected[], int *num_selected, const struct starneig_b200_chain *next)
+{
+    // argument checks: reference src/common/combined.c:56-63
+    if (n < 1) return -1;
+    if (A == NULL) return -2;
+    if (ldA < n) return -3;
+    if (Q == NULL) return -4;
+    if (ldQ < n) return -5;
+    if (next == NULL || (next->schur == NULL && next->schur_device == NULL)) return -12;
+    if (predicate && (next->select == NULL || next->reorder_schur == NULL)) return -12;
+    if (!starneig_node_initialized()) return STARNEIG_NOT_INITIALIZED;
+
+    starneig_error_t ret = STARNEIG_SUCCESS;
+    int *own_selected = NULL;
+    if (next->schur_device) {
+        double *dH, *dQ;
+        int lddH, lddQ;
+        ret = starneig_b200_SEP_SM_Hessenberg_stage(n, A, ldA, Q, ldQ, &dH, &lddH, &dQ, &lddQ);
+        if (ret != STARNEIG_SUCCESS) goto cleanup;
+        ret = next->schur_device(n, dH, lddH, dQ, lddQ, real, imag);       // leaves S and Q on the device
+        if (ret != STARNEIG_SUCCESS) goto cleanup;
+        ret = starneig_b200_stage_fetch(n, A, ldA, Q, ldQ);
+        if (ret != STARNEIG_SUCCESS) goto cleanup;
+    } else {
+        ret = starneig_SEP_SM_Hessenberg(n, A, ldA, Q, ldQ);
+        if (ret != STARNEIG_SUCCESS) goto cleanup;
+        ret = next->schur(n, A, ldA, Q, ldQ, real, imag);
+        if (ret != STARNEIG_SUCCESS) goto cleanup;
+    }
+    if (predicate) {
+        if (selected == NULL) selected = own_selected = (int *)malloc((size_t)n * sizeof(int));
+        ret = next->select(n, A, ldA, predicate, arg, selected, num_selected);
+        if (ret != STARNEIG_SUCCESS) goto cleanup;
+        ret = next->reorder_schur(n, selected, A, ldA, Q, ldQ, real, imag);
+    }
+cleanup:
+    free(own_selected);
+    return ret;
 }
 
 extern "C" __attribute__((visibility("default")))
@@ -492,7 +636,7 @@ int starneig_b200_dist_init(int world, int rank, int n_max, int panel_width_max,
     SB_CUDA(cudaGetDevice(&dev));
     g_dist = new Rank();
     g_dist->open(world, rank, dev);
-    if (panel_width_max < 8) panel_width_max = default_panel_width(n_max);
+    if (panel_width_max < 8) panel_width_max = default_panel_width(n_max, 1);      // the widest default: any rank count fits
     panel_width_max = std::min(panel_width_max, PANEL_MAX_NB);
     memset(handle_out, 0, 64);
     if (world > 1) {
@@ -551,7 +695,7 @@ starneig_error_t starneig_b200_dist_hessenberg_device(int n, int begin, int end,
     q_row_range(r.P, r.g, n, &q0, &q1);
     if (ldQ < q1 - q0 || (ldQ & 1) || ((uintptr_t)dQ_loc & 15)) return -8;
     if (n > SB_MAX_N) return STARNEIG_INVALID_ARGUMENTS;
-    if (panel_width < 0) panel_width = default_panel_width(n);
+    if (panel_width < 0) panel_width = default_panel_width(n, r.P);
     if (panel_width < 8) return STARNEIG_INVALID_CONFIGURATION;
     if (r.P > 1 && (n > r.al.n_cap || std::min(panel_width, PANEL_MAX_NB) > r.al.nb_cap)) return STARNEIG_INVALID_ARGUMENTS;
     memset(&r.stats, 0, sizeof(r.stats));
@@ -576,7 +720,7 @@ starneig_error_t starneig_b200_dist_hessenberg_host(int n, int begin, int end, i
     if (Q == NULL) return -7;
     if (ldQ < n) return -8;
     if (n > SB_MAX_N) return STARNEIG_INVALID_ARGUMENTS;
-    if (panel_width < 0) panel_width = default_panel_width(n);
+    if (panel_width < 0) panel_width = default_panel_width(n, r.P);
     if (panel_width < 8) return STARNEIG_INVALID_CONFIGURATION;
     if (r.P > 1 && (n > r.al.n_cap || std::min(panel_width, PANEL_MAX_NB) > r.al.nb_cap)) return STARNEIG_INVALID_ARGUMENTS;
     memset(&r.stats, 0, sizeof(r.stats));
@@ -604,7 +748,7 @@ int starneig_b200_plan_check(int n, int panel_width, int ranks, long long out[4]
 {
     static_assert(STARNEIG_B200_MAX_N == SB_MAX_N, "header and engine disagree on the largest supported order");
     if (n < 1 || n > SB_MAX_N || ranks < 1 || ranks > MAX_RANKS) return STARNEIG_INVALID_ARGUMENTS;
-    if (panel_width < 0) panel_width = default_panel_width(n);
+    if (panel_width < 0) panel_width = default_panel_width(n, ranks);
     if (panel_width < 8) return STARNEIG_INVALID_CONFIGURATION;
     const int ctas = 148, slots = 148 * 8;      // a B200: one persistent CTA per SM; k_col_gemv: 8 resident blocks per SM
     int nb = std::min(panel_width, PANEL_MAX_NB);

@@ -22,9 +22,10 @@
 // VT columns are written and re-read by the same SM; everything that crosses CTAs inside the launch (pcol, s,
 // w2, partials, scalars, row j of V) is read with ld.global.cg.
 // (Round 1 carried opt-in variants of this kernel -- LL-entry reductions instead of grid barriers, a single-pass phase R,
-// rows spread over all CTAs, L2 prefetch of the GEMV's head, a 64-register build for co-resident DMMA tiles. All of them
+// rows spread over all CTAs, L2 prefetch of the GEMV's head, "evict last" loads for columns that every GEMV of a panel
+// reads, a 64-register build for co-resident DMMA tiles. All of them
 // were timed on B200 at n = 6000 and n = 20000 and lost to this kernel (profiles/r2_v1_switch_sweep_n20000.txt,
-// profiles/r1_s8_variant_smoke*_n6000.log); they were removed in round 2.)
+// profiles/r2_v4_visit8_sweep_parity_n20000_n50000_8gpu.log, profiles/r1_s8_variant_smoke*_n6000.log); they were removed in round 2.)
 #pragma once
 #include "panel.cuh"
 
@@ -50,10 +51,6 @@ struct FusedArgs {
     int nsub;                   // 32-row sub-tiles per CTA
     int rpc;                    // rows owned by a CTA (32 * nsub)
     int kc;                     // columns of v a GEMV group stages in shared memory at a time (each refill drains its load pipeline)
-    int res_cols;               // at most this many local columns (the last ones: they are part of every GEMV of the panel) are read
-                                // with the "keep in L2" policy; at column j as many of them as l2_budget leaves next to V, Y, VT
-                                // of the panel so far (24 m j bytes). 0: everything streams
-    long long l2_budget;        // bytes of L2 that V, Y, VT (3 * 8 * m * j at column j) and the resident columns may fill together
     unsigned *gbar;             // grid barrier counter, zero at launch
     unsigned long long *rbar;   // one arrival word per panel column for the barrier that ends phase R, zero at launch: arrivals in
                                 // the low 32 bits, and above them how many CTAs saw a medium-range (bits 32-47) / a huge (bits
@@ -269,48 +266,6 @@ struct FusedSmem {
         total = o;
     }
 };
-
-// One chunk (nk columns, vs = the matching entries of v) of a thread's GEMV rows, read with the "keep in L2" policy: the
-// columns the host marked resident (FusedArgs::res_cols) are part of every GEMV of the panel, so after the first column
-// they come from L2 instead of HBM. Same arithmetic in the same order as the streaming loop of phase G.
-template <int U>
-__device__ __forceinline__ void gemv_chunk_resident(const double *P0, size_t step, int nk, const double *vs, double2 &acc,
-                                                    unsigned long long policy)
-{
-    double2 cur[U], nxt[U];
-    int k = 0;
-    if (nk >= U) {
-#pragma unroll
-        for (int u = 0; u < U; u++) cur[u] = ld_l2_keep((const double2 *)(P0 + u * step), policy);
-        const double *Pn = P0 + U * step;
-        for (; k + 2 * U <= nk; k += U) {
-#pragma unroll
-            for (int u = 0; u < U; u++) nxt[u] = ld_l2_keep((const double2 *)(Pn + u * step), policy);
-            Pn += U * step;
-#pragma unroll
-            for (int u = 0; u < U; u++) {
-                const double vk = vs[k + u];
-                acc.x = fma(cur[u].x, vk, acc.x);
-                acc.y = fma(cur[u].y, vk, acc.y);
-            }
-#pragma unroll
-            for (int u = 0; u < U; u++) cur[u] = nxt[u];
-        }
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-            const double vk = vs[k + u];
-            acc.x = fma(cur[u].x, vk, acc.x);
-            acc.y = fma(cur[u].y, vk, acc.y);
-        }
-        k += U;
-    }
-    for (; k < nk; k++) {
-        const double vk = vs[k];
-        const double2 xx = ld_l2_keep((const double2 *)(P0 + (size_t)k * step), policy);
-        acc.x = fma(xx.x, vk, acc.x);
-        acc.y = fma(xx.y, vk, acc.y);
-    }
-}
 
 // LAPACK's DLARFG rescaling branch inside the persistent kernel (a column in the denormal range; every CTA takes it
 // together): the row owners multiply x by 2^969 before anybody forms v = x * scale, and z = V^T x is taken again from the
@@ -607,11 +562,6 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_panel_fused(FusedArgs f)
                 long long it = (long long)v * gq.per;
                 const long long it_end = min(items, it + gq.per);
                 const int mp = m + gs.skip;
-                // resident columns of this column's GEMV: the set shrinks as V, Y, VT of the panel grow (a line that is
-                // read with the streaming policy again gives its place up)
-                const int res_now = (int)max(0ll, min((long long)f.res_cols, (f.l2_budget - 24ll * m * j) / (8ll * max(m, 1))));
-                const int ks = f.lc_end - res_now - lc0;    // first resident column relative to lc0 (>= nloc: none)
-                const unsigned long long keep_policy = res_now > 0 ? l2_policy_evict_last() : 0ull;
                 while (it < it_end) {
                     const int rb = (int)(it / nloc);
                     const int cbeg = (int)(it - (long long)rb * nloc);
@@ -622,19 +572,13 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_panel_fused(FusedArgs f)
                     const double *Ap = f.Aloc + (size_t)lc0 * f.lda + f.i + 1 - gs.skip + rp;
                     for (int k0 = cbeg, nk = 0; k0 < cend; k0 += nk) {
                         nk = min(f.kc, cend - k0);
-                        // columns >= ks are resident in L2 for the whole panel (read with another load policy): a chunk
-                        // is either streamed or resident
-                        const bool resident = k0 >= ks;
-                        if (!resident && k0 + nk > ks) nk = ks - k0;
                         group_barrier(1 + vb, 128);          // previous chunk's vs fully consumed
                         for (int k = vt; k < nk; k += 128) {
                             const int kk = f.cm.l2g(lc0 + k0 + k) - gc0;
                             vs[k] = (kk == 0) ? v_first : __ldcg(pc_cur + j + kk) * scale;
                         }
                         group_barrier(1 + vb, 128);
-                        if (rows_ok && resident) {
-                            gemv_chunk_resident<GEMV_U>(Ap + (size_t)k0 * f.lda, (size_t)f.lda, nk, vs, acc, keep_policy);
-                        } else if (rows_ok) {
+                        if (rows_ok) {
                             constexpr int U = GEMV_U;
                             const size_t step = (size_t)f.lda;
                             const double *P0 = Ap + (size_t)k0 * step;

@@ -70,16 +70,26 @@ def init(n_max, panel_width_max=-1, group=None):
     return Layout(world, rank, n_max)
 
 
-def hessenberg_device(n, A_loc, ldA, Q_loc, ldQ, begin=0, end=None, panel_width=-1):
+def _rendezvous(group=None):
+    """Host-side rendezvous before a collective reduction: the device-side waits between the ranks have a time-out of a few
+    seconds, so the ranks should enter the call together (allocation, garbage collection or I/O may delay one of them)."""
+    import torch.distributed as dist
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.barrier(group)
+
+
+def hessenberg_device(n, A_loc, ldA, Q_loc, ldQ, begin=0, end=None, panel_width=-1, group=None):
     """Collective. A_loc: this rank's columns (torch CUDA, column-major ldA x local_cols); Q_loc: its row slab."""
     end = n if end is None else end
+    _rendezvous(group)
     return api.lib().starneig_b200_dist_hessenberg_device(n, begin, end, panel_width, A_loc.data_ptr(), ldA,
                                                           Q_loc.data_ptr(), ldQ)
 
 
-def hessenberg_host(n, A, ldA, Q, ldQ, begin=0, end=None, panel_width=-1):
+def hessenberg_host(n, A, ldA, Q, ldQ, begin=0, end=None, panel_width=-1, group=None):
     """Collective. A, Q: column-major float64 numpy arrays holding the WHOLE matrices in memory shared by the ranks."""
     end = n if end is None else end
+    _rendezvous(group)
     return api.lib().starneig_b200_dist_hessenberg_host(n, begin, end, panel_width, A.ctypes.data, ldA, Q.ctypes.data, ldQ)
 
 

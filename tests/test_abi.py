@@ -19,7 +19,7 @@ def declared_symbols():
         text = open(path).read()
         text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
         names.update(re.findall(r"\b(starneig_[A-Za-z0-9_]+)\s*\(", text))
-    return names
+    return {x for x in names if not x.endswith("_t")}       # (a type in front of a function-pointer member is not a function)
 
 
 def exported_symbols():
@@ -160,7 +160,12 @@ def test_workspace_plan_bounds_up_to_the_largest_supported_order(sn):
                 assert worst <= cap, (n, ranks, pw, worst, cap)
     # the reference default survives wherever the persistent kernel's layout holds it
     assert lib.starneig_b200_plan_check(20000, -1, 1, out) == 0 and out[0] == 312 and out[1] > 0
-    assert lib.starneig_b200_plan_check(50000, -1, 8, out) == 0 and out[0] == 368 and out[1] > 0
+    assert lib.starneig_b200_plan_check(50000, -1, 1, out) == 0 and out[0] == 368 and out[1] > 0
+    # several GPUs: narrower automatic panels (the level-2 phases of a column are replicated on every rank)
+    assert lib.starneig_b200_plan_check(20000, -1, 2, out) == 0 and out[0] == 256
+    assert lib.starneig_b200_plan_check(20000, -1, 4, out) == 0 and out[0] == 192
+    assert lib.starneig_b200_plan_check(20000, -1, 8, out) == 0 and out[0] == 192
+    assert lib.starneig_b200_plan_check(50000, -1, 8, out) == 0 and out[0] == 224 and out[1] > 0
     assert lib.starneig_b200_plan_check(100000, -1, 1, out) == 0 and out[0] < sn.default_panel_width(100000)
     assert lib.starneig_b200_plan_check(MAX_N + 1, -1, 1, out) == 4          # STARNEIG_INVALID_ARGUMENTS
     assert lib.starneig_b200_plan_check(0, -1, 1, out) == 4

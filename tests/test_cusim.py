@@ -352,15 +352,13 @@ def test_sim_linear_gemv_with_lagging_blocks(simlib, sms, skew, seed):
     assert r.returncode == 0 and r.stdout.strip().endswith("OK"), r.stdout[-1000:] + r.stderr[-2000:]
 
 
-@pytest.mark.parametrize("gpus,n,pw,kb", [(1, 131, 24, 3), (1, 131, 24, 100), (2, 96, 16, 5)])
-def test_sim_gemv_resident_columns(sim, ora, gpus, n, pw, kb):
-    """STARNEIG_B200_GEMV_RESIDENT_KB: the last local columns of the trailing matrix are read with a keep-in-L2 load policy
-    (they are part of every GEMV of the panel), the rest streams; a chunk of a group's columns is split where the two
-    meet. Also STARNEIG_B200_GEMV_KC (columns of v staged per group at a time: 64 = many refills, 2048 = few).
-    Same sums in the same order => bitwise the same H and Q"""
+@pytest.mark.parametrize("gpus,n,pw,kc", [(1, 131, 24, 64), (2, 96, 16, 2048)])
+def test_sim_gemv_staging_chunk(sim, ora, gpus, n, pw, kc):
+    """STARNEIG_B200_GEMV_KC (columns of v staged per group at a time: 64 = many refills, 2048 = few): same sums in the same
+    order => bitwise the same H and Q"""
     with _Env(STARNEIG_B200_COL_BLOCK=8, CUSIM_SMS=3):
         A, Q, _ = _reduce(sim, ora, n, pw, gpus=gpus)
-        with _Env(STARNEIG_B200_GEMV_RESIDENT_KB=kb, STARNEIG_B200_GEMV_KC=(64 if kb == 3 else 2048)):
+        with _Env(STARNEIG_B200_GEMV_KC=kc):
             A1, Q1, _ = _reduce(sim, ora, n, pw, gpus=gpus)
     assert np.array_equal(A, A1) and np.array_equal(Q, Q1)
 
@@ -372,3 +370,103 @@ def test_sim_side_stream_overlap_mode(sim, ora):
     assert st["overlap"] == 1
 
 
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# chain hand-off: the Hessenberg stage with H, Q left on the device, and the Reduce-shaped entry
+# ---------------------------------------------------------------------------------------------------------------------
+def _chain_callbacks(ora, n, log, device):
+    """next stages of starneig_b200_SEP_SM_Reduce for the tests: `schur` = eigenvalues of H by LAPACK dhseqr (the oracle's
+    stand-in for starneig_SEP_SM_Schur; H and Q are left as they are), `select` / `reorder_schur` record their calls.
+    device = True: the Schur stage is handed the DEVICE pointers (host memory under the emulator)."""
+    import ctypes
+    from starneig_b200 import Chain, SCHUR_FN, SELECT_FN, REORDER_FN
+
+    def schur(nn, pH, ldH, pQ, ldQ, preal, pimag):
+        H = np.ctypeslib.as_array(ctypes.cast(pH, ctypes.POINTER(ctypes.c_double)), shape=(nn, ldH)).T      # (ldH x nn) view
+        ev = ora.eigenvalues(nn, np.asfortranarray(H), ldH)
+        np.ctypeslib.as_array(ctypes.cast(preal, ctypes.POINTER(ctypes.c_double)), shape=(nn,))[:] = ev.real
+        np.ctypeslib.as_array(ctypes.cast(pimag, ctypes.POINTER(ctypes.c_double)), shape=(nn,))[:] = ev.imag
+        log.append(("schur_device" if device else "schur", int(pH), ldH, int(pQ), ldQ))
+        return 0
+
+    def select(nn, pS, ldS, pred, arg, psel, pnum):
+        sel = np.ctypeslib.as_array(ctypes.cast(psel, ctypes.POINTER(ctypes.c_int)), shape=(nn,))
+        sel[:] = 0
+        sel[: nn // 2] = 1
+        pnum[0] = nn // 2
+        log.append(("select", nn))
+        return 0
+
+    def reorder(nn, psel, pS, ldS, pQ, ldQ, preal, pimag):
+        log.append(("reorder_schur", nn))
+        return 0
+
+    fns = (SCHUR_FN(schur), SELECT_FN(select), REORDER_FN(reorder))
+    chain = Chain()
+    if device:
+        chain.schur_device = fns[0]
+    else:
+        chain.schur = fns[0]
+    chain.select, chain.reorder_schur = fns[1], fns[2]
+    return chain, fns        # keep the callbacks alive
+
+
+def test_sim_hessenberg_stage_leaves_h_and_q_on_the_device(sim, ora):
+    n = 90
+    A0, Q0, ld = ora.fullpos(n, 2019)
+    A, Q = A0.copy(order="F"), Q0.copy(order="F")
+    sim.starneig_node_init(sim.STARNEIG_USE_ALL, 1, sim.STARNEIG_NO_MESSAGES)
+    try:
+        assert sim.starneig_SEP_SM_Hessenberg(n, A, ld, Q, ld) == 0
+        A1, Q1 = A0.copy(order="F"), Q0.copy(order="F")
+        ret, dH, lddH, dQ, lddQ = sim.hessenberg_stage(n, A1, ld, Q1, ld)
+        assert ret == 0 and dH and dQ and lddH >= n and lddQ >= n
+        assert np.array_equal(A1, A0) and np.array_equal(Q1, Q0)               # host arrays are inputs only
+        assert sim.get_stats()["d2h_bytes"] == 0
+        assert sim.stage_fetch(n, A1, ld, Q1, ld) == 0
+        assert np.array_equal(A1, A) and np.array_equal(Q1, Q)                 # what the host-pointer call returns
+        assert sim.stage_fetch(n + 1, A1, ld, Q1, ld) == -1
+        # argument numbering of starneig_SEP_SM_Hessenberg
+        assert sim.hessenberg_stage(0, A1, ld, Q1, ld)[0] == -1 and sim.hessenberg_stage(n, A1, n - 1, Q1, ld)[0] == -3
+    finally:
+        sim.starneig_node_finalize()
+    sim.starneig_node_init(sim.STARNEIG_USE_ALL, 2, sim.STARNEIG_NO_MESSAGES)
+    try:
+        assert sim.hessenberg_stage(n, A1, ld, Q1, ld)[0] == sim.STARNEIG_GENERIC_ERROR        # one GPU only
+    finally:
+        sim.starneig_node_finalize()
+
+
+@pytest.mark.parametrize("device", [False, True])
+def test_sim_reduce_shaped_chain(sim, ora, device):
+    """starneig_b200_SEP_SM_Reduce: Hessenberg here, Schur / Select / ReorderSchur from the caller (reference
+    src/common/combined.c:45-98); eigenvalues of the chain against numpy's"""
+    import ctypes
+    from starneig_b200 import PREDICATE_FN
+    n = 120
+    A0, Q0, ld = ora.full(n, 12)
+    A, Q = A0.copy(order="F"), Q0.copy(order="F")
+    real, imag = np.zeros(n), np.zeros(n)
+    log = []
+    chain, keep = _chain_callbacks(ora, n, log, device)
+    sim.starneig_node_init(sim.STARNEIG_USE_ALL, 1, sim.STARNEIG_NO_MESSAGES)
+    try:
+        ret, num = sim.starneig_b200_SEP_SM_Reduce(n, A, ld, Q, ld, real, imag, chain)
+        assert ret == 0 and [e[0] for e in log] == ["schur_device" if device else "schur"]
+        ev = np.sort_complex(real + 1j * imag)
+        want = np.sort_complex(np.linalg.eigvals(A0[:n]))
+        d = np.abs(ev[:, None] - want[None, :]).min(axis=1)
+        assert d.max() <= 1e-10 * np.linalg.norm(A0[:n])
+        assert ora.hessenberg_form_violations(n, A, ld) == 0 and ora.residual_u(n, Q, ld, A, ld, A0, ld) <= 500
+        # with a predicate the selection stages run too
+        A, Q = A0.copy(order="F"), Q0.copy(order="F")
+        selected = np.zeros(n, dtype=np.int32)
+        pred = PREDICATE_FN(lambda re, im, arg: int(re < 0.0))
+        ret, num = sim.starneig_b200_SEP_SM_Reduce(n, A, ld, Q, ld, real, imag, chain, predicate=pred, selected=selected)
+        assert ret == 0 and num == n // 2 and [e[0] for e in log][-2:] == ["select", "reorder_schur"] and selected.sum() == n // 2
+        # an incomplete chain is an argument error (the reference's numbering stops at 11)
+        from starneig_b200 import Chain
+        assert sim.starneig_b200_SEP_SM_Reduce(n, A, ld, Q, ld, real, imag, Chain())[0] == -12
+    finally:
+        sim.starneig_node_finalize()

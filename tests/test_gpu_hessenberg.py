@@ -309,3 +309,61 @@ def test_invariants_n10000(node, ora):
     inv = _gpu_invariants(n, A, Q, A0, ld)
     assert inv["ok"] and inv["trace_rel_err"] <= 100 * n * U, inv
     print("n=10000 invariants:", inv)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# chain hand-off
+# ---------------------------------------------------------------------------------------------------------------------
+def _device_to_host(ptr, ldd, n):
+    """(ldd x n) column-major device matrix -> numpy, through the CUDA runtime (no product code involved)"""
+    from cuda import cudart
+    out = np.zeros((ldd, n), order="F")
+    err, = cudart.cudaMemcpy(out.ctypes.data, ptr, ldd * n * 8, cudart.cudaMemcpyKind.cudaMemcpyDeviceToHost)
+    assert int(err) == 0
+    return out
+
+
+def test_hessenberg_stage_leaves_h_and_q_on_the_device(node, ora):
+    n = 700
+    A0, Q0, ld = ora.fullpos(n, 2019)
+    A, Q = A0.copy(order="F"), Q0.copy(order="F")
+    assert node.starneig_SEP_SM_Hessenberg(n, A, ld, Q, ld) == 0
+    A1, Q1 = A0.copy(order="F"), Q0.copy(order="F")
+    ret, dH, lddH, dQ, lddQ = node.hessenberg_stage(n, A1, ld, Q1, ld)
+    assert ret == 0 and np.array_equal(A1, A0) and np.array_equal(Q1, Q0) and node.get_stats()["d2h_bytes"] == 0
+    H = _device_to_host(dH, lddH, n)
+    Qd = _device_to_host(dQ, lddQ, n)
+    assert np.array_equal(H[:n], A[:n]) and np.array_equal(Qd[:n], Q[:n])       # the device copies ARE the result
+    assert node.stage_fetch(n, A1, ld, Q1, ld) == 0
+    assert np.array_equal(A1[:n], A[:n]) and np.array_equal(Q1[:n], Q[:n])
+
+
+def test_reduce_shaped_chain_with_a_device_schur_stage(node, ora):
+    """starneig_b200_SEP_SM_Reduce (shape of reference src/common/combined.c:45-98): the next stage receives DEVICE pointers;
+    the stand-in for the Schur stage pulls H from the device itself and takes its eigenvalues with LAPACK dhseqr"""
+    import ctypes
+    from starneig_b200 import Chain, SCHUR_FN
+    n = 600
+    A0, Q0, ld = ora.full(n, 12)
+    A, Q = A0.copy(order="F"), Q0.copy(order="F")
+    real, imag = np.zeros(n), np.zeros(n)
+    seen = []
+
+    def schur_device(nn, pH, ldH, pQ, ldQ, preal, pimag):
+        H = _device_to_host(pH, ldH, nn)
+        ev = ora.eigenvalues(nn, H, ldH)
+        np.ctypeslib.as_array(ctypes.cast(preal, ctypes.POINTER(ctypes.c_double)), shape=(nn,))[:] = ev.real
+        np.ctypeslib.as_array(ctypes.cast(pimag, ctypes.POINTER(ctypes.c_double)), shape=(nn,))[:] = ev.imag
+        seen.append((ldH, ldQ))
+        return 0
+
+    chain = Chain()
+    fn = SCHUR_FN(schur_device)
+    chain.schur_device = fn
+    ret, _ = node.starneig_b200_SEP_SM_Reduce(n, A, ld, Q, ld, real, imag, chain)
+    assert ret == 0 and len(seen) == 1
+    ev = real + 1j * imag
+    want = np.linalg.eigvals(A0[:n])
+    d = np.abs(ev[:, None] - want[None, :]).min(axis=1)
+    assert d.max() <= 1e-10 * np.linalg.norm(A0[:n])
+    _check_invariants(ora, n, A, Q, A0, ld)         # H and Q came back through the fetch at the end of the chain

@@ -1,6 +1,6 @@
 """GPU tests of the engine's switches and rare branches, each in its own process with a time-out (a fault or a hang fails
 one test instead of taking the whole GPU suite with it): the DLARFG rescaling branch, GEMV linearity against the
-sequential order of operations, the switches that must not change a single bit (resident GEMV columns, staging chunk),
+sequential order of operations, the switch that must not change a single bit (staging chunk of the GEMV),
 and the side-stream schedule of the deferred updates. All of it is also stepped through the kernel-logic emulator
 (tests/test_cusim.py)."""
 import os
@@ -92,7 +92,7 @@ def test_denormal_range_takes_dlarfg_rescaling_branch(fused):
     _child("denormal", 333, 45, fused)
 
 
-@pytest.mark.parametrize("switch", ["STARNEIG_B200_GEMV_RESIDENT_KB=4096", "STARNEIG_B200_GEMV_KC=2048"])
+@pytest.mark.parametrize("switch", ["STARNEIG_B200_GEMV_KC=2048"])
 def test_switch_is_bitwise_equal_to_the_default(switch):
     _child("variant", 1500, 200, switch)
 

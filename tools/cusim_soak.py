@@ -52,7 +52,7 @@ while time.time() < t_end:
                STARNEIG_B200_COL_BLOCK=str(random.choice([8, 16, 24])))
     sw = {}
     if random.random() < 0.3: sw["GEMV_LINEAR"] = 0
-    if random.random() < 0.4: sw["GEMV_RESIDENT_KB"] = random.choice([1, 5, 30, 500])
+    if random.random() < 0.3: sw["GEMM_TMA"] = random.choice([0, 1, 2])
     if random.random() < 0.4: sw["GEMV_KC"] = random.choice([64, 128, 2048])
     if random.random() < 0.25: sw["OVERLAP"] = 1
     if random.random() < 0.15: sw["FUSED_PANEL"] = 0
