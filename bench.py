@@ -236,6 +236,62 @@ def run_reference_arm(args):
     }))
 
 
+def run_threads_child(args):
+    """N > 1: the reference-facing call itself -- ONE process, starneig_node_init(cores, N, ...) + starneig_SEP_SM_Hessenberg
+    on pinned host arrays, one host thread of the library per GPU (reference src/include/starneig/node.h:178,
+    sep_sm.h:89-92). Runs as a child process of rank 0 after the ranks of the process-per-GPU arms have gone, so that a
+    failure here cannot take the bench line with it. Prints one JSON object."""
+    import numpy as np
+    import torch
+    import starneig_b200 as sn
+    from tools import invariants
+    n, N = args.n, args.gpus
+    ld = (n + 15) // 16 * 16
+    torch.cuda.set_device(0)
+    gen = torch.Generator(device="cuda").manual_seed(2019)
+    dA0 = torch.rand((n, ld), dtype=torch.float64, device="cuda", generator=gen)
+    hostA0 = dA0.cpu()
+    pinned = torch.empty((2, n, ld), dtype=torch.float64).pin_memory()
+    hA, hQ = pinned[0].numpy().T, pinned[1].numpy().T
+    diag = np.arange(n)
+    sn.starneig_node_init(sn.STARNEIG_USE_ALL, N, sn.STARNEIG_NO_MESSAGES)
+    sn.set_profile_level(1)
+    times, st = [], None
+    for it in range(1 + args.steps):
+        pinned[0].copy_(hostA0)
+        pinned[1].zero_()
+        hQ[diag, diag] = 1.0
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        assert sn.starneig_SEP_SM_Hessenberg(n, hA, ld, hQ, ld) == 0
+        dt = 1e3 * (time.perf_counter() - t0)
+        st = sn.get_stats()
+        if it > 0:
+            times.append(dt)
+    sn.starneig_node_finalize()
+    parity = invariants.evaluate(dA0, pinned[0].cuda(), pinned[1].cuda(), n)
+    ms = sum(times) / len(times)
+    print(json.dumps({"ms_per_step": ms, "value": flops(n) / (ms * 1e-3) / 1e9, "h2d_bytes_per_step": int(st["h2d_bytes"]),
+                      "d2h_bytes_per_step": int(st["d2h_bytes"]), "ranks": int(st["ranks"]), "panel_width": int(st["panel_width_used"]),
+                      "staging_overlapped": int(st["staging_overlapped"]), "device_ms": st["device_ms"], "parity": parity}))
+
+
+def reference_call_e2e(args, world):
+    """rank 0, N > 1: times the one-process call through a child process (run_threads_child); returns (dict | None, error | None)"""
+    cmd = [sys.executable, os.path.abspath(__file__), "--e2e-threads-child", "--gpus", str(world), "--n", str(args.n),
+           "--steps", str(max(1, min(args.steps, 5)))]
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT",
+                                                             "TORCHELASTIC_RUN_ID", "GROUP_RANK", "ROLE_RANK", "LOCAL_WORLD_SIZE")}
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=420, cwd=ROOT, env=env)
+    except subprocess.TimeoutExpired:
+        return None, "timed out after 420 s"
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    if r.returncode != 0 or not lines:
+        return None, f"exit code {r.returncode}: {(r.stderr or r.stdout)[-300:]}"
+    return json.loads(lines[-1]), None
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -440,6 +496,29 @@ def run_ours(args):
     if rank != 0:
         return
 
+    # ---------------- N > 1: the reference-facing call (one process drives all GPUs) ----------------
+    e2e_calls = {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms_per_step, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h}
+    e2e_extra = {}
+    if world == 1:
+        e2e_calls["path"] = "starneig_node_init(cores, 1, ...) + starneig_SEP_SM_Hessenberg(n, A, ldA, Q, ldQ) on pinned host arrays"
+    if world > 1:
+        e2e_calls["path"] = ("one process per GPU (torchrun): starneig_b200_dist_hessenberg_host on one shared, page-locked host copy "
+                             "of A and Q, every rank stages its own shards")
+        if not args.no_threads_e2e:
+            del dA, dQ, dA0
+            torch.cuda.empty_cache()
+            child, err = reference_call_e2e(args, world)
+            if child is not None and child["parity"]["ok"] and child["ranks"] == world:
+                e2e_extra["e2e_process_per_gpu"] = e2e_calls
+                e2e_calls = {"value": child["value"], "unit": UNIT, "ms_per_step": child["ms_per_step"],
+                             "h2d_bytes_per_step": child["h2d_bytes_per_step"], "d2h_bytes_per_step": child["d2h_bytes_per_step"],
+                             "path": f"ONE process: starneig_node_init(cores, {world}, ...) + starneig_SEP_SM_Hessenberg(n, A, ldA, Q, ldQ) on "
+                                     "pinned host arrays, one host thread of the library per GPU (the reference's own calling convention)",
+                             "steps": max(1, min(args.steps, 5)), "panel_width": child["panel_width"],
+                             "staging_overlapped": child["staging_overlapped"], "parity": child["parity"]}
+            else:
+                e2e_extra["e2e_reference_call_error"] = err or f"child result rejected: {child}"
+
     # ---------------- roofline of the dominant kernel ----------------
     peak, peak_kind = measured_peaks()
     t_roof_ms = 1e3 * (8.0 * (n - 1) * n * (2 * n - 1) / 6.0 / (peak * 1e9) + (14.0 / 3.0) * n ** 3 / (FP64_CUBLAS_TFLOPS * 1e12)) / world
@@ -504,7 +583,7 @@ def run_ours(args):
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": shared_config(n, world),
-        "engine": {"panel_width": int(st["panel_width"]), "ld": ld,
+        "engine": {"panel_width": int(st["panel_width_used"]), "ld": ld,
                    # engine switches taken from the environment (none: the defaults of DESIGN.md section 4)
                    "switches": {k: v for k, v in sorted(os.environ.items()) if k.startswith("STARNEIG_B200_")},
                    "l2": "inputs (A, Q: 2 x %.1f GB) are larger than the 126 MB L2; no explicit flush" % (n * ld * 8 / 1e9),
@@ -519,8 +598,8 @@ def run_ours(args):
         "phases_ms_per_step": {"column_loops": phase[0] / args.steps, "trailing_updates": phase[1] / args.steps,
                                "deferred_busy": phase[2] / args.steps, "deferred_tail": side_tail / args.steps,
                                "overlap": overlap},
-        "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms_per_step,
-                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "e2e": e2e_calls,
+        **e2e_extra,
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": roofline,
@@ -537,10 +616,14 @@ def main():
     ap.add_argument("--n", type=int, default=int(os.environ.get("STARNEIG_BENCH_N", "20000")))
     ap.add_argument("--cpu-n", type=int, default=CPU_SAMPLE_N)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-threads-e2e", action="store_true", help="N > 1: skip the one-process (thread per GPU) timing of the reference-facing call")
+    ap.add_argument("--e2e-threads-child", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--no-e2e", action="store_true",
                     help="skip the host-buffer arm (development runs at sizes whose host copies do not fit comfortably)")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.e2e_threads_child:
+        run_threads_child(args)
+    elif args.impl == "reference":
         run_reference_arm(args)
     else:
         run_ours(args)

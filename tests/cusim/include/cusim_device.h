@@ -179,7 +179,7 @@ template <int N> static inline void cp_async_wait() {}
 // on a 1024-byte boundary, where the address-based pattern of the hardware is the same), and an mbarrier is
 // {phase : 1, pending arrivals : 15, arrival count : 16, pending bytes : 32} in its 8 bytes. The fibers of a CTA run on
 // one host thread, so no atomics are needed.
-struct alignas(64) SbTensorMap { const double *base; unsigned long long dim0, dim1, ld; unsigned box0, box1; char pad[80]; };
+struct alignas(64) SbTensorMap { const double *base; unsigned long long dim0, dim1, ld; unsigned box0, box1; int swizzle; char pad[76]; };
 #define SB_GRID_CONSTANT
 static inline void sb_make_tensor_map(SbTensorMap *map, const double *base, unsigned long long dim0, unsigned long long dim1,
                                       unsigned long long ld, unsigned box0, unsigned box1)
@@ -188,7 +188,7 @@ static inline void sb_make_tensor_map(SbTensorMap *map, const double *base, unsi
         fprintf(stderr, "cusim: invalid tensor map (base %p ld %llu box %u x %u)\n", (const void *)base, ld, box0, box1);
         abort();
     }
-    map->base = base; map->dim0 = dim0; map->dim1 = dim1; map->ld = ld; map->box0 = box0; map->box1 = box1;
+    map->base = base; map->dim0 = dim0; map->dim1 = dim1; map->ld = ld; map->box0 = box0; map->box1 = box1; map->swizzle = 1;
 }
 static inline double *sb_align_shared(double *p, unsigned align) { return (double *)(((uintptr_t)p + align - 1) / align * align); }
 namespace mbar_bits {
@@ -225,12 +225,14 @@ static inline void tma_load_2d(void *smem_dst, const SbTensorMap *map, int c0, i
 {
     double *dst = (double *)smem_dst;
     // the hardware addresses global memory in 16-byte units: an odd coordinate in the contiguous dimension traps
+    if (((uintptr_t)smem_dst & 127) != 0) { fprintf(stderr, "cusim: TMA destination is not 128-byte aligned\n"); abort(); }
     if (c0 & 1) { fprintf(stderr, "cusim: TMA box starts at an odd element of the contiguous dimension (c0 = %d)\n", c0); abort(); }
     for (unsigned r = 0; r < map->box1; r++)
         for (unsigned e = 0; e < map->box0; e++) {
             const long long x0 = (long long)c0 + e, x1 = (long long)c1 + r;
             const bool inside = x0 >= 0 && x1 >= 0 && (unsigned long long)x0 < map->dim0 && (unsigned long long)x1 < map->dim1;
-            dst[r * 16 + ((((e >> 1) ^ (r & 7)) << 1) | (e & 1))] = inside ? map->base[(size_t)x1 * map->ld + x0] : 0.0;
+            const size_t off = map->swizzle ? r * 16 + ((((e >> 1) ^ (r & 7)) << 1) | (e & 1)) : (size_t)r * map->box0 + e;
+            dst[off] = inside ? map->base[(size_t)x1 * map->ld + x0] : 0.0;
         }
     const unsigned long long b = *bar;
     *bar = mbar_bits::pack(mbar_bits::phase(b), mbar_bits::pending(b), mbar_bits::count(b), mbar_bits::tx(b) - (int)(map->box0 * map->box1 * sizeof(double)));
