@@ -62,22 +62,12 @@ using TmaTN12 = GemmTmaConfig<true,  true,  4, 1, 2, 12, 3, 2>;
 using TmaNN13 = GemmTmaConfig<false, true,  4, 1, 2, 13, 3, 2>;
 using TmaNN12 = GemmTmaConfig<false, true,  4, 1, 2, 12, 3, 2>;
 
-// "Fat" variants for the side stream: 256 threads x ~200 registers fill the register file of an SM, so a CTA owns
-// its SM exclusively. When it retires the SM is completely free and the (higher-priority, equally SM-exclusive)
-// persistent panel kernel can claim it at once; with the 2-CTAs-per-SM variants an SM never drains while the
-// deferred GEMM still has CTAs queued, and the panel kernel would wait for the whole GEMM to finish.
-using GemmNTfat   = GemmConfig<false, false, 2, 4, 8, 4, 4, 1>;     // 128 x 128
-using GemmNN13fat = GemmConfig<false, true,  8, 1, 2, 13, 4, 1>;    // 128 x 104
-using GemmNN12fat = GemmConfig<false, true,  8, 1, 2, 12, 4, 1>;    // 128 x  96
-
 static const size_t PANEL_SMEM_MAX = 200 * 1024;
-constexpr int PANEL_RING = 3;           // V / VT buffer sets: the deferred updates may lag two panels behind
 
 // per-device function attributes (opt-in shared memory sizes)
 static void prepare_device_functions()
 {
     GemmNT::prepare(); GemmTN13::prepare(); GemmTN12::prepare(); GemmNN13::prepare(); GemmNN12::prepare();
-    GemmNTfat::prepare(); GemmNN13fat::prepare(); GemmNN12fat::prepare();
     TmaNT::prepare(); TmaTN13::prepare(); TmaTN12::prepare(); TmaNN13::prepare(); TmaNN12::prepare();
     SB_CUDA(cudaFuncSetAttribute(k_col_finish_update<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM_MAX));
     SB_CUDA(cudaFuncSetAttribute(k_col_finish_update<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM_MAX));
@@ -147,10 +137,6 @@ struct Workspace {
     int n_cap = 0, nb_cap = 0;
     int ldv = 0, nbp = 0;
     double *V = nullptr, *Y = nullptr, *VT = nullptr, *W = nullptr, *Wpart = nullptr;
-    // Ring of V / VT buffers (Vb[0] == V, VTb[0] == VT): panel k factorises into set k % PANEL_RING, so that the
-    // deferred updates of panel k (side stream) can still read its reflectors while the next panels are factorised.
-    double *Vb[PANEL_RING] = {}, *VTb[PANEL_RING] = {};
-    double *Wside = nullptr, *Wpart_side = nullptr;     // W and split-K partials of the side stream
     double *Vg = nullptr, *VTg = nullptr;      // rows of V, VT of the local columns (P > 1)
     size_t wpart_cap = 0;           // doubles
     double *pcol = nullptr, *ypart = nullptr;
@@ -186,14 +172,10 @@ struct Workspace {
         nbp = round_up(nb, 8);
         size_t panel = (size_t)ldv * nbp;
         V = alloc<double>(panel); Y = alloc<double>(panel); VT = alloc<double>(panel); W = alloc<double>(panel);
-        Vb[0] = V; VTb[0] = VT;
-        for (int k = 1; k < PANEL_RING; k++) { Vb[k] = alloc<double>(panel); VTb[k] = alloc<double>(panel); }
-        Wside = alloc<double>(panel);
         if (dist) { Vg = alloc<double>(panel); VTg = alloc<double>(panel); }
         else Vg = VTg = nullptr;
         wpart_cap = 8 * (size_t)std::max(ldv, 4096) * nbp;
         Wpart = alloc<double>(wpart_cap);
-        Wpart_side = alloc<double>(wpart_cap);
         pcol = alloc<double>(ldv);
         ypart_cap = ypart_doubles(n);
         ypart = alloc<double>(ypart_cap);
@@ -271,20 +253,9 @@ struct PanelGrid { int blocks; TileGeom tg; size_t smem_fu, smem_rf; };
 struct Rank {
     int P = 1, g = 0, device = 0, cb = 64;
     bool ready = false;
-    cudaStream_t stream = nullptr;          // critical path: column loops and trailing updates (highest priority)
-    cudaStream_t side = nullptr;            // deferred updates (Q, rows above the panel), lowest priority
-    cudaEvent_t ev_panel[PANEL_RING] = {}, ev_side[PANEL_RING] = {};
+    cudaStream_t stream = nullptr;          // the launch sequence of the reduction
     cudaStream_t copy = nullptr;            // host staging that overlaps the reduction (Q upload, write-back of finished columns)
     cudaEvent_t ev_q_up = nullptr, ev_cols_final = nullptr;
-    // 1: deferred updates run on `side`, concurrently with the next column loops. Off by default: measured on B200 at
-    // n = 20000 (profiles/r1_s5_overlap_sweep.txt) the concurrent DMMA GEMMs cost the HBM-bound column loops far more
-    // (GEMV phases 6335 -> 3850-4540 GB/s) than the 770 ms of deferred work they hide: 5334 ms without, 6216-6854 ms with.
-    int overlap = 0;
-    int overlap_ctas = 0;                   // grid of the fused panel kernel while deferred updates are pending (0: automatic)
-    int side_chunk = 0;                     // rows per launch of the deferred GEMMs (0: one launch)
-    int side_fat = 1;                       // deferred GEMMs use the SM-exclusive tile configurations
-    double side_rate = 22e12;               // flop/s of the deferred GEMMs if they had the whole GPU (SM-split model)
-    int side_max_sms = 48;
     Workspace ws;
     ArenaLayout al;
     char *arena = nullptr;                  // own arena (device memory on `device`)
@@ -309,14 +280,7 @@ struct Rank {
         if (ready) return;
         P = P_; g = g_; device = device_;
         SB_CUDA(cudaSetDevice(device));
-        int prio_lo = 0, prio_hi = 0;
-        SB_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
-        SB_CUDA(cudaStreamCreateWithPriority(&stream, cudaStreamNonBlocking, prio_hi));
-        SB_CUDA(cudaStreamCreateWithPriority(&side, cudaStreamNonBlocking, prio_lo));
-        for (int k = 0; k < PANEL_RING; k++) {
-            SB_CUDA(cudaEventCreateWithFlags(&ev_panel[k], cudaEventDisableTiming));
-            SB_CUDA(cudaEventCreateWithFlags(&ev_side[k], cudaEventDisableTiming));
-        }
+        SB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
         SB_CUDA(cudaStreamCreateWithFlags(&copy, cudaStreamNonBlocking));
         SB_CUDA(cudaEventCreateWithFlags(&ev_q_up, cudaEventDisableTiming));
         SB_CUDA(cudaEventCreateWithFlags(&ev_cols_final, cudaEventDisableTiming));
@@ -334,18 +298,6 @@ struct Rank {
         if (e) gemm_tma = atoi(e);
         e = getenv("STARNEIG_B200_GEMV_LINEAR");
         if (e) gemv_linear = atoi(e);
-        e = getenv("STARNEIG_B200_OVERLAP");
-        if (e) overlap = atoi(e);
-        e = getenv("STARNEIG_B200_OVERLAP_CTAS");
-        if (e && atoi(e) >= 1) overlap_ctas = atoi(e);
-        e = getenv("STARNEIG_B200_SIDE_CHUNK");
-        if (e && atoi(e) >= 0) side_chunk = atoi(e);
-        e = getenv("STARNEIG_B200_SIDE_FAT");
-        if (e) side_fat = atoi(e);
-        e = getenv("STARNEIG_B200_SIDE_RATE");
-        if (e && atof(e) > 0) side_rate = atof(e) * 1e12;
-        e = getenv("STARNEIG_B200_SIDE_MAX_SMS");
-        if (e && atoi(e) >= 1) side_max_sms = atoi(e);
         int coop = 0;
         SB_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
         if (!coop) fused = 0;
@@ -365,12 +317,10 @@ struct Rank {
         if (arena) cudaFree(arena);
         arena = nullptr;
         al = ArenaLayout();
-        for (int k = 0; k < PANEL_RING; k++) { cudaEventDestroy(ev_panel[k]); cudaEventDestroy(ev_side[k]); }
         cudaEventDestroy(ev_q_up); cudaEventDestroy(ev_cols_final);
         cudaStreamDestroy(stream);
-        cudaStreamDestroy(side);
         cudaStreamDestroy(copy);
-        stream = side = copy = nullptr;
+        stream = copy = nullptr;
         ready = false;
     }
     // (re)allocates the own arena for (n, nb); returns true if a new allocation was made (peers must re-exchange)
@@ -406,20 +356,17 @@ struct Rank {
     enum GemmKind { GEMM_NT, GEMM_TN, GEMM_NN };
 
     // C = alpha*op(A)*op(B) + beta*C on the rank's stream; split-K through ws.Wpart for skinny outputs
-    // (ws.Wpart_side when issued on the side stream)
     // k_guard: see GemmTmaConfig::launch (an operand whose k runs over the panel's rows may start at an odd element; the
     // engine's V / VT / Y buffers carry a zero row in front for that case)
     void gemm(GemmKind kind, int M, int N, int K, double alpha, const double *A, int lda,
-              const double *B, int ldb, double beta, double *C, int ldc, bool on_side = false, bool k_guard = false)
+              const double *B, int ldb, double beta, double *C, int ldc, bool k_guard = false)
     {
         if (M < 1 || N < 1) return;
-        cudaStream_t st = on_side ? side : stream;
-        double *wpart = on_side ? ws.Wpart_side : ws.Wpart;
+        cudaStream_t st = stream;
+        double *wpart = ws.Wpart;
         stats.gemm_flops += 2.0 * M * N * (double)K;
-        const bool fat = on_side && side_fat;
         if (kind == GEMM_NT) {
-            if (fat) GemmNTfat::launch(st, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, 1, K, 0);
-            else if ((gemm_tma & 1) && TmaNT::launch(st, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, 1, K, 0, 0, k_guard)) stats.gemm_tma_launches++;
+            if ((gemm_tma & 1) && TmaNT::launch(st, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, 1, K, 0, 0, k_guard)) stats.gemm_tma_launches++;
             else { GemmNT::launch(st, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, 1, K, 0); stats.gemm_cpasync_launches++; }
             stats.kernel_launches++;
             return;
@@ -428,9 +375,9 @@ struct Rank {
         // grid would not fill the GPU twice
         int bn = (ceil_div(N, 96) * 96 <= ceil_div(N, 104) * 104) ? 96 : 104;
         // 2 CTAs per SM are resident; split K so that the grid is >= ~8 waves (tail quantisation < ~6 %)
-        int tiles = ceil_div(M, fat ? 128 : 64) * ceil_div(N, bn);
+        int tiles = ceil_div(M, 64) * ceil_div(N, bn);
         int splits = 1;
-        const int want = fat ? 6 * 148 : 8 * 2 * 148;
+        const int want = 8 * 2 * 148;
         if (beta == 0.0 && alpha == 1.0 && wpart != nullptr && tiles < want) {
             splits = std::min(32, ceil_div(want, tiles));
             splits = std::min(splits, std::max(1, K / 512));
@@ -444,9 +391,7 @@ struct Rank {
         double b = splits > 1 ? 0.0 : beta;
 #define SB_SKINNY(CFG) CFG::launch(st, M, N, K, alpha, A, lda, B, ldb, b, out, ldc, splits, klen, stride, 1)
 #define SB_SKINNY_TMA(CFG) ((gemm_tma & 2) && CFG::launch(st, M, N, K, alpha, A, lda, B, ldb, b, out, ldc, splits, klen, stride, 1, k_guard))
-        if (kind == GEMM_NN && fat) {
-            if (bn == 96) SB_SKINNY(GemmNN12fat); else SB_SKINNY(GemmNN13fat);
-        } else if (kind == GEMM_TN) {
+        if (kind == GEMM_TN) {
             if (bn == 96) { if (SB_SKINNY_TMA(TmaTN12)) stats.gemm_tma_launches++; else { SB_SKINNY(GemmTN12); stats.gemm_cpasync_launches++; } }
             else          { if (SB_SKINNY_TMA(TmaTN13)) stats.gemm_tma_launches++; else { SB_SKINNY(GemmTN13); stats.gemm_cpasync_launches++; } }
         } else {
@@ -640,32 +585,11 @@ struct Rank {
         stats.kernel_launches++;
     }
 
-    // X(rows x m) <- X (I - V T V^T) = X - (X VT) V^T  (reference update_right_a/b, src/hessenberg/cpu.c:443-560),
-    // optionally in row chunks so that no single launch of the side stream holds the SMs for long
-    void deferred_right_update(int rows, int m, int w, double *X, int ldx, const double *V, const double *VT, int ld,
-                               double *W, bool on_side)
+    // X(rows x m) <- X (I - V T V^T) = X - (X VT) V^T  (reference update_right_a/b, src/hessenberg/cpu.c:443-560)
+    void deferred_right_update(int rows, int m, int w, double *X, int ldx, const double *V, const double *VT, int ld, double *W)
     {
-        const int chunk = (on_side && side_chunk > 0) ? side_chunk : rows;
-        for (int r0 = 0; r0 < rows; r0 += chunk) {
-            const int nr = std::min(chunk, rows - r0);
-            gemm(GEMM_NN, nr, w, m, 1.0, X + r0, ldx, VT, ld, 0.0, W + r0, ld, on_side, true);
-            gemm(GEMM_NT, nr, m, w, -1.0, W + r0, ld, V, ld, 1.0, X + r0, ldx, on_side);
-        }
-    }
-
-    // Grid of the persistent panel kernel while deferred updates are in flight on the side stream: the SMs it
-    // leaves free are the ones the deferred GEMMs run on. Balance: the column loop is HBM-bound (needs ~3/4 of the
-    // SMs to saturate the memory system), the deferred GEMMs of one panel need
-    // flops / (per-SM DMMA rate * free SMs) seconds and should finish within the column loop of the next panel.
-    int panel_ctas(int m, int w, int n, int qrows, int i) const
-    {
-        if (overlap_ctas > 0) return std::min(overlap_ctas, fused_ctas);
-        const double t_col = 8.0 * (double)m * m * w / 6.3e12 + w * 24e-6;                 // s, all SMs
-        const double side_flops = 4.0 * (double)w * m * ((double)qrows + (P == 1 ? i + 1 : 0));
-        const double per_sm = side_rate / 148.0;
-        int free_sms = (int)std::ceil(side_flops / (per_sm * t_col));
-        free_sms = std::max(8, std::min(free_sms, std::min(side_max_sms, fused_ctas / 2)));
-        return std::max(1, fused_ctas - free_sms);
+        gemm(GEMM_NN, rows, w, m, 1.0, X, ldx, VT, ld, 0.0, W, ld, true);
+        gemm(GEMM_NT, rows, m, w, -1.0, W, ld, V, ld, 1.0, X, ldx);
     }
 
     // -----------------------------------------------------------------------------------------
@@ -703,33 +627,28 @@ struct Rank {
         }
         const int lc_end = cm.lower(end);
 
-        // Schedule. Critical path (main stream): column loop of panel k, then its trailing right/left updates. The
-        // updates of Q and of the rows above the panel only need V and VT of panel k and touch data that no later
-        // column loop or trailing update reads, so (overlap) they go to the low-priority side stream and run
-        // concurrently with the column loops of the next panels: those are HBM-bound and leave the FP64 tensor
-        // pipes idle, the deferred GEMMs are tensor-bound and need little bandwidth. The persistent panel kernel
-        // then runs on fewer SMs (panel_ctas) and the deferred GEMMs fill the others.
-        const bool ovl = overlap != 0;
-        int side_pending = 0;           // panels whose deferred updates have been issued
+        // Schedule: one stream. Per panel: column loop (persistent kernel), trailing right / left updates, then the updates
+        // the reference defers (rows above the panel, columns right of the block, Q). Running the deferred updates next to
+        // the column loops -- on a side stream with SMs set aside, or co-resident on the same SMs -- was measured on B200 at 1
+        // and at 8 GPUs and lost both times: the GEMV needs every SM to saturate HBM and the part is power-limited
+        // (profiles/r1_s5_overlap_sweep.txt, profiles/r2_v1_switch_sweep_n20000.txt,
+        // profiles/r2_v5_visit8b_panelwidth_by_gpus_overlap.log); those variants were removed in round 2.
         for (int i = begin; i < end - 1; i += nb, panel++) {
             const int w = std::min(nb, end - i - 1);
             const int m = end - i - 1;
-            const int slot = panel % PANEL_RING;
             // V and VT of the panel are stored with the row parity of the panel's first row in A (row i + 1; A is 16-byte
             // aligned with an even leading dimension), behind a zero guard row: the products over the panel's rows whose
             // operands are both K-major (W = A^T VT) then agree on where 16-byte units start, and moving the k frame by one
             // element for TMA adds a term that is zero (dgemm_tma.cuh)
             const int par = (i + 1) & 1;
-            double *V = ws.Vb[slot] + par, *VT = ws.VTb[slot] + par;
+            double *V = ws.V + par, *VT = ws.VT + par;
             if (par) {
-                SB_CUDA(cudaMemset2DAsync(ws.Vb[slot], (size_t)ld * sizeof(double), 0, sizeof(double), (size_t)w, st));
-                SB_CUDA(cudaMemset2DAsync(ws.VTb[slot], (size_t)ld * sizeof(double), 0, sizeof(double), (size_t)w, st));
+                SB_CUDA(cudaMemset2DAsync(ws.V, (size_t)ld * sizeof(double), 0, sizeof(double), (size_t)w, st));
+                SB_CUDA(cudaMemset2DAsync(ws.VT, (size_t)ld * sizeof(double), 0, sizeof(double), (size_t)w, st));
             }
-            // the buffers of this slot were last read by the deferred updates of panel - PANEL_RING
-            if (ovl && panel >= PANEL_RING) SB_CUDA(cudaStreamWaitEvent(st, ev_side[slot], 0));
             if (lvl >= 1) SB_CUDA(cudaEventRecord(phase_event(2 + 6 * panel + 0), st));
             const int pl0 = cm.lower(i), pl1 = cm.lower(i + w);
-            const int ctas = (ovl && side_pending > 0) ? panel_ctas(m, w, n, qrows, i) : fused_ctas;
+            const int ctas = fused_ctas;
             if (P == 1) {
                 panel_factor(cm, i, end, w, A, ldA, A + (size_t)i * ldA + i + 1, ldA, V, ws.Y, VT, ld, ctas);
             } else {
@@ -749,7 +668,6 @@ struct Rank {
                     stats.kernel_launches++;
                 }
             }
-            if (ovl) SB_CUDA(cudaEventRecord(ev_panel[slot], st));
             if (lvl >= 1) SB_CUDA(cudaEventRecord(phase_event(2 + 6 * panel + 1), st));
 
             // rows of V, VT that belong to the local columns of the global range [i+1, end)
@@ -768,21 +686,17 @@ struct Rank {
             if (ntr > 0) {
                 double *Atr = A + (size_t)tl0 * ldA + i + 1;
                 gemm(GEMM_NT, m, ntr, w, -1.0, ws.Y, ld, Vg + (tl0 - cl0), ldg, 1.0, Atr, ldA);
-                gemm(GEMM_TN, ntr, w, m, 1.0, Atr, ldA, VT, ld, 0.0, ws.W, ld, false, true);
+                gemm(GEMM_TN, ntr, w, m, 1.0, Atr, ldA, VT, ld, 0.0, ws.W, ld, true);
                 gemm(GEMM_NT, m, ntr, w, -1.0, V, ld, ws.W, ld, 1.0, Atr, ldA);
             }
             if (lvl >= 1) SB_CUDA(cudaEventRecord(phase_event(2 + 6 * panel + 2), st));
 
             // ---- deferred updates
-            const bool top_on_side = ovl && P == 1;     // P > 1: the sum over ranks uses the main-stream barriers
-            cudaStream_t sq = ovl ? side : st;
-            if (ovl) SB_CUDA(cudaStreamWaitEvent(side, ev_panel[slot], 0));
-            if (lvl >= 1) SB_CUDA(cudaEventRecord(phase_event(2 + 6 * panel + 3), ovl ? side : st));
+            if (lvl >= 1) SB_CUDA(cudaEventRecord(phase_event(2 + 6 * panel + 3), st));
             {   // rows above the panel
                 double *X = A + (size_t)cl0 * ldA;
                 if (P == 1) {
-                    double *Wt = top_on_side ? ws.Wside : ws.W;
-                    deferred_right_update(i + 1, m, w, X, ldA, V, VT, ld, Wt, top_on_side);
+                    deferred_right_update(i + 1, m, w, X, ldA, V, VT, ld, ws.W);
                 } else {
                     gemm(GEMM_NN, i + 1, w, ncl, 1.0, X, ldA, VTg, ldg, 0.0, wxp.p[g], al.ldv);
                     barrier();
@@ -794,22 +708,19 @@ struct Rank {
             if (end < n) {   // columns right of the reduced block (partial reduction)
                 const int xl0 = cm.lower(end), nx = cm.lower(n) - xl0;
                 double *X = A + (size_t)xl0 * ldA + i + 1;
-                gemm(GEMM_TN, nx, w, m, 1.0, X, ldA, VT, ld, 0.0, ws.W, ld, false, true);
+                gemm(GEMM_TN, nx, w, m, 1.0, X, ldA, VT, ld, 0.0, ws.W, ld, true);
                 gemm(GEMM_NT, m, nx, w, -1.0, V, ld, ws.W, ld, 1.0, X, ldA);
             }
-            if (hook && panel == 0) hook->before_q(sq);
+            if (hook && panel == 0) hook->before_q(st);
             if (qrows > 0)     // Q <- Q (I - V T V^T) on the rank's rows
-                deferred_right_update(qrows, m, w, Q + (size_t)(i + 1) * ldQ, ldQ, V, VT, ld, ovl ? ws.Wside : ws.W, ovl);
-            if (lvl >= 1) SB_CUDA(cudaEventRecord(phase_event(2 + 6 * panel + 4), sq));
-            if (ovl) { SB_CUDA(cudaEventRecord(ev_side[slot], side)); side_pending++; }
-            if (hook) hook->panel_done(sq, i + w);
+                deferred_right_update(qrows, m, w, Q + (size_t)(i + 1) * ldQ, ldQ, V, VT, ld, ws.W);
+            if (lvl >= 1) SB_CUDA(cudaEventRecord(phase_event(2 + 6 * panel + 4), st));
+            if (hook) hook->panel_done(st, i + w);
         }
         barrier();
         if (lvl >= 1) SB_CUDA(cudaEventRecord(phase_event(2 + 6 * panel), st));       // end of the critical path
-        if (ovl && side_pending > 0) SB_CUDA(cudaStreamWaitEvent(st, ev_side[(panel - 1) % PANEL_RING], 0));
         SB_CUDA(cudaEventRecord(ev_last, st));
         SB_CUDA(cudaStreamSynchronize(st));
-        SB_CUDA(cudaStreamSynchronize(side));
         SB_CUDA(cudaGetLastError());
         if (P > 1) {
             unsigned status = 0;
@@ -823,13 +734,13 @@ struct Rank {
         float ms = 0.f;
         SB_CUDA(cudaEventElapsedTime(&ms, ev_first, ev_last));
         stats.device_ms = ms;
-        stats.overlap = ovl ? 1 : 0;
+        stats.overlap = 0;
         if (lvl >= 1) {
             for (int p = 0; p < panel; p++) {
                 cudaEvent_t *e = &events[2 + 6 * p];
                 SB_CUDA(cudaEventElapsedTime(&ms, e[0], e[1])); stats.panel_ms += ms;
                 SB_CUDA(cudaEventElapsedTime(&ms, e[1], e[2])); stats.trail_ms += ms;
-                // deferred updates: busy time of the stream they ran on (overlaps the column loops when ovl)
+                // the updates the reference defers (rows above the panel, columns right of the block, Q)
                 SB_CUDA(cudaEventElapsedTime(&ms, e[3], e[4])); stats.other_ms += ms;
             }
             // what the deferred updates add to the critical path: end of the last trailing update -> end of the call

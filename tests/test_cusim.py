@@ -363,13 +363,6 @@ def test_sim_gemv_staging_chunk(sim, ora, gpus, n, pw, kc):
     assert np.array_equal(A, A1) and np.array_equal(Q, Q1)
 
 
-def test_sim_side_stream_overlap_mode(sim, ora):
-    """STARNEIG_B200_OVERLAP=1 (round-1 variant: deferred updates on the side stream, fat tiles, panel kernel on fewer CTAs)"""
-    with _Env(CUSIM_SMS=6, STARNEIG_B200_OVERLAP=1, STARNEIG_B200_OVERLAP_CTAS=4):
-        _, _, st = _reduce(sim, ora, 150, 24)
-    assert st["overlap"] == 1
-
-
 
 
 # ---------------------------------------------------------------------------------------------------------------------

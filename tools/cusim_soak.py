@@ -54,7 +54,6 @@ while time.time() < t_end:
     if random.random() < 0.3: sw["GEMV_LINEAR"] = 0
     if random.random() < 0.3: sw["GEMM_TMA"] = random.choice([0, 1, 2])
     if random.random() < 0.4: sw["GEMV_KC"] = random.choice([64, 128, 2048])
-    if random.random() < 0.25: sw["OVERLAP"] = 1
     if random.random() < 0.15: sw["FUSED_PANEL"] = 0
     if random.random() < 0.3: env["CUSIM_SHUFFLE"] = str(random.randint(1, 99))
     if random.random() < 0.3: env["CUSIM_SKEW"] = str(random.choice([2, 3, 5]))
