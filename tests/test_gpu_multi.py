@@ -147,3 +147,25 @@ def test_processes_torchrun(world, tmp_path):
     out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert "DIST_WORKER_OK" in out.stdout
+
+
+def test_real_peers_at_size(team, ora):
+    """every visible GPU as one rank (real NVLink peers where the box has several), n = 4000, default (per-GPU-count) panel
+    width: the reference driver's acceptance checks on the whole result and agreement with the one-GPU result"""
+    import torch
+    from tools import invariants
+    P = max(1, min(8, torch.cuda.device_count()))
+    n = 4000
+    A0, Q0, ld = ora.fullpos(n, 2019)
+    A1, Q1 = A0.copy(order="F"), Q0.copy(order="F")
+    assert _run(team(1), n, A1, ld, Q1) == 0
+    A, Q = A0.copy(order="F"), Q0.copy(order="F")
+    sn = team(P)
+    assert _run(sn, n, A, ld, Q) == 0
+    st = sn.get_stats()
+    assert st["ranks"] == P
+    t = lambda M: torch.from_numpy(np.ascontiguousarray(M.T)).cuda()
+    inv = invariants.evaluate(t(A0), t(A), t(Q), n)
+    assert inv["ok"], inv
+    assert np.abs(A[:n] - A1[:n]).max() <= 200 * n * U * np.abs(A1[:n]).max() and np.abs(Q[:n] - Q1[:n]).max() <= 200 * n * U
+    print(f"real peers: {P} GPUs, n = {n}, panel width {st['panel_width_used']}: {inv}")
