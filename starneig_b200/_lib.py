@@ -58,7 +58,8 @@ def load(path=None):
     """Binds the C ABI. `path` is only given by tests/test_cusim.py, which binds the same entry points of the
     kernel-logic emulator build of the library (tests/cusim); the product always loads LIB_PATH."""
     if path is None:
-        path = LIB_PATH
+        # STARNEIG_B200_LIB: another build of the same sources (A/B experiments on hardware, csrc/Makefile `exp`)
+        path = os.environ.get("STARNEIG_B200_LIB") or LIB_PATH
         if not os.path.exists(path):
             raise ImportError(
                 f"{LIB_PATH} is missing: build it with `make -C starneig_b200/csrc` "

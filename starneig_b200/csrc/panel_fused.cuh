@@ -31,10 +31,23 @@
 
 namespace sb200 {
 
-constexpr int FUSED_THREADS = 640;
+// Geometry of the CTA (build-time, for A/B experiments on hardware: csrc/Makefile `exp` target): threads, 128-thread GEMV
+// groups, 16-byte loads in flight per GEMV thread (U being accumulated + U being fetched).
+#ifndef SB_FUSED_THREADS
+#define SB_FUSED_THREADS 640
+#endif
+#ifndef SB_FUSED_VB
+#define SB_FUSED_VB 4
+#endif
+#ifndef SB_GEMV_U
+#define SB_GEMV_U 8
+#endif
+constexpr int FUSED_THREADS = SB_FUSED_THREADS;
 constexpr int FUSED_WARPS = FUSED_THREADS / 32;
 constexpr int FUSED_MAX_NB = 512;
-constexpr int FUSED_VB = 4;                          // 128-thread GEMV groups per CTA (warps 0..15); warps 16..19 look ahead
+constexpr int FUSED_VB = SB_FUSED_VB;                // 128-thread GEMV groups per CTA (warps 0..15); the other warps (16..19) look ahead
+constexpr int FUSED_LA_BARRIER = FUSED_VB + 1;       // named barrier of the look-ahead warps (1 .. FUSED_VB belong to the GEMV groups)
+static_assert(FUSED_THREADS % 32 == 0 && FUSED_THREADS <= 1024 && FUSED_THREADS > 128 * FUSED_VB && FUSED_VB + 1 <= 15, "CTA geometry");
 constexpr int FUSED_KC = 512;                        // columns of v staged per group at a time (default; FusedArgs::kc)
 constexpr int FUSED_MINSEG = 16;                     // fewest (row block, column) items per group
 
@@ -297,7 +310,7 @@ template <bool DIST>
 __global__ void __launch_bounds__(FUSED_THREADS, 1) k_panel_fused(FusedArgs f)
 {
     // 16-byte loads in flight per GEMV thread: U columns being accumulated + U being fetched
-    constexpr int GEMV_U = 8;
+    constexpr int GEMV_U = SB_GEMV_U;
     SB_DYNAMIC_SMEM(double, sh);
     const PanelArgs &a = f.a;
     const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
@@ -534,7 +547,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_panel_fused(FusedArgs f)
                 const double acc = sum_over_ctas(a.colpart + t, a.ldt, nblk, lane);
                 if (lane == 0) a.s[t] = fma(scale, acc, __ldcg(a.V + (size_t)t * ld + j));
             }
-            if (lin) group_barrier(5, FUSED_SHADOW_THREADS); else __syncthreads();
+            if (lin) group_barrier(FUSED_LA_BARRIER, FUSED_SHADOW_THREADS); else __syncthreads();
             // "my part of s is written": only the look-ahead warps wait for this, the GEMV starts at once
             if (wpr == 0 && lane == 0) red_release_gpu_add(bar2, 1u);
         }
@@ -632,12 +645,12 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_panel_fused(FusedArgs f)
                 const int xt = tid - 32 * FUSED_GEMV_WARPS, xw = wp - FUSED_GEMV_WARPS;
                 gen2 += G;
                 if (xt == 0) while ((int)(ld_acquire_gpu(bar2) - gen2) < 0) { }
-                group_barrier(5, FUSED_SHADOW_THREADS);
+                group_barrier(FUSED_LA_BARRIER, FUSED_SHADOW_THREADS);
                 for (int t = xt; t < j; t += FUSED_SHADOW_THREADS) {
                     s_sh[t] = __ldcg(a.s + t);
                     vrow_sh[t] = __ldcg(a.V + (size_t)t * ld + j);
                 }
-                group_barrier(5, FUSED_SHADOW_THREADS);
+                group_barrier(FUSED_LA_BARRIER, FUSED_SHADOW_THREADS);
                 const int NWn = max(1, (j + 31) >> 5);
                 for (int item = xw; item < nsub * NWn; item += FUSED_WARPS - FUSED_GEMV_WARPS) {
                     const int sub = item / NWn, g = item - sub * NWn, t0 = g * 32;
