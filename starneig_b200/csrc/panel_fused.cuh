@@ -365,6 +365,13 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_panel_fused(FusedArgs f)
             const int NWa = max(1, (jm1 + 31) >> 5);
             const bool do_update = j < f.w;
             const double tau = __ldcg(&a.scal[jm1].tau), beta_prev = __ldcg(&a.scal[jm1].beta), scale_prev = __ldcg(&a.scal[jm1].scale);
+            // the epilogue's inputs that do not depend on the GEMV (p'' of column j-1 and column j of the panel, own rows of the
+            // warp's first sub-tile) are fetched before the partial sums instead of after them: one L2 round trip less
+            double pre_p = 0.0, pre_a = 0.0;
+            if (wp < nsub) {
+                const int r = row0 + wp * 32 + lane;
+                if (r < row_end) { pre_p = pc_prev[r]; pre_a = acol[r]; }       // (j == w: the column right of the panel)
+            }
             double *acol_prev = f.pan + (size_t)jm1 * f.ldpan;
             {
                 // y(r) of the CTA's rows: sum of the local GEMV partials of column j-1 (fixed order); on P GPUs the
@@ -407,13 +414,15 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_panel_fused(FusedArgs f)
                 const bool valid = r < row_end;
                 double pp = 0.0;
                 if (valid) {
-                    const double pprev = pc_prev[r];
-                    const double ac = do_update ? acol[r] : 0.0;
+                    const bool pre = sub == wp;
+                    const double pprev = pre ? pre_p : pc_prev[r];
+                    const double ac_raw = pre ? pre_a : ((do_update || lin_prev) ? acol[r] : 0.0);
+                    const double ac = do_update ? ac_raw : 0.0;
                     // the GEMV of column j-1 was linear: its partials are g = A(:, c+1:) x and column j of the panel (not
                     // yet updated) is A(:, c), the column that belongs to the leading one of v
                     double D3 = ysm[sub * 32 + lane];
                     // (j == w: column i + w, the first one right of the panel; it exists -- the last panel ends at end - 2)
-                    if (lin_prev) D3 = fma(scale_prev, D3, do_update ? ac : acol[r]);
+                    if (lin_prev) D3 = fma(scale_prev, D3, ac_raw);
                     const double *rd = red + (size_t)sub * 3 * NWa * 32 + lane;
                     double D0 = 0.0, D1 = 0.0, D2 = 0.0;
                     for (int q = 0; q < NWa; q++) { D0 += rd[q * 32]; D1 += rd[(NWa + q) * 32]; D2 += rd[(2 * NWa + q) * 32]; }
@@ -585,6 +594,18 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_panel_fused(FusedArgs f)
                     const double *Ap = f.Aloc + (size_t)lc0 * f.lda + f.i + 1 - gs.skip + rp;
                     for (int k0 = cbeg, nk = 0; k0 < cend; k0 += nk) {
                         nk = min(f.kc, cend - k0);
+                        constexpr int U = GEMV_U;
+                        const size_t step = (size_t)f.lda;
+                        const double *P0 = Ap + (size_t)k0 * step;
+                        double2 cur[U], nxt[U];
+                        // the first loads of the block do not depend on v: they are on their way to HBM while v is staged
+                        // (no drain of the stream at the top of a column, at a re-staging of v or at a new row block)
+#ifdef SB_HOIST_LOADS
+                        if (rows_ok && nk >= U) {
+#pragma unroll
+                            for (int u = 0; u < U; u++) cur[u] = __ldcs((const double2 *)(P0 + u * step));
+                        }
+#endif
                         group_barrier(1 + vb, 128);          // previous chunk's vs fully consumed
                         for (int k = vt; k < nk; k += 128) {
                             const int kk = f.cm.l2g(lc0 + k0 + k) - gc0;
@@ -592,14 +613,12 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_panel_fused(FusedArgs f)
                         }
                         group_barrier(1 + vb, 128);
                         if (rows_ok) {
-                            constexpr int U = GEMV_U;
-                            const size_t step = (size_t)f.lda;
-                            const double *P0 = Ap + (size_t)k0 * step;
-                            double2 cur[U], nxt[U];
                             int k = 0;
                             if (nk >= U) {
+#ifndef SB_HOIST_LOADS
 #pragma unroll
                                 for (int u = 0; u < U; u++) cur[u] = __ldcs((const double2 *)(P0 + u * step));
+#endif
                                 const double *Pn = P0 + U * step;
                                 for (; k + 2 * U <= nk; k += U) {
 #pragma unroll

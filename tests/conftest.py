@@ -47,6 +47,25 @@ def node(sn):
     sn.starneig_node_finalize()
 
 
+def same_zero_pattern(A, Aref, n, scale=None):
+    """The exact zeros of two reductions of the same matrix agree: everything strictly below the first sub-diagonal is a
+    STRUCTURAL zero (written as 0.0 by both: reference src/hessenberg/cpu.c:153) and must match exactly; on and above the
+    sub-diagonal an entry that is zero only through cancellation (tau = 0 inputs, the last sub-diagonal entry of such a
+    matrix) may come out as 0.0 in one and as rounding noise in the other, so there a mismatch is accepted if both values are
+    below 200 n u max|Aref|."""
+    import numpy as np
+    u = 2.0 ** -52
+    Z, Zr = A[:n] == 0.0, Aref[:n] == 0.0
+    low = np.tril(np.ones((n, A.shape[1]), dtype=bool), -2)
+    if not np.array_equal(Z & low, Zr & low):
+        return False
+    diff = (Z != Zr) & ~low
+    if not diff.any():
+        return True
+    tol = 200 * n * u * max(1.0, float(np.abs(Aref[:n]).max()) if scale is None else scale)
+    return bool((np.maximum(np.abs(A[:n]), np.abs(Aref[:n]))[diff] <= tol).all())
+
+
 GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
 
 
@@ -117,7 +136,7 @@ def aed_window_check(sn, ora, n, end, pw, gpus=None):
     assert ora.hessenberg_port(n, A2, ld, Q2, ld, 0, end, pw) == 0
     assert np.isfinite(A[:n]).all() and np.isfinite(Q[:n]).all()
     assert np.count_nonzero(np.tril(A[:end, :end], -2)) == 0 and np.count_nonzero(A[end:n, :end]) == 0
-    assert np.array_equal(A[:n] == 0.0, A2[:n] == 0.0)
+    assert same_zero_pattern(A, A2, n)
     assert ora.orthogonality_u(n, Q, ld) <= 500
     res = np.linalg.norm(Q[:n] @ A[:n] @ Q[:n].T - Qr @ A0[:n] @ Qr.T) / np.linalg.norm(A0[:n]) / u
     assert res <= 500, res

@@ -16,7 +16,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import GOLDEN_DIR, STRUCTURED, aed_window_check, golden_cases, structured_input
+from conftest import GOLDEN_DIR, STRUCTURED, aed_window_check, golden_cases, same_zero_pattern, structured_input
 
 pytestmark = pytest.mark.gpu
 U = 2.0 ** -52
@@ -41,7 +41,7 @@ def _check_invariants(ora, n, A, Q, A0, ld, begin=0, end=None, outside=False):
 def _check_entrywise(n, A, Q, Aref, Qref):
     assert np.abs(A[:n] - Aref[:n]).max() <= 200 * n * U * max(1.0, np.abs(Aref[:n]).max())
     assert np.abs(Q[:n] - Qref[:n]).max() <= 200 * n * U
-    assert np.array_equal(A[:n] == 0.0, Aref[:n] == 0.0)          # same exact-zero pattern
+    assert same_zero_pattern(A, Aref, n)                          # same exact zeros (tests/conftest.py)
 
 
 @pytest.mark.parametrize("case", golden_cases())
@@ -97,7 +97,7 @@ def test_structured_inputs(node, ora, name, n, pw, end):
     if entrywise:
         _check_entrywise(n, A, Q, A2, Q2)
     else:
-        assert np.array_equal(A[:n] == 0.0, A2[:n] == 0.0)
+        assert same_zero_pattern(A, A2, n)
     if np.any(A0[:n]):
         res = ora.residual_u(n, Q, ld, A, ld, A0, ld)
         assert res <= 500, res
