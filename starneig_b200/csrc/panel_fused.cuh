@@ -598,14 +598,8 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_panel_fused(FusedArgs f)
                         const size_t step = (size_t)f.lda;
                         const double *P0 = Ap + (size_t)k0 * step;
                         double2 cur[U], nxt[U];
-                        // the first loads of the block do not depend on v: they are on their way to HBM while v is staged
-                        // (no drain of the stream at the top of a column, at a re-staging of v or at a new row block)
-#ifdef SB_HOIST_LOADS
-                        if (rows_ok && nk >= U) {
-#pragma unroll
-                            for (int u = 0; u < U; u++) cur[u] = __ldcs((const double2 *)(P0 + u * step));
-                        }
-#endif
+                        // (Issuing the first loads of the block here, before v is staged, was measured: the registers they hold
+                        // across the staging code spill and the kernel loses 2 %, profiles/r2_v10_sweep_microopts.txt.)
                         group_barrier(1 + vb, 128);          // previous chunk's vs fully consumed
                         for (int k = vt; k < nk; k += 128) {
                             const int kk = f.cm.l2g(lc0 + k0 + k) - gc0;
@@ -615,10 +609,8 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_panel_fused(FusedArgs f)
                         if (rows_ok) {
                             int k = 0;
                             if (nk >= U) {
-#ifndef SB_HOIST_LOADS
 #pragma unroll
                                 for (int u = 0; u < U; u++) cur[u] = __ldcs((const double2 *)(P0 + u * step));
-#endif
                                 const double *Pn = P0 + U * step;
                                 for (; k + 2 * U <= nk; k += U) {
 #pragma unroll
