@@ -1,19 +1,27 @@
 #!/usr/bin/env python
-"""bench.py -- FP64 Hessenberg GFLOP/s (10 n^3 / 3) of the B200-native path, n = 20000 on 1 GPU.
+"""bench.py -- FP64 Hessenberg GFLOP/s (10 n^3 / 3) of the B200-native path, n = 20000 on N GPUs of one box.
 
 A "step" is one full reduction (with Q) of a random dense n x n FP64 matrix.
-  value     device-resident arm: A and Q already in HBM when the timed region starts
-            (starneig_b200_hessenberg_device); time = CUDA events on the launching stream.
-  e2e       the reference-facing call starneig_SEP_SM_Hessenberg(n, A, ldA, Q, ldQ) on pinned HOST
-            buffers: H2D of A and Q, the reduction and D2H of H and Q are all inside the timed region.
-  roofline  the dominant kernel (k_panel_fused: one persistent launch per panel that streams the trailing matrix
-            once per panel column): algorithmic GEMV bytes of a launch (sum over its columns of 8 * rows * cols)
-            / mean launch duration from CUDA events recorded around every launch during the timed steps, against
-            the measured HBM copy bandwidth in MEASURED_PEAKS.json. (With STARNEIG_B200_FUSED_PANEL=0 the
-            per-column k_col_gemv launches are the dominant kernel and are reported instead.)
-  cpu_baseline  the reference's own CPU sources (oracle/_ref, sequential StarPU stand-in + threaded
-            OpenBLAS) -- or the oracle port when _ref is absent -- on a bounded sample.
-`--impl reference` times that CPU implementation instead and prints the same JSON line.
+  value     device-resident arm: A and Q (N > 1: every rank's shards) already in HBM when the timed region starts
+            (starneig_b200_hessenberg_device / starneig_b200_dist_hessenberg_device); time = CUDA events on the launching
+            stream, max over ranks.
+  e2e       the reference-facing call on pinned HOST buffers: H2D of A and Q, the reduction and D2H of H and Q are all
+            inside the timed region. N = 1: starneig_SEP_SM_Hessenberg(n, A, ldA, Q, ldQ). N > 1: the same call in ONE
+            process after starneig_node_init(cores, N, ...) (one host thread of the library per GPU), timed in a child
+            process of rank 0; the one-process-per-GPU host arm (starneig_b200_dist_hessenberg_host) is reported beside it
+            as `e2e_process_per_gpu` and is the fallback if the child fails.
+  parity    outside the timed region, at every N: the reference test driver's acceptance checks (exact-zero Hessenberg
+            form, |Q H Q^T - A|_F / |A|_F and |Q Q^T - I|_F / sqrt(n) in units of u; tools/invariants.py) on the WHOLE last
+            timed result, evaluated on rank 0's GPU, asserted <= min(500 u, 10 n u); and bitwise equality of the host-buffer
+            result with the device-resident one.
+  roofline  the dominant kernel (k_panel_fused: one persistent launch per panel that streams the trailing matrix once per
+            panel column): algorithmic GEMV bytes of a launch (sum over its columns of 8 * rows * cols) / mean launch
+            duration from CUDA events recorded around every launch during the timed steps, against the measured HBM copy
+            bandwidth in MEASURED_PEAKS.json; plus the device-side phase timers and the whole-path roofline.
+  cpu_baseline  the reference's own CPU sources (oracle/_ref, sequential StarPU stand-in + threaded OpenBLAS) -- or the
+            oracle port when _ref is absent -- on a bounded n = 6000 sample, and LAPACK dgehrd + dormhr (the reference
+            driver's `lapack` solver) on the same sample.
+`--impl reference` times that CPU implementation instead and prints the same JSON line with the same `config`.
 """
 import argparse
 import json

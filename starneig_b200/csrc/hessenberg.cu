@@ -327,7 +327,6 @@ extern "C" void starneig_b200_context_close(void)
     g_team.close();
     if (g_dist) { g_dist_shard.release(); g_dist->close(); delete g_dist; g_dist = nullptr; }
 }
-extern "C" void starneig_b200_staging_release(void) {}
 
 extern "C" __attribute__((visibility("default")))
 void starneig_b200_get_stats(struct starneig_b200_stats *stats) { *stats = g_team.stats; }

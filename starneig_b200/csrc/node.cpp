@@ -12,7 +12,6 @@
 #include <thread>
 
 extern "C" void starneig_b200_context_close(void);
-extern "C" void starneig_b200_staging_release(void);
 
 namespace {
 struct NodeState {
@@ -83,7 +82,6 @@ void starneig_node_finalize(void)
 {
     check_init();
     starneig_b200_context_close();
-    starneig_b200_staging_release();
     state.avail_cores = state.avail_gpus = 0;
     state.used_cores = state.used_gpus = 0;
     state.is_init = false;
