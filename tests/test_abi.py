@@ -169,3 +169,19 @@ def test_workspace_plan_bounds_up_to_the_largest_supported_order(sn):
     assert lib.starneig_b200_plan_check(100000, -1, 1, out) == 0 and out[0] < sn.default_panel_width(100000)
     assert lib.starneig_b200_plan_check(MAX_N + 1, -1, 1, out) == 4          # STARNEIG_INVALID_ARGUMENTS
     assert lib.starneig_b200_plan_check(0, -1, 1, out) == 4
+
+
+def test_dmma_fragment_loads_are_bank_conflict_free():
+    """the k permutation of the TMA-fed DMMA kernels (dgemm_tma.cuh::tma_kperm) against the 128-byte swizzle pattern: brute force
+    over every warp position, step and half-warp for both operand layouts (tools/swizzle_check.py)"""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("swizzle_check", os.path.join(ROOT, "tools", "swizzle_check.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    natural = [[4 * s + t for t in range(4)] for s in range(4)]
+    assert mod.worst(mod.addr_mn, natural) == 2 and mod.worst(mod.addr_k, natural) == 2
+    assert mod.worst(mod.addr_mn, mod.KSETS) == 1 and mod.worst(mod.addr_k, mod.KSETS) == 1
+    # the header's table is the one checked here
+    src = open(os.path.join(ROOT, "starneig_b200", "csrc", "dgemm_tma.cuh")).read()
+    for s, ks in enumerate(mod.KSETS):
+        assert "t == 0 ? %d : t == 1 ? %d : t == 2 ? %d : %d" % tuple(ks) in src, (s, ks)
