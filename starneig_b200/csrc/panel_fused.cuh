@@ -261,7 +261,7 @@ constexpr int FUSED_SHADOW_THREADS = FUSED_THREADS - 32 * FUSED_GEMV_WARPS;     
 
 // shared-memory layout (doubles), fixed for the whole launch
 struct FusedSmem {
-    int vs, s, vrow, w2, red, pv, ysm, sqred, scal, total;
+    int vs, s, vrow, w2, red, pv, ysm, ysum, sqred, scal, total;
     __host__ __device__ FusedSmem(int w, int nsub, int kc = FUSED_KC)
     {
         const int NW = (w + 31) / 32 > 1 ? (w + 31) / 32 : 1;
@@ -274,6 +274,7 @@ struct FusedSmem {
         red = o;   o += nsub * 3 * NW * 32;
         pv = o;    o += nsub * 32;
         ysm = o;   o += nsub * 32;
+        ysum = o;  o += FUSED_THREADS;          // per-thread shares of the GEMV partial sums of a row (phase A)
         sqred = o; o += 3 * FUSED_WARPS;
         scal = o;  o += 4;
         total = o;
@@ -324,6 +325,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_panel_fused(FusedArgs f)
     const FusedSmem L(f.w, nsub, f.kc);
     double *const vs_all = sh + L.vs, *const s_sh = sh + L.s, *const vrow_sh = sh + L.vrow, *const w2_sh = sh + L.w2;
     double *const red = sh + L.red, *const pv = sh + L.pv, *const ysm = sh + L.ysm, *const sqred = sh + L.sqred;
+    double *const ysum = sh + L.ysum;
     unsigned gen = 0, gen2 = 0;
     bool lin = false, lin_prev = false;     // the GEMV of this / of the previous column runs (ran) against the unscaled x
     unsigned *const bar2 = f.gbar + 32;         // arrival counter "s of this column is complete" (look-ahead warps only)
@@ -382,11 +384,43 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_panel_fused(FusedArgs f)
                 gp.per = max(FUSED_MINSEG, (int)(((long long)gs.RB * nloc_prev + G * FUSED_VB - 1) / (G * FUSED_VB)));
                 const unsigned epoch = f.x.epoch + jm1;
                 const int par = epoch & 1;
+                // The S partials of a row (one per GEMV group that touched its row block; S = 8 at m = 20000 on one GPU, but 15-25
+                // on 8 GPUs and 70+ for matrices of order 2000) are shared out over the `parts` threads that the CTA has per
+                // owned row, so that they are fetched in ONE batch of independent loads instead of S / 8 dependent batches;
+                // the shares meet in shared memory and are added in a fixed order.
+                const int RP = (rows_here + 31) & ~31;
+                const int parts = RP > 0 ? FUSED_THREADS / RP : 0;
+                if (parts >= 2) {
+                    double e = 0.0;
+                    if (tid < parts * RP) {
+                        const int part = tid / RP, rr = tid - part * RP, r = row0 + rr;
+                        if (rr < rows_here && nloc_prev > 0) {
+                            const int rb = (r + gs.skip) >> 8;
+                            const int S = gp.last_group(rb) - gp.first_group(rb) + 1;
+                            const double *p = a.ypart + r;
+                            int z = part;
+                            for (; z + 7 * parts < S; z += 8 * parts) {
+                                double x[8];
+#pragma unroll
+                                for (int u = 0; u < 8; u++) x[u] = __ldcg(p + (size_t)(z + u * parts) * a.ldp);
+                                e += ((x[0] + x[1]) + (x[2] + x[3])) + ((x[4] + x[5]) + (x[6] + x[7]));
+                            }
+                            double x[8];
+#pragma unroll
+                            for (int u = 0; u < 8; u++) x[u] = (z + u * parts < S) ? __ldcg(p + (size_t)(z + u * parts) * a.ldp) : 0.0;
+                            e += ((x[0] + x[1]) + (x[2] + x[3])) + ((x[4] + x[5]) + (x[6] + x[7]));
+                        }
+                        ysum[tid] = e;
+                    }
+                    __syncthreads();
+                }
                 for (int rr = tid; rr < rows_here; rr += FUSED_THREADS) {
                     const int r = row0 + rr;
                     const int rb = (r + gs.skip) >> 8;
                     double sum = 0.0;
-                    if (nloc_prev > 0) {
+                    if (parts >= 2) {
+                        for (int q = 0; q < parts; q++) sum += ysum[q * RP + rr];
+                    } else if (nloc_prev > 0) {
                         const int S = gp.last_group(rb) - gp.first_group(rb) + 1;
                         sum = sum_partials(a.ypart + r, a.ldp, S);
                     }
@@ -460,6 +494,8 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_panel_fused(FusedArgs f)
 
         // ================= phase R: p'' = p' - V w2; ||x||^2, z = V^T x =================
         {
+            // (Loading the warp's first tile of V before w2 arrives was measured: the 64 registers it holds across the barrier
+            // spill and phase R doubles, profiles/r2_v13_sweep_ysum.txt.)
             for (int t = tid; t < j; t += FUSED_THREADS) w2_sh[t] = __ldcg(a.w2 + t);
             __syncthreads();
             if (j > 0) {
