@@ -55,6 +55,8 @@ struct starneig_b200_stats {
                               * alone and d2h_ms what was left of the write-back when the reduction ended) */
     int panel_width_used;    /* panel width of the reduction (the requested one unless it exceeds what the panel kernels'
                               * shared-memory layout holds: > 1024 columns, or a narrower limit for n > ~70000) */
+    int fused_slab_panels[2];/* panels of the persistent kernel without [0] / with [1] the CTA's rows of V resident in shared
+                              * memory (panel_fused.cuh, FusedSmem) */
 };
 void starneig_b200_get_stats(struct starneig_b200_stats *stats);
 

@@ -34,10 +34,11 @@ class Stats(ctypes.Structure):
         ("overlap", ctypes.c_int), ("side_tail_ms", ctypes.c_double),
         ("gemm_tma_launches", ctypes.c_longlong), ("gemm_cpasync_launches", ctypes.c_longlong),
         ("staging_overlapped", ctypes.c_int), ("panel_width_used", ctypes.c_int),
+        ("fused_slab_panels", ctypes.c_int * 2),
     ]
 
     def as_dict(self):
-        return {name: (list(getattr(self, name)) if name == "fused_phase_ms" else getattr(self, name)) for name, _ in self._fields_}
+        return {name: (list(getattr(self, name)) if name in ("fused_phase_ms", "fused_slab_panels") else getattr(self, name)) for name, _ in self._fields_}
 
 
 SCHUR_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,

@@ -146,6 +146,7 @@ def set_profile_level(level):
 
 
 def default_panel_width(n):
-    """reference src/hessenberg/interface.c:74-78"""
+    """the REFERENCE's automatic panel width (src/hessenberg/interface.c:74-78), e.g. to run both with one blocking; the
+    library's own automatic width is 192 (engine.cuh::default_panel_width, measured on B200)"""
     import math
     return max(64, int(math.ceil((0.001875596476 * n + 273.5908216) / 8.0)) * 8)

@@ -63,6 +63,10 @@ using TmaNN13 = GemmTmaConfig<false, true,  4, 1, 2, 13, 3, 2>;
 using TmaNN12 = GemmTmaConfig<false, true,  4, 1, 2, 12, 3, 2>;
 
 static const size_t PANEL_SMEM_MAX = 200 * 1024;
+// The persistent panel kernel keeps the CTA's rows of V in shared memory only while the launch stays below this: the GEMV
+// needs the rest of the SM's 256 KB as L1 for its loads in flight (FusedSmem; profiles/r2_v15_sweep_l1_split.txt)
+static const size_t FUSED_SLAB_SMEM_MAX = 131 * 1024;
+static const size_t FUSED_SMEM_OPTIN = 227 * 1024;
 
 // per-device function attributes (opt-in shared memory sizes)
 static void prepare_device_functions()
@@ -85,8 +89,9 @@ static void prepare_device_functions()
     SB_CUDA(cudaFuncGetAttributes(&fa, k_sum_peers));
     SB_CUDA(cudaFuncGetAttributes(&fa, k_barrier));
     SB_CUDA(cudaFuncGetAttributes(&fa, splitk_reduce_kernel));
-    SB_CUDA(cudaFuncSetAttribute(k_panel_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM_MAX));
-    SB_CUDA(cudaFuncSetAttribute(k_panel_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM_MAX));
+#define SB_FUSED_PREP(D, S) SB_CUDA(cudaFuncSetAttribute(k_panel_fused<D, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FUSED_SMEM_OPTIN))
+    SB_FUSED_PREP(false, 0); SB_FUSED_PREP(false, 1); SB_FUSED_PREP(true, 0); SB_FUSED_PREP(true, 1);
+#undef SB_FUSED_PREP
 }
 
 struct GemvPlan { int skip, RB, S, kc; const double *A0; };
@@ -271,6 +276,8 @@ struct Rank {
     int gemm_tma = 3;                       // DMMA kernels fed by the TMA engine (dgemm_tma.cuh): bit 0 = the rank-nb updates (NT),
                                             // bit 1 = the skinny products (TN, NN); 0: the cp.async kernels (dgemm.cuh)
     int gemv_linear = 1;                    // fused kernel: the GEMV streams against the unscaled x (FusedArgs::linear)
+    size_t fused_smem_pad = 0;              // tuning aid: unused shared memory added to the fused kernel's launch (moves the L1 / shared-memory split)
+    int fused_slabs = 1;                    // fused kernel: the CTA's rows of V in shared memory when they fit (FusedSmem)
     std::vector<cudaEvent_t> events;        // phase events: 4 per panel
     std::vector<cudaEvent_t> gemv_events;   // 4 per timed column (profile level 2)
     size_t gemv_events_used = 0;
@@ -298,6 +305,17 @@ struct Rank {
         if (e) gemm_tma = atoi(e);
         e = getenv("STARNEIG_B200_GEMV_LINEAR");
         if (e) gemv_linear = atoi(e);
+        e = getenv("STARNEIG_B200_FUSED_SLABS");
+        if (e) fused_slabs = std::max(0, std::min(1, atoi(e)));
+        e = getenv("STARNEIG_B200_FUSED_SMEM_PAD_KB");
+        fused_smem_pad = e ? (size_t)std::max(0, atoi(e)) * 1024 : 0;
+        e = getenv("STARNEIG_B200_FUSED_CARVEOUT");
+        {   // tuning aid: preferred carve-out in percent (-1: the driver's choice)
+            const int pct = e ? atoi(e) : -1;
+#define SB_FUSED_CARVE(D, S) SB_CUDA(cudaFuncSetAttribute(k_panel_fused<D, S>, cudaFuncAttributePreferredSharedMemoryCarveout, pct))
+            SB_FUSED_CARVE(false, 0); SB_FUSED_CARVE(true, 0);
+#undef SB_FUSED_CARVE
+        }
         int coop = 0;
         SB_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
         if (!coop) fused = 0;
@@ -518,10 +536,19 @@ struct Rank {
                 y_epoch += w;
                 SB_CUDA(cudaMemsetAsync(ws.gbar, 0, 1024 * sizeof(unsigned), st));
                 SB_CUDA(cudaMemsetAsync(ws.rbar, 0, (FUSED_MAX_NB + 8) * sizeof(unsigned long long), st));
-                if (P > 1) SB_LAUNCH_COOP(k_panel_fused<true>, ctas, FUSED_THREADS, smem, st, f);
-                else       SB_LAUNCH_COOP(k_panel_fused<false>, ctas, FUSED_THREADS, smem, st, f);
+                // the CTA's rows of V in shared memory when they fit beside the fixed layout (m <= 32 * ctas rows at the
+                // AED client's width 224, twice that at width 192)
+                int slabs = fused_slabs;
+                while (slabs > 0 && fused_smem_bytes(w, f.nsub, f.kc, slabs) > FUSED_SLAB_SMEM_MAX) slabs--;
+                smem = fused_smem_bytes(w, f.nsub, f.kc, slabs);
+                smem = std::min(FUSED_SMEM_OPTIN, smem + fused_smem_pad);
+#define SB_FUSED_GO(S) do { if (P > 1) SB_LAUNCH_COOP((k_panel_fused<true, S>), ctas, FUSED_THREADS, smem, st, f); \
+                            else       SB_LAUNCH_COOP((k_panel_fused<false, S>), ctas, FUSED_THREADS, smem, st, f); } while (0)
+                if (slabs) SB_FUSED_GO(1); else SB_FUSED_GO(0);
+#undef SB_FUSED_GO
                 stats.kernel_launches++;
                 stats.fused_panels++;
+                stats.fused_slab_panels[slabs]++;
                 for (int j = 0; j < w; j++) {
                     const double bytes = 8.0 * (double)m * (lc_end - cm.lower(i + j + 1));
                     stats.gemv_bytes += bytes; stats.gemv_timed_bytes += bytes;
@@ -770,21 +797,22 @@ static inline void q_row_range(int P, int g, int n, int *q0, int *q1)
     *q1 = std::min(n, (g + 1) * per);
 }
 
-// The "automatic" panel width (conf->panel_width == STARNEIG_HESSENBERG_DEFAULT_PANEL_WIDTH). One GPU: the reference's
-// formula (src/hessenberg/interface.c:74-78: 312 at n = 20000; measured flat between 256 and 384 on B200). Several GPUs:
-// narrower, because the level-2 phases of a column (replicated on every rank, streaming V, Y, VT of the panel from L2) grow
-// with the panel width while a rank's share of everything else shrinks with the number of GPUs -- measured at n = 20000
-// (profiles/r2_v5_visit8b_panelwidth_by_gpus_overlap.log): 2 GPUs 256 (-0.6 %), 4 GPUs 192 (-3.7 %), 8 GPUs 192 (-6 %,
-// flat between 96 and 192). An explicit conf->panel_width is always taken as given.
+// The "automatic" panel width (conf->panel_width == STARNEIG_HESSENBERG_DEFAULT_PANEL_WIDTH). The reference fits a width to
+// its CPU codelets (src/hessenberg/interface.c:74-78: 0.0019 n + 274, i.e. 312 at n = 20000). Here the trade is another one:
+// the level-2 phases of a column stream V, Y, VT of the panel from L2 and grow with the width (and are replicated on every
+// rank), the TMA-fed DMMA kernels lose little at a smaller K, and the skinny products W = A^T VT / X VT run on 96- or
+// 104-column tiles, so that widths of 192, 208, 288, 312 waste no tile columns while 160 or 256 do. Measured on one B200
+// (profiles/r2_v16_sweep_panel_width_1gpu.txt, n = 1000 ... 30000): 192 beats the reference formula by 1.4-2.8 % at every
+// size (208 within 0.5 % of it; 96 loses at n >= 10000: +76 ms of level-3 time at n = 20000); on 4 and 8 GPUs 192 was the
+// winner already (profiles/r2_v5_visit8b_panelwidth_by_gpus_overlap.log: -3.7 % / -6 %, flat between 96 and 192).
+// An explicit conf->panel_width is always taken as given.
 static inline int default_panel_width(int n, int P = 1)
 {
     // tuning aid (tools/sweep.py): another "automatic" width without touching the caller's configuration
     const char *e = getenv("STARNEIG_B200_AUTO_PANEL_WIDTH");
     if (e && atoi(e) >= 8) return atoi(e);
-    const double ref = 0.001875596476 * n + 273.5908216;
-    if (P >= 4) return std::max(64, (int)std::ceil(0.6 * ref / 16.0) * 16);
-    if (P >= 2) return std::max(64, (int)std::ceil(0.8 * ref / 16.0) * 16);
-    return std::max(64, (int)std::ceil(ref / 8.0) * 8);
+    (void)n; (void)P;
+    return 192;
 }
 
 } // namespace sb200

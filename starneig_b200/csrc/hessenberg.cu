@@ -635,7 +635,8 @@ int starneig_b200_dist_init(int world, int rank, int n_max, int panel_width_max,
     SB_CUDA(cudaGetDevice(&dev));
     g_dist = new Rank();
     g_dist->open(world, rank, dev);
-    if (panel_width_max < 8) panel_width_max = default_panel_width(n_max, 1);      // the widest default: any rank count fits
+    // no limit given: room for the automatic width and for the reference's own default (src/hessenberg/interface.c:74-78)
+    if (panel_width_max < 8) panel_width_max = std::max(default_panel_width(n_max, 1), (int)std::ceil((0.001875596476 * n_max + 273.5908216) / 8.0) * 8);
     panel_width_max = std::min(panel_width_max, PANEL_MAX_NB);
     memset(handle_out, 0, 64);
     if (world > 1) {

@@ -193,8 +193,9 @@ __device__ __forceinline__ double sum_partials(const double *p, int ld, int S)
 // Column-wise dots of one CTA: out[t] = sum over the CTA's rows of M(r, t) * p(r) for t in [tb, tb+NC), t < tmax.
 // One warp; NC columns x NS sub-tiles = 32 independent loads are in flight per lane. p(r) comes from shared
 // memory (pv[sub*32 + lane], zero for rows >= m). Result: see transpose_reduce8 / transpose_reduce32.
+// `rbase`: row index of M's first stored row (0: a matrix in global memory; row0: the CTA's slab in shared memory).
 template <int NC, int NS>
-__device__ __forceinline__ void coldots(const double *__restrict__ M, int ld, int tb, int tmax, int row0, int m, int nsub,
+__device__ __forceinline__ void coldots(const double *__restrict__ M, int ld, int rbase, int tb, int tmax, int row0, int m, int nsub,
                                         const double *pv, int lane, double (&acc)[NC])
 {
 #pragma unroll
@@ -205,7 +206,7 @@ __device__ __forceinline__ void coldots(const double *__restrict__ M, int ld, in
         for (int s = 0; s < NS; s++) {
             const int r = row0 + (sub0 + s) * 32 + lane;
             const bool okr = sub0 + s < nsub && r < m;
-            const double *Mr = M + (size_t)tb * ld + r;
+            const double *Mr = M + (size_t)tb * ld + (r - rbase);
 #pragma unroll
             for (int q = 0; q < NC; q++) v[s][q] = (okr && tb + q < tmax) ? Mr[(size_t)q * ld] : 0.0;
         }
@@ -235,13 +236,13 @@ __device__ __forceinline__ double transpose_reduce16(double (&v)[16], int lane)
 }
 
 // partial column dots of the CTA -> colpart[b][t], t < tmax; warps [0, T) share the column batches
-__device__ __forceinline__ void coldots_all(const double *__restrict__ M, int ld, int tmax, int row0, int m, int nsub,
+__device__ __forceinline__ void coldots_all(const double *__restrict__ M, int ld, int rbase, int tmax, int row0, int m, int nsub,
                                             const double *pv, int wp, int T, int lane, double *out)
 {
     if (nsub >= 3) {
         for (int tb = 8 * wp; tb < tmax; tb += 8 * T) {
             double acc[8];
-            coldots<8, 4>(M, ld, tb, tmax, row0, m, nsub, pv, lane, acc);
+            coldots<8, 4>(M, ld, rbase, tb, tmax, row0, m, nsub, pv, lane, acc);
             const double xx = transpose_reduce8(acc, lane);
             const int t = tb + (lane >> 2);
             if ((lane & 3) == 0 && t < tmax) out[t] = xx;
@@ -249,7 +250,7 @@ __device__ __forceinline__ void coldots_all(const double *__restrict__ M, int ld
     } else {
         for (int tb = 16 * wp; tb < tmax; tb += 16 * T) {
             double acc[16];
-            coldots<16, 2>(M, ld, tb, tmax, row0, m, nsub, pv, lane, acc);
+            coldots<16, 2>(M, ld, rbase, tb, tmax, row0, m, nsub, pv, lane, acc);
             const double xx = transpose_reduce16(acc, lane);
             if (lane < 16 && tb + lane < tmax) out[tb + lane] = xx;
         }
@@ -260,9 +261,16 @@ constexpr int FUSED_GEMV_WARPS = 4 * FUSED_VB;                       // warps 0.
 constexpr int FUSED_SHADOW_THREADS = FUSED_THREADS - 32 * FUSED_GEMV_WARPS;      // warps 16..19: look-ahead during phase G
 
 // shared-memory layout (doubles), fixed for the whole launch
+// `slabs` (0 or 1): the CTA keeps its own rows of V for the whole panel in shared memory (w columns of 32 * nsub rows) next
+// to the copy in global memory (which the level-3 updates and the other CTAs read): phase R reads those rows twice per
+// column, from L2 at ~0.8 us per dependent round trip. Measured on B200 (profiles/r2_v14_sweep_slabs.txt,
+// r2_v15_sweep_l1_split.txt): -2 % at AED-window sizes (n = 1000 ... 4000, width 224) as long as the launch stays at or below
+// ~130 KB of shared memory; slabs of VT and Y as well (read by phase A and by the look-ahead warps) LOSE, and so does any
+// layout beyond ~190 KB: the GEMV keeps up to 128 KB of loads in flight per SM and L1 is what is left of 256 KB (a launch
+// padded to 224 KB streams 21 % slower, one at 190 KB 1 % slower, below 150 KB no difference).
 struct FusedSmem {
-    int vs, s, vrow, w2, red, pv, ysm, ysum, sqred, scal, total;
-    __host__ __device__ FusedSmem(int w, int nsub, int kc = FUSED_KC)
+    int vs, s, vrow, w2, red, pv, ysm, ysum, sqred, scal, slab, slab_doubles, total;
+    __host__ __device__ FusedSmem(int w, int nsub, int kc = FUSED_KC, int slabs = 0)
     {
         const int NW = (w + 31) / 32 > 1 ? (w + 31) / 32 : 1;
         const int wp8 = (w + 8) / 8 * 8;
@@ -277,6 +285,7 @@ struct FusedSmem {
         ysum = o;  o += FUSED_THREADS;          // per-thread shares of the GEMV partial sums of a row (phase A)
         sqred = o; o += 3 * FUSED_WARPS;
         scal = o;  o += 4;
+        slab = o;  slab_doubles = w * nsub * 32; o += slabs * slab_doubles;
         total = o;
     }
 };
@@ -301,13 +310,14 @@ __device__ __noinline__ double fused_rescale_x(double *pcol, const double *V, in
         if (row0 + rr > j) pcol[row0 + rr] *= xmul;
     for (int rr = tid; rr < nsub * 32; rr += FUSED_THREADS) pv[rr] *= xmul;
     __syncthreads();
-    if (j > 0) coldots_all(V, ld, j, row0, row_end, nsub, pv, wp, FUSED_WARPS, lane, colpart + (size_t)b * ldt);
+    if (j > 0) coldots_all(V, ld, 0, j, row0, row_end, nsub, pv, wp, FUSED_WARPS, lane, colpart + (size_t)b * ldt);
     grid_barrier(gbar, gen);
     return t_first < j ? sum_over_ctas(colpart + t_first, ldt, nblk, lane) : 0.0;
 }
 
 // The kernel. 640 threads x 96 registers: the CTA owns the register file of its SM (one CTA per SM, cooperative launch).
-template <bool DIST>
+// SLABS = 1: the CTA's rows of V resident in shared memory (FusedSmem); chosen per launch by what fits.
+template <bool DIST, int SLABS>
 __global__ void __launch_bounds__(FUSED_THREADS, 1) k_panel_fused(FusedArgs f)
 {
     // 16-byte loads in flight per GEMV thread: U columns being accumulated + U being fetched
@@ -322,7 +332,9 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_panel_fused(FusedArgs f)
     const int row_end = min(m, row0 + f.rpc);
     const int rows_here = max(0, row_end - row0);
     const int nblk = (m + f.rpc - 1) / f.rpc;                   // CTAs that own rows
-    const FusedSmem L(f.w, nsub, f.kc);
+    const FusedSmem L(f.w, nsub, f.kc, SLABS);
+    // the CTA's slabs: element (row row0 + rr, panel column t) at [t * rpc + rr]
+    double *const Vs = sh + L.slab;
     double *const vs_all = sh + L.vs, *const s_sh = sh + L.s, *const vrow_sh = sh + L.vrow, *const w2_sh = sh + L.w2;
     double *const red = sh + L.red, *const pv = sh + L.pv, *const ysm = sh + L.ysm, *const sqred = sh + L.sqred;
     double *const ysum = sh + L.ysum;
@@ -463,6 +475,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_panel_fused(FusedArgs f)
                     // column j-1 of V and of the reduced matrix (the row owner writes: no cross-CTA traffic)
                     const double vr = (r < jm1) ? 0.0 : (r == jm1 ? 1.0 : pprev * scale_prev);
                     a.V[(size_t)jm1 * ld + r] = vr;
+                    if (SLABS >= 1) Vs[(size_t)jm1 * f.rpc + sub * 32 + lane] = vr;
                     if (r == jm1) acol_prev[r] = beta_prev;
                     else if (r > jm1) acol_prev[r] = 0.0;
                     const double ynew = tau * (D3 - D0);                 // finish_column: Y(:,j-1)
@@ -479,7 +492,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_panel_fused(FusedArgs f)
             __syncthreads();
 
             // ---- w2part[t] = sum over the CTA's rows of VT(r,t) * p'(r), t < j (column j-1 was stored just above)
-            coldots_all(a.VT, ld, j, row0, row_end, nsub, pv, wp, FUSED_WARPS, lane, a.colpart + (size_t)b * a.ldt);
+            coldots_all(a.VT, ld, 0, j, row0, row_end, nsub, pv, wp, FUSED_WARPS, lane, a.colpart + (size_t)b * a.ldt);
             grid_barrier(f.gbar, gen);
             SB_PHASE_MARK(0);
 
@@ -504,10 +517,11 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_panel_fused(FusedArgs f)
                     const int sub = item / NW, g = item - sub * NW, t0 = g * 32;
                     const int r = row0 + sub * 32 + lane;
                     const bool valid = r < row_end;
-                    const double *Vr = a.V + (size_t)t0 * ld + r;
+                    const double *Vr = SLABS >= 1 ? Vs + (size_t)t0 * f.rpc + sub * 32 + lane : a.V + (size_t)t0 * ld + r;
+                    const size_t vstep = SLABS >= 1 ? (size_t)f.rpc : (size_t)ld;
                     double v32[32];
 #pragma unroll
-                    for (int q = 0; q < 32; q++) v32[q] = (valid && t0 + q < j) ? Vr[(size_t)q * ld] : 0.0;
+                    for (int q = 0; q < 32; q++) v32[q] = (valid && t0 + q < j) ? Vr[(size_t)q * vstep] : 0.0;
                     double d = 0.0;
 #pragma unroll
                     for (int q = 0; q < 32; q++) d = fma(v32[q], w2_sh[min(t0 + q, j - 1)], d);
@@ -522,7 +536,8 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_panel_fused(FusedArgs f)
                 const bool valid = r < row_end;
                 double xx = 0.0;
                 if (valid) {
-                    double pp = j > 0 ? pc_cur[r] : acol[r];
+                    // p' of the row: this thread left it in pv at the end of phase A (one L2 round trip less than pc_cur[r])
+                    double pp = j > 0 ? pv[sub * 32 + lane] : acol[r];
                     if (j > 0) {
                         double D = 0.0;
                         for (int q = 0; q < NW; q++) D += red[((size_t)sub * NW + q) * 32 + lane];
@@ -541,7 +556,10 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_panel_fused(FusedArgs f)
             if (__any_sync(0xffffffffu, sq.big != 0.0 || sq.sml != 0.0)) { sq.big = warp_sum(sq.big); sq.sml = warp_sum(sq.sml); }
             if (lane == 0) { sqred[wp] = sq.med; sqred[FUSED_WARPS + wp] = sq.big; sqred[2 * FUSED_WARPS + wp] = sq.sml; }
             __syncthreads();
-            if (j > 0) coldots_all(a.V, ld, j, row0, row_end, nsub, pv, wp, FUSED_WARPS, lane, a.colpart + (size_t)b * a.ldt);
+            if (j > 0) {
+                if (SLABS >= 1) coldots_all(Vs, f.rpc, row0, j, row0, row_end, nsub, pv, wp, FUSED_WARPS, lane, a.colpart + (size_t)b * a.ldt);
+                else            coldots_all(a.V, ld, 0, j, row0, row_end, nsub, pv, wp, FUSED_WARPS, lane, a.colpart + (size_t)b * a.ldt);
+            }
             if (tid < 3) {
                 double sum = 0.0;
                 for (int q = 0; q < FUSED_WARPS; q++) sum += sqred[tid * FUSED_WARPS + q];
@@ -744,6 +762,6 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_panel_fused(FusedArgs f)
 }
 
 // dynamic shared memory of k_panel_fused for a panel of w columns with nsub sub-tiles per CTA
-static inline size_t fused_smem_bytes(int w, int nsub, int kc = FUSED_KC) { return (size_t)FusedSmem(w, nsub, kc).total * sizeof(double); }
+static inline size_t fused_smem_bytes(int w, int nsub, int kc = FUSED_KC, int slabs = 0) { return (size_t)FusedSmem(w, nsub, kc, slabs).total * sizeof(double); }
 
 } // namespace sb200

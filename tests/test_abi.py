@@ -158,14 +158,12 @@ def test_workspace_plan_bounds_up_to_the_largest_supported_order(sn):
                 assert 8 <= used <= 1024 and (pw < 0 or used <= max(pw, 8))
                 assert smem <= 200 * 1024
                 assert worst <= cap, (n, ranks, pw, worst, cap)
-    # the reference default survives wherever the persistent kernel's layout holds it
-    assert lib.starneig_b200_plan_check(20000, -1, 1, out) == 0 and out[0] == 312 and out[1] > 0
-    assert lib.starneig_b200_plan_check(50000, -1, 1, out) == 0 and out[0] == 368 and out[1] > 0
-    # several GPUs: narrower automatic panels (the level-2 phases of a column are replicated on every rank)
-    assert lib.starneig_b200_plan_check(20000, -1, 2, out) == 0 and out[0] == 256
-    assert lib.starneig_b200_plan_check(20000, -1, 4, out) == 0 and out[0] == 192
-    assert lib.starneig_b200_plan_check(20000, -1, 8, out) == 0 and out[0] == 192
-    assert lib.starneig_b200_plan_check(50000, -1, 8, out) == 0 and out[0] == 224 and out[1] > 0
+    # the automatic width (192: two 96-column tiles of the skinny DMMA products, measured on B200) at any size and GPU count
+    for n, ranks in ((20000, 1), (50000, 1), (20000, 2), (20000, 4), (20000, 8), (50000, 8)):
+        assert lib.starneig_b200_plan_check(n, -1, ranks, out) == 0 and out[0] == 192 and out[1] > 0
+    # the reference's own default (312 / 368) is still held by the persistent kernel's layout when a caller asks for it
+    assert lib.starneig_b200_plan_check(20000, 312, 1, out) == 0 and out[0] == 312 and out[1] > 0
+    assert lib.starneig_b200_plan_check(50000, 368, 1, out) == 0 and out[0] == 368 and out[1] > 0
     assert lib.starneig_b200_plan_check(100000, -1, 1, out) == 0 and out[0] < sn.default_panel_width(100000)
     assert lib.starneig_b200_plan_check(MAX_N + 1, -1, 1, out) == 4          # STARNEIG_INVALID_ARGUMENTS
     assert lib.starneig_b200_plan_check(0, -1, 1, out) == 4

@@ -352,6 +352,20 @@ def test_sim_linear_gemv_with_lagging_blocks(simlib, sms, skew, seed):
     assert r.returncode == 0 and r.stdout.strip().endswith("OK"), r.stdout[-1000:] + r.stderr[-2000:]
 
 
+@pytest.mark.parametrize("gpus,n,pw,sms", [(1, 131, 24, 4), (1, 200, 40, 2), (2, 96, 16, 2), (1, 90, 16, 1), (2, 150, 24, 1)])
+def test_sim_v_slab_in_shared_memory(sim, ora, gpus, n, pw, sms):
+    """The CTA's rows of V kept in shared memory for the whole panel (FusedSmem, the default when they fit): the slab holds a
+    copy of what goes to global memory, so H and Q are bitwise those of the kernel that re-reads global memory
+    (STARNEIG_B200_FUSED_SLABS=0). One, two and three sub-tiles per CTA, one and two ranks."""
+    with _Env(STARNEIG_B200_COL_BLOCK=8, CUSIM_SMS=sms):
+        with _Env(STARNEIG_B200_FUSED_SLABS=0):
+            A0, Q0, st0 = _reduce(sim, ora, n, pw, gpus=gpus)
+        assert st0["fused_slab_panels"][0] == st0["panels"] == st0["fused_panels"]
+        A, Q, st = _reduce(sim, ora, n, pw, gpus=gpus, entrywise=False)          # the default
+        assert st["fused_slab_panels"][1] == st["panels"], st["fused_slab_panels"]
+        assert np.array_equal(A, A0) and np.array_equal(Q, Q0)
+
+
 @pytest.mark.parametrize("gpus,n,pw,kc", [(1, 131, 24, 64), (2, 96, 16, 2048)])
 def test_sim_gemv_staging_chunk(sim, ora, gpus, n, pw, kc):
     """STARNEIG_B200_GEMV_KC (columns of v staged per group at a time: 64 = many refills, 2048 = few): same sums in the same

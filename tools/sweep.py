@@ -39,7 +39,7 @@ def run_configs(n, configs):
         print(f"[{cfg or 'default':58s}] ret {ret} device_ms {st['device_ms']:8.1f} GFLOP/s {10 / 3 * n ** 3 / st['device_ms'] / 1e6:7.0f} "
               f"col {st['panel_ms']:7.1f} trail {st['trail_ms']:6.1f} deferred {st['other_ms']:7.1f} tail {st['side_tail_ms']:6.1f} "
               f"gemv_ms {st['gemv_ms']:7.1f} ({gb:5.0f} GB/s) ph {[round(x) for x in st['fused_phase_ms']]} ovl {st['overlap']} "
-              f"form_ok {form_ok}", flush=True)
+              f"slabs {st['fused_slab_panels']} form_ok {form_ok}", flush=True)
         sn.starneig_node_finalize()
         for k in added:
             os.environ.pop(k, None)
