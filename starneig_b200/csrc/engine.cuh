@@ -66,7 +66,7 @@ static const size_t PANEL_SMEM_MAX = 200 * 1024;
 // The persistent panel kernel keeps the CTA's rows of V in shared memory only while the launch stays below this: the GEMV
 // needs the rest of the SM's 256 KB as L1 for its loads in flight (FusedSmem; profiles/r2_v15_sweep_l1_split.txt)
 static const size_t FUSED_SLAB_SMEM_MAX = 131 * 1024;
-static const size_t FUSED_SMEM_OPTIN = 227 * 1024;
+static const size_t FUSED_SMEM_OPTIN = 226 * 1024;
 
 // per-device function attributes (opt-in shared memory sizes)
 static void prepare_device_functions()
@@ -542,8 +542,8 @@ struct Rank {
                 while (slabs > 0 && fused_smem_bytes(w, f.nsub, f.kc, slabs) > FUSED_SLAB_SMEM_MAX) slabs--;
                 smem = fused_smem_bytes(w, f.nsub, f.kc, slabs);
                 smem = std::min(FUSED_SMEM_OPTIN, smem + fused_smem_pad);
-#define SB_FUSED_GO(S) do { if (P > 1) SB_LAUNCH_COOP((k_panel_fused<true, S>), ctas, FUSED_THREADS, smem, st, f); \
-                            else       SB_LAUNCH_COOP((k_panel_fused<false, S>), ctas, FUSED_THREADS, smem, st, f); } while (0)
+#define SB_FUSED_GO(S) do { if (P > 1) SB_LAUNCH_COOP((k_panel_fused<true, S>), ctas, FUSED_LAUNCH_THREADS, smem, st, f); \
+                            else       SB_LAUNCH_COOP((k_panel_fused<false, S>), ctas, FUSED_LAUNCH_THREADS, smem, st, f); } while (0)
                 if (slabs) SB_FUSED_GO(1); else SB_FUSED_GO(0);
 #undef SB_FUSED_GO
                 stats.kernel_launches++;
@@ -779,6 +779,8 @@ struct Rank {
             stats.gemv_ms = 1e-6 * (double)t[0];            // %globaltimer around the GEMV phases (incl. their barrier)
             stats.fused_kernel_ms = 1e-6 * (double)t[1];
             for (int k = 0; k < 4; k++) stats.fused_phase_ms[k] = 1e-6 * (double)t[2 + k];
+            if (SB_FUSED_BURN) fprintf(stderr, "[burn experiment] %.3e DMMA on SM 0 during %.1f ms of panel kernels: %.1f GFLOP/s per SM\n",
+                                       (double)t[6], stats.fused_kernel_ms, (double)t[6] * 512.0 / (stats.fused_kernel_ms * 1e6));
         } else if (lvl >= 2) {
             for (size_t k = 0; k + 3 < gemv_events_used; k += 4) {
                 SB_CUDA(cudaEventElapsedTime(&ms, gemv_events[k], gemv_events[k + 1])); stats.finish_update_ms += ms;
