@@ -375,7 +375,7 @@ def run_ours(args):
     sampler.start()
     dev_ms, gemv_ms, gemv_bytes, gemv_launches, launches, phase = [], 0.0, 0.0, 0, 0, [0.0, 0.0, 0.0]
     gemv_tbytes, gemv_tlaunches = 0.0, 0
-    fused_panels, panels = 0, 0
+    fused_panels, panels, gemm_flops = 0, 0, 0.0
     fused_ph = [0.0] * 5
     side_tail, overlap = 0.0, 0
     t_wall0 = time.perf_counter()
@@ -387,7 +387,7 @@ def run_ours(args):
         dev_ms.append(st["device_ms"])
         gemv_ms += st["gemv_ms"]; gemv_bytes += st["gemv_bytes"]; gemv_launches += st["gemv_launches"]
         gemv_tbytes += st["gemv_timed_bytes"]; gemv_tlaunches += st["gemv_timed_launches"]
-        launches += st["kernel_launches"]
+        launches += st["kernel_launches"]; gemm_flops += st["gemm_flops"]
         fused_panels += st["fused_panels"]; panels += st["panels"]
         side_tail += st["side_tail_ms"]; overlap = st["overlap"]
         fused_ph = [a + b for a, b in zip(fused_ph, list(st["fused_phase_ms"]) + [st["fused_kernel_ms"]])]
@@ -529,7 +529,12 @@ def run_ours(args):
 
     # ---------------- roofline of the dominant kernel ----------------
     peak, peak_kind = measured_peaks()
-    t_roof_ms = 1e3 * (8.0 * (n - 1) * n * (2 * n - 1) / 6.0 / (peak * 1e9) + (14.0 / 3.0) * n ** 3 / (FP64_CUBLAS_TFLOPS * 1e12)) / world
+    # level-3 flops of a reduction with Q: 14/3 n^3 (trailing 2, top rows 2/3, Q 2); 4 n^3 when Q = I is
+    # accumulated backward after the last panel (Q: 4/3 n^3; engine.cuh, Rank::reduce) -- the roofline follows the algorithm run
+    q_backward = bool(st.get("q_backward", 0))
+    def t_roof(l3_coeff):
+        return 1e3 * (8.0 * (n - 1) * n * (2 * n - 1) / 6.0 / (peak * 1e9) + l3_coeff * n ** 3 / (FP64_CUBLAS_TFLOPS * 1e12)) / world
+    t_roof_ms = t_roof(4.0 if q_backward else 14.0 / 3.0)
     if fused_panels == panels and panels > 0:
         # One persistent kernel per panel (k_panel_fused): a launch streams the trailing matrix once per panel
         # column. Algorithmic bytes per launch = sum over its columns of 8 * rows * cols; launch duration = CUDA
@@ -570,6 +575,8 @@ def run_ours(args):
         }
     # whole-path roofline: T_roof(n, P) = (B / BW_hbm + (8/3 + 2) n^3 / F64_peak) / P
     roofline["t_roof_ms"] = t_roof_ms
+    roofline["t_roof_ms_forward_q"] = t_roof(14.0 / 3.0)
+    roofline["level3_flops_per_step"] = gemm_flops / args.steps
     roofline["fp64_peak_tflops"] = FP64_CUBLAS_TFLOPS
     roofline["fp64_peak_source"] = "cublasDgemm 8192^3 measured on this pool (profiles/r1_probe_peaks.log)"
     roofline["path_frac"] = roofline["t_roof_ms"] / ms_per_step
@@ -592,6 +599,8 @@ def run_ours(args):
         "dtype": "f64", "data": "synthetic",
         "config": shared_config(n, world),
         "engine": {"panel_width": int(st["panel_width_used"]), "ld": ld,
+                   "q_accumulation": "backward after the last panel (Q = I on entry: 4/3 n^3 flops)" if q_backward
+                   else "forward, panel by panel (2 n^3 flops)",
                    # engine switches taken from the environment (none: the defaults of DESIGN.md section 4)
                    "switches": {k: v for k, v in sorted(os.environ.items()) if k.startswith("STARNEIG_B200_")},
                    "l2": "inputs (A, Q: 2 x %.1f GB) are larger than the 126 MB L2; no explicit flush" % (n * ld * 8 / 1e9),

@@ -55,6 +55,9 @@ struct starneig_b200_stats {
                               * alone and d2h_ms what was left of the write-back when the reduction ended) */
     int panel_width_used;    /* panel width of the reduction (the requested one unless it exceeds what the panel kernels'
                               * shared-memory layout holds: > 1024 columns, or a narrower limit for n > ~70000) */
+    int q_backward;          /* 1: Q was the identity on entry and was accumulated backward after the last panel (one GPU, full
+                              * reduction: 4/3 n^3 instead of 2 n^3 flops for Q; engine.cuh, Rank::reduce) */
+    double q_backward_ms;    /* duration of that backward pass (also counted in other_ms) */
     int fused_slab_panels[2];/* panels of the persistent kernel without [0] / with [1] the CTA's rows of V resident in shared
                               * memory (panel_fused.cuh, FusedSmem) */
 };

@@ -34,6 +34,7 @@ class Stats(ctypes.Structure):
         ("overlap", ctypes.c_int), ("side_tail_ms", ctypes.c_double),
         ("gemm_tma_launches", ctypes.c_longlong), ("gemm_cpasync_launches", ctypes.c_longlong),
         ("staging_overlapped", ctypes.c_int), ("panel_width_used", ctypes.c_int),
+        ("q_backward", ctypes.c_int), ("q_backward_ms", ctypes.c_double),
         ("fused_slab_panels", ctypes.c_int * 2),
     ]
 

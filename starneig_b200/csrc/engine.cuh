@@ -152,6 +152,10 @@ struct Workspace {
     unsigned *gbar = nullptr;                   // grid barrier counter of the fused panel kernel
     unsigned long long *rbar = nullptr;         // its per-column arrival words (barrier after phase R + the vote on `linear`)
     unsigned long long *timers = nullptr;       // device-side phase timers of the fused panel kernel (ns)
+    // Reflector history (backward accumulation of Q, Rank::reduce): V and VT = V T of EVERY panel, panel columns i .. i+w-1 at
+    // columns i .. i+w-1 of two ldv x (n + 8) arrays (3.2 GB each at n = 20000, 20 GB each at n = 50000: HBM is 180 GB)
+    double *Vh = nullptr, *VTh = nullptr;
+    int hist_n = 0;
     std::vector<void *> allocs;
 
     template <typename T> T *alloc(size_t count)
@@ -161,8 +165,29 @@ struct Workspace {
         allocs.push_back(p);
         return (T *)p;
     }
+    void release_history()
+    {
+        if (Vh) cudaFree(Vh);
+        if (VTh) cudaFree(VTh);
+        Vh = VTh = nullptr; hist_n = 0;
+    }
+    // after ensure(): room for the reflectors of a whole reduction of order n; false (nothing allocated) if the device
+    // cannot spare the memory -- the caller then accumulates Q forward, panel by panel
+    bool ensure_history(int n)
+    {
+        if (Vh && n <= hist_n) return true;
+        release_history();
+        const size_t bytes = ((size_t)ldv * (n_cap + 8) + 16) * sizeof(double);
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess || free_b < 2 * bytes + ((size_t)4 << 30)) { cudaGetLastError(); return false; }
+        if (cudaMalloc((void **)&Vh, bytes) != cudaSuccess) { cudaGetLastError(); Vh = nullptr; return false; }
+        if (cudaMalloc((void **)&VTh, bytes) != cudaSuccess) { cudaGetLastError(); cudaFree(Vh); Vh = VTh = nullptr; return false; }
+        hist_n = n_cap;
+        return true;
+    }
     void release()
     {
+        release_history();
         for (void *p : allocs) cudaFree(p);
         allocs.clear();
         n_cap = nb_cap = 0;
@@ -248,9 +273,9 @@ static inline int fit_panel_width(int m, int nb, int ctas, bool fused)
 struct StageHook {
     // the stream is about to touch Q for the first time
     virtual void before_q(cudaStream_t s) = 0;
-    // Everything enqueued on `s` so far completes panel [.., final_cols): global columns [0, final_cols) of A and
-    // [0, final_cols] of Q will not change any more.
-    virtual void panel_done(cudaStream_t s, int final_cols) = 0;
+    // Everything enqueued on `s` so far completes panel [.., final_cols): global columns [0, final_cols) of A and -- with
+    // `q_too` -- [0, final_cols] of Q will not change any more (backward accumulation: no column of Q is final before the end).
+    virtual void panel_done(cudaStream_t s, int final_cols, bool q_too) = 0;
     virtual ~StageHook() {}
 };
 struct PanelGrid { int blocks; TileGeom tg; size_t smem_fu, smem_rf; };
@@ -277,6 +302,8 @@ struct Rank {
                                             // bit 1 = the skinny products (TN, NN); 0: the cp.async kernels (dgemm.cuh)
     int gemv_linear = 1;                    // fused kernel: the GEMV streams against the unscaled x (FusedArgs::linear)
     size_t fused_smem_pad = 0;              // tuning aid: unused shared memory added to the fused kernel's launch (moves the L1 / shared-memory split)
+    int q_backward = 256;                   // an identity Q on entry is accumulated backward after the reduction (reduce()) for
+                                            // matrices of at least this order; 0: never (STARNEIG_B200_Q_BACKWARD)
     int fused_slabs = 1;                    // fused kernel: the CTA's rows of V in shared memory when they fit (FusedSmem)
     std::vector<cudaEvent_t> events;        // phase events: 4 per panel
     std::vector<cudaEvent_t> gemv_events;   // 4 per timed column (profile level 2)
@@ -305,6 +332,8 @@ struct Rank {
         if (e) gemm_tma = atoi(e);
         e = getenv("STARNEIG_B200_GEMV_LINEAR");
         if (e) gemv_linear = atoi(e);
+        e = getenv("STARNEIG_B200_Q_BACKWARD");
+        if (e) q_backward = atoi(e);
         e = getenv("STARNEIG_B200_FUSED_SLABS");
         if (e) fused_slabs = std::max(0, std::min(1, atoi(e)));
         e = getenv("STARNEIG_B200_FUSED_SMEM_PAD_KB");
@@ -654,6 +683,17 @@ struct Rank {
         }
         const int lc_end = cm.lower(end);
 
+        // Backward accumulation of Q (one GPU, full reduction, Q = I on entry -- the reference driver's and the usual
+        // caller's case; LAPACK's dorghr does the same). Q U for a general Q costs 2 n^3 flops, panel by panel (forward: the
+        // reference's order, core.c:338-340). U itself = H_0 H_1 ... H_K-1 applied to the identity from the LAST panel to the
+        // first touches only the trailing (n - i - 1)^2 block at panel i: 4/3 n^3 flops, 2/3 n^3 (14 % of the level-3 work
+        // of a reduction) less. It needs V and VT of every panel until the end: the panels write them into the history
+        // arrays (Workspace::Vh / VTh) instead of one recycled buffer. Whether Q is the identity is decided on the device
+        // when Q is touched for the first time (after the first panel; the upload of a host Q hides behind that panel).
+        const bool hist = P == 1 && q_backward > 0 && n >= q_backward && begin == 0 && end == n && qrows == n && Q != nullptr && ws.ensure_history(n);
+        bool backward = false;
+        stats.q_backward = 0;
+
         // Schedule: one stream. Per panel: column loop (persistent kernel), trailing right / left updates, then the updates
         // the reference defers (rows above the panel, columns right of the block, Q). Running the deferred updates next to
         // the column loops -- on a side stream with SMs set aside, or co-resident on the same SMs -- was measured on B200 at 1
@@ -668,10 +708,11 @@ struct Rank {
             // operands are both K-major (W = A^T VT) then agree on where 16-byte units start, and moving the k frame by one
             // element for TMA adds a term that is zero (dgemm_tma.cuh)
             const int par = (i + 1) & 1;
-            double *V = ws.V + par, *VT = ws.VT + par;
+            double *const Vbase = hist ? ws.Vh + (size_t)i * ld : ws.V, *const VTbase = hist ? ws.VTh + (size_t)i * ld : ws.VT;
+            double *V = Vbase + par, *VT = VTbase + par;
             if (par) {
-                SB_CUDA(cudaMemset2DAsync(ws.V, (size_t)ld * sizeof(double), 0, sizeof(double), (size_t)w, st));
-                SB_CUDA(cudaMemset2DAsync(ws.VT, (size_t)ld * sizeof(double), 0, sizeof(double), (size_t)w, st));
+                SB_CUDA(cudaMemset2DAsync(Vbase, (size_t)ld * sizeof(double), 0, sizeof(double), (size_t)w, st));
+                SB_CUDA(cudaMemset2DAsync(VTbase, (size_t)ld * sizeof(double), 0, sizeof(double), (size_t)w, st));
             }
             if (lvl >= 1) SB_CUDA(cudaEventRecord(phase_event(2 + 6 * panel + 0), st));
             const int pl0 = cm.lower(i), pl1 = cm.lower(i + w);
@@ -739,11 +780,35 @@ struct Rank {
                 gemm(GEMM_NT, m, nx, w, -1.0, V, ld, ws.W, ld, 1.0, X, ldA);
             }
             if (hook && panel == 0) hook->before_q(st);
-            if (qrows > 0)     // Q <- Q (I - V T V^T) on the rank's rows
+            if (hist && panel == 0) {
+                // is Q the identity? (one pass over Q: ~0.5 ms at n = 20000; the host waits for the answer once per reduction)
+                unsigned *flag = ws.counter + 2, h_flag = 1;
+                SB_CUDA(cudaMemsetAsync(flag, 0, sizeof(unsigned), st));
+                SB_LAUNCH(k_is_identity, dim3(std::min(n, 148 * 8)), 256, 0, st, n, Q, ldQ, flag);
+                stats.kernel_launches++;
+                SB_CUDA(cudaMemcpyAsync(&h_flag, flag, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+                SB_CUDA(cudaStreamSynchronize(st));
+                backward = h_flag == 0;
+                stats.q_backward = backward ? 1 : 0;
+            }
+            if (qrows > 0 && !backward)     // Q <- Q (I - V T V^T) on the rank's rows
                 deferred_right_update(qrows, m, w, Q + (size_t)(i + 1) * ldQ, ldQ, V, VT, ld, ws.W);
             if (lvl >= 1) SB_CUDA(cudaEventRecord(phase_event(2 + 6 * panel + 4), st));
-            if (hook) hook->panel_done(st, i + w);
+            if (hook) hook->panel_done(st, i + w, !backward);
         }
+        if (lvl >= 1) SB_CUDA(cudaEventRecord(phase_event(2 + 6 * panel + 1), st));
+        if (backward) {
+            // Q = H_0 ( H_1 ( ... H_K-1 I)): panel k acts on rows >= i + 1 and, the product so far being the identity
+            // outside its trailing block, on columns >= i + 1 only:  Qb <- (I - V T V^T) Qb = Qb - VT (Qb^T V)^T
+            for (int k = panel - 1; k >= 0; k--) {
+                const int i = begin + k * nb, w = std::min(nb, end - i - 1), m = end - i - 1, par = (i + 1) & 1;
+                const double *V = ws.Vh + (size_t)i * ld + par, *VT = ws.VTh + (size_t)i * ld + par;
+                double *Qb = Q + (size_t)(i + 1) * ldQ + i + 1;
+                gemm(GEMM_TN, m, w, m, 1.0, Qb, ldQ, V, ld, 0.0, ws.W, ld, true);
+                gemm(GEMM_NT, m, m, w, -1.0, VT, ld, ws.W, ld, 1.0, Qb, ldQ);
+            }
+        }
+        if (lvl >= 1) SB_CUDA(cudaEventRecord(phase_event(2 + 6 * panel + 2), st));
         barrier();
         if (lvl >= 1) SB_CUDA(cudaEventRecord(phase_event(2 + 6 * panel), st));       // end of the critical path
         SB_CUDA(cudaEventRecord(ev_last, st));
@@ -770,6 +835,8 @@ struct Rank {
                 // the updates the reference defers (rows above the panel, columns right of the block, Q)
                 SB_CUDA(cudaEventElapsedTime(&ms, e[3], e[4])); stats.other_ms += ms;
             }
+            // backward accumulation of Q after the last panel (part of the deferred work)
+            SB_CUDA(cudaEventElapsedTime(&ms, events[2 + 6 * panel + 1], events[2 + 6 * panel + 2])); stats.q_backward_ms = ms; stats.other_ms += ms;
             // what the deferred updates add to the critical path: end of the last trailing update -> end of the call
             SB_CUDA(cudaEventElapsedTime(&ms, events[2 + 6 * panel], ev_last)); stats.side_tail_ms = ms;
         }

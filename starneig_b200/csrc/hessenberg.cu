@@ -125,20 +125,20 @@ struct HostStage : StageHook {
     {
         if (overlap) SB_CUDA(cudaStreamWaitEvent(s, r.ev_q_up, 0));
     }
-    void send_back(int final_cols, cudaStream_t st)
+    void send_back(int final_cols, bool q_too, cudaStream_t st)
     {
         const ColMap cm{r.P, r.g, cb};
         const int a1 = std::min(sh.ncols, cm.lower(std::min(final_cols, n)));
         if (a1 > a_done) { copy_a(a_done, a1, false, st); a_done = a1; }
-        const int q1 = std::min(n, final_cols + 1);
+        const int q1 = q_too ? std::min(n, final_cols + 1) : 0;
         if (q1 > q_done) { copy_q(q_done, q1, false, st); q_done = q1; }
     }
-    void panel_done(cudaStream_t s, int final_cols) override
+    void panel_done(cudaStream_t s, int final_cols, bool q_too) override
     {
         if (!overlap || !writeback) return;
         SB_CUDA(cudaEventRecord(r.ev_cols_final, s));
         SB_CUDA(cudaStreamWaitEvent(r.copy, r.ev_cols_final, 0));
-        send_back(final_cols, r.copy);
+        send_back(final_cols, q_too, r.copy);
     }
     // after the reduction (its streams are idle): whatever is still on the device
     void finish()

@@ -786,4 +786,16 @@ __global__ void k_barrier(int P, int g, unsigned epoch, BarPtrs bar, unsigned *s
     __threadfence_system();
 }
 
+// flag |= 1 unless Q (n x n, leading dimension ld) is exactly the identity (-0.0 counts as zero, a NaN as a mismatch):
+// decides between forward and backward accumulation of Q (engine.cuh, Rank::reduce). One block per column, grid-stride.
+__global__ void __launch_bounds__(256) k_is_identity(int n, const double *__restrict__ Q, int ld, unsigned *flag)
+{
+    bool bad = false;
+    for (int c = blockIdx.x; c < n; c += gridDim.x) {
+        const double *q = Q + (size_t)c * ld;
+        for (int r = threadIdx.x; r < n; r += blockDim.x) bad = bad || !(q[r] == (r == c ? 1.0 : 0.0));
+    }
+    if (bad) atomicExch(flag, 1u);
+}
+
 } // namespace sb200

@@ -7,6 +7,7 @@
 // waits on events that were recorded earlier in program order), and a kernel launch runs the kernel body on
 // fibers -- one per CUDA thread -- with the block/warp/grid semantics the kernels rely on (cusim_device.h, cusim.cpp).
 #pragma once
+#include <cstdlib>
 #include <cstddef>
 #include <cstdint>
 #include <cstring>
@@ -51,6 +52,14 @@ cudaError_t cudaDeviceEnablePeerAccess(int peer, unsigned flags);
 cudaError_t cusimMalloc(void **p, size_t bytes);
 template <class T> static inline cudaError_t cudaMalloc(T **p, size_t bytes) { return cusimMalloc((void **)p, bytes); }
 cudaError_t cudaFree(void *p);
+// free / total device memory: 64 GiB, or CUSIM_FREE_MB (tests of the low-memory fall-backs)
+static inline cudaError_t cudaMemGetInfo(size_t *free_b, size_t *total_b)
+{
+    const char *e = getenv("CUSIM_FREE_MB");
+    *total_b = (size_t)64 << 30;
+    *free_b = e ? (size_t)atoll(e) << 20 : *total_b;
+    return cudaSuccess;
+}
 cudaError_t cudaMemset(void *p, int v, size_t bytes);
 cudaError_t cudaMemsetAsync(void *p, int v, size_t bytes, cudaStream_t st);
 cudaError_t cudaMemset2DAsync(void *p, size_t pitch, int v, size_t width, size_t height, cudaStream_t st);

@@ -366,6 +366,59 @@ def test_sim_v_slab_in_shared_memory(sim, ora, gpus, n, pw, sms):
         assert np.array_equal(A, A0) and np.array_equal(Q, Q0)
 
 
+@pytest.mark.parametrize("n,pw,sms", [(131, 24, 4), (200, 40, 2), (90, 35, 1), (64, 64, 3), (47, 16, 4)])
+def test_sim_q_backward_accumulation(sim, ora, n, pw, sms):
+    """Q = I on entry (one GPU, full reduction): the reflectors of every panel are kept and Q = H_0 (H_1 (... H_K-1 I)) is
+    formed after the last panel on the trailing blocks only (4/3 n^3 instead of 2 n^3 flops; engine.cuh, Rank::reduce).
+    Same H bit for bit, Q equal to the forward product up to rounding, same invariants (checked by _reduce against the oracle,
+    which accumulates forward like the reference)."""
+    with _Env(CUSIM_SMS=sms, STARNEIG_B200_Q_BACKWARD=1):
+        A, Q, st = _reduce(sim, ora, n, pw)
+        assert st["q_backward"] == 1
+        with _Env(STARNEIG_B200_Q_BACKWARD=0):
+            A1, Q1, st1 = _reduce(sim, ora, n, pw)
+        assert st1["q_backward"] == 0
+        assert np.array_equal(A, A1)
+        assert np.abs(Q[:n] - Q1[:n]).max() <= 50 * n * U
+        if st["panels"] > 1:            # (one panel: both orders are the same product)
+            assert not np.array_equal(Q, Q1) and st["gemm_flops"] < st1["gemm_flops"]
+
+
+def test_sim_q_backward_only_for_an_identity_q(sim, ora):
+    """a general Q (the AED client's case), a partial reduction, several ranks or too little device memory: forward, as before"""
+    n, pw = 96, 16
+    A0, Q0, ld = ora.fullpos(n, 2019)
+    rng = np.random.default_rng(5)
+    Qg, _ = np.linalg.qr(rng.standard_normal((n, n)))
+    Qin = np.zeros_like(Q0); Qin[:n, :n] = Qg
+    with _Env(CUSIM_SMS=3, STARNEIG_B200_Q_BACKWARD=1, STARNEIG_B200_COL_BLOCK=8):
+        # (general Q: Q H Q^T is not A0 any more, so the oracle comparison is done here instead of in _reduce)
+        A, Q = A0.copy(order="F"), np.asfortranarray(Qin)
+        sim.starneig_node_init(sim.STARNEIG_USE_ALL, 1, sim.STARNEIG_NO_MESSAGES)
+        conf = sim.starneig_hessenberg_init_conf()
+        conf.panel_width = pw
+        assert sim.starneig_SEP_SM_Hessenberg_expert(conf, n, 0, n, A, ld, Q, ld) == 0
+        st = sim.get_stats()
+        sim.starneig_node_finalize()
+        assert st["q_backward"] == 0
+        A2, Q2 = A0.copy(order="F"), np.asfortranarray(Qin)
+        assert ora.hessenberg_port(n, A2, ld, Q2, ld, 0, n, pw) == 0
+        assert np.abs(A[:n] - A2[:n]).max() <= 200 * n * U * np.abs(A2[:n]).max() and np.abs(Q[:n] - Q2[:n]).max() <= 200 * n * U
+        Qneg = Q0.copy(order="F"); Qneg[3, 5] = -0.0                     # -0.0 is a zero
+        _, _, st = _reduce(sim, ora, n, pw, given=(A0, Qneg, ld))
+        assert st["q_backward"] == 1
+        Qnan = Q0.copy(order="F"); Qnan[n - 1, 0] = 1e-300             # one tiny entry in a corner: not the identity
+        _, _, st = _reduce(sim, ora, n, pw, given=(A0, Qnan, ld))
+        assert st["q_backward"] == 0
+        _, _, st = _reduce(sim, ora, n, pw, begin=0, end=n - 7, generator="partial")
+        assert st["q_backward"] == 0
+        _, _, st = _reduce(sim, ora, n, pw, gpus=2)
+        assert st["q_backward"] == 0
+        with _Env(CUSIM_FREE_MB=16):
+            _, _, st = _reduce(sim, ora, n, pw)
+        assert st["q_backward"] == 0
+
+
 @pytest.mark.parametrize("gpus,n,pw,kc", [(1, 131, 24, 64), (2, 96, 16, 2048)])
 def test_sim_gemv_staging_chunk(sim, ora, gpus, n, pw, kc):
     """STARNEIG_B200_GEMV_KC (columns of v staged per group at a time: 64 = many refills, 2048 = few): same sums in the same

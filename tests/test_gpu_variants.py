@@ -32,6 +32,7 @@ def run(A0, Q0, ld, env):
         for _ in range(2):          # twice: the LL tags of the second call continue where the first one stopped
             A[:], Q[:] = A0, Q0
             assert sn.starneig_SEP_SM_Hessenberg_expert(conf, n, 0, n, A, ld, Q, ld) == 0
+        run.stats = sn.get_stats()
     finally:
         sn.starneig_node_finalize()
     for k in env:
@@ -68,6 +69,22 @@ elif mode == "sequential_gemv":
         A1, Q1 = run(A0, Q0, ld, {})
         assert np.abs(A[:n] - A1[:n]).max() <= 200 * n * U * max(1.0, np.abs(A1[:n]).max())
         assert np.abs(Q[:n] - Q1[:n]).max() <= 200 * n * U and not np.array_equal(A, A1)
+elif mode == "q_forward":
+    # Q = I on entry: the default accumulates Q backward after the last panel (engine.cuh, Rank::reduce); the forward order
+    # (the reference's, STARNEIG_B200_Q_BACKWARD=0) gives the same H bit for bit and the same Q up to rounding
+    A0, Q0, ld = ora.fullpos(n, 2019)
+    A, Q = run(A0, Q0, ld, {})
+    assert run.stats["q_backward"] == 1, run.stats
+    A1, Q1 = run(A0, Q0, ld, {"STARNEIG_B200_Q_BACKWARD": "0"})
+    assert run.stats["q_backward"] == 0
+    assert np.array_equal(A, A1)
+    assert np.abs(Q[:n] - Q1[:n]).max() <= 50 * n * U and not np.array_equal(Q, Q1)
+    for (AA, QQ) in ((A, Q), (A1, Q1)):
+        assert ora.hessenberg_form_violations(n, AA, ld) == 0
+        assert ora.residual_u(n, QQ, ld, AA, ld, A0, ld) <= 500 and ora.orthogonality_u(n, QQ, ld) <= 500
+    A2, Q2 = A0.copy(order="F"), Q0.copy(order="F")
+    assert ora.hessenberg_port(n, A2, ld, Q2, ld, 0, n, pw) == 0
+    assert np.abs(Q[:n] - Q2[:n]).max() <= 200 * n * U
 else:
     # opt-in variant against the default kernels: same partial sums in the same order => bitwise the same H and Q
     key, val = sys.argv[4].split("=")
@@ -91,9 +108,14 @@ def test_denormal_range_takes_dlarfg_rescaling_branch(fused):
     _child("denormal", 333, 45, fused)
 
 
-@pytest.mark.parametrize("switch", ["STARNEIG_B200_GEMV_KC=2048"])
+@pytest.mark.parametrize("switch", ["STARNEIG_B200_GEMV_KC=2048", "STARNEIG_B200_FUSED_SLABS=0"])
 def test_switch_is_bitwise_equal_to_the_default(switch):
     _child("variant", 1500, 200, switch)
+
+
+@pytest.mark.parametrize("n,pw", [(1500, 200), (2001, 192)])
+def test_backward_accumulation_of_q_agrees_with_the_forward_order(n, pw):
+    _child("q_forward", n, pw, 0)
 
 
 def test_sequential_gemv_order_agrees_with_the_linear_default():
