@@ -301,7 +301,6 @@ struct Rank {
     int gemm_tma = 3;                       // DMMA kernels fed by the TMA engine (dgemm_tma.cuh): bit 0 = the rank-nb updates (NT),
                                             // bit 1 = the skinny products (TN, NN); 0: the cp.async kernels (dgemm.cuh)
     int gemv_linear = 1;                    // fused kernel: the GEMV streams against the unscaled x (FusedArgs::linear)
-    size_t fused_smem_pad = 0;              // tuning aid: unused shared memory added to the fused kernel's launch (moves the L1 / shared-memory split)
     int q_backward = 256;                   // an identity Q on entry is accumulated backward after the reduction (reduce()) for
                                             // matrices of at least this order; 0: never (STARNEIG_B200_Q_BACKWARD)
     int fused_slabs = 1;                    // fused kernel: the CTA's rows of V in shared memory when they fit (FusedSmem)
@@ -336,15 +335,6 @@ struct Rank {
         if (e) q_backward = atoi(e);
         e = getenv("STARNEIG_B200_FUSED_SLABS");
         if (e) fused_slabs = std::max(0, std::min(1, atoi(e)));
-        e = getenv("STARNEIG_B200_FUSED_SMEM_PAD_KB");
-        fused_smem_pad = e ? (size_t)std::max(0, atoi(e)) * 1024 : 0;
-        e = getenv("STARNEIG_B200_FUSED_CARVEOUT");
-        {   // tuning aid: preferred carve-out in percent (-1: the driver's choice)
-            const int pct = e ? atoi(e) : -1;
-#define SB_FUSED_CARVE(D, S) SB_CUDA(cudaFuncSetAttribute(k_panel_fused<D, S>, cudaFuncAttributePreferredSharedMemoryCarveout, pct))
-            SB_FUSED_CARVE(false, 0); SB_FUSED_CARVE(true, 0);
-#undef SB_FUSED_CARVE
-        }
         int coop = 0;
         SB_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
         if (!coop) fused = 0;
@@ -570,9 +560,8 @@ struct Rank {
                 int slabs = fused_slabs;
                 while (slabs > 0 && fused_smem_bytes(w, f.nsub, f.kc, slabs) > FUSED_SLAB_SMEM_MAX) slabs--;
                 smem = fused_smem_bytes(w, f.nsub, f.kc, slabs);
-                smem = std::min(FUSED_SMEM_OPTIN, smem + fused_smem_pad);
-#define SB_FUSED_GO(S) do { if (P > 1) SB_LAUNCH_COOP((k_panel_fused<true, S>), ctas, FUSED_LAUNCH_THREADS, smem, st, f); \
-                            else       SB_LAUNCH_COOP((k_panel_fused<false, S>), ctas, FUSED_LAUNCH_THREADS, smem, st, f); } while (0)
+#define SB_FUSED_GO(S) do { if (P > 1) SB_LAUNCH_COOP((k_panel_fused<true, S>), ctas, FUSED_THREADS, smem, st, f); \
+                            else       SB_LAUNCH_COOP((k_panel_fused<false, S>), ctas, FUSED_THREADS, smem, st, f); } while (0)
                 if (slabs) SB_FUSED_GO(1); else SB_FUSED_GO(0);
 #undef SB_FUSED_GO
                 stats.kernel_launches++;
@@ -846,8 +835,6 @@ struct Rank {
             stats.gemv_ms = 1e-6 * (double)t[0];            // %globaltimer around the GEMV phases (incl. their barrier)
             stats.fused_kernel_ms = 1e-6 * (double)t[1];
             for (int k = 0; k < 4; k++) stats.fused_phase_ms[k] = 1e-6 * (double)t[2 + k];
-            if (SB_FUSED_BURN) fprintf(stderr, "[burn experiment] %.3e DMMA on SM 0 during %.1f ms of panel kernels: %.1f GFLOP/s per SM\n",
-                                       (double)t[6], stats.fused_kernel_ms, (double)t[6] * 512.0 / (stats.fused_kernel_ms * 1e6));
         } else if (lvl >= 2) {
             for (size_t k = 0; k + 3 < gemv_events_used; k += 4) {
                 SB_CUDA(cudaEventElapsedTime(&ms, gemv_events[k], gemv_events[k + 1])); stats.finish_update_ms += ms;

@@ -42,20 +42,7 @@ namespace sb200 {
 #ifndef SB_GEMV_U
 #define SB_GEMV_U 8
 #endif
-// Feasibility experiment (build flag, hardware A/B only): one extra warp per CTA issues FP64 tensor instructions on registers
-// while the panel kernel runs -- SB_FUSED_BURN = DMMAs per burst, SB_FUSED_BURN_SLEEP = ns between bursts -- to measure what
-// tensor work inside the persistent kernel (deferred updates by a dedicated warp) would cost the GEMV stream.
-#ifndef SB_FUSED_BURN
-#define SB_FUSED_BURN 0
-#endif
-#ifndef SB_FUSED_BURN_SLEEP
-#define SB_FUSED_BURN_SLEEP 0
-#endif
 constexpr int FUSED_THREADS = SB_FUSED_THREADS;
-constexpr int FUSED_LAUNCH_THREADS = FUSED_THREADS + (SB_FUSED_BURN ? 32 : 0);
-#if SB_FUSED_BURN
-#define __syncthreads() sb200::group_barrier(0, sb200::FUSED_THREADS)
-#endif
 constexpr int FUSED_WARPS = FUSED_THREADS / 32;
 constexpr int FUSED_MAX_NB = 512;
 constexpr int FUSED_VB = SB_FUSED_VB;                // 128-thread GEMV groups per CTA (warps 0..15); the other warps (16..19) look ahead
@@ -331,33 +318,8 @@ __device__ __noinline__ double fused_rescale_x(double *pcol, const double *V, in
 // The kernel. 640 threads x 96 registers: the CTA owns the register file of its SM (one CTA per SM, cooperative launch).
 // SLABS = 1: the CTA's rows of V resident in shared memory (FusedSmem); chosen per launch by what fits.
 template <bool DIST, int SLABS>
-__global__ void __launch_bounds__(FUSED_LAUNCH_THREADS, 1) k_panel_fused(FusedArgs f)
+__global__ void __launch_bounds__(FUSED_THREADS, 1) k_panel_fused(FusedArgs f)
 {
-#if SB_FUSED_BURN
-    __shared__ volatile int burn_done;
-    if (threadIdx.x == 0) burn_done = 0;
-    group_barrier(15, FUSED_LAUNCH_THREADS);
-    if (threadIdx.x >= FUSED_THREADS) {
-        double c[16];
-#pragma unroll
-        for (int q = 0; q < 16; q++) c[q] = 0.0;
-        const double av = 1.0 + threadIdx.x * 1e-9, bv = 1.0 - threadIdx.x * 1e-9;
-        unsigned long long count = 0;
-        while (!burn_done) {
-            for (int it = 0; it < SB_FUSED_BURN / 8; it++) {
-#pragma unroll
-                for (int q = 0; q < 8; q++) dmma884(c[2 * q], c[2 * q + 1], av, bv);
-            }
-            count += SB_FUSED_BURN / 8 * 8;
-            if (SB_FUSED_BURN_SLEEP) __nanosleep(SB_FUSED_BURN_SLEEP);
-        }
-        double sum = 0.0;
-#pragma unroll
-        for (int q = 0; q < 16; q++) sum += c[q];
-        if (blockIdx.x == 0 && threadIdx.x == FUSED_THREADS) { f.timers[6] += count; if (sum == 12345.678) f.timers[7] = 1; }
-        return;
-    }
-#endif
     // 16-byte loads in flight per GEMV thread: U columns being accumulated + U being fetched
     constexpr int GEMV_U = SB_GEMV_U;
     SB_DYNAMIC_SMEM(double, sh);
@@ -791,10 +753,6 @@ __global__ void __launch_bounds__(FUSED_LAUNCH_THREADS, 1) k_panel_fused(FusedAr
             if (timer) { t_mark = globaltimer_ns(); t_gemv += t_mark; }
         }
     }
-#if SB_FUSED_BURN
-    __syncthreads();
-    if (tid == 0) burn_done = 1;
-#endif
     if (timer) {
         f.timers[0] += t_gemv;
         f.timers[1] += globaltimer_ns() - t_begin;
@@ -807,6 +765,3 @@ __global__ void __launch_bounds__(FUSED_LAUNCH_THREADS, 1) k_panel_fused(FusedAr
 static inline size_t fused_smem_bytes(int w, int nsub, int kc = FUSED_KC, int slabs = 0) { return (size_t)FusedSmem(w, nsub, kc, slabs).total * sizeof(double); }
 
 } // namespace sb200
-#if SB_FUSED_BURN
-#undef __syncthreads
-#endif
