@@ -227,9 +227,10 @@ struct Workspace {
 // of (P, n_cap, nb_cap) and therefore identical on every rank.
 struct ArenaLayout {
     int P = 0, n_cap = 0, nb_cap = 0, ldv = 0, nbp = 0, ldp = 0;
-    size_t off_bar = 0, off_status = 0, off_rbcount = 0, off_yflag = 0, off_inbox = 0, off_pan = 0, off_wx = 0, bytes = 0;
+    size_t off_bar = 0, off_status = 0, off_rbcount = 0, off_yflag = 0, off_inbox = 0, off_pan = 0, off_wx = 0, off_qc = 0, bytes = 0;
+    int qc_cols = 0;            // columns of the rank's column-distributed Q (backward accumulation, Rank::reduce); 0: no such region
     static size_t align(size_t x) { return (x + 255) / 256 * 256; }
-    void set(int P_, int n, int nb)
+    void set(int P_, int n, int nb, int cb = 0)
     {
         P = P_; n_cap = n; nb_cap = nb;
         ldv = round_up(n, 16); nbp = round_up(nb, 8); ldp = round_up(n + 2, 16);
@@ -241,6 +242,11 @@ struct ArenaLayout {
         off_inbox = o;    o = align(o + (size_t)2 * P * ldp * 16);      // 16-byte LL entries (fused kernel) or doubles
         off_pan = o;      o = align(o + (size_t)ldv * (nbp + 8) * sizeof(double));    // the panel and the column right of it
         off_wx = o;       o = align(o + (size_t)ldv * nbp * sizeof(double));
+        // cb > 0: the rank's columns (block-cyclic like A: at most ceil(ceil(n / cb) / P) blocks) of Q = H_0 ... H_K-1, formed
+        // backward after the last panel and pulled into the row slabs by the peers (k_qcols_to_rows)
+        qc_cols = cb > 0 ? ceil_div(ceil_div(n, cb), P) * cb : 0;
+        off_qc = qc_cols > 0 ? o : 0;
+        o = align(o + (size_t)ldv * qc_cols * sizeof(double));
         bytes = o;
     }
 };
@@ -278,6 +284,14 @@ struct StageHook {
     virtual void panel_done(cudaStream_t s, int final_cols, bool q_too) = 0;
     virtual ~StageHook() {}
 };
+// the rank's row slab of Q: rows [q0, q1)
+static inline void q_row_range(int P, int g, int n, int *q0, int *q1)
+{
+    const int per = round_up(ceil_div(n, P), 8);
+    *q0 = std::min(n, g * per);
+    *q1 = std::min(n, (g + 1) * per);
+}
+
 struct PanelGrid { int blocks; TileGeom tg; size_t smem_fu, smem_rf; };
 
 struct Rank {
@@ -367,7 +381,7 @@ struct Rank {
         n = std::max(n, al.n_cap); nb = std::max(nb, al.nb_cap);
         SB_CUDA(cudaSetDevice(device));
         if (arena) { SB_CUDA(cudaDeviceSynchronize()); SB_CUDA(cudaFree(arena)); }
-        al.set(P, n, nb);
+        al.set(P, n, nb, q_backward > 0 ? cb : 0);
         SB_CUDA(cudaMalloc((void **)&arena, al.bytes));
         SB_CUDA(cudaMemset(arena, 0, al.off_pan));          // flags, counters, inbox
         SB_CUDA(cudaDeviceSynchronize());
@@ -679,7 +693,16 @@ struct Rank {
         // of a reduction) less. It needs V and VT of every panel until the end: the panels write them into the history
         // arrays (Workspace::Vh / VTh) instead of one recycled buffer. Whether Q is the identity is decided on the device
         // when Q is touched for the first time (after the first panel; the upload of a host Q hides behind that panel).
-        const bool hist = P == 1 && q_backward > 0 && n >= q_backward && begin == 0 && end == n && qrows == n && Q != nullptr && ws.ensure_history(n);
+        // Several GPUs: each rank forms ITS COLUMNS of the product (block-cyclic like A; the left-multiplications need no
+        // communication at all), and the ranks then pull their row slabs out of the peers' column blocks over NVLink
+        // (k_qcols_to_rows). Every rank must take the same branch (the barriers have to match): `bw_possible` depends on
+        // the arguments and the environment only, and the ranks agree on "every slab is a slab of the identity and every
+        // rank has room for the history" by a sum over ranks when Q is touched for the first time.
+        int q0 = 0, q1 = n;
+        if (P > 1) q_row_range(P, g, n, &q0, &q1);
+        const bool bw_possible = q_backward > 0 && n >= q_backward && begin == 0 && end == n && Q != nullptr &&
+                                 (P == 1 ? qrows == n : (al.off_qc != 0 && qrows == q1 - q0));
+        const bool hist = bw_possible && ws.ensure_history(n);
         bool backward = false;
         stats.q_backward = 0;
 
@@ -769,15 +792,30 @@ struct Rank {
                 gemm(GEMM_NT, m, nx, w, -1.0, V, ld, ws.W, ld, 1.0, X, ldA);
             }
             if (hook && panel == 0) hook->before_q(st);
-            if (hist && panel == 0) {
+            if (bw_possible && panel == 0) {
                 // is Q the identity? (one pass over Q: ~0.5 ms at n = 20000; the host waits for the answer once per reduction)
                 unsigned *flag = ws.counter + 2, h_flag = 1;
-                SB_CUDA(cudaMemsetAsync(flag, 0, sizeof(unsigned), st));
-                SB_LAUNCH(k_is_identity, dim3(std::min(n, 148 * 8)), 256, 0, st, n, Q, ldQ, flag);
-                stats.kernel_launches++;
-                SB_CUDA(cudaMemcpyAsync(&h_flag, flag, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
-                SB_CUDA(cudaStreamSynchronize(st));
-                backward = h_flag == 0;
+                SB_CUDA(cudaMemsetAsync(flag, hist ? 0 : 1, sizeof(unsigned), st));
+                if (hist) {
+                    SB_LAUNCH(k_is_identity, dim3(std::min(n, 148 * 8)), 256, 0, st, qrows, q0, n, Q, ldQ, flag);
+                    stats.kernel_launches++;
+                }
+                if (P == 1) {
+                    SB_CUDA(cudaMemcpyAsync(&h_flag, flag, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+                    SB_CUDA(cudaStreamSynchronize(st));
+                    backward = h_flag == 0;
+                } else {
+                    // sum over ranks of "my slab is not the identity / I have no room": through Wx, like the top-row products
+                    double h_sum = 1.0;
+                    barrier();                  // every rank has read Wx of the top-row update above
+                    SB_LAUNCH(k_flag_to_double, 1, 32, 0, st, flag, wxp.p[g]);
+                    barrier();
+                    SB_LAUNCH(k_sum_peers, dim3(1, 1), 32, 0, st, P, 1, wxp, al.ldv, ws.W, ld);
+                    stats.kernel_launches += 2;
+                    SB_CUDA(cudaMemcpyAsync(&h_sum, ws.W, sizeof(double), cudaMemcpyDeviceToHost, st));
+                    SB_CUDA(cudaStreamSynchronize(st));
+                    backward = h_sum == 0.0;
+                }
                 stats.q_backward = backward ? 1 : 0;
             }
             if (qrows > 0 && !backward)     // Q <- Q (I - V T V^T) on the rank's rows
@@ -789,12 +827,35 @@ struct Rank {
         if (backward) {
             // Q = H_0 ( H_1 ( ... H_K-1 I)): panel k acts on rows >= i + 1 and, the product so far being the identity
             // outside its trailing block, on columns >= i + 1 only:  Qb <- (I - V T V^T) Qb = Qb - VT (Qb^T V)^T
+            // One GPU: in place in Q. Several: on the rank's columns Qc (n x nloc in the exchange arena, identity at first).
+            double *Qc = Q;
+            int ldc = ldQ;
+            const int nloc = cm.lower(n);
+            if (P > 1) {
+                Qc = at<double>(g, al.off_qc); ldc = al.ldv;
+                if (nloc > 0) {
+                    SB_LAUNCH(k_identity_cols, dim3(ceil_div(n, 1024), nloc), 256, 0, st, cm, n, Qc, ldc);
+                    stats.kernel_launches++;
+                }
+            }
             for (int k = panel - 1; k >= 0; k--) {
                 const int i = begin + k * nb, w = std::min(nb, end - i - 1), m = end - i - 1, par = (i + 1) & 1;
                 const double *V = ws.Vh + (size_t)i * ld + par, *VT = ws.VTh + (size_t)i * ld + par;
-                double *Qb = Q + (size_t)(i + 1) * ldQ + i + 1;
-                gemm(GEMM_TN, m, w, m, 1.0, Qb, ldQ, V, ld, 0.0, ws.W, ld, true);
-                gemm(GEMM_NT, m, m, w, -1.0, VT, ld, ws.W, ld, 1.0, Qb, ldQ);
+                const int cl0 = cm.lower(i + 1), ncl = nloc - cl0;          // local columns of the trailing block
+                if (ncl <= 0) continue;
+                double *Qb = Qc + (size_t)cl0 * ldc + i + 1;
+                gemm(GEMM_TN, ncl, w, m, 1.0, Qb, ldc, V, ld, 0.0, ws.W, ld, true);
+                gemm(GEMM_NT, m, ncl, w, -1.0, VT, ld, ws.W, ld, 1.0, Qb, ldc);
+            }
+            if (P > 1) {
+                PeerPtrs qcp;
+                for (int s = 0; s < MAX_RANKS; s++) qcp.p[s] = s < P ? at<double>(s, al.off_qc) : nullptr;
+                barrier();                      // every rank's columns are complete
+                if (qrows > 0) {
+                    SB_LAUNCH(k_qcols_to_rows, dim3(ceil_div(qrows, 256), std::min(n, 16384)), 256, 0, st, cm, n, q0, qrows, qcp, al.ldv, Q, ldQ);
+                    stats.kernel_launches++;
+                }
+                // (the barrier that ends the reduction keeps the columns alive until every peer has pulled its rows)
             }
         }
         if (lvl >= 1) SB_CUDA(cudaEventRecord(phase_event(2 + 6 * panel + 2), st));
@@ -844,14 +905,6 @@ struct Rank {
         }
     }
 };
-
-// the rank's row slab of Q: rows [q0, q1)
-static inline void q_row_range(int P, int g, int n, int *q0, int *q1)
-{
-    const int per = round_up(ceil_div(n, P), 8);
-    *q0 = std::min(n, g * per);
-    *q1 = std::min(n, (g + 1) * per);
-}
 
 // The "automatic" panel width (conf->panel_width == STARNEIG_HESSENBERG_DEFAULT_PANEL_WIDTH). The reference fits a width to
 // its CPU codelets (src/hessenberg/interface.c:74-78: 0.0019 n + 274, i.e. 312 at n = 20000). Here the trade is another one:

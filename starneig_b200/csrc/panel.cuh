@@ -786,16 +786,44 @@ __global__ void k_barrier(int P, int g, unsigned epoch, BarPtrs bar, unsigned *s
     __threadfence_system();
 }
 
-// flag |= 1 unless Q (n x n, leading dimension ld) is exactly the identity (-0.0 counts as zero, a NaN as a mismatch):
-// decides between forward and backward accumulation of Q (engine.cuh, Rank::reduce). One block per column, grid-stride.
-__global__ void __launch_bounds__(256) k_is_identity(int n, const double *__restrict__ Q, int ld, unsigned *flag)
+// flag |= 1 unless rows [q0, q0 + rows) of the n-column matrix Q (leading dimension ld; Q points at row q0) are exactly those
+// rows of the identity (-0.0 counts as zero, a NaN as a mismatch): decides between forward and backward accumulation of Q
+// (engine.cuh, Rank::reduce). One block per column, grid-stride.
+__global__ void __launch_bounds__(256) k_is_identity(int rows, int q0, int n, const double *__restrict__ Q, int ld, unsigned *flag)
 {
     bool bad = false;
     for (int c = blockIdx.x; c < n; c += gridDim.x) {
         const double *q = Q + (size_t)c * ld;
-        for (int r = threadIdx.x; r < n; r += blockDim.x) bad = bad || !(q[r] == (r == c ? 1.0 : 0.0));
+        for (int r = threadIdx.x; r < rows; r += blockDim.x) bad = bad || !(q[r] == (r + q0 == c ? 1.0 : 0.0));
     }
     if (bad) atomicExch(flag, 1u);
+}
+
+// the rank's contribution to the sum over ranks that decides the accumulation order of Q: 0.0 = "identity slab, room for the history"
+__global__ void k_flag_to_double(const unsigned *flag, double *dst)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0) *dst = *flag != 0u ? 1.0 : 0.0;
+}
+
+// the rank's columns of the n x n identity: Qc(r, lc) = (r == global index of local column lc). grid = (row chunks of 1024, nloc)
+__global__ void __launch_bounds__(256) k_identity_cols(ColMap cm, int n, double *__restrict__ Qc, int ldc)
+{
+    const int lc = blockIdx.y, c = cm.l2g(lc);
+    double *q = Qc + (size_t)lc * ldc;
+    const int r_end = min(n, (int)(blockIdx.x + 1) * 1024);
+    for (int r = blockIdx.x * 1024 + threadIdx.x; r < r_end; r += 256) q[r] = r == c ? 1.0 : 0.0;
+}
+
+// Column blocks -> row slabs: Q(r - q0, c) = Qc_owner(c)(r, local index of c) for the rank's rows r in [q0, q0 + rows), pulled
+// from the owner's exchange arena over NVLink (a column is contiguous there). grid = (row chunks of 256, columns, grid-stride)
+__global__ void __launch_bounds__(256) k_qcols_to_rows(ColMap cm, int n, int q0, int rows, PeerPtrs qc, int ldc, double *__restrict__ Q, int ldq)
+{
+    const int rr = blockIdx.x * 256 + threadIdx.x;
+    if (rr >= rows) return;
+    for (int c = blockIdx.y; c < n; c += gridDim.y) {
+        const int lc = (c / (cm.cb * cm.P)) * cm.cb + c % cm.cb;
+        Q[(size_t)c * ldq + rr] = __ldcg(qc.p[cm.owner(c)] + (size_t)lc * ldc + q0 + rr);
+    }
 }
 
 } // namespace sb200

@@ -384,8 +384,25 @@ def test_sim_q_backward_accumulation(sim, ora, n, pw, sms):
             assert not np.array_equal(Q, Q1) and st["gemm_flops"] < st1["gemm_flops"]
 
 
+@pytest.mark.parametrize("gpus,n,pw,cb,sms", [(2, 96, 16, 8, 2), (3, 70, 16, 8, 2), (4, 150, 40, 16, 2), (8, 131, 24, 8, 1), (4, 20, 8, 16, 2)])
+def test_sim_q_backward_accumulation_multi_rank(sim, ora, gpus, n, pw, cb, sms):
+    """Several ranks: every rank forms its columns (block-cyclic like A) of Q = H_0 ... H_K-1 backward without any
+    communication, then the ranks pull their row slabs out of the peers' column blocks (k_qcols_to_rows). The ranks agree on
+    the order of accumulation by a sum over ranks. Same H bit for bit as the forward order, Q equal up to rounding."""
+    with _Env(CUSIM_SMS=sms, STARNEIG_B200_Q_BACKWARD=1, STARNEIG_B200_COL_BLOCK=cb):
+        A, Q, st = _reduce(sim, ora, n, pw, gpus=gpus)
+        assert st["q_backward"] == 1
+        with _Env(STARNEIG_B200_Q_BACKWARD=0):
+            A1, Q1, st1 = _reduce(sim, ora, n, pw, gpus=gpus)
+        assert st1["q_backward"] == 0
+        assert np.array_equal(A, A1)
+        assert np.abs(Q[:n] - Q1[:n]).max() <= 50 * n * U
+        if st["panels"] > 1:
+            assert not np.array_equal(Q, Q1)
+
+
 def test_sim_q_backward_only_for_an_identity_q(sim, ora):
-    """a general Q (the AED client's case), a partial reduction, several ranks or too little device memory: forward, as before"""
+    """a general Q (the AED client's case), a partial reduction or too little device memory: forward, as before"""
     n, pw = 96, 16
     A0, Q0, ld = ora.fullpos(n, 2019)
     rng = np.random.default_rng(5)
@@ -412,7 +429,7 @@ def test_sim_q_backward_only_for_an_identity_q(sim, ora):
         assert st["q_backward"] == 0
         _, _, st = _reduce(sim, ora, n, pw, begin=0, end=n - 7, generator="partial")
         assert st["q_backward"] == 0
-        _, _, st = _reduce(sim, ora, n, pw, gpus=2)
+        _, _, st = _reduce(sim, ora, n, pw, gpus=2, given=(A0, Qnan, ld))        # only the LAST rank's slab differs from I
         assert st["q_backward"] == 0
         with _Env(CUSIM_FREE_MB=16):
             _, _, st = _reduce(sim, ora, n, pw)
