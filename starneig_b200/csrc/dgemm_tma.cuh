@@ -65,7 +65,11 @@ static inline void sb_make_tensor_map(SbTensorMap *map, const double *base, unsi
     CUresult r = sb_encode_tiled()(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void *)base, dims, strides, box, estr,
                                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) fatal("cuTensorMapEncodeTiled failed", __FILE__, __LINE__);
+    if (r != CUDA_SUCCESS) {
+        fprintf(stderr, "[starneig] cuTensorMapEncodeTiled: result %d, base %p, dims %llu x %llu, ld %llu, box %u x %u\n", (int)r, (const void *)base,
+                dim0, dim1, ld, box0, box1);
+        fatal("cuTensorMapEncodeTiled failed", __FILE__, __LINE__);
+    }
 }
 #endif
 

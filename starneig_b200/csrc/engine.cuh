@@ -89,6 +89,10 @@ static void prepare_device_functions()
     SB_CUDA(cudaFuncGetAttributes(&fa, k_sum_peers));
     SB_CUDA(cudaFuncGetAttributes(&fa, k_barrier));
     SB_CUDA(cudaFuncGetAttributes(&fa, splitk_reduce_kernel));
+    SB_CUDA(cudaFuncGetAttributes(&fa, k_is_identity));
+    SB_CUDA(cudaFuncGetAttributes(&fa, k_flag_to_double));
+    SB_CUDA(cudaFuncGetAttributes(&fa, k_identity_cols));
+    SB_CUDA(cudaFuncGetAttributes(&fa, k_qcols_to_rows));
 #define SB_FUSED_PREP(D, S) SB_CUDA(cudaFuncSetAttribute(k_panel_fused<D, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FUSED_SMEM_OPTIN))
     SB_FUSED_PREP(false, 0); SB_FUSED_PREP(false, 1); SB_FUSED_PREP(true, 0); SB_FUSED_PREP(true, 1);
 #undef SB_FUSED_PREP
@@ -300,6 +304,9 @@ struct Rank {
     cudaStream_t stream = nullptr;          // the launch sequence of the reduction
     cudaStream_t copy = nullptr;            // host staging that overlaps the reduction (Q upload, write-back of finished columns)
     cudaEvent_t ev_q_up = nullptr, ev_cols_final = nullptr;
+    double *host_word = nullptr;            // page-locked: results the host waits for in the middle of a reduction. (A device-to-host
+                                            // copy into PAGEABLE memory blocks inside the driver while it waits for the stream; ranks
+                                            // that share a device then cannot launch the kernels this stream is waiting for.)
     Workspace ws;
     ArenaLayout al;
     char *arena = nullptr;                  // own arena (device memory on `device`)
@@ -332,6 +339,7 @@ struct Rank {
         SB_CUDA(cudaEventCreateWithFlags(&ev_q_up, cudaEventDisableTiming));
         SB_CUDA(cudaEventCreateWithFlags(&ev_cols_final, cudaEventDisableTiming));
         prepare_device_functions();
+        SB_CUDA(cudaMallocHost((void **)&host_word, 64));
         const char *e = getenv("STARNEIG_B200_COL_BLOCK");
         if (e && atoi(e) >= 8) cb = atoi(e) / 8 * 8;
         e = getenv("STARNEIG_B200_FUSED_PANEL");
@@ -368,6 +376,8 @@ struct Rank {
         if (arena) cudaFree(arena);
         arena = nullptr;
         al = ArenaLayout();
+        if (host_word) cudaFreeHost(host_word);
+        host_word = nullptr;
         cudaEventDestroy(ev_q_up); cudaEventDestroy(ev_cols_final);
         cudaStreamDestroy(stream);
         cudaStreamDestroy(copy);
@@ -644,6 +654,13 @@ struct Rank {
         stats.kernel_launches++;
     }
 
+    // room for the reflectors of a whole reduction when reduce() may accumulate Q backward (same conditions as there); callers
+    // that drive several ranks allocate it before the ranks start
+    void prepare_history(int n, int begin, int end, bool has_q)
+    {
+        if (q_backward > 0 && n >= q_backward && begin == 0 && end == n && has_q) ws.ensure_history(n);
+    }
+
     // X(rows x m) <- X (I - V T V^T) = X - (X VT) V^T  (reference update_right_a/b, src/hessenberg/cpu.c:443-560)
     void deferred_right_update(int rows, int m, int w, double *X, int ldx, const double *V, const double *VT, int ld, double *W)
     {
@@ -794,27 +811,30 @@ struct Rank {
             if (hook && panel == 0) hook->before_q(st);
             if (bw_possible && panel == 0) {
                 // is Q the identity? (one pass over Q: ~0.5 ms at n = 20000; the host waits for the answer once per reduction)
-                unsigned *flag = ws.counter + 2, h_flag = 1;
+                unsigned *flag = ws.counter + 2;
                 SB_CUDA(cudaMemsetAsync(flag, hist ? 0 : 1, sizeof(unsigned), st));
                 if (hist) {
                     SB_LAUNCH(k_is_identity, dim3(std::min(n, 148 * 8)), 256, 0, st, qrows, q0, n, Q, ldQ, flag);
                     stats.kernel_launches++;
                 }
                 if (P == 1) {
-                    SB_CUDA(cudaMemcpyAsync(&h_flag, flag, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+                    unsigned *h_flag = (unsigned *)host_word;
+                    *h_flag = 1;
+                    SB_CUDA(cudaMemcpyAsync(h_flag, flag, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
                     SB_CUDA(cudaStreamSynchronize(st));
-                    backward = h_flag == 0;
+                    backward = *h_flag == 0;
                 } else {
                     // sum over ranks of "my slab is not the identity / I have no room": through Wx, like the top-row products
-                    double h_sum = 1.0;
+                    double *h_sum = host_word;
+                    *h_sum = 1.0;
                     barrier();                  // every rank has read Wx of the top-row update above
                     SB_LAUNCH(k_flag_to_double, 1, 32, 0, st, flag, wxp.p[g]);
                     barrier();
                     SB_LAUNCH(k_sum_peers, dim3(1, 1), 32, 0, st, P, 1, wxp, al.ldv, ws.W, ld);
                     stats.kernel_launches += 2;
-                    SB_CUDA(cudaMemcpyAsync(&h_sum, ws.W, sizeof(double), cudaMemcpyDeviceToHost, st));
+                    SB_CUDA(cudaMemcpyAsync(h_sum, ws.W, sizeof(double), cudaMemcpyDeviceToHost, st));
                     SB_CUDA(cudaStreamSynchronize(st));
-                    backward = h_sum == 0.0;
+                    backward = *h_sum == 0.0;
                 }
                 stats.q_backward = backward ? 1 : 0;
             }
@@ -834,7 +854,7 @@ struct Rank {
             if (P > 1) {
                 Qc = at<double>(g, al.off_qc); ldc = al.ldv;
                 if (nloc > 0) {
-                    SB_LAUNCH(k_identity_cols, dim3(ceil_div(n, 1024), nloc), 256, 0, st, cm, n, Qc, ldc);
+                    SB_LAUNCH(k_identity_cols, dim3(ceil_div(n, 1024), std::min(nloc, 16384)), 256, 0, st, cm, n, nloc, Qc, ldc);
                     stats.kernel_launches++;
                 }
             }

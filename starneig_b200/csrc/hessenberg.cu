@@ -444,6 +444,9 @@ static starneig_error_t hessenberg_host(struct starneig_hessenberg_conf *conf, i
             SB_CUDA(cudaSetDevice(g_team.ranks[g]->device));
             g_team.shards[g].ensure(*g_team.ranks[g], n);
             g_team.ranks[g]->ws.ensure(n, std::min(nb, PANEL_MAX_NB), P > 1);
+            // (allocations happen here, before any rank's kernels wait for a peer: a cudaMalloc / cudaFree may wait for the
+            // device, and ranks that share a device -- STARNEIG_B200_VIRTUAL_RANKS -- would then wait for each other)
+            g_team.ranks[g]->prepare_history(n, begin, end, Q != nullptr);
         }
         SB_CUDA(cudaSetDevice(cur));
     }

@@ -805,13 +805,16 @@ __global__ void k_flag_to_double(const unsigned *flag, double *dst)
     if (threadIdx.x == 0 && blockIdx.x == 0) *dst = *flag != 0u ? 1.0 : 0.0;
 }
 
-// the rank's columns of the n x n identity: Qc(r, lc) = (r == global index of local column lc). grid = (row chunks of 1024, nloc)
-__global__ void __launch_bounds__(256) k_identity_cols(ColMap cm, int n, double *__restrict__ Qc, int ldc)
+// the rank's columns of the n x n identity: Qc(r, lc) = (r == global index of local column lc).
+// grid = (row chunks of 1024, local columns, grid-stride)
+__global__ void __launch_bounds__(256) k_identity_cols(ColMap cm, int n, int nloc, double *__restrict__ Qc, int ldc)
 {
-    const int lc = blockIdx.y, c = cm.l2g(lc);
-    double *q = Qc + (size_t)lc * ldc;
     const int r_end = min(n, (int)(blockIdx.x + 1) * 1024);
-    for (int r = blockIdx.x * 1024 + threadIdx.x; r < r_end; r += 256) q[r] = r == c ? 1.0 : 0.0;
+    for (int lc = blockIdx.y; lc < nloc; lc += gridDim.y) {
+        const int c = cm.l2g(lc);
+        double *q = Qc + (size_t)lc * ldc;
+        for (int r = blockIdx.x * 1024 + threadIdx.x; r < r_end; r += 256) q[r] = r == c ? 1.0 : 0.0;
+    }
 }
 
 // Column blocks -> row slabs: Q(r - q0, c) = Qc_owner(c)(r, local index of c) for the rank's rows r in [q0, q0 + rows), pulled

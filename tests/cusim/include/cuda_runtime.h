@@ -78,6 +78,8 @@ cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t s);
 cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t a, cudaEvent_t b);
 cudaError_t cudaPointerGetAttributes(cudaPointerAttributes *attr, const void *p);
 cudaError_t cudaHostRegister(void *p, size_t bytes, unsigned flags);
+static inline cudaError_t cudaMallocHost(void **p, size_t bytes) { *p = malloc(bytes); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
+static inline cudaError_t cudaFreeHost(void *p) { free(p); return cudaSuccess; }
 cudaError_t cudaHostUnregister(void *p);
 cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *h, void *p);
 cudaError_t cudaIpcOpenMemHandle(void **p, cudaIpcMemHandle_t h, unsigned flags);
