@@ -27,6 +27,7 @@
 // priority; they only depend on this panel's V and VT and touch disjoint data, so issuing them right
 // after the panel is the same computation.
 #pragma once
+#include <chrono>
 #include "panel.cuh"
 #include "panel_fused.cuh"
 #include "dgemm.cuh"
@@ -722,6 +723,14 @@ struct Rank {
         const bool hist = bw_possible && ws.ensure_history(n);
         bool backward = false;
         stats.q_backward = 0;
+        // STARNEIG_B200_TRACE: host-side progress of the rank on stderr (where is which rank when a cross-GPU wait times out)
+        const bool tracing = getenv("STARNEIG_B200_TRACE") != nullptr;
+        const auto trace_t0 = std::chrono::steady_clock::now();
+        auto trace = [&](const char *msg, int panel_no) {
+            if (!tracing) return;
+            const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - trace_t0).count();
+            fprintf(stderr, "[starneig][trace] rank %d (device %d) +%.1f ms: %s (panel %d, barriers %u)\n", g, device, ms, msg, panel_no, bar_epoch);
+        };
 
         // Schedule: one stream. Per panel: column loop (persistent kernel), trailing right / left updates, then the updates
         // the reference defers (rows above the panel, columns right of the block, Q). Running the deferred updates next to
@@ -810,6 +819,7 @@ struct Rank {
             }
             if (hook && panel == 0) hook->before_q(st);
             if (bw_possible && panel == 0) {
+                trace("order of the Q accumulation: asking the device", panel);
                 // is Q the identity? (one pass over Q: ~0.5 ms at n = 20000; the host waits for the answer once per reduction)
                 unsigned *flag = ws.counter + 2;
                 SB_CUDA(cudaMemsetAsync(flag, hist ? 0 : 1, sizeof(unsigned), st));
@@ -837,6 +847,7 @@ struct Rank {
                     backward = *h_sum == 0.0;
                 }
                 stats.q_backward = backward ? 1 : 0;
+                trace(backward ? "order of the Q accumulation: backward" : "order of the Q accumulation: forward", panel);
             }
             if (qrows > 0 && !backward)     // Q <- Q (I - V T V^T) on the rank's rows
                 deferred_right_update(qrows, m, w, Q + (size_t)(i + 1) * ldQ, ldQ, V, VT, ld, ws.W);
@@ -844,6 +855,7 @@ struct Rank {
             if (hook) hook->panel_done(st, i + w, !backward);
         }
         if (lvl >= 1) SB_CUDA(cudaEventRecord(phase_event(2 + 6 * panel + 1), st));
+        trace("all panels enqueued", panel);
         if (backward) {
             // Q = H_0 ( H_1 ( ... H_K-1 I)): panel k acts on rows >= i + 1 and, the product so far being the identity
             // outside its trailing block, on columns >= i + 1 only:  Qb <- (I - V T V^T) Qb = Qb - VT (Qb^T V)^T
@@ -882,7 +894,9 @@ struct Rank {
         barrier();
         if (lvl >= 1) SB_CUDA(cudaEventRecord(phase_event(2 + 6 * panel), st));       // end of the critical path
         SB_CUDA(cudaEventRecord(ev_last, st));
+        trace("everything enqueued", panel);
         SB_CUDA(cudaStreamSynchronize(st));
+        trace("stream idle", panel);
         SB_CUDA(cudaGetLastError());
         if (P > 1) {
             unsigned status = 0;

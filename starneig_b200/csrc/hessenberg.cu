@@ -226,11 +226,18 @@ struct Team {
         shards.resize(P);
         // ranks that share a device (development aid) must share its SMs: the persistent panel kernels of all of
         // them have to be co-resident
+        bool shared = false;
         for (int g = 0; g < P; g++) {
             int sharing = 0;
             for (int s = 0; s < P; s++) sharing += ranks[s]->device == ranks[g]->device;
             ranks[g]->fused_ctas = std::max(1, ranks[g]->fused_ctas / sharing);
+            shared = shared || sharing > 1;
         }
+        // Ranks that share a device accumulate Q forward: the backward order makes every rank's host wait for its stream in the
+        // middle of the reduction, and with several host threads on ONE device such waits can hold up the launches of the ranks
+        // the stream is waiting for (seen with 8 ranks on 2 GPUs; one rank per GPU is not affected).
+        if (shared)
+            for (Rank *r : ranks) r->q_backward = 0;
         for (int g = 0; g < P; g++)
             for (int s = 0; s < P; s++)
                 if (ranks[g]->device != ranks[s]->device) {
