@@ -42,9 +42,10 @@ FP64_DMMA_TFLOPS = 37.0      # measured DMMA issue peak (profiles/r1_probe_peaks
 FP64_CUBLAS_TFLOPS = 35.7    # measured cublasDgemm 8192^3 (profiles/r1_probe_peaks.log)
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full captures (profiles/), relative to
 # the algorithmic GEMV bytes of that launch.
-# k_panel_fused (profiles/r1_s4_ncu_full_fused_and_dgemm.txt, panel i=624): 944.8 GB DRAM vs 929.5 GB algorithmic; the
-# extra 1.6 % is the level-2 side traffic of the panel (Y, V, VT re-read per column once they no longer fit in L2)
-FUSED_TRAFFIC_RATIO = 1.016
+# k_panel_fused<0, 0> at the automatic width 192 (profiles/r2_final2_ncu_full_fused.txt, panel i=384): 589.9 GB DRAM vs 588.1 GB
+# algorithmic; the extra 0.3 % is the level-2 side traffic of the panel (Y, V, VT of 192 columns stay in L2 for most of it;
+# at width 312, round 1, it was 1.6 %: profiles/r1_s4_ncu_full_fused_and_dgemm.txt)
+FUSED_TRAFFIC_RATIO = 1.003
 # k_col_gemv alone (profiles/r1_ncu_full_baseline.txt): 3.1807 GB DRAM vs 3.1757 GB algorithmic
 GEMV_TRAFFIC_RATIO = 1.0015
 
