@@ -45,7 +45,7 @@ random.seed(int(sys.argv[1]) if len(sys.argv) > 1 else 1)
 t_end = time.time() + (float(sys.argv[2]) if len(sys.argv) > 2 else 240.0)
 bad = runs = 0
 while time.time() < t_end:
-    P = random.choice([1, 1, 1, 2, 3, 4])
+    P = random.choice([1, 1, 1, 2, 2, 3, 4, 8])
     n = random.choice([random.randint(3, 170), random.randint(260, 340)])
     pw = random.choice([8, 16, 24, 35, 64, 100])
     env = dict(os.environ, CUSIM_SMS=str(random.choice([1, 2, 3, 4, 6])), CUSIM_DEVICES="8", CUSIM_CHECK_PREFETCH="1",
@@ -55,6 +55,8 @@ while time.time() < t_end:
     if random.random() < 0.3: sw["GEMM_TMA"] = random.choice([0, 1, 2])
     if random.random() < 0.4: sw["GEMV_KC"] = random.choice([64, 128, 2048])
     if random.random() < 0.15: sw["FUSED_PANEL"] = 0
+    if random.random() < 0.25: sw["Q_BACKWARD"] = 0          # the reference's forward order (default: backward for Q = I)
+    if random.random() < 0.2: sw["FUSED_SLABS"] = 0
     if random.random() < 0.3: env["CUSIM_SHUFFLE"] = str(random.randint(1, 99))
     if random.random() < 0.3: env["CUSIM_SKEW"] = str(random.choice([2, 3, 5]))
     for k, v in sw.items():
