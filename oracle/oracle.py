@@ -118,8 +118,8 @@ class Oracle:
 
 
 class Reference:
-    """The reference's own src/hessenberg + src/common sources, compiled against the sequential StarPU
-    stand-in (oracle/ref_shim). Only available where oracle/_ref has been built."""
+    """The reference's own src/hessenberg + src/common sources, compiled against the StarPU stand-in
+    (oracle/ref_shim). Only available where oracle/_ref has been built."""
 
     def __init__(self):
         if not os.path.exists(REF_SO):
@@ -134,7 +134,17 @@ class Reference:
         self.lib.oracle_ref_set_threads(t)
 
     def set_workers(self, w):
+        """number of workers REPORTED to the reference (its default tile size depends on it)"""
         self.lib.oracle_ref_set_workers(w)
+
+    def set_executors(self, count):
+        """threads that execute the task graph in parallel under its data dependencies (0: every task inline at its
+        insertion point, the default and what the fixtures use); oracle/ref_shim/mini_starpu.c"""
+        self.lib.oracle_ref_set_executors(count)
+
+    def tasks_executed(self, reset=False):
+        self.lib.oracle_ref_tasks_executed.restype = ctypes.c_ulong
+        return int(self.lib.oracle_ref_tasks_executed(1 if reset else 0))
 
     def hessenberg(self, n, A, ldA, Q, ldQ):
         return self.lib.starneig_SEP_SM_Hessenberg(n, _p(A), ldA, _p(Q), ldQ)

@@ -2,8 +2,9 @@
  *
  * The reference's node lifecycle (src/common/node.c) starts StarPU, hwloc and cuBLAS; none of which exist
  * here. The Hessenberg interface only needs the five internal hooks below (src/common/node_internal.h,
- * called from src/hessenberg/interface.c:152-164), so they are provided as no-ops: the sequential StarPU
- * stand-in needs no workers, and BLAS threading is left to the caller (oracle_ref_set_threads).
+ * called from src/hessenberg/interface.c:152-164), so they are provided as no-ops: the StarPU stand-in's
+ * executor threads (if any) are started by oracle_ref_set_executors, and BLAS threading is left to the caller
+ * (oracle_ref_set_threads).
  */
 #include "ref_shim/starpu.h"
 #include "ref_shim/cblas.h"
@@ -17,4 +18,5 @@ void starneig_node_resume_awake_starpu(void) {}
 
 void oracle_ref_set_threads(int threads) { openblas_set_num_threads(threads); }
 void oracle_ref_set_workers(int workers) { oracle_starpu_set_worker_count((unsigned)workers); }
+void oracle_ref_set_executors(int count) { oracle_starpu_set_executors(count); }
 unsigned long oracle_ref_tasks_executed(int reset) { return oracle_starpu_tasks_executed(reset); }

@@ -1,11 +1,13 @@
-/* Sequential stand-in for the StarPU task runtime (NOT StarPU, no StarPU code).
+/* Stand-in for the StarPU task runtime (NOT StarPU, no StarPU code).
  *
  * Purpose: let the reference's own Hessenberg path -- src/hessenberg/{interface,core,tasks,cpu}.c
  * and the src/common plumbing it uses -- compile from where it lies under /root/reference and run
  * on this image, which has no StarPU. StarPU's sequential-task-flow contract guarantees that
- * executing every task at its insertion point is a valid schedule, so starpu_task_insert() here
- * simply runs the codelet's CPU body immediately on the calling thread. Data handles are plain
- * host buffers. Only the API surface the hot path touches is declared.
+ * executing every task at its insertion point is a valid schedule, so by default starpu_task_insert()
+ * here simply runs the codelet's CPU body immediately on the calling thread; with executor threads
+ * (oracle_starpu_set_executors) the tasks run in parallel under the dependencies their access modes
+ * imply (mini_starpu.c). Data handles are plain host buffers. Only the API surface the hot path
+ * touches is declared.
  *
  * Test infrastructure only (oracle/_ref); never linked into the product library.
  */
@@ -149,6 +151,8 @@ int starpu_task_nsubmitted(void);
 
 /* stand-in control: number of workers reported to the reference's default-tile-size formula */
 void oracle_starpu_set_worker_count(unsigned workers);
+/* stand-in control: number of threads that execute tasks in parallel (0: inline at the insertion point, the default) */
+void oracle_starpu_set_executors(int count);
 /* statistics: tasks executed since the last reset */
 unsigned long oracle_starpu_tasks_executed(int reset);
 

@@ -24,7 +24,7 @@ def ora():
 
 @pytest.fixture(scope="session")
 def ref():
-    """the reference's own sources built against the sequential StarPU stand-in (absent => skip)"""
+    """the reference's own sources built against the StarPU stand-in, inline schedule (absent => skip)"""
     from oracle.oracle import Reference
     if not Reference.available():
         pytest.skip("oracle/_ref not built (needs /root/reference at build time)")

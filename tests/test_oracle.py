@@ -65,6 +65,34 @@ def test_port_matches_live_reference(ora, ref, n, tile, pw):
     assert ora.hessenberg_form_violations(n, A1, ld) == 0
 
 
+@pytest.mark.parametrize("n,tile,pw,executors,begin,end", [
+    (60, 16, 8, 3, 0, None), (200, 48, 45, 8, 0, None), (333, 64, 35, 2, 0, None), (554, 96, 170, 5, 0, None),
+    (400, 56, -1, 1, 0, None), (333, 24, 16, 4, 83, 249), (1000, -1, -1, 8, 0, None)])
+def test_reference_task_graph_in_parallel(ora, ref, n, tile, pw, executors, begin, end):
+    """The StarPU stand-in's parallel schedule (oracle/ref_shim/mini_starpu.c: worker threads, dependencies inferred from the
+    access modes in insertion order) against its inline schedule on the reference's own task graph: with sequential BLAS the
+    order of every floating-point sum is the same, so H and Q agree bit for bit. bench.py --impl reference times the parallel
+    schedule; this is what makes that number a number of the reference's algorithm."""
+    end = n if end is None else end
+    A0, Q0, ld = ora.partial(n, begin, end, 9) if (begin, end) != (0, n) else ora.fullpos(n, 5)
+    A1, Q1 = A0.copy(order="F"), Q0.copy(order="F")
+    A2, Q2 = A0.copy(order="F"), Q0.copy(order="F")
+    ref.set_workers(executors)
+    try:
+        assert ref.hessenberg_expert(n, A1, ld, Q1, ld, begin, end, tile, pw) == 0
+        ref.tasks_executed(reset=True)
+        ref.set_executors(executors)
+        assert ref.hessenberg_expert(n, A2, ld, Q2, ld, begin, end, tile, pw) == 0
+        tasks = ref.tasks_executed(reset=True)
+    finally:
+        ref.set_executors(0)
+        ref.set_workers(1)
+    assert tasks > (end - begin - 1) * 3               # at least prepare / compute / finish per column
+    assert np.array_equal(A1, A2) and np.array_equal(Q1, Q2)
+    assert ora.hessenberg_form_violations(n, A2, ld, begin, end, check_outside=True) == 0
+    assert ora.residual_u(n, Q2, ld, A2, ld, A0, ld) < 500 and ora.orthogonality_u(n, Q2, ld) < 500
+
+
 @pytest.mark.parametrize("n", [47, 88, 333])
 def test_live_reference_partial(ora, ref, n):
     # partial-hessenberg ctest sizes (test/CMakeLists.txt:389-406): begin = n/4, end = 3n/4
