@@ -225,13 +225,37 @@ def cpu_reference_run(n, threads, schedule="task-parallel"):
     return dt, kind
 
 
+def cpu_reference_child(n, schedule, count, timeout_s):
+    """`count` reductions under `schedule` in a CHILD process with a time limit (the task-parallel executor of the stand-in is
+    the one piece of the CPU arm that could deadlock; a child keeps that from taking the bench line with it).
+    Returns the list of seconds, or None when the child failed or ran out of time."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--cpu-child", schedule, "--steps", str(count), "--cpu-n", str(n)]
+    try:
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout_s)
+        if out.returncode != 0:
+            print(f"[bench] CPU reference child ({schedule}) failed: {out.stderr[-400:]}", file=sys.stderr)
+            return None
+        return json.loads(out.stdout.strip().splitlines()[-1])["seconds"]
+    except (subprocess.TimeoutExpired, ValueError, KeyError, IndexError) as e:
+        print(f"[bench] CPU reference child ({schedule}) gave no result: {e!r}", file=sys.stderr)
+        return None
+
+
+def run_cpu_child(args):
+    cores = min(os.cpu_count() or 1, 64)
+    secs = [cpu_reference_run(args.cpu_n, cores, args.cpu_child)[0] for _ in range(args.steps)]
+    print(json.dumps({"seconds": secs}))
+
+
 def cpu_reference_probe(n, threads):
-    """Both schedules of the reference's task graph once each; returns (faster schedule, {schedule: seconds}, kind)."""
-    secs, kind = {}, "port"
-    for schedule in SCHEDULES:
-        secs[schedule], kind = cpu_reference_run(n, threads, schedule)
-        if kind == "port":          # no reference build: the port has one schedule (threaded BLAS)
-            return "blas-parallel", {"blas-parallel": secs[schedule]}, kind
+    """Both schedules of the reference's task graph once each; returns (faster schedule, {schedule: seconds}, kind).
+    A schedule that failed is missing from the dict."""
+    t_blas, kind = cpu_reference_run(n, threads, "blas-parallel")
+    secs = {"blas-parallel": t_blas}
+    if kind == "reference":         # (the port has one schedule: threaded BLAS)
+        t = cpu_reference_child(n, "task-parallel", 1, max(180.0, 8.0 * t_blas))
+        if t:
+            secs["task-parallel"] = t[0]
     return min(secs, key=secs.get), secs, kind
 
 
@@ -245,17 +269,23 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
+    cores = min(os.cpu_count() or 1, 64)
     n = args.cpu_n
     # the reference's task graph under both schedules, once each (untimed: they are also the first two warm-up steps);
     # the timed steps use the faster one
     schedule, probe, kind = cpu_reference_probe(n, cores)
-    for _ in range(max(0, args.warmup - len(probe))):
-        cpu_reference_run(n, cores, schedule)
-    times = []
-    for _ in range(args.steps):
-        dt, kind = cpu_reference_run(n, cores, schedule)
-        times.append(dt)
+    extra_warmup = max(0, args.warmup - len(probe))
+    times = None
+    if schedule == "task-parallel":
+        t = cpu_reference_child(n, schedule, extra_warmup + args.steps, (extra_warmup + args.steps) * 4.0 * probe[schedule] + 120.0)
+        if t:
+            times = t[extra_warmup:]
+        else:
+            schedule = "blas-parallel"
+    if times is None:
+        for _ in range(extra_warmup):
+            cpu_reference_run(n, cores, schedule)
+        times = [cpu_reference_run(n, cores, schedule)[0] for _ in range(args.steps)]
     ms = 1e3 * sum(times) / len(times)
     value = flops(n) / (ms * 1e-3) / 1e9
     # the reference test driver's other CPU solver (LAPACK dgehrd + dormhr, threaded BLAS) on the same sample, once
@@ -620,7 +650,7 @@ def run_ours(args):
     # ---------------- CPU baseline (bounded sample) ----------------
     cpu = None
     if world == 1 and not args.no_cpu:
-        cores = os.cpu_count() or 1
+        cores = min(os.cpu_count() or 1, 64)
         schedule, probe, kind = cpu_reference_probe(args.cpu_n, cores)
         dt = probe[schedule]
         lapack_s = cpu_lapack_run(args.cpu_n, cores)
@@ -674,11 +704,14 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-threads-e2e", action="store_true", help="N > 1: skip the one-process (thread per GPU) timing of the reference-facing call")
     ap.add_argument("--e2e-threads-child", action="store_true", help=argparse.SUPPRESS)
+    ap.add_argument("--cpu-child", default=None, choices=list(SCHEDULES), help=argparse.SUPPRESS)
     ap.add_argument("--no-e2e", action="store_true",
                     help="skip the host-buffer arm (development runs at sizes whose host copies do not fit comfortably)")
     args = ap.parse_args()
     if args.e2e_threads_child:
         run_threads_child(args)
+    elif args.cpu_child:
+        run_cpu_child(args)
     elif args.impl == "reference":
         run_reference_arm(args)
     else:

@@ -18,7 +18,7 @@
  *
  * Pinning (see oracle/README.md, DESIGN.md "Oracle"): the reference ships NO golden vectors for this
  * path; its tests are invariants. The port is pinned against (i) the reference's OWN
- * sources compiled from /root/reference with a sequential StarPU stand-in (oracle/_ref, built by
+ * sources compiled from /root/reference with a StarPU stand-in (oracle/_ref, built by
  * oracle/Makefile; tests/test_oracle.py compares entrywise) with outputs committed as fixtures under
  * tests/golden/, (ii) LAPACK dgehrd/dormhr, and (iii) the reference driver's invariants
  * (exact-zero Hessenberg form, residual and orthogonality thresholds).
