@@ -327,9 +327,12 @@ bool inside_device_allocation(const void *p, size_t bytes)
 }
 cudaError_t cusimMalloc(void **p, size_t bytes)
 {
-    const size_t rounded = (bytes + 255) / 256 * 256 + 256;
-    void *q = aligned_alloc(256, rounded);
-    if (!q) return cudaErrorMemoryAllocation;
+    // CUSIM_EXACT_ALLOC=1 (runs under AddressSanitizer): exactly `bytes`, so that the first byte past a device allocation is a
+    // red zone; otherwise the allocation granularity of the hardware is mimicked
+    static const bool exact = getenv("CUSIM_EXACT_ALLOC") && atoi(getenv("CUSIM_EXACT_ALLOC")) != 0;
+    const size_t rounded = exact ? std::max<size_t>(bytes, 1) : (bytes + 255) / 256 * 256 + 256;
+    void *q = nullptr;
+    if (posix_memalign(&q, 256, rounded) != 0 || !q) return cudaErrorMemoryAllocation;
     memset(q, 0xff, rounded);       // NaN doubles, 0xffffffff flags: nothing may rely on fresh memory being zero
     *p = q;
     std::lock_guard<std::mutex> lock(alloc_mutex);
