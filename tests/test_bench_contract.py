@@ -31,6 +31,11 @@ def test_reference_arm_line():
     cb = j["cpu_baseline"]
     assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == j["value"] and cb["sample"]
     assert cb["lapack"]["value"] > 0 and "dgehrd" in cb["lapack"]["what"]
+    # the reference's task graph is timed under both schedules of the StarPU stand-in; the faster one carries the value
+    if cb["kind"] == "reference":
+        probed = cb["schedules_probed"]
+        assert set(probed) == {"task-parallel", "blas-parallel"} and all(v["value"] > 0 for v in probed.values())
+        assert cb["schedule"] == max(probed, key=lambda k: probed[k]["value"]) and cb["schedule"] in cb["sample"]
     assert j["e2e"] == {"value": j["value"], "unit": j["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 
