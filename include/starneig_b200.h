@@ -18,7 +18,8 @@ extern "C" {
 /* Device-resident reduction: same semantics as starneig_SEP_SM_Hessenberg_expert
  * (reference src/hessenberg/interface.c:138-167) but dA/dQ already live in HBM. Requirements:
  * 16-byte aligned pointers and even leading dimensions (returns -6 / -8 otherwise).
- * panel_width < 0 selects the reference default (interface.c:74-78). Blocking. */
+ * panel_width < 0 selects the automatic width (192 on this hardware; the reference's own default,
+ * interface.c:74-78, is fitted to its CPU codelets). Blocking. */
 starneig_error_t starneig_b200_hessenberg_device(
     int n, int begin, int end, int panel_width, double *dA, int ldA, double *dQ, int ldQ);
 
@@ -30,8 +31,7 @@ struct starneig_b200_stats {
     double device_ms;        /* first kernel to last kernel */
     double panel_ms;         /* sum over panels: column loops (panel kernels + GEMV) */
     double trail_ms;         /* sum over panels: trailing right + left updates (critical path) */
-    double other_ms;         /* sum over panels: top rows, partial columns and Q updates (busy time of the stream they
-                              * ran on: with `overlap` they run concurrently with the next column loops) */
+    double other_ms;         /* sum over panels: top rows, partial columns and Q updates, plus the backward pass over Q */
     double gemv_ms;          /* sum of the durations of the event-timed GEMV launches (profile level >= 2) */
     long long gemv_launches;
     double gemv_bytes;       /* algorithmic bytes read by all GEMV launches: 8 * sum rows*cols */
@@ -47,7 +47,7 @@ struct starneig_b200_stats {
     double fused_kernel_ms;  /* total run time of the persistent panel kernels (device-side timer) */
     double fused_phase_ms[4];/* its level-2 phases, each including the grid barrier that ends it: finish+update (A),
                               * w2 reduction (A'), reflector (R), scalars + s (R') */
-    int overlap;             /* 1: the Q / top-row updates ran on the side stream, overlapped with the column loops */
+    int overlap;             /* always 0: the deferred updates run in line (every overlapped variant lost on hardware) */
     double side_tail_ms;     /* end of the last trailing update -> end of the call (what the deferred updates still add) */
     long long gemm_tma_launches, gemm_cpasync_launches;   /* DMMA kernel launches by kind of tile movement (dgemm_tma.cuh / dgemm.cuh) */
     int staging_overlapped;  /* host API: 1 if the host buffers were page-locked from end to end, so that Q's upload and the
@@ -55,8 +55,8 @@ struct starneig_b200_stats {
                               * alone and d2h_ms what was left of the write-back when the reduction ended) */
     int panel_width_used;    /* panel width of the reduction (the requested one unless it exceeds what the panel kernels'
                               * shared-memory layout holds: > 1024 columns, or a narrower limit for n > ~70000) */
-    int q_backward;          /* 1: Q was the identity on entry and was accumulated backward after the last panel (one GPU, full
-                              * reduction: 4/3 n^3 instead of 2 n^3 flops for Q; engine.cuh, Rank::reduce) */
+    int q_backward;          /* 1: Q was the identity on entry and was accumulated backward after the last panel (full reduction,
+                              * one or several GPUs: 4/3 n^3 instead of 2 n^3 flops for Q; engine.cuh, Rank::reduce) */
     double q_backward_ms;    /* duration of that backward pass (also counted in other_ms) */
     int fused_slab_panels[2];/* panels of the persistent kernel without [0] / with [1] the CTA's rows of V resident in shared
                               * memory (panel_fused.cuh, FusedSmem) */
@@ -95,7 +95,7 @@ starneig_error_t starneig_b200_SEP_SM_Reduce(int n, double A[], int ldA, double 
 #define STARNEIG_B200_MAX_N 131056
 
 /* Host-only arithmetic (no GPU needed): the workspace plan for an n x n reduction with the given panel width
- * (< 0: reference default) on `ranks` GPUs. out[0] = panel width that would be used, out[1] = dynamic shared memory
+ * (< 0: the automatic width) on `ranks` GPUs. out[0] = panel width that would be used, out[1] = dynamic shared memory
  * (bytes) of the persistent panel kernel for the first panel (0: it does not fit, the per-column kernels run),
  * out[2] = capacity of the GEMV partial-sum buffer (doubles), out[3] = largest number of doubles any column of the
  * per-column path would write into it. Returns 0, or STARNEIG_INVALID_ARGUMENTS if n is not supported. */
@@ -109,7 +109,7 @@ void starneig_b200_set_profile_level(int level);
  *
  * Every rank process selects its CUDA device, calls starneig_node_init, then
  *   starneig_b200_dist_init(world, rank, n_max, panel_width_max, handle)   -> 64-byte cudaIpcMemHandle of the
- *       rank's exchange arena (panel_width_max < 8: reference default for n_max),
+ *       rank's exchange arena (panel_width_max < 8: the automatic width for n_max),
  *   all-gathers the handles (e.g. torch.distributed.all_gather) and passes them, in rank order, to
  *   starneig_b200_dist_connect(handles).
  * After that the ranks call the reduction collectively. All data-path communication (the per-column sum of
