@@ -5,7 +5,8 @@
  *   inline   (executor threads = 0, the default): starpu_task_insert() runs the codelet's CPU body at its insertion point on
  *            the calling thread. The golden fixtures and the parity tests use this one.
  *   parallel (oracle_starpu_set_executors(W), W >= 1): W worker threads execute the tasks as soon as their data dependencies
- *            allow, three priority levels, highest first, first-in first-out inside a level. Dependencies are inferred per data
+ *            allow, three priority levels, highest first, first-in first-out inside a level (one central queue: the shape of
+ *            StarPU's "prio" policy, which the reference selects for CPU-only runs, src/common/node.c:326-331). Dependencies are inferred per data
  *            handle from the access modes in insertion order -- StarPU's sequential-consistency rule: a reader waits for the
  *            last writer, a writer for the last writer and for every reader since. STARPU_COMMUTE is honoured conservatively
  *            (ordered like a plain RW access: a valid schedule with less freedom than StarPU's; it also keeps the order of
